@@ -1,0 +1,181 @@
+"""ctypes bindings used by the tests: the reference build (oracle/_ref, checker only) and the oracle port.
+
+The structs mirror astcenc.h (astcenc_config :427-605, astcenc_image :613-629, astcenc_swizzle :300-313).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libastcenc_ref_avx2.so")
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libastc_oracle.so")
+
+PRF_LDR_SRGB, PRF_LDR, PRF_HDR_RGB_LDR_A, PRF_HDR = 0, 1, 2, 3
+PRE_FASTEST, PRE_FAST, PRE_MEDIUM, PRE_THOROUGH, PRE_VERYTHOROUGH, PRE_EXHAUSTIVE = 0.0, 10.0, 60.0, 98.0, 99.0, 100.0
+FLG_MAP_NORMAL, FLG_USE_DECODE_UNORM8, FLG_USE_ALPHA_WEIGHT, FLG_USE_PERCEPTUAL = 1, 2, 4, 8
+FLG_DECOMPRESS_ONLY, FLG_SELF_DECOMPRESS_ONLY, FLG_MAP_RGBM = 16, 32, 64
+TYPE_U8, TYPE_F16, TYPE_F32 = 0, 1, 2
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("profile", C.c_int), ("flags", C.c_uint), ("block_x", C.c_uint), ("block_y", C.c_uint), ("block_z", C.c_uint),
+        ("cw_r_weight", C.c_float), ("cw_g_weight", C.c_float), ("cw_b_weight", C.c_float), ("cw_a_weight", C.c_float),
+        ("a_scale_radius", C.c_uint), ("rgbm_m_scale", C.c_float),
+        ("tune_partition_count_limit", C.c_uint), ("tune_2partition_index_limit", C.c_uint),
+        ("tune_3partition_index_limit", C.c_uint), ("tune_4partition_index_limit", C.c_uint),
+        ("tune_block_mode_limit", C.c_uint), ("tune_refinement_limit", C.c_uint), ("tune_candidate_limit", C.c_uint),
+        ("tune_2partitioning_candidate_limit", C.c_uint), ("tune_3partitioning_candidate_limit", C.c_uint),
+        ("tune_4partitioning_candidate_limit", C.c_uint),
+        ("tune_db_limit", C.c_float), ("tune_mse_overshoot", C.c_float),
+        ("tune_2partition_early_out_limit_factor", C.c_float), ("tune_3partition_early_out_limit_factor", C.c_float),
+        ("tune_2plane_early_out_limit_correlation", C.c_float), ("tune_search_mode0_enable", C.c_float),
+        ("progress_callback", C.c_void_p),
+    ]
+
+
+class Image(C.Structure):
+    _fields_ = [("dim_x", C.c_uint), ("dim_y", C.c_uint), ("dim_z", C.c_uint), ("data_type", C.c_int), ("data", C.POINTER(C.c_void_p))]
+
+
+class Swizzle(C.Structure):
+    _fields_ = [("r", C.c_int), ("g", C.c_int), ("b", C.c_int), ("a", C.c_int)]
+
+
+def _bind(lib):
+    lib.astcenc_config_init.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_float, C.c_uint, C.POINTER(Config)]
+    lib.astcenc_config_init.restype = C.c_int
+    lib.astcenc_context_alloc.argtypes = [C.POINTER(Config), C.c_uint, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.astcenc_context_alloc.restype = C.c_int
+    lib.astcenc_compress_image.argtypes = [C.c_void_p, C.POINTER(Image), C.POINTER(Swizzle), C.c_void_p, C.c_size_t, C.c_uint]
+    lib.astcenc_compress_image.restype = C.c_int
+    lib.astcenc_compress_reset.argtypes = [C.c_void_p]
+    lib.astcenc_compress_reset.restype = C.c_int
+    lib.astcenc_context_free.argtypes = [C.c_void_p]
+    lib.astcenc_context_free.restype = None
+    lib.astcenc_get_error_string.argtypes = [C.c_int]
+    lib.astcenc_get_error_string.restype = C.c_char_p
+    return lib
+
+
+class AstcencLib:
+    """Any library exporting the astcenc.h C ABI (the reference build or the B200 product)."""
+
+    def __init__(self, path):
+        self.lib = _bind(C.CDLL(path, mode=os.RTLD_LOCAL))
+
+    def config(self, profile, bx, by, quality, flags=0, **overrides):
+        cfg = Config()
+        err = self.lib.astcenc_config_init(profile, bx, by, 1, quality, flags, C.byref(cfg))
+        if err:
+            raise RuntimeError("config_init failed: %d" % err)
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        return cfg
+
+    def compress(self, img, profile, bx, by, quality, flags=0, swz=(0, 1, 2, 3), threads=1, cfg=None, **overrides):
+        """img: numpy (H, W, 4) uint8 / float16 / float32. Returns bytes of blocks."""
+        if cfg is None:
+            cfg = self.config(profile, bx, by, quality, flags, **overrides)
+        ctx = C.c_void_p()
+        err = self.lib.astcenc_context_alloc(C.byref(cfg), threads, C.byref(ctx), None)
+        if err:
+            raise RuntimeError("context_alloc failed: %d" % err)
+        try:
+            return self.compress_ctx(ctx, img, bx, by, swz, threads)
+        finally:
+            self.lib.astcenc_context_free(ctx)
+
+    def compress_ctx(self, ctx, img, bx, by, swz=(0, 1, 2, 3), threads=1):
+        img = np.ascontiguousarray(img)
+        h, w = img.shape[:2]
+        dt = {np.dtype(np.uint8): TYPE_U8, np.dtype(np.float16): TYPE_F16, np.dtype(np.float32): TYPE_F32}[img.dtype]
+        slices = (C.c_void_p * 1)(img.ctypes.data)
+        image = Image(w, h, 1, dt, slices)
+        sw = Swizzle(*swz)
+        nblocks = ((w + bx - 1) // bx) * ((h + by - 1) // by)
+        out = np.zeros(nblocks * 16, dtype=np.uint8)
+        if threads == 1:
+            err = self.lib.astcenc_compress_image(ctx, C.byref(image), C.byref(sw), out.ctypes.data, out.nbytes, 0)
+            if err:
+                raise RuntimeError("compress_image failed: %d" % err)
+        else:
+            import threading
+            errs = [0] * threads
+
+            def run(i):
+                errs[i] = self.lib.astcenc_compress_image(ctx, C.byref(image), C.byref(sw), out.ctypes.data, out.nbytes, i)
+            ts = [threading.Thread(target=run, args=(i,)) for i in range(threads)]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+            if any(errs):
+                raise RuntimeError("compress_image failed: %s" % errs)
+            self.lib.astcenc_compress_reset(ctx)
+        return out
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref_lib():
+    return AstcencLib(REF_SO)
+
+
+class OracleConfig(C.Structure):
+    _fields_ = [
+        ("profile", C.c_int), ("flags", C.c_uint), ("block_x", C.c_uint), ("block_y", C.c_uint),
+        ("cw_r_weight", C.c_float), ("cw_g_weight", C.c_float), ("cw_b_weight", C.c_float), ("cw_a_weight", C.c_float),
+        ("a_scale_radius", C.c_uint), ("rgbm_m_scale", C.c_float),
+        ("tune_partition_count_limit", C.c_uint), ("tune_2partition_index_limit", C.c_uint),
+        ("tune_3partition_index_limit", C.c_uint), ("tune_4partition_index_limit", C.c_uint),
+        ("tune_block_mode_limit", C.c_uint), ("tune_refinement_limit", C.c_uint), ("tune_candidate_limit", C.c_uint),
+        ("tune_2partitioning_candidate_limit", C.c_uint), ("tune_3partitioning_candidate_limit", C.c_uint),
+        ("tune_4partitioning_candidate_limit", C.c_uint),
+        ("tune_db_limit", C.c_float), ("tune_mse_overshoot", C.c_float),
+        ("tune_2partition_early_out_limit_factor", C.c_float), ("tune_3partition_early_out_limit_factor", C.c_float),
+        ("tune_2plane_early_out_limit_correlation", C.c_float), ("tune_search_mode0_enable", C.c_float),
+    ]
+
+
+class Oracle:
+    def __init__(self, path=ORACLE_SO):
+        lib = C.CDLL(path)
+        lib.oracle_context_create.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float, C.c_uint, C.POINTER(C.c_float)]
+        lib.oracle_context_create.restype = C.c_void_p
+        lib.oracle_context_destroy.argtypes = [C.c_void_p]
+        lib.oracle_compress_image.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.POINTER(C.c_int), C.c_void_p]
+        lib.oracle_compress_image.restype = C.c_int
+        lib.oracle_get_config.argtypes = [C.c_void_p, C.POINTER(OracleConfig)]
+        self.lib = lib
+
+    def compress(self, img, profile, bx, by, quality, flags=0, swz=None, partition_count_limit=0, plane2_correlation=-1.0):
+        img = np.ascontiguousarray(img)
+        h, w = img.shape[:2]
+        dt = {np.dtype(np.uint8): TYPE_U8, np.dtype(np.float16): TYPE_F16, np.dtype(np.float32): TYPE_F32}[img.dtype]
+        ov = (C.c_float * 3)(float(partition_count_limit), float(plane2_correlation), 0.0)
+        ctx = self.lib.oracle_context_create(profile, bx, by, quality, flags, ov)
+        if not ctx:
+            raise RuntimeError("oracle context failed")
+        try:
+            nblocks = ((w + bx - 1) // bx) * ((h + by - 1) // by)
+            out = np.zeros(nblocks * 16, dtype=np.uint8)
+            sw = (C.c_int * 4)(*swz) if swz is not None else None
+            self.lib.oracle_compress_image(ctx, img.ctypes.data, dt, w, h, sw, out.ctypes.data)
+            return out
+        finally:
+            self.lib.oracle_context_destroy(ctx)
+
+    def config(self, profile, bx, by, quality, flags=0):
+        ctx = self.lib.oracle_context_create(profile, bx, by, quality, flags, None)
+        cfg = OracleConfig()
+        self.lib.oracle_get_config(ctx, C.byref(cfg))
+        self.lib.oracle_context_destroy(ctx)
+        return cfg
+
+
+def block_diff(a, b):
+    """Indices of 16-byte blocks that differ."""
+    a = np.asarray(a).reshape(-1, 16)
+    b = np.asarray(b).reshape(-1, 16)
+    return np.nonzero((a != b).any(axis=1))[0]
