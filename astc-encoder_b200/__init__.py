@@ -1,0 +1,184 @@
+"""astc-encoder_b200: B200-native ASTC block compressor behind the astcenc.h C ABI.
+
+This module is the thin Python mirror of the C interface (same names and argument meaning as
+astcenc.h: config_init -> context_alloc -> compress_image); all compression happens in
+libastcenc_b200.so (hand-written sm_100a kernels). There is no CPU fallback: importing works
+anywhere, but creating a context without a CUDA device raises.
+
+PyTorch is used only as plumbing (device buffers, streams, torch.distributed); see
+compress_device() for the device-resident entry point used by bench.py and the multi-GPU path.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libastcenc_b200.so")
+
+PRF_LDR_SRGB, PRF_LDR, PRF_HDR_RGB_LDR_A, PRF_HDR = 0, 1, 2, 3
+PRE_FASTEST, PRE_FAST, PRE_MEDIUM, PRE_THOROUGH, PRE_VERYTHOROUGH, PRE_EXHAUSTIVE = 0.0, 10.0, 60.0, 98.0, 99.0, 100.0
+FLG_MAP_NORMAL, FLG_USE_DECODE_UNORM8, FLG_USE_ALPHA_WEIGHT, FLG_USE_PERCEPTUAL = 1, 2, 4, 8
+FLG_DECOMPRESS_ONLY, FLG_SELF_DECOMPRESS_ONLY, FLG_MAP_RGBM = 16, 32, 64
+TYPE_U8, TYPE_F16, TYPE_F32 = 0, 1, 2
+ERROR_NAMES = ["ASTCENC_SUCCESS", "ASTCENC_ERR_OUT_OF_MEM", "ASTCENC_ERR_BAD_CPU_FLOAT", "ASTCENC_ERR_BAD_PARAM", "ASTCENC_ERR_BAD_BLOCK_SIZE",
+               "ASTCENC_ERR_BAD_PROFILE", "ASTCENC_ERR_BAD_QUALITY", "ASTCENC_ERR_BAD_SWIZZLE", "ASTCENC_ERR_BAD_FLAGS", "ASTCENC_ERR_BAD_CONTEXT",
+               "ASTCENC_ERR_NOT_IMPLEMENTED", "ASTCENC_ERR_BAD_DECODE_MODE"]
+
+
+class AstcencError(RuntimeError):
+    def __init__(self, code, what):
+        self.code = code
+        RuntimeError.__init__(self, "%s: %s" % (what, ERROR_NAMES[code] if 0 <= code < len(ERROR_NAMES) else code))
+
+
+class Config(C.Structure):
+    """astcenc_config (astcenc.h:427-605)."""
+    _fields_ = [
+        ("profile", C.c_int), ("flags", C.c_uint), ("block_x", C.c_uint), ("block_y", C.c_uint), ("block_z", C.c_uint),
+        ("cw_r_weight", C.c_float), ("cw_g_weight", C.c_float), ("cw_b_weight", C.c_float), ("cw_a_weight", C.c_float),
+        ("a_scale_radius", C.c_uint), ("rgbm_m_scale", C.c_float),
+        ("tune_partition_count_limit", C.c_uint), ("tune_2partition_index_limit", C.c_uint),
+        ("tune_3partition_index_limit", C.c_uint), ("tune_4partition_index_limit", C.c_uint),
+        ("tune_block_mode_limit", C.c_uint), ("tune_refinement_limit", C.c_uint), ("tune_candidate_limit", C.c_uint),
+        ("tune_2partitioning_candidate_limit", C.c_uint), ("tune_3partitioning_candidate_limit", C.c_uint),
+        ("tune_4partitioning_candidate_limit", C.c_uint),
+        ("tune_db_limit", C.c_float), ("tune_mse_overshoot", C.c_float),
+        ("tune_2partition_early_out_limit_factor", C.c_float), ("tune_3partition_early_out_limit_factor", C.c_float),
+        ("tune_2plane_early_out_limit_correlation", C.c_float), ("tune_search_mode0_enable", C.c_float),
+        ("progress_callback", C.c_void_p),
+    ]
+
+
+class Image(C.Structure):
+    _fields_ = [("dim_x", C.c_uint), ("dim_y", C.c_uint), ("dim_z", C.c_uint), ("data_type", C.c_int), ("data", C.POINTER(C.c_void_p))]
+
+
+class Swizzle(C.Structure):
+    _fields_ = [("r", C.c_int), ("g", C.c_int), ("b", C.c_int), ("a", C.c_int)]
+
+
+def build(verbose=False):
+    """Compile libastcenc_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", _HERE], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode != 0:
+        raise RuntimeError("building libastcenc_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C library. Fails loudly if it was not built - there is no Python/CPU fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libastcenc_b200.so is missing: run `make -C %s` (or __graft_entry__.build())" % _HERE)
+        l = C.CDLL(LIB_PATH, mode=os.RTLD_LOCAL)
+        l.astcenc_config_init.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_float, C.c_uint, C.POINTER(Config)]
+        l.astcenc_config_init.restype = C.c_int
+        l.astcenc_context_alloc.argtypes = [C.POINTER(Config), C.c_uint, C.POINTER(C.c_void_p), C.c_void_p]
+        l.astcenc_context_alloc.restype = C.c_int
+        l.astcenc_compress_image.argtypes = [C.c_void_p, C.POINTER(Image), C.POINTER(Swizzle), C.c_void_p, C.c_size_t, C.c_uint]
+        l.astcenc_compress_image.restype = C.c_int
+        l.astcenc_compress_reset.argtypes = [C.c_void_p]
+        l.astcenc_compress_reset.restype = C.c_int
+        l.astcenc_compress_cancel.argtypes = [C.c_void_p]
+        l.astcenc_compress_cancel.restype = C.c_int
+        l.astcenc_context_free.argtypes = [C.c_void_p]
+        l.astcenc_context_free.restype = None
+        l.astcenc_get_error_string.argtypes = [C.c_int]
+        l.astcenc_get_error_string.restype = C.c_char_p
+        l.astcenc_b200_compress_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.POINTER(Swizzle), C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]
+        l.astcenc_b200_compress_device.restype = C.c_int
+        l.astcenc_b200_launch_count.argtypes = [C.c_void_p]
+        l.astcenc_b200_launch_count.restype = C.c_ulonglong
+        l.astcenc_b200_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        l.astcenc_b200_last_timing.restype = C.c_int
+        _lib = l
+    return _lib
+
+
+def config_init(profile, block_x, block_y, quality, flags=0, block_z=1, **overrides):
+    """astcenc_config_init (astcenc.h:725-749); keyword overrides edit tune_* fields like the CLI's power-user switches."""
+    cfg = Config()
+    err = lib().astcenc_config_init(profile, block_x, block_y, block_z, quality, flags, C.byref(cfg))
+    if err:
+        raise AstcencError(err, "astcenc_config_init")
+    for k, v in overrides.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+_DTYPES = {np.dtype(np.uint8): TYPE_U8, np.dtype(np.float16): TYPE_F16, np.dtype(np.float32): TYPE_F32}
+
+
+class Context:
+    """astcenc_context (astcenc_context_alloc / astcenc_compress_image / astcenc_context_free)."""
+
+    def __init__(self, config, thread_count=1):
+        self.config = config
+        self.thread_count = thread_count
+        self.handle = C.c_void_p()
+        err = lib().astcenc_context_alloc(C.byref(config), thread_count, C.byref(self.handle), None)
+        if err:
+            self.handle = None
+            raise AstcencError(err, "astcenc_context_alloc")
+
+    def close(self):
+        if self.handle:
+            lib().astcenc_context_free(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def blocks(self, dim_x, dim_y):
+        bx, by = self.config.block_x, self.config.block_y
+        return (dim_x + bx - 1) // bx, (dim_y + by - 1) // by
+
+    def compress_image(self, img, swizzle=(0, 1, 2, 3), out=None, thread_index=0):
+        """Host-pointer path: img is a (H, W, 4) or (D, H, W, 4) numpy array of uint8 / float16 / float32."""
+        img = np.ascontiguousarray(img)
+        if img.ndim == 3:
+            img = img[None]
+        d, h, w = img.shape[:3]
+        slices = (C.c_void_p * d)(*[img[z].ctypes.data for z in range(d)])
+        image = Image(w, h, d, _DTYPES[img.dtype], slices)
+        sw = Swizzle(*swizzle)
+        nbx, nby = self.blocks(w, h)
+        if out is None:
+            out = np.empty(nbx * nby * d * 16, dtype=np.uint8)
+        err = lib().astcenc_compress_image(self.handle, C.byref(image), C.byref(sw), out.ctypes.data, out.nbytes, thread_index)
+        if err:
+            raise AstcencError(err, "astcenc_compress_image")
+        return out
+
+    def compress_device(self, d_pixels_ptr, data_type, dim_x, dim_y, d_out_ptr, block_row0=0, block_rows=None, swizzle=(0, 1, 2, 3), stream=0):
+        """Device-resident path (astcenc_b200_compress_device): raw device pointers, enqueued on `stream`, no sync."""
+        nbx, nby = self.blocks(dim_x, dim_y)
+        if block_rows is None:
+            block_rows = nby - block_row0
+        sw = Swizzle(*swizzle)
+        err = lib().astcenc_b200_compress_device(self.handle, C.c_void_p(d_pixels_ptr), data_type, dim_x, dim_y, C.byref(sw), block_row0, block_rows,
+                                                 C.c_void_p(d_out_ptr), C.c_void_p(stream))
+        if err:
+            raise AstcencError(err, "astcenc_b200_compress_device")
+
+    def launch_count(self):
+        return int(lib().astcenc_b200_launch_count(self.handle))
+
+    def last_timing(self):
+        ms = C.c_float(); a = C.c_size_t(); b = C.c_size_t()
+        lib().astcenc_b200_last_timing(self.handle, C.byref(ms), C.byref(a), C.byref(b))
+        return ms.value, a.value, b.value
+
+
+def slab_rows(blocks_y, rank, world):
+    """Block-row slab [r0, r1) of `rank` among `world` ranks."""
+    r0 = (blocks_y * rank) // world
+    r1 = (blocks_y * (rank + 1)) // world
+    return r0, r1

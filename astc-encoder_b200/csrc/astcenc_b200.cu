@@ -1,0 +1,527 @@
+// libastcenc_b200: the astcenc.h C ABI on top of hand-written sm_100a kernels.
+//
+// Host side of the drop-in boundary. Behavioural spec: /root/reference/Source/astcenc_entry.cpp
+//   astcenc_context_alloc :726-860, astcenc_compress_image :1113-1228 (check order :1134-1182),
+//   astcenc_compress_reset :1231, astcenc_compress_cancel :1251, astcenc_context_free :862,
+//   ParallelManager protocol astcenc_internal_entry.h:97-324 (N callers, first arrival initialises,
+//   everyone returns when the image is done).
+// There is deliberately no CPU compression path in this library: without a usable CUDA device
+// astcenc_context_alloc() fails (ASTCENC_ERR_BAD_CONTEXT) instead of falling back.
+#include <cuda_runtime.h>
+#include <mutex>
+#include <condition_variable>
+#include <atomic>
+#include <vector>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "astc_dev_search.cuh"
+#include "astc_host_pack.h"
+#include "astc_host_config.h"
+
+// ---------------------------------------------------------------------------------------------
+// The kernel: persistent warps, one block per warp at a time, dynamic ticket scheduling (the GPU analogue
+// of the reference's ParallelManager::get_task_assignment ticket counter).
+// ---------------------------------------------------------------------------------------------
+#define ASTC_CTA_THREADS 256
+
+__global__ void __launch_bounds__(ASTC_CTA_THREADS, 2)
+astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img,
+                     unsigned int* __restrict__ ticket, uint8_t* __restrict__ global_arena, int arena_in_smem) {
+	extern __shared__ __align__(16) uint8_t smem[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int warps_per_cta = blockDim.x >> 5;
+	uint8_t* arena = arena_in_smem ? smem + (size_t)warp * bsd.arena_bytes
+	                               : global_arena + ((size_t)blockIdx.x * warps_per_cta + warp) * bsd.arena_bytes;
+	WCtx w;
+	init_wctx(w, lane, &bsd, &cfg, arena);
+	const unsigned int total = img.blocks_x * img.block_rows;
+	while (true) {
+		unsigned int b = 0;
+		if (lane == 0) {
+			b = atomicAdd(ticket, 1u);
+		}
+		b = __shfl_sync(0xffffffffu, b, 0);
+		if (b >= total) {
+			break;
+		}
+		unsigned int by = b / img.blocks_x;
+		unsigned int bx = b - by * img.blocks_x;
+		load_block(w, img, bx * bsd.dim_x, (by + img.block_row0) * bsd.dim_y);
+		compress_block(w, img.out + (size_t)b * 16);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------------------------
+#define CUDA_TRY(expr, onfail) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+	if (getenv("ASTCENC_B200_DEBUG")) fprintf(stderr, "astcenc_b200: %s failed: %s\n", #expr, cudaGetErrorString(e_)); onfail; } } while (0)
+
+struct DeviceTables {            // shared between a parent context and its children
+	std::atomic<int> refcount;
+	uint8_t* d_blob;
+	DevBsd bsd;                  // device pointers
+	astc_host::BlockSizeTables* host_tables;
+};
+
+struct astcenc_context {
+	astcenc_config config;
+	unsigned int thread_count;
+	int device;
+	DeviceTables* tables;
+	DevConfig dcfg;
+	cudaStream_t stream;
+	cudaEvent_t ev0, ev1;
+	unsigned int* d_ticket;
+	uint8_t* d_arena;            // only when the arena does not fit shared memory
+	int arena_in_smem;
+	int warps_per_cta;
+	int grid;
+	size_t smem_bytes;
+	// staging buffers for the host-pointer API, grown on demand
+	uint8_t* d_image;
+	size_t d_image_bytes;
+	uint8_t* d_out;
+	size_t d_out_bytes;
+	// caller protocol
+	std::mutex mtx;
+	std::condition_variable cv;
+	int state;                   // 0 idle, 1 running, 2 done
+	astcenc_error result;
+	std::atomic<bool> cancel;
+	// stats
+	unsigned long long launches;
+	float last_kernel_ms;
+	size_t last_h2d, last_d2h;
+};
+
+static std::mutex g_const_mtx;
+static DevConstTables* g_d_consts[64];
+
+static astcenc_error ensure_const_tables(int device) {
+	std::lock_guard<std::mutex> lk(g_const_mtx);
+	if (device < 0 || device >= 64) {
+		return ASTCENC_ERR_BAD_CONTEXT;
+	}
+	if (g_d_consts[device]) {
+		return ASTCENC_SUCCESS;
+	}
+	DevConstTables* h = new DevConstTables;
+	astc_host::fill_dev_const_tables(*h);
+	DevConstTables* d = nullptr;
+	CUDA_TRY(cudaMalloc(&d, sizeof(DevConstTables)), { delete h; return ASTCENC_ERR_OUT_OF_MEM; });
+	CUDA_TRY(cudaMemcpy(d, h, sizeof(DevConstTables), cudaMemcpyHostToDevice), { delete h; return ASTCENC_ERR_BAD_CONTEXT; });
+	const DevConstTables* dc = d;
+	CUDA_TRY(cudaMemcpyToSymbol(g_astc_ct, &dc, sizeof(dc)), { delete h; return ASTCENC_ERR_BAD_CONTEXT; });
+	delete h;
+	g_d_consts[device] = d;
+	return ASTCENC_SUCCESS;
+}
+
+static void release_tables(DeviceTables* t) {
+	if (t && t->refcount.fetch_sub(1) == 1) {
+		cudaFree(t->d_blob);
+		astc_host::free_block_size_tables(t->host_tables);
+		delete t;
+	}
+}
+
+extern "C" {
+
+astcenc_error astcenc_config_init(astcenc_profile profile, unsigned int block_x, unsigned int block_y, unsigned int block_z, float quality,
+                                  unsigned int flags, astcenc_config* config) {
+	return astc_host::config_init(profile, block_x, block_y, block_z, quality, flags, config);
+}
+
+astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int thread_count, astcenc_context** context, const astcenc_context* parent) {
+	astcenc_error status = astc_host::validate_cpu_float();
+	if (status != ASTCENC_SUCCESS) {
+		return status;
+	}
+	if (thread_count == 0) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	bool has_config = configp != nullptr;
+	bool has_parent = parent != nullptr;
+	if (!(has_config ^ has_parent)) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	if (has_parent) {
+		configp = &parent->config;
+	}
+	astcenc_context* ctx = new (std::nothrow) astcenc_context;
+	if (!ctx) {
+		return ASTCENC_ERR_OUT_OF_MEM;
+	}
+	ctx->config = *configp;
+	ctx->thread_count = thread_count;
+	ctx->tables = nullptr;
+	ctx->stream = nullptr;
+	ctx->ev0 = ctx->ev1 = nullptr;
+	ctx->d_ticket = nullptr;
+	ctx->d_arena = nullptr;
+	ctx->d_image = nullptr;
+	ctx->d_out = nullptr;
+	ctx->d_image_bytes = ctx->d_out_bytes = 0;
+	ctx->state = 0;
+	ctx->result = ASTCENC_SUCCESS;
+	ctx->cancel = false;
+	ctx->launches = 0;
+	ctx->last_kernel_ms = 0.0f;
+	ctx->last_h2d = ctx->last_d2h = 0;
+	status = astc_host::validate_config(ctx->config);
+	if (status != ASTCENC_SUCCESS) {
+		delete ctx;
+		return status;
+	}
+	// The GPU is mandatory: no device, no context.
+	int device = 0;
+	CUDA_TRY(cudaGetDevice(&device), { delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+	ctx->device = device;
+	status = ensure_const_tables(device);
+	if (status != ASTCENC_SUCCESS) {
+		delete ctx;
+		return status;
+	}
+	const astcenc_config& cfg = ctx->config;
+	if (has_parent) {
+		ctx->tables = parent->tables;
+		ctx->tables->refcount.fetch_add(1);
+	} else {
+		DeviceTables* t = new DeviceTables;
+		t->refcount = 1;
+		t->d_blob = nullptr;
+		bool can_omit = (cfg.flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0;
+		t->host_tables = astc_host::build_block_size_tables(cfg.block_x, cfg.block_y, can_omit, cfg.tune_partition_count_limit,
+		                                                    static_cast<float>(cfg.tune_block_mode_limit) / 100.0f);
+		astc_host::PackedTables pk;
+		unsigned int lim[3] = {cfg.tune_2partition_index_limit, cfg.tune_3partition_index_limit, cfg.tune_4partition_index_limit};
+		astc_host::pack_device_tables(*t->host_tables, lim, pk);
+		CUDA_TRY(cudaMalloc(&t->d_blob, pk.blob.size()), { release_tables(t); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
+		CUDA_TRY(cudaMemcpy(t->d_blob, pk.blob.data(), pk.blob.size(), cudaMemcpyHostToDevice), { release_tables(t); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+		t->bsd = pk.bsd;
+		astc_host::relocate_bsd(t->bsd, t->d_blob);
+		ctx->tables = t;
+	}
+	astc_host::make_device_config(cfg, ctx->dcfg);
+
+	if (!(cfg.flags & ASTCENC_FLG_DECOMPRESS_ONLY)) {
+		cudaDeviceProp prop;
+		CUDA_TRY(cudaGetDeviceProperties(&prop, device), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+		size_t smem_limit = prop.sharedMemPerBlockOptin;
+		size_t arena = ctx->tables->bsd.arena_bytes;
+		const char* force_global = getenv("ASTCENC_B200_ARENA_GLOBAL");
+		int warps = ASTC_CTA_THREADS / 32;
+		// two CTAs per SM when both arenas fit (the SM has ~228 KB, 1 KB reserved per CTA)
+		size_t per_sm = prop.sharedMemPerMultiprocessor;
+		if (!force_global && arena * warps + 1024 <= per_sm / 2 && arena * warps <= smem_limit) {
+			ctx->arena_in_smem = 1;
+			ctx->warps_per_cta = warps;
+			ctx->grid = prop.multiProcessorCount * 2;
+		} else if (!force_global && arena * warps <= smem_limit) {
+			ctx->arena_in_smem = 1;
+			ctx->warps_per_cta = warps;
+			ctx->grid = prop.multiProcessorCount;
+		} else if (!force_global && arena * 4 <= smem_limit) {
+			ctx->arena_in_smem = 1;
+			ctx->warps_per_cta = (int)(smem_limit / arena);
+			if (ctx->warps_per_cta > warps) ctx->warps_per_cta = warps;
+			ctx->grid = prop.multiProcessorCount;
+		} else {
+			ctx->arena_in_smem = 0;
+			ctx->warps_per_cta = warps;
+			ctx->grid = prop.multiProcessorCount * 2;
+		}
+		ctx->smem_bytes = ctx->arena_in_smem ? arena * ctx->warps_per_cta : 0;
+		if (ctx->smem_bytes > 48 * 1024) {
+			CUDA_TRY(cudaFuncSetAttribute(astc_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
+			         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+		}
+		if (!ctx->arena_in_smem) {
+			CUDA_TRY(cudaMalloc(&ctx->d_arena, arena * ctx->warps_per_cta * ctx->grid), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
+		}
+		CUDA_TRY(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
+	}
+	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+	CUDA_TRY(cudaEventCreate(&ctx->ev0), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+	CUDA_TRY(cudaEventCreate(&ctx->ev1), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+	*context = ctx;
+	return ASTCENC_SUCCESS;
+}
+
+void astcenc_context_free(astcenc_context* ctx) {
+	if (!ctx) {
+		return;
+	}
+	cudaSetDevice(ctx->device);
+	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	cudaFree(ctx->d_ticket);
+	cudaFree(ctx->d_arena);
+	cudaFree(ctx->d_image);
+	cudaFree(ctx->d_out);
+	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	release_tables(ctx->tables);
+	delete ctx;
+}
+
+static astcenc_error validate_compression_swizzle(const astcenc_swizzle& s) {
+	const int v[4] = {(int)s.r, (int)s.g, (int)s.b, (int)s.a};
+	for (int i = 0; i < 4; i++) {
+		if (v[i] < ASTCENC_SWZ_R || v[i] > ASTCENC_SWZ_1) {
+			return ASTCENC_ERR_BAD_SWIZZLE;
+		}
+	}
+	return ASTCENC_SUCCESS;
+}
+
+static size_t mul_safe(size_t a, size_t b, bool& overflow) {
+	size_t r = a * b;
+	overflow = overflow || ((b != 0) && ((r / b) != a));
+	return r;
+}
+
+static size_t block_count_axis(size_t dim, size_t blk) {
+	size_t n = dim / blk;
+	if (dim != blk * n) {
+		n++;
+	}
+	return n;
+}
+
+static astcenc_error launch_slab(astcenc_context* ctx, const void* d_pixels, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
+                                 unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream) {
+	const DevBsd& bsd = ctx->tables->bsd;
+	DevImage img;
+	img.data = d_pixels;
+	img.data_type = data_type;
+	img.dim_x = dim_x;
+	img.dim_y = dim_y;
+	img.blocks_x = (dim_x + bsd.dim_x - 1) / bsd.dim_x;
+	img.block_row0 = block_row0;
+	img.block_rows = block_rows;
+	for (int i = 0; i < 4; i++) {
+		img.swz[i] = swz[i];
+	}
+	img.out = d_out;
+	CUDA_TRY(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), stream), return ASTCENC_ERR_BAD_CONTEXT);
+	size_t total = (size_t)img.blocks_x * block_rows;
+	int grid = ctx->grid;
+	size_t needed = (total + ctx->warps_per_cta - 1) / ctx->warps_per_cta;
+	if ((size_t)grid > needed) {
+		grid = (int)(needed ? needed : 1);
+	}
+	astc_compress_kernel<<<grid, ctx->warps_per_cta * 32, ctx->smem_bytes, stream>>>(bsd, ctx->dcfg, img, ctx->d_ticket, ctx->d_arena, ctx->arena_in_smem);
+	CUDA_TRY(cudaGetLastError(), return ASTCENC_ERR_BAD_CONTEXT);
+	ctx->launches++;
+	return ASTCENC_SUCCESS;
+}
+
+static astcenc_error compress_image_gpu(astcenc_context* ctx, const astcenc_image& image, const astcenc_swizzle& swizzle, uint8_t* data_out) {
+	const DevBsd& bsd = ctx->tables->bsd;
+	CUDA_TRY(cudaSetDevice(ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
+	size_t bpt = image.data_type == ASTCENC_TYPE_U8 ? 4 : image.data_type == ASTCENC_TYPE_F16 ? 8 : 16;
+	size_t slice_bytes = (size_t)image.dim_x * image.dim_y * bpt;
+	size_t blocks_x = block_count_axis(image.dim_x, bsd.dim_x);
+	size_t blocks_y = block_count_axis(image.dim_y, bsd.dim_y);
+	size_t out_bytes = blocks_x * blocks_y * 16;
+	if (ctx->d_image_bytes < slice_bytes) {
+		cudaFree(ctx->d_image);
+		ctx->d_image = nullptr;
+		ctx->d_image_bytes = 0;
+		CUDA_TRY(cudaMalloc(&ctx->d_image, slice_bytes), return ASTCENC_ERR_OUT_OF_MEM);
+		ctx->d_image_bytes = slice_bytes;
+	}
+	if (ctx->d_out_bytes < out_bytes) {
+		cudaFree(ctx->d_out);
+		ctx->d_out = nullptr;
+		ctx->d_out_bytes = 0;
+		CUDA_TRY(cudaMalloc(&ctx->d_out, out_bytes), return ASTCENC_ERR_OUT_OF_MEM);
+		ctx->d_out_bytes = out_bytes;
+	}
+	int swz[4] = {(int)swizzle.r, (int)swizzle.g, (int)swizzle.b, (int)swizzle.a};
+	ctx->last_h2d = ctx->last_d2h = 0;
+	ctx->last_kernel_ms = 0.0f;
+	float total_ms = 0.0f;
+	// 3D images with 2D blocks are an array of independent 2D slices (astcenc.h:94-100)
+	for (unsigned int z = 0; z < image.dim_z; z++) {
+		if (ctx->cancel.load()) {
+			break;
+		}
+		CUDA_TRY(cudaMemcpyAsync(ctx->d_image, image.data[z], slice_bytes, cudaMemcpyHostToDevice, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		astcenc_error st = launch_slab(ctx, ctx->d_image, (int)image.data_type, image.dim_x, image.dim_y, swz, 0, (unsigned int)blocks_y, ctx->d_out, ctx->stream);
+		if (st != ASTCENC_SUCCESS) {
+			return st;
+		}
+		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		CUDA_TRY(cudaMemcpyAsync(data_out + (size_t)z * out_bytes, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		CUDA_TRY(cudaStreamSynchronize(ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		float ms = 0.0f;
+		cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+		total_ms += ms;
+		ctx->last_h2d += slice_bytes;
+		ctx->last_d2h += out_bytes;
+		if (ctx->config.progress_callback) {
+			ctx->config.progress_callback(100.0f * static_cast<float>(z + 1) / static_cast<float>(image.dim_z));
+		}
+	}
+	ctx->last_kernel_ms = total_ms;
+	return ASTCENC_SUCCESS;
+}
+
+astcenc_error astcenc_compress_reset(astcenc_context* ctx);
+
+astcenc_error astcenc_compress_image(astcenc_context* ctx, astcenc_image* imagep, const astcenc_swizzle* swizzle, uint8_t* data_out, size_t data_len,
+                                     unsigned int thread_index) {
+	if (ctx->config.flags & ASTCENC_FLG_DECOMPRESS_ONLY) {
+		return ASTCENC_ERR_BAD_CONTEXT;
+	}
+	astcenc_error status = validate_compression_swizzle(*swizzle);
+	if (status != ASTCENC_SUCCESS) {
+		return status;
+	}
+	if (thread_index >= ctx->thread_count) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	const astcenc_image& image = *imagep;
+	bool overflow = false;
+	size_t texel_count = mul_safe(mul_safe(image.dim_x, image.dim_y, overflow), image.dim_z, overflow);
+	if (overflow || texel_count == 0) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	size_t blocks_x = block_count_axis(image.dim_x, ctx->config.block_x);
+	size_t blocks_y = block_count_axis(image.dim_y, ctx->config.block_y);
+	size_t blocks_z = block_count_axis(image.dim_z, ctx->config.block_z);
+	overflow = false;
+	size_t block_count = mul_safe(mul_safe(blocks_x, blocks_y, overflow), blocks_z, overflow);
+	mul_safe(block_count, 16, overflow);
+	if (overflow || block_count == 0) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	if (data_len < block_count * 16) {
+		return ASTCENC_ERR_OUT_OF_MEM;
+	}
+	if (ctx->config.a_scale_radius != 0) {
+		// alpha-scale RDO pre-pass (compute_variance.cpp) is outside the hot path built here
+		return ASTCENC_ERR_NOT_IMPLEMENTED;
+	}
+	if (ctx->thread_count == 1) {
+		astcenc_compress_reset(ctx);
+	}
+	std::unique_lock<std::mutex> lk(ctx->mtx);
+	if (ctx->state == 0) {
+		ctx->state = 1;
+		lk.unlock();
+		astcenc_error r = compress_image_gpu(ctx, image, *swizzle, data_out);
+		lk.lock();
+		ctx->result = r;
+		ctx->state = 2;
+		ctx->cv.notify_all();
+		return r;
+	}
+	ctx->cv.wait(lk, [ctx] { return ctx->state == 2; });
+	return ctx->result;
+}
+
+astcenc_error astcenc_compress_reset(astcenc_context* ctx) {
+	if (ctx->config.flags & ASTCENC_FLG_DECOMPRESS_ONLY) {
+		return ASTCENC_ERR_BAD_CONTEXT;
+	}
+	std::lock_guard<std::mutex> lk(ctx->mtx);
+	if (ctx->state != 1) {
+		ctx->state = 0;
+	}
+	ctx->cancel = false;
+	return ASTCENC_SUCCESS;
+}
+
+astcenc_error astcenc_compress_cancel(astcenc_context* ctx) {
+	if (ctx->config.flags & ASTCENC_FLG_DECOMPRESS_ONLY) {
+		return ASTCENC_ERR_BAD_CONTEXT;
+	}
+	ctx->cancel = true;
+	return ASTCENC_SUCCESS;
+}
+
+astcenc_error astcenc_decompress_image(astcenc_context* ctx, const uint8_t* data, size_t data_len, astcenc_image* image_out, const astcenc_swizzle* swizzle,
+                                       unsigned int thread_index) {
+	(void)data; (void)data_len; (void)image_out; (void)swizzle;
+	if (thread_index >= ctx->thread_count) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	// Decompression is the first "next" row of the scope table; not built yet.
+	return ASTCENC_ERR_NOT_IMPLEMENTED;
+}
+
+astcenc_error astcenc_decompress_reset(astcenc_context* ctx) {
+	(void)ctx;
+	return ASTCENC_SUCCESS;
+}
+
+astcenc_error astcenc_get_block_info(astcenc_context* ctx, const uint8_t data[16], astcenc_block_info* info) {
+	(void)ctx; (void)data; (void)info;
+	return ASTCENC_ERR_NOT_IMPLEMENTED;
+}
+
+const char* astcenc_get_error_string(astcenc_error status) {
+	switch (static_cast<int>(status)) {
+	case ASTCENC_SUCCESS: return "ASTCENC_SUCCESS";
+	case ASTCENC_ERR_OUT_OF_MEM: return "ASTCENC_ERR_OUT_OF_MEM";
+	case ASTCENC_ERR_BAD_CPU_FLOAT: return "ASTCENC_ERR_BAD_CPU_FLOAT";
+	case ASTCENC_ERR_BAD_PARAM: return "ASTCENC_ERR_BAD_PARAM";
+	case ASTCENC_ERR_BAD_BLOCK_SIZE: return "ASTCENC_ERR_BAD_BLOCK_SIZE";
+	case ASTCENC_ERR_BAD_PROFILE: return "ASTCENC_ERR_BAD_PROFILE";
+	case ASTCENC_ERR_BAD_QUALITY: return "ASTCENC_ERR_BAD_QUALITY";
+	case ASTCENC_ERR_BAD_FLAGS: return "ASTCENC_ERR_BAD_FLAGS";
+	case ASTCENC_ERR_BAD_SWIZZLE: return "ASTCENC_ERR_BAD_SWIZZLE";
+	case ASTCENC_ERR_BAD_CONTEXT: return "ASTCENC_ERR_BAD_CONTEXT";
+	case ASTCENC_ERR_NOT_IMPLEMENTED: return "ASTCENC_ERR_NOT_IMPLEMENTED";
+	case ASTCENC_ERR_BAD_DECODE_MODE: return "ASTCENC_ERR_BAD_DECODE_MODE";
+	default: return nullptr;
+	}
+}
+
+// ---- extensions ----
+astcenc_error astcenc_b200_compress_device(astcenc_context* ctx, const void* d_pixels, astcenc_type data_type, unsigned int dim_x, unsigned int dim_y,
+                                           const astcenc_swizzle* swizzle, unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, void* cuda_stream) {
+	if (ctx->config.flags & ASTCENC_FLG_DECOMPRESS_ONLY) {
+		return ASTCENC_ERR_BAD_CONTEXT;
+	}
+	astcenc_error status = validate_compression_swizzle(*swizzle);
+	if (status != ASTCENC_SUCCESS) {
+		return status;
+	}
+	if (dim_x == 0 || dim_y == 0 || !d_pixels || !d_out) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	size_t blocks_y = block_count_axis(dim_y, ctx->config.block_y);
+	if ((size_t)block_row0 + block_rows > blocks_y) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	if (block_rows == 0) {
+		return ASTCENC_SUCCESS;
+	}
+	CUDA_TRY(cudaSetDevice(ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
+	int swz[4] = {(int)swizzle->r, (int)swizzle->g, (int)swizzle->b, (int)swizzle->a};
+	cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+	return launch_slab(ctx, d_pixels, (int)data_type, dim_x, dim_y, swz, block_row0, block_rows, d_out, s);
+}
+
+unsigned long long astcenc_b200_launch_count(astcenc_context* ctx) {
+	return ctx->launches;
+}
+
+astcenc_error astcenc_b200_last_timing(astcenc_context* ctx, float* kernel_ms, size_t* h2d_bytes, size_t* d2h_bytes) {
+	if (kernel_ms) *kernel_ms = ctx->last_kernel_ms;
+	if (h2d_bytes) *h2d_bytes = ctx->last_h2d;
+	if (d2h_bytes) *d2h_bytes = ctx->last_d2h;
+	return ASTCENC_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+// TEST TOOL (not a product path): compiles the warp-cooperative device source for the host with a
+// single simulated lane (ASTC_HOSTSIM), so the lane-independent logic of the kernels can be checked
+// against the oracle / reference without a GPU. Races and shuffle bugs are NOT visible here; those are
+// covered by the -m gpu tests. The product library never links this.
+#define ASTC_HOSTSIM 1
+#include "../../astc-encoder_b200/csrc/astc_dev_search.cuh"
+#include "../../astc-encoder_b200/csrc/astc_host_pack.h"
+#include "../../astc-encoder_b200/csrc/astc_host_config.h"
+#include <vector>
+#include <cstdio>
+
+extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int by, float quality, unsigned int flags,
+                                      const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, const int* swz, uint8_t* out) {
+	astcenc_config cfg;
+	if (astc_host::config_init((astcenc_profile)profile, bx, by, 1, quality, flags, &cfg) != ASTCENC_SUCCESS) return 1;
+	if (astc_host::validate_config(cfg) != ASTCENC_SUCCESS) return 2;
+	astc_host::BlockSizeTables* t = astc_host::build_block_size_tables(bx, by, (flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0, cfg.tune_partition_count_limit,
+	                                                                   static_cast<float>(cfg.tune_block_mode_limit) / 100.0f);
+	astc_host::PackedTables pk;
+	unsigned int lim[3] = {cfg.tune_2partition_index_limit, cfg.tune_3partition_index_limit, cfg.tune_4partition_index_limit};
+	astc_host::pack_device_tables(*t, lim, pk);
+	astc_host::relocate_bsd(pk.bsd, pk.blob.data());
+	astc_host::fill_dev_const_tables(pk.consts);
+	g_astc_ct = &pk.consts;
+	DevConfig dcfg;
+	astc_host::make_device_config(cfg, dcfg);
+	std::vector<uint8_t> arena(pk.bsd.arena_bytes + 64, 0xCD);
+	DevImage img;
+	img.data = data;
+	img.data_type = data_type;
+	img.dim_x = dim_x;
+	img.dim_y = dim_y;
+	img.blocks_x = (dim_x + bx - 1) / bx;
+	img.block_row0 = 0;
+	img.block_rows = (dim_y + by - 1) / by;
+	for (int i = 0; i < 4; i++) img.swz[i] = swz ? swz[i] : i;
+	img.out = out;
+	WCtx w;
+	init_wctx(w, 0, &pk.bsd, &dcfg, arena.data());
+	for (unsigned int y = 0; y < img.block_rows; y++) {
+		for (unsigned int x = 0; x < img.blocks_x; x++) {
+			load_block(w, img, x * bx, y * by);
+			compress_block(w, out + ((size_t)y * img.blocks_x + x) * 16);
+		}
+	}
+	astc_host::free_block_size_tables(t);
+	return 0;
+}
+
+extern "C" unsigned int hostsim_arena_bytes(int profile, unsigned int bx, unsigned int by, float quality, unsigned int flags) {
+	astcenc_config cfg;
+	if (astc_host::config_init((astcenc_profile)profile, bx, by, 1, quality, flags, &cfg) != ASTCENC_SUCCESS) return 0;
+	astc_host::validate_config(cfg);
+	astc_host::BlockSizeTables* t = astc_host::build_block_size_tables(bx, by, (flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0, cfg.tune_partition_count_limit,
+	                                                                   static_cast<float>(cfg.tune_block_mode_limit) / 100.0f);
+	astc_host::PackedTables pk;
+	unsigned int lim[3] = {cfg.tune_2partition_index_limit, cfg.tune_3partition_index_limit, cfg.tune_4partition_index_limit};
+	astc_host::pack_device_tables(*t, lim, pk);
+	astc_host::free_block_size_tables(t);
+	return pk.bsd.arena_bytes;
+}
