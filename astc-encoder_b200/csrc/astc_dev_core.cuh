@@ -34,7 +34,11 @@
 #else
 	#define ASTC_FN static __device__ __forceinline__
 	#define ASTC_COOP static __device__ __noinline__
-	#define ASTC_WARP 32
+	#if defined(ASTC_DEBUG_SINGLE_LANE)
+		#define ASTC_WARP 1       /* debug build: lane 0 of each warp does all the work serially */
+	#else
+		#define ASTC_WARP 32
+	#endif
 	#define ASTC_RINT(a) rintf(a)
 	#define ASTC_F2U(f) __float_as_uint(f)
 	#define ASTC_U2F(u) __uint_as_float(u)
@@ -48,6 +52,16 @@
 #include "astc_dev_math.cuh"
 #include "astc_dev_color.cuh"
 
+// Optional tracing of intermediate values (debug builds only: -DASTC_TRACE), printed by lane 0.
+#if defined(ASTC_TRACE)
+	#include <stdio.h>
+	#define TRACE(...) do { if (w.lane == 0) printf(__VA_ARGS__); } while (0)
+	#define TRACE_F(name, v) TRACE("%s %08x\n", name, ASTC_F2U(v))
+#else
+	#define TRACE(...) do { } while (0)
+	#define TRACE_F(name, v) do { } while (0)
+#endif
+
 static const float ERROR_CALC_DEFAULT = 1e30f;
 #define TUNE_MAX_ANGULAR_QUANT 7
 #define TUNE_MAX_TRIAL_CANDIDATES 8
@@ -59,7 +73,7 @@ enum { SYM_BTYPE_ERROR = 0, SYM_BTYPE_CONST_F16 = 1, SYM_BTYPE_CONST_U16 = 2, SY
 // ---------------------------------------------------------------------------------------------
 // Warp primitives
 // ---------------------------------------------------------------------------------------------
-#if defined(ASTC_HOSTSIM)
+#if defined(ASTC_HOSTSIM) || defined(ASTC_DEBUG_SINGLE_LANE)
 ASTC_FN void wsync() {}
 ASTC_FN float wmin_f(float v) { return v; }
 ASTC_FN float wmax_f(float v) { return v; }

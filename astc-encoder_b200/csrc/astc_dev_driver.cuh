@@ -135,8 +135,13 @@ ASTC_COOP float refine_candidates(WCtx& w, const PartView& pi, bool dual, unsign
 			}
 
 			bool stop_all = false;
+			for (unsigned int j = 0; j < partition_count; j++) {
+				TRACE("refine cand=%u l=%u fmt[%u]=%u colors %u %u %u %u %u %u %u %u\n", i, l, j, work.color_formats[j], w.work_colors[j*8], w.work_colors[j*8+1], w.work_colors[j*8+2], w.work_colors[j*8+3],
+				      w.work_colors[j*8+4], w.work_colors[j*8+5], w.work_colors[j*8+6], w.work_colors[j*8+7]);
+			}
 			if (l == 0) {
 				float errorval = compute_symbolic_block_difference(w, work, pi, di, dual, rs);
+				TRACE_F("err_pre", errorval);
 				if (errorval == -ERROR_CALC_DEFAULT) {
 					errorval = -errorval;
 					work.block_type = SYM_BTYPE_ERROR;
@@ -163,6 +168,7 @@ ASTC_COOP float refine_candidates(WCtx& w, const PartView& pi, bool dual, unsign
 			}
 			bool adjustments = realign_weights(w, work, pi, qw_bm, di, rs);
 			float errorval = compute_symbolic_block_difference(w, work, pi, di, dual, rs);
+			TRACE_F("err_post", errorval);
 			if (errorval == -ERROR_CALC_DEFAULT) {
 				errorval = -errorval;
 				work.block_type = SYM_BTYPE_ERROR;
@@ -218,13 +224,41 @@ ASTC_COOP float compress_symbolic_block_for_partition_1plane(WCtx& w, bool only_
 		min_ep.w = min_ep_cutoff(e0.w, e1.w, min_ep.w);
 	}
 	float min_wt_cutoff = hmin_s(min_ep);
+	TRACE("trial1p pc=%u pidx=%u only_always=%d maxq=%d\n", partition_count, partition_index, (int)only_always, max_weight_quant);
+	for (unsigned int i = 0; i < partition_count; i++) {
+		TRACE("ep0[%u] %08x %08x %08x %08x ep1 %08x %08x %08x %08x\n", i, ASTC_F2U(w.ep[EP_EI1_0 + i].x), ASTC_F2U(w.ep[EP_EI1_0 + i].y), ASTC_F2U(w.ep[EP_EI1_0 + i].z), ASTC_F2U(w.ep[EP_EI1_0 + i].w),
+		      ASTC_F2U(w.ep[EP_EI1_1 + i].x), ASTC_F2U(w.ep[EP_EI1_1 + i].y), ASTC_F2U(w.ep[EP_EI1_1 + i].z), ASTC_F2U(w.ep[EP_EI1_1 + i].w));
+	}
+	for (int t = 0; t < w.T; t++) {
+		TRACE("eiw[%d] %08x wes %08x\n", t, ASTC_F2U(w.eiw[0][t]), ASTC_F2U(w.eis[0][t]));
+	}
+	for (unsigned int i = 0; i < max_decimation_modes; i++) {
+		if ((bsd.dec_modes[i].refprec_1plane & refmask) == 0) continue;
+		for (int k = 0; k < bsd.dec_modes[i].weight_count; k++) {
+			TRACE("dwi[%u][%d] %08x\n", i, k, ASTC_F2U(w.dwi[bsd.dec_modes[i].dwi_offset + k]));
+		}
+	}
+	TRACE_F("min_wt_cutoff", min_wt_cutoff);
 
 	compute_angular_endpoints(w, only_always, 1, (unsigned int)max_weight_quant);
+	for (unsigned int i = 0; i < max_decimation_modes; i++) {
+		if ((bsd.dec_modes[i].refprec_1plane & refmask) == 0) continue;
+		for (int k = 0; k < 16; k++) {
+			TRACE("lowhigh[%u][%d] %08x\n", i, k, ASTC_F2U(w.lowhigh[(i * 2) * 16 + k]));
+		}
+	}
 
 	unsigned int max_block_modes = only_always ? bsd.block_mode_count_1plane_always : bsd.block_mode_count_1plane_selected;
 	quantize_and_score_modes(w, 0, max_block_modes, 1, partition_count, max_weight_quant, min_wt_cutoff, min_wt_cutoff);
 
+	for (unsigned int i = 0; i < max_block_modes; i++) {
+		TRACE("qwt_err[%u] %08x\n", i, ASTC_F2U(w.mode_err[i]));
+	}
 	unsigned int candidate_count = compute_ideal_endpoint_formats(w, pi, EP_EI1_0, EP_EI1_1, 1, 0, max_block_modes);
+	for (unsigned int i = 0; i < candidate_count; i++) {
+		const Candidate* cc = reinterpret_cast<const Candidate*>(w.cand) + i;
+		TRACE("cand[%u] mode=%u ql=%u qlm=%u fmt=%u %u %u %u\n", i, cc->block_mode, cc->quant_level, cc->quant_level_mod, cc->formats[0], cc->formats[1], cc->formats[2], cc->formats[3]);
+	}
 	for (int k = w.lane; k < 4; k += ASTC_WARP) {
 		w.ep[EP_BASE_0 + k] = w.ep[EP_EI1_0 + k];
 		w.ep[EP_BASE_1 + k] = w.ep[EP_EI1_1 + k];
@@ -397,8 +431,11 @@ ASTC_COOP void compress_block(WCtx& w, uint8_t* out) {
 	float block_is_la_scale = block_is_la ? 1.0f / 1.05f : 1.0f;
 	int max_partitions = (int)config.tune_partition_count_limit;
 
+	TRACE("blk min %08x %08x %08x %08x max %08x %08x %08x %08x mean %08x %08x %08x %08x gray=%d\n", ASTC_F2U(bi.data_min.x), ASTC_F2U(bi.data_min.y), ASTC_F2U(bi.data_min.z), ASTC_F2U(bi.data_min.w),
+	      ASTC_F2U(bi.data_max.x), ASTC_F2U(bi.data_max.y), ASTC_F2U(bi.data_max.z), ASTC_F2U(bi.data_max.w), ASTC_F2U(bi.data_mean.x), ASTC_F2U(bi.data_mean.y), ASTC_F2U(bi.data_mean.z), ASTC_F2U(bi.data_mean.w), (int)bi.grayscale);
 	float error_weight_sum = hadd_s(bi.channel_weight) * bsd.texel_count;
 	float error_threshold = config.tune_db_limit * error_weight_sum * block_is_l_scale * block_is_la_scale;
+	TRACE_F("error_threshold", error_threshold);
 
 	scb.errorval = ERROR_CALC_DEFAULT;
 	scb.block_type = SYM_BTYPE_ERROR;

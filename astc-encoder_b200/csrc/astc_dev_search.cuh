@@ -1230,96 +1230,108 @@ ASTC_COOP bool realign_weights(WCtx& w, const ScbHdr& hdr, const PartView& pi, c
 // Physical block packing (astcenc_symbolic_physical.cpp:102-286, astcenc_integer_sequence.cpp:493-648).
 // Pure bit twiddling on ~100 values: executed by lane 0.
 // =============================================================================================
-ASTC_FN void write_bits(unsigned int value, unsigned int bitcount, unsigned int bitoffset, uint8_t* ptr) {
-	unsigned int mask = (1u << bitcount) - 1;
-	value &= mask;
-	ptr += bitoffset >> 3;
-	bitoffset &= 7;
-	value <<= bitoffset;
-	mask <<= bitoffset;
-	mask = ~mask;
-	ptr[0] &= mask;
-	ptr[0] |= value;
-	ptr[1] &= mask >> 8;
-	ptr[1] |= value >> 8;
+// The 128-bit block is assembled in two 64-bit registers; fields never overlap, so OR-ing a field in is
+// equivalent to the reference's masked byte writes (symbolic_physical.cpp:63-85).
+struct Bits128 {
+	uint64_t lo, hi;
+};
+
+ASTC_FN void put_bits(Bits128& b, unsigned int value, unsigned int bitcount, unsigned int bitoffset) {
+	uint64_t v = (uint64_t)(value & ((1u << bitcount) - 1u));
+	if (bitoffset < 64) {
+		b.lo |= v << bitoffset;
+		if (bitoffset + bitcount > 64) {
+			b.hi |= v >> (64 - bitoffset);
+		}
+	} else if (bitoffset < 128) {
+		b.hi |= v << (bitoffset - 64);
+	}
 }
 
-ASTC_FN void encode_ise(int quant_level, unsigned int character_count, const uint8_t* input_data, uint8_t* output_data, unsigned int bit_offset) {
+ASTC_FN uint64_t brev64(uint64_t v) {
+#if defined(ASTC_HOSTSIM)
+	v = ((v >> 1) & 0x5555555555555555ULL) | ((v & 0x5555555555555555ULL) << 1);
+	v = ((v >> 2) & 0x3333333333333333ULL) | ((v & 0x3333333333333333ULL) << 2);
+	v = ((v >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((v & 0x0F0F0F0F0F0F0F0FULL) << 4);
+	v = ((v >> 8) & 0x00FF00FF00FF00FFULL) | ((v & 0x00FF00FF00FF00FFULL) << 8);
+	v = ((v >> 16) & 0x0000FFFF0000FFFFULL) | ((v & 0x0000FFFF0000FFFFULL) << 16);
+	return (v >> 32) | (v << 32);
+#else
+	return __brevll(v);
+#endif
+}
+
+// encode_ise (astcenc_integer_sequence.cpp:493-648); get(i) yields the i-th value to encode
+template <typename GetFn>
+ASTC_FN void encode_ise(int quant_level, unsigned int character_count, GetFn get, Bits128& out, unsigned int bit_offset) {
 	const DevConstTables* ct = ASTC_CT;
 	unsigned int bits, trits, quints;
 	ise_btq(quant_level, bits, trits, quints);
 	unsigned int mask = (1u << bits) - 1;
 	if (trits) {
-		const uint8_t tbits[5] = {2, 2, 1, 2, 1};
-		const uint8_t tshift[5] = {0, 2, 4, 5, 7};
 		unsigned int i = 0;
 		while (i < character_count) {
-			unsigned int t[5];
-			for (unsigned int k = 0; k < 5; k++) {
-				t[k] = (i + k < character_count) ? (unsigned int)(input_data[i + k] >> bits) : 0u;
-			}
-			unsigned int T = ct->integer_of_trits[(((t[4] * 3 + t[3]) * 3 + t[2]) * 3 + t[1]) * 3 + t[0]];
-			for (unsigned int k = 0; k < 5 && i < character_count; k++, i++) {
-				unsigned int pack = (input_data[i] & mask) | (((T >> tshift[k]) & ((1u << tbits[k]) - 1)) << bits);
-				write_bits(pack, bits + tbits[k], bit_offset, output_data);
-				bit_offset += bits + tbits[k];
-			}
+			unsigned int v0 = get(i);
+			unsigned int v1 = (i + 1 < character_count) ? get(i + 1) : 0u;
+			unsigned int v2 = (i + 2 < character_count) ? get(i + 2) : 0u;
+			unsigned int v3 = (i + 3 < character_count) ? get(i + 3) : 0u;
+			unsigned int v4 = (i + 4 < character_count) ? get(i + 4) : 0u;
+			unsigned int T = ct->integer_of_trits[(((((v4 >> bits) * 3 + (v3 >> bits)) * 3 + (v2 >> bits)) * 3 + (v1 >> bits)) * 3) + (v0 >> bits)];
+			put_bits(out, (v0 & mask) | (((T >> 0) & 3) << bits), bits + 2, bit_offset);
+			bit_offset += bits + 2;
+			if (++i >= character_count) break;
+			put_bits(out, (v1 & mask) | (((T >> 2) & 3) << bits), bits + 2, bit_offset);
+			bit_offset += bits + 2;
+			if (++i >= character_count) break;
+			put_bits(out, (v2 & mask) | (((T >> 4) & 1) << bits), bits + 1, bit_offset);
+			bit_offset += bits + 1;
+			if (++i >= character_count) break;
+			put_bits(out, (v3 & mask) | (((T >> 5) & 3) << bits), bits + 2, bit_offset);
+			bit_offset += bits + 2;
+			if (++i >= character_count) break;
+			put_bits(out, (v4 & mask) | (((T >> 7) & 1) << bits), bits + 1, bit_offset);
+			bit_offset += bits + 1;
+			++i;
 		}
 	} else if (quints) {
-		const uint8_t qbits[3] = {3, 2, 2};
-		const uint8_t qshift[3] = {0, 3, 5};
 		unsigned int i = 0;
 		while (i < character_count) {
-			unsigned int q[3];
-			for (unsigned int k = 0; k < 3; k++) {
-				q[k] = (i + k < character_count) ? (unsigned int)(input_data[i + k] >> bits) : 0u;
-			}
-			unsigned int Q = ct->integer_of_quints[(q[2] * 5 + q[1]) * 5 + q[0]];
-			for (unsigned int k = 0; k < 3 && i < character_count; k++, i++) {
-				unsigned int pack = (input_data[i] & mask) | (((Q >> qshift[k]) & ((1u << qbits[k]) - 1)) << bits);
-				write_bits(pack, bits + qbits[k], bit_offset, output_data);
-				bit_offset += bits + qbits[k];
-			}
+			unsigned int v0 = get(i);
+			unsigned int v1 = (i + 1 < character_count) ? get(i + 1) : 0u;
+			unsigned int v2 = (i + 2 < character_count) ? get(i + 2) : 0u;
+			unsigned int Q = ct->integer_of_quints[((v2 >> bits) * 5 + (v1 >> bits)) * 5 + (v0 >> bits)];
+			put_bits(out, (v0 & mask) | (((Q >> 0) & 7) << bits), bits + 3, bit_offset);
+			bit_offset += bits + 3;
+			if (++i >= character_count) break;
+			put_bits(out, (v1 & mask) | (((Q >> 3) & 3) << bits), bits + 2, bit_offset);
+			bit_offset += bits + 2;
+			if (++i >= character_count) break;
+			put_bits(out, (v2 & mask) | (((Q >> 5) & 3) << bits), bits + 2, bit_offset);
+			bit_offset += bits + 2;
+			++i;
 		}
 	} else {
 		for (unsigned int i = 0; i < character_count; i++) {
-			write_bits(input_data[i], bits, bit_offset, output_data);
+			put_bits(out, get(i), bits, bit_offset);
 			bit_offset += bits;
 		}
 	}
 }
 
-ASTC_FN int bitrev8(int p) {
-	p = ((p & 0x0F) << 4) | ((p >> 4) & 0x0F);
-	p = ((p & 0x33) << 2) | ((p >> 2) & 0x33);
-	p = ((p & 0x55) << 1) | ((p >> 1) & 0x55);
-	return p;
-}
-
 // Writes the 16 physical bytes of the best block (header hdr, arrays in w.best_*) to out. Lane 0 only.
 ASTC_FN void symbolic_to_physical(const WCtx& w, const ScbHdr& scb, uint8_t* out) {
-	uint8_t pcb[18];
-	for (int i = 0; i < 18; i++) {
-		pcb[i] = 0;
-	}
+	Bits128 pcb;
+	pcb.lo = 0;
+	pcb.hi = 0;
 	if (scb.block_type == SYM_BTYPE_CONST_U16 || scb.block_type == SYM_BTYPE_CONST_F16) {
-		pcb[0] = 0xFC;
-		pcb[1] = scb.block_type == SYM_BTYPE_CONST_U16 ? 0xFD : 0xFF;
-		for (int i = 2; i < 8; i++) {
-			pcb[i] = 0xFF;
-		}
-		for (int i = 0; i < 4; i++) {
-			pcb[2 * i + 8] = (uint8_t)(scb.constant_color[i] & 0xFF);
-			pcb[2 * i + 9] = (uint8_t)((scb.constant_color[i] >> 8) & 0xFF);
-		}
+		// FC FD FF .. FF (UNORM16) or FC FF FF .. FF (FP16), then the four 16-bit components
+		pcb.lo = scb.block_type == SYM_BTYPE_CONST_U16 ? 0xFFFFFFFFFFFFFDFCULL : 0xFFFFFFFFFFFFFFFCULL;
+		pcb.hi = ((uint64_t)(scb.constant_color[0] & 0xFFFF)) | ((uint64_t)(scb.constant_color[1] & 0xFFFF) << 16) |
+		         ((uint64_t)(scb.constant_color[2] & 0xFFFF) << 32) | ((uint64_t)(scb.constant_color[3] & 0xFFFF) << 48);
 	} else {
 		const DevBsd& bsd = *w.bsd;
 		const DevConstTables* ct = ASTC_CT;
 		unsigned int partition_count = scb.partition_count;
-		uint8_t weightbuf[18];
-		for (int i = 0; i < 18; i++) {
-			weightbuf[i] = 0;
-		}
 		const DevBlockMode bm = bsd.block_modes[bsd.block_mode_packed_index[scb.block_mode]];
 		int weight_count = bsd.dec_modes[bm.decimation_mode].weight_count;
 		int weight_quant_method = bm.quant_mode;
@@ -1328,33 +1340,30 @@ ASTC_FN void symbolic_to_physical(const WCtx& w, const ScbHdr& scb, uint8_t* out
 		const uint8_t* scramble = ct->wq_scramble_map[weight_quant_method];
 		int real_weight_count = is_dual_plane ? 2 * weight_count : weight_count;
 		int bits_for_weights = (int)ise_sequence_bitcount((unsigned int)real_weight_count, weight_quant_method);
-		uint8_t weights[64];
-		for (int i = 0; i < weight_count; i++) {
-			float uqw = static_cast<float>(w.best_weights[i]);
+		const uint8_t* bw = w.best_weights;
+		// the i-th weight in transmission order: planes interleave for dual-plane modes (:127-150)
+		auto get_weight = [&](unsigned int i) -> unsigned int {
+			unsigned int src = is_dual_plane ? ((i >> 1) + ((i & 1) ? 32u : 0u)) : i;
+			float uqw = static_cast<float>(bw[src]);
 			float qw = (uqw / 64.0f) * (weight_quant_levels - 1.0f);
 			int qwi = static_cast<int>(qw + 0.5f);
-			if (is_dual_plane) {
-				weights[2 * i] = scramble[qwi];
-				uqw = static_cast<float>(w.best_weights[i + 32]);
-				qw = (uqw / 64.0f) * (weight_quant_levels - 1.0f);
-				qwi = static_cast<int>(qw + 0.5f);
-				weights[2 * i + 1] = scramble[qwi];
-			} else {
-				weights[i] = scramble[qwi];
-			}
-		}
-		encode_ise(weight_quant_method, (unsigned int)real_weight_count, weights, weightbuf, 0);
-		for (int i = 0; i < 16; i++) {
-			pcb[i] = static_cast<uint8_t>(bitrev8(weightbuf[15 - i]));
-		}
-		write_bits(scb.block_mode, 11, 0, pcb);
-		write_bits(partition_count - 1, 2, 11, pcb);
+			return scramble[qwi];
+		};
+		Bits128 wb;
+		wb.lo = 0;
+		wb.hi = 0;
+		encode_ise(weight_quant_method, (unsigned int)real_weight_count, get_weight, wb, 0);
+		// the weight stream is stored bit-reversed from the top of the block (:153-156)
+		pcb.lo = brev64(wb.hi);
+		pcb.hi = brev64(wb.lo);
+		put_bits(pcb, scb.block_mode, 11, 0);
+		put_bits(pcb, partition_count - 1, 2, 11);
 		int below_weights_pos = 128 - bits_for_weights;
 		if (partition_count > 1) {
-			write_bits(scb.partition_index, 6, 13, pcb);
-			write_bits(scb.partition_index >> 6, 10 - 6, 19, pcb);
+			put_bits(pcb, scb.partition_index, 6, 13);
+			put_bits(pcb, scb.partition_index >> 6, 10 - 6, 19);
 			if (scb.color_formats_matched) {
-				write_bits((unsigned int)scb.color_formats[0] << 2, 6, 13 + 10, pcb);
+				put_bits(pcb, (unsigned int)scb.color_formats[0] << 2, 6, 13 + 10);
 			} else {
 				int low_class = 4;
 				for (unsigned int i = 0; i < partition_count; i++) {
@@ -1380,30 +1389,33 @@ ASTC_FN void symbolic_to_physical(const WCtx& w, const ScbHdr& scb, uint8_t* out
 				int encoded_type_highpart = encoded_type >> 6;
 				int encoded_type_highpart_size = (3 * (int)partition_count) - 4;
 				int encoded_type_highpart_pos = 128 - bits_for_weights - encoded_type_highpart_size;
-				write_bits((unsigned int)encoded_type_lowpart, 6, 13 + 10, pcb);
-				write_bits((unsigned int)encoded_type_highpart, (unsigned int)encoded_type_highpart_size, (unsigned int)encoded_type_highpart_pos, pcb);
+				put_bits(pcb, (unsigned int)encoded_type_lowpart, 6, 13 + 10);
+				put_bits(pcb, (unsigned int)encoded_type_highpart, (unsigned int)encoded_type_highpart_size, (unsigned int)encoded_type_highpart_pos);
 				below_weights_pos -= encoded_type_highpart_size;
 			}
 		} else {
-			write_bits(scb.color_formats[0], 4, 13, pcb);
+			put_bits(pcb, scb.color_formats[0], 4, 13);
 		}
 		if (is_dual_plane) {
-			write_bits((unsigned int)scb.plane2_component, 2, (unsigned int)(below_weights_pos - 2), pcb);
+			put_bits(pcb, (unsigned int)scb.plane2_component, 2, (unsigned int)(below_weights_pos - 2));
 		}
-		uint8_t values_to_encode[32];
-		int valuecount_to_encode = 0;
+		// colour values: partition after partition, 2 * (class + 1) values each (:268-285)
 		const uint8_t* pack_table = ct->color_uquant_to_scrambled_pquant[scb.quant_mode - QUANT_6];
-		for (unsigned int i = 0; i < scb.partition_count; i++) {
-			int vals = 2 * (scb.color_formats[i] >> 2) + 2;
-			for (int j = 0; j < vals; j++) {
-				values_to_encode[j + valuecount_to_encode] = pack_table[w.best_colors[i * 8 + j]];
-			}
-			valuecount_to_encode += vals;
-		}
-		encode_ise(scb.quant_mode, (unsigned int)valuecount_to_encode, values_to_encode, pcb, scb.partition_count == 1 ? 17 : 19 + 10);
+		unsigned int n0 = 2u * (scb.color_formats[0] >> 2) + 2u;
+		unsigned int n1 = partition_count > 1 ? 2u * (scb.color_formats[1] >> 2) + 2u : 0u;
+		unsigned int n2 = partition_count > 2 ? 2u * (scb.color_formats[2] >> 2) + 2u : 0u;
+		unsigned int n3 = partition_count > 3 ? 2u * (scb.color_formats[3] >> 2) + 2u : 0u;
+		const uint8_t* bc = w.best_colors;
+		auto get_color = [&](unsigned int i) -> unsigned int {
+			unsigned int p = 0;
+			if (i >= n0) { i -= n0; p = 1; if (i >= n1) { i -= n1; p = 2; if (i >= n2) { i -= n2; p = 3; } } }
+			return pack_table[bc[p * 8 + i]];
+		};
+		encode_ise(scb.quant_mode, n0 + n1 + n2 + n3, get_color, pcb, scb.partition_count == 1 ? 17 : 19 + 10);
 	}
-	for (int i = 0; i < 16; i++) {
-		out[i] = pcb[i];
+	for (int i = 0; i < 8; i++) {
+		out[i] = (uint8_t)(pcb.lo >> (8 * i));
+		out[8 + i] = (uint8_t)(pcb.hi >> (8 * i));
 	}
 }
 

@@ -39,12 +39,19 @@ astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__
 	WCtx w;
 	init_wctx(w, lane, &bsd, &cfg, arena);
 	const unsigned int total = img.blocks_x * img.block_rows;
+#if defined(ASTC_DEBUG_SINGLE_LANE)
+	if (lane != 0) {
+		return;
+	}
+#endif
 	while (true) {
 		unsigned int b = 0;
 		if (lane == 0) {
 			b = atomicAdd(ticket, 1u);
 		}
+#if !defined(ASTC_DEBUG_SINGLE_LANE)
 		b = __shfl_sync(0xffffffffu, b, 0);
+#endif
 		if (b >= total) {
 			break;
 		}

@@ -5,7 +5,8 @@ import numpy as np
 from astc_ref import *
 import astc_images as I
 
-PROD = os.path.join(ROOT, "astc-encoder_b200", "libastcenc_b200.so")
+PROD = os.environ.get("ASTC_LIB", os.path.join(ROOT, "astc-encoder_b200", "libastcenc_b200.so"))
+QUICK = int(os.environ.get("ASTC_QUICK", "0"))
 prod = AstcencLib(PROD)
 chk = ref_lib() if have_ref() else None
 orc = Oracle()
@@ -21,6 +22,12 @@ def check(name, img, prof, bx, by, q, fl=0, swz=(0, 1, 2, 3)):
 
 bad = 0
 img = I.photo_like(256, 256)
+if QUICK:
+    small = I.photo_like(24 * QUICK, 24, seed=11)
+    bad += check("tiny 4x4", small, PRF_LDR, 4, 4, 10)
+    bad += check("tiny 6x6", small, PRF_LDR, 6, 6, 60)
+    print("TOTAL DIFF BLOCKS", bad)
+    sys.exit(1 if bad else 0)
 bad += check("photo", img, PRF_LDR, 6, 6, 60)
 bad += check("photo", img, PRF_LDR, 4, 4, 10)
 bad += check("photo", img, PRF_LDR, 8, 8, 98)
