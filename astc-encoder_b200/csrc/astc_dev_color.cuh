@@ -34,7 +34,7 @@ ASTC_FN void bit_transfer_signed4(i4& a, i4& b) {
 	bit_transfer_signed1(a.w, b.w);
 }
 
-ASTC_FN void rgba_delta_unpack(i4 in0, i4 in1, i4& out0, i4& out1) {   // :61-102
+ASTC_NOINLINE void rgba_delta_unpack(i4 in0, i4 in1, i4& out0, i4& out1) {   // :61-102
 	bit_transfer_signed4(in1, in0);
 	int rgb_sum = in1.x + in1.y + in1.z;
 	in1 = mki4(in1.x + in0.x, in1.y + in0.y, in1.z + in0.z, in1.w + in0.w);
@@ -60,7 +60,7 @@ ASTC_FN void rgba_unpack(i4 in0, i4 in1, i4& out0, i4& out1) {   // :105-135
 #include "astc_dev_color_hdr_unpack.cuh"
 
 // unpack_color_endpoints (astcenc_color_unquantize.cpp:844-1022)
-ASTC_FN void unpack_color_endpoints(int decode_mode, int format, const uint8_t* in, bool& rgb_hdr, bool& alpha_hdr, i4& o0, i4& o1) {
+ASTC_NOINLINE void unpack_color_endpoints(int decode_mode, int format, const uint8_t* in, bool& rgb_hdr, bool& alpha_hdr, i4& o0, i4& o1) {
 	rgb_hdr = false;
 	alpha_hdr = false;
 	bool alpha_hdr_default = false;
@@ -237,7 +237,7 @@ ASTC_FN float get_rgba_encoding_error(f4 uq0, f4 uq1, i4 q0, i4 q1) {   // :50-6
 	return hadd_s(e0 * e0 + e1 * e1);
 }
 
-ASTC_FN void quantize_rgb(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {   // :169-193
+ASTC_NOINLINE void quantize_rgb(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {   // :169-193
 	i4 c0i, c1i;
 	do {
 		i4 a = f4_to_i4_rtn(c0);
@@ -269,7 +269,7 @@ ASTC_FN f4 blue_contract_fwd(f4 c) {   // c += c - c.bbba
 	return mk4(c.x + (c.x - c.z), c.y + (c.y - c.z), c.z + (c.z - c.z), c.w + (c.w - c.w));
 }
 
-ASTC_FN bool try_quantize_rgb_blue_contract(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {   // :237-267
+ASTC_NOINLINE bool try_quantize_rgb_blue_contract(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {   // :237-267
 	c0 = blue_contract_fwd(c0);
 	c1 = blue_contract_fwd(c1);
 	if (!in_0_255(c0) || !in_0_255(c1)) {
@@ -295,7 +295,7 @@ ASTC_FN bool try_quantize_rgba_blue_contract(f4 c0, f4 c1, i4& o0, i4& o1, const
 }
 
 // common body of try_quantize_rgb_delta (:321-400) and ..._delta_blue_contract (:403-488)
-ASTC_FN bool rgb_delta_core(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q, bool want_negative_sum) {
+ASTC_NOINLINE bool rgb_delta_core(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q, bool want_negative_sum) {
 	i4 c0a = f4_to_i4_rtn(c0);
 	c0a = mki4(c0a.x << 1, c0a.y << 1, c0a.z << 1, c0a.w << 1);
 	i4 c0b = mki4(c0a.x & 0xFF, c0a.y & 0xFF, c0a.z & 0xFF, c0a.w & 0xFF);
@@ -342,7 +342,7 @@ ASTC_FN bool try_quantize_rgb_delta_blue_contract(f4 c0, f4 c1, i4& o0, i4& o1, 
 	return rgb_delta_core(c0, c1, o0, o1, q, true);
 }
 
-ASTC_FN bool try_quantize_alpha_delta(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {   // :504-570
+ASTC_NOINLINE bool try_quantize_alpha_delta(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {   // :504-570
 	float a0 = c0.w, a1 = c1.w;
 	int a0a = f2i_rtn(a0);
 	a0a <<= 1;
@@ -376,7 +376,7 @@ ASTC_FN bool try_quantize_alpha_delta(f4 c0, f4 c1, i4& o0, i4& o1, const QuantC
 	return true;
 }
 
-ASTC_FN bool try_quantize_luminance_alpha_delta(f4 c0, f4 c1, uint8_t out[4], const QuantCtx& q) {   // :573-694
+ASTC_NOINLINE bool try_quantize_luminance_alpha_delta(f4 c0, f4 c1, uint8_t out[4], const QuantCtx& q) {   // :573-694
 	float l0 = hadd_rgb_s(c0) * (1.0f / 3.0f);
 	float l1 = hadd_rgb_s(c1) * (1.0f / 3.0f);
 	float a0 = c0.w, a1 = c1.w;
@@ -419,7 +419,7 @@ ASTC_FN bool try_quantize_luminance_alpha_delta(f4 c0, f4 c1, uint8_t out[4], co
 	return true;
 }
 
-ASTC_FN void quantize_rgbs(f4 color, uint8_t out[4], const QuantCtx& q) {   // :734-763
+ASTC_NOINLINE void quantize_rgbs(f4 color, uint8_t out[4], const QuantCtx& q) {   // :734-763
 	float scale = 1.0f / 257.0f;
 	float r = clampf(color.x * scale, 0.0f, 255.0f);
 	float g = clampf(color.y * scale, 0.0f, 255.0f);
@@ -462,7 +462,7 @@ ASTC_FN void quantize_luminance_alpha(f4 c0, f4 c1, uint8_t out[4], const QuantC
 #include "astc_dev_color_hdr_pack.cuh"
 
 // pack_color_endpoints (astcenc_color_quantize.cpp:1909-2147)
-ASTC_FN uint8_t pack_color_endpoints(f4 color0, f4 color1, f4 rgbs_color, f4 rgbo_color, int format, uint8_t* output, int quant_level) {
+ASTC_NOINLINE uint8_t pack_color_endpoints(f4 color0, f4 color1, f4 rgbs_color, f4 rgbo_color, int format, uint8_t* output, int quant_level) {
 	QuantCtx q;
 	q.tab = ASTC_CT->color_unquant_to_uquant[quant_level - QUANT_6];
 	q.quant_level = quant_level;

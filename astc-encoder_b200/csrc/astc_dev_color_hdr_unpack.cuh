@@ -4,7 +4,7 @@ ASTC_FN int safe_signed_lsh(int val, int shift) {
 	return (int)((unsigned int)val << shift);
 }
 
-ASTC_FN void hdr_rgbo_unpack(const uint8_t in[4], i4& o0, i4& o1) {   // :310-500
+ASTC_NOINLINE void hdr_rgbo_unpack(const uint8_t in[4], i4& o0, i4& o1) {   // :310-500
 	int v0 = in[0], v1 = in[1], v2 = in[2], v3 = in[3];
 	int modeval = ((v0 & 0xC0) >> 6) | (((v1 & 0x80) >> 7) << 2) | (((v2 & 0x80) >> 7) << 3);
 	int majcomp, mode;
@@ -66,7 +66,7 @@ ASTC_FN void hdr_rgbo_unpack(const uint8_t in[4], i4& o0, i4& o1) {   // :310-50
 	o1 = mki4(red << 4, green << 4, blue << 4, 0x7800);
 }
 
-ASTC_FN void hdr_rgb_unpack(const uint8_t in[6], i4& o0, i4& o1) {   // :503-700
+ASTC_NOINLINE void hdr_rgb_unpack(const uint8_t in[6], i4& o0, i4& o1) {   // :503-700
 	int v0 = in[0], v1 = in[1], v2 = in[2], v3 = in[3], v4 = in[4], v5 = in[5];
 	int modeval = ((v1 & 0x80) >> 7) | (((v2 & 0x80) >> 7) << 1) | (((v3 & 0x80) >> 7) << 2);
 	int majcomp = ((v4 & 0x80) >> 7) | (((v5 & 0x80) >> 7) << 1);
@@ -157,7 +157,7 @@ ASTC_FN void hdr_luminance_large_range_unpack(const uint8_t in[2], i4& o0, i4& o
 	o1 = mki4(y1 << 4, y1 << 4, y1 << 4, 0x7800);
 }
 
-ASTC_FN void hdr_alpha_unpack(const uint8_t in[2], int& o0, int& o1) {   // :801-838
+ASTC_NOINLINE void hdr_alpha_unpack(const uint8_t in[2], int& o0, int& o1) {   // :801-838
 	int v6 = in[0], v7 = in[1];
 	int selector = ((v6 >> 7) & 1) | ((v7 >> 6) & 2);
 	v6 &= 0x7F;

@@ -19,6 +19,7 @@
 
 #if defined(ASTC_HOSTSIM)
 	#define ASTC_FN static inline
+	#define ASTC_NOINLINE static
 	#define ASTC_COOP static
 	#define ASTC_WARP 1
 	#define ASTC_RINT(a) nearbyintf(a)
@@ -33,6 +34,7 @@
 	#define ASTC_CT g_astc_ct
 #else
 	#define ASTC_FN static __device__ __forceinline__
+	#define ASTC_NOINLINE static __device__ __noinline__
 	#define ASTC_COOP static __device__ __noinline__
 	#if defined(ASTC_DEBUG_SINGLE_LANE)
 		#define ASTC_WARP 1       /* debug build: lane 0 of each warp does all the work serially */
@@ -856,7 +858,7 @@ ASTC_COOP void compute_ideal_weights_for_decimation(WCtx& w, const DecView& di, 
 // Angular weight-range search (astcenc_weight_align.cpp:94-355). One lane owns one (grid, plane) and walks
 // all its angular steps; every sum over the grid's weights is a chain.
 // =============================================================================================
-ASTC_FN void compute_angular_endpoints_for_quant_levels(int weight_count, const float* dwi, unsigned int max_quant_level, float* lowhigh /* [8][2] */) {
+ASTC_NOINLINE void compute_angular_endpoints_for_quant_levels(int weight_count, const float* dwi, unsigned int max_quant_level, float* lowhigh /* [8][2] */) {
 	const uint8_t steps_for_quant_level[12] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32};
 	const DevConstTables* ct = ASTC_CT;
 	int max_quant_steps = steps_for_quant_level[max_quant_level];

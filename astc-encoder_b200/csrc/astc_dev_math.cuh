@@ -116,7 +116,7 @@ ASTC_FN f4 unit3() { return mk4(0.577350258827209473f, 0.577350258827209473f, 0.
 ASTC_FN f4 unit2() { return mk4(0.707106769084930420f, 0.707106769084930420f, 0.0f, 0.0f); }
 
 // fp16 <-> fp32 (F16C semantics: round to nearest even) (astcenc_vecmathlib_sse_4.h:967-1000)
-ASTC_FN uint16_t float_to_sf16(float f) {
+ASTC_NOINLINE uint16_t float_to_sf16(float f) {
 	uint32_t u = f_as_u(f);
 	uint32_t sign = (u >> 16) & 0x8000u;
 	uint32_t exp = (u >> 23) & 0xFF;
@@ -153,7 +153,7 @@ ASTC_FN uint16_t float_to_sf16(float f) {
 	return (uint16_t)(sign | half);
 }
 
-ASTC_FN float sf16_to_float(uint16_t h) {
+ASTC_NOINLINE float sf16_to_float(uint16_t h) {
 	uint32_t sign = ((uint32_t)h & 0x8000u) << 16;
 	uint32_t exp = (h >> 10) & 0x1F;
 	uint32_t mant = h & 0x3FFu;
@@ -210,7 +210,7 @@ ASTC_FN int unorm16_to_sf16(int p) {
 }
 
 // float_to_lns (astcenc_vecmathlib.h:566-620)
-ASTC_FN float float_to_lns(float a) {
+ASTC_NOINLINE float float_to_lns(float a) {
 	uint32_t ai = f_as_u(a);
 	int exp = (int)((ai >> 23) & 0xFF) - 126;
 	float mant = u_as_f((ai & 0x807FFFFFu) | 0x3F000000u);

@@ -161,7 +161,7 @@ ASTC_FN uint8_t partition_mismatch2(const uint64_t a[2], const uint64_t b[2]) { 
 	return static_cast<uint8_t>(mini(v1, v2) / 2);
 }
 
-ASTC_FN uint8_t partition_mismatch3(const uint64_t a[3], const uint64_t b[3]) {   // :273-304
+ASTC_NOINLINE uint8_t partition_mismatch3(const uint64_t a[3], const uint64_t b[3]) {   // :273-304
 	int p00 = ASTC_POPCLL(a[0] ^ b[0]), p01 = ASTC_POPCLL(a[0] ^ b[1]), p02 = ASTC_POPCLL(a[0] ^ b[2]);
 	int p10 = ASTC_POPCLL(a[1] ^ b[0]), p11 = ASTC_POPCLL(a[1] ^ b[1]), p12 = ASTC_POPCLL(a[1] ^ b[2]);
 	int p20 = ASTC_POPCLL(a[2] ^ b[0]), p21 = ASTC_POPCLL(a[2] ^ b[1]), p22 = ASTC_POPCLL(a[2] ^ b[2]);
@@ -171,7 +171,7 @@ ASTC_FN uint8_t partition_mismatch3(const uint64_t a[3], const uint64_t b[3]) { 
 	return static_cast<uint8_t>(min3i(v0, v1, v2) / 2);
 }
 
-ASTC_FN uint8_t partition_mismatch4(const uint64_t a[4], const uint64_t b[4]) {   // :314-353
+ASTC_NOINLINE uint8_t partition_mismatch4(const uint64_t a[4], const uint64_t b[4]) {   // :314-353
 	int p00 = ASTC_POPCLL(a[0] ^ b[0]), p01 = ASTC_POPCLL(a[0] ^ b[1]), p02 = ASTC_POPCLL(a[0] ^ b[2]), p03 = ASTC_POPCLL(a[0] ^ b[3]);
 	int p10 = ASTC_POPCLL(a[1] ^ b[0]), p11 = ASTC_POPCLL(a[1] ^ b[1]), p12 = ASTC_POPCLL(a[1] ^ b[2]), p13 = ASTC_POPCLL(a[1] ^ b[3]);
 	int p20 = ASTC_POPCLL(a[2] ^ b[0]), p21 = ASTC_POPCLL(a[2] ^ b[1]), p22 = ASTC_POPCLL(a[2] ^ b[2]), p23 = ASTC_POPCLL(a[2] ^ b[3]);
@@ -279,7 +279,7 @@ ASTC_COOP unsigned int compute_kmeans_partition_ordering(WCtx& w, unsigned int p
 // Evaluate one candidate partitioning on one lane: compute_avgs_and_dirs_{4_comp,3_comp_rgb}
 // (averages_and_directions.cpp:388-456, :568-628) + compute_error_squared_{rgba,rgb} (:723-945) + the
 // line-length penalty of find_best_partition_candidates (:676-690, :733-747).
-ASTC_FN void evaluate_partitioning(const WCtx& w, unsigned int pc, unsigned int packed, bool uses_alpha, float weight_imprecision_estim,
+ASTC_NOINLINE void evaluate_partitioning(const WCtx& w, unsigned int pc, unsigned int packed, bool uses_alpha, float weight_imprecision_estim,
                                    float& uncor_error_out, float& samec_error_out) {
 	PartView pi = part_view_packed(*w.bsd, pc, packed);
 	int T = w.T;

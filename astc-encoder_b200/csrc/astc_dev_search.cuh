@@ -422,7 +422,7 @@ ASTC_COOP void multi_partition_find_best_combination(WCtx& w, int pc, EfTables* 
 }
 
 // one_partition_/N-partition _find_best_combination_for_bitcount (:678-725, :768-1093)
-ASTC_FN float find_best_combination_for_bitcount(int pc, const EfTables* ef, int bits_available, uint8_t& best_quant_level, uint8_t& best_quant_level_mod, uint8_t* best_formats) {
+ASTC_NOINLINE float find_best_combination_for_bitcount(int pc, const EfTables* ef, int bits_available, uint8_t& best_quant_level, uint8_t& best_quant_level_mod, uint8_t* best_formats) {
 	const DevConstTables* ct = ASTC_CT;
 	if (pc == 1) {
 		int best_integer_count = 0;
@@ -553,7 +553,7 @@ ASTC_COOP unsigned int compute_ideal_endpoint_formats(WCtx& w, const PartView& p
 // =============================================================================================
 // Least-squares endpoint refit (astcenc_ideal_endpoints_and_weights.cpp:1099-1650)
 // =============================================================================================
-ASTC_FN f4 compute_rgbo_vector(f4 rgba_weight_sum, f4 weight_weight_sum, f4 rgbq_sum, float psum) {
+ASTC_NOINLINE f4 compute_rgbo_vector(f4 rgba_weight_sum, f4 weight_weight_sum, f4 rgbq_sum, float psum) {
 	float X = rgba_weight_sum.x, Y = rgba_weight_sum.y, Z = rgba_weight_sum.z;
 	float P = weight_weight_sum.x, Q = weight_weight_sum.y, R = weight_weight_sum.z;
 	float S = psum;
@@ -1319,7 +1319,7 @@ ASTC_FN void encode_ise(int quant_level, unsigned int character_count, GetFn get
 }
 
 // Writes the 16 physical bytes of the best block (header hdr, arrays in w.best_*) to out. Lane 0 only.
-ASTC_FN void symbolic_to_physical(const WCtx& w, const ScbHdr& scb, uint8_t* out) {
+ASTC_NOINLINE void symbolic_to_physical(const WCtx& w, const ScbHdr& scb, uint8_t* out) {
 	Bits128 pcb;
 	pcb.lo = 0;
 	pcb.hi = 0;

@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py - Mtexels/s of the ASTC compress hot path (BASELINE.json metric).
+
+A "step" = one pass of the block compressor over one 4096x4096 LDR RGBA image at 6x6 -medium
+(BASELINE.json configs[1]) per GPU. Synthetic, seeded image (tests/astc_images.photo_like).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
+  python bench.py --impl reference [...]                        the reference's own CPU implementation (oracle/_ref)
+
+value : whole-job Mtexels/s with the image already resident in HBM (kernel time from CUDA events on the
+        launching stream, L2 flushed between steps).
+e2e   : the same metric through the astcenc.h C ABI with HOST buffers (pinned): H2D of the image and D2H of the
+        blocks inside the timed region.
+N > 1 : one process per GPU (torchrun); every rank compresses its own image of the batch (weak scaling), the
+        compressed payload (16 B/block) is gathered to rank 0 over NCCL inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DIM = 4096
+BLOCK = 6
+QUALITY = 60.0           # -medium
+PROFILE = 1              # ASTCENC_PRF_LDR
+FLAGS = 32               # ASTCENC_FLG_SELF_DECOMPRESS_ONLY, what the reference CLI sets for -cl
+BLOCKS = ((DIM + BLOCK - 1) // BLOCK) ** 2
+ALGO_BYTES = DIM * DIM * 4 + BLOCKS * 16      # read every texel once, write 16 B per block
+WORKLOAD = "4096x4096 LDR RGBA8, 6x6 block, -medium (BASELINE.json configs[1])"
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            p = [x.strip() for x in l.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_image(seed):
+    import astc_images
+    return astc_images.photo_like(DIM, DIM, seed=seed)
+
+
+def run_reference_cpu(image, threads, repeats):
+    """The unmodified reference build (oracle/_ref) on the host cores; returns best seconds per image."""
+    import astc_ref
+    lib = astc_ref.ref_lib()
+    import ctypes as C
+    cfg = lib.config(PROFILE, BLOCK, BLOCK, QUALITY, FLAGS)
+    ctx = C.c_void_p()
+    err = lib.lib.astcenc_context_alloc(C.byref(cfg), threads, C.byref(ctx), None)
+    assert err == 0, err
+    best = 1e30
+    try:
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            lib.compress_ctx(ctx, image, BLOCK, BLOCK, threads=threads)
+            best = min(best, time.perf_counter() - t0)
+    finally:
+        lib.lib.astcenc_context_free(ctx)
+    return best
+
+
+def cpu_baseline(image, max_seconds=20.0):
+    import astc_ref
+    cores = os.cpu_count() or 1
+    if not astc_ref.have_ref():
+        # fall back to the oracle port (single thread) on a crop
+        crop = np.ascontiguousarray(image[:512, :512])
+        o = astc_ref.Oracle()
+        t0 = time.perf_counter()
+        o.compress(crop, PROFILE, BLOCK, BLOCK, QUALITY, FLAGS)
+        dt = time.perf_counter() - t0
+        return {"value": crop.shape[0] * crop.shape[1] / dt / 1e6, "unit": "Mtexels/s", "cores": 1, "kind": "port", "sample": "512x512 crop of the workload image, 1 thread"}
+    t = run_reference_cpu(image, cores, 1)
+    reps = int(max(1, min(4, max_seconds / max(t, 1e-3) - 1)))
+    t = min(t, run_reference_cpu(image, cores, reps))
+    return {"value": DIM * DIM / t / 1e6, "unit": "Mtexels/s", "cores": cores, "kind": "reference",
+            "sample": "whole 4096x4096 workload image, best of %d, %d caller threads, astcenc avx2 invariance build" % (reps + 1, cores)}
+
+
+def traffic_from_profile():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    W = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
+    K = max(args.steps, 1)
+    config = {"workload": WORKLOAD, "block": "6x6", "preset": "medium", "profile": "LDR", "images_per_step": world,
+              "l2": "flushed between timed steps (256 MiB memset)", "sharding": "one image per rank, NCCL gather of 16 B/block payloads to rank 0" if world > 1 else "single GPU"}
+
+    if args.impl == "reference":
+        # rank 0 alone times the reference's CPU implementation; other ranks exit without work
+        if rank != 0:
+            return
+        image = make_image(2024)
+        cores = os.cpu_count() or 1
+        for _ in range(W):
+            run_reference_cpu(image, cores, 1)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            run_reference_cpu(image, cores, 1)
+        dt = (time.perf_counter() - t0) / K
+        v = DIM * DIM / dt / 1e6
+        line = {"impl": "reference", "metric": "Mtexels/s at 4K RGBA 6x6 -medium", "value": v, "unit": "Mtexels/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(config, images_per_step=1, sharding="host CPU"),
+                "cpu_baseline": {"value": v, "unit": "Mtexels/s", "cores": cores, "kind": "reference", "sample": "whole 4096x4096 workload image per step, %d caller threads" % cores},
+                "e2e": {"value": v, "unit": "Mtexels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    image = make_image(2024 + rank)                       # every rank has its own image of the batch
+    cfg = pkg.config_init(PROFILE, BLOCK, BLOCK, QUALITY, FLAGS)
+    ctx = pkg.Context(cfg)
+    nbx, nby = ctx.blocks(DIM, DIM)
+    payload = nbx * nby * 16
+    d_img = torch.from_numpy(image).to(dev)
+    d_out = torch.empty(payload, dtype=torch.uint8, device=dev)
+    gather_list = [torch.empty(payload, dtype=torch.uint8, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # a non-default stream: the C ABI treats stream 0 as "use the context's own stream", and CUDA events must be
+    # recorded on the stream the kernel is launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    def step(timed_events=None):
+        flush.zero_()
+        if timed_events is not None:
+            timed_events[0].record(stream)
+        ctx.compress_device(d_img.data_ptr(), pkg.TYPE_U8, DIM, DIM, d_out.data_ptr(), stream=stream.cuda_stream)
+        if world > 1:
+            dist.gather(d_out, gather_list, dst=0)
+        if timed_events is not None:
+            timed_events[1].record(stream)
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(K):
+        step(evs[k])
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    launches = ctx.launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs) / K
+    clocks = sampler.stop() if rank == 0 else None
+
+    # kernel-only duration (roofline): events tightly around the kernel on its stream, no gather
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 5))]
+    for a, b in kev:
+        flush.zero_()
+        a.record(stream)
+        ctx.compress_device(d_img.data_ptr(), pkg.TYPE_U8, DIM, DIM, d_out.data_ptr(), stream=stream.cuda_stream)
+        b.record(stream)
+    torch.cuda.synchronize()
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
+
+    # end to end through the C ABI with pinned host buffers (H2D + kernel + D2H inside the timed region)
+    pin_in = torch.empty((DIM, DIM, 4), dtype=torch.uint8, pin_memory=True)
+    pin_in.numpy()[...] = image
+    pin_out = torch.empty(payload, dtype=torch.uint8, pin_memory=True)
+    h_in, h_out = pin_in.numpy(), pin_out.numpy()
+    for _ in range(2):
+        ctx.compress_image(h_in, out=h_out)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_steps = min(K, 5)
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.compress_image(h_in, out=h_out)
+    e2e_s = (time.perf_counter() - t1) / e2e_steps
+    assert np.array_equal(h_out, d_out.cpu().numpy()), "host-pointer path and device-resident path disagree"
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, kernel_ms = [float(x) for x in times.cpu()]
+
+    if rank == 0:
+        texels = DIM * DIM * world
+        value = texels / (dev_ms * 1e-3) / 1e6
+        peak, peak_kind = measured_peak_hbm()
+        achieved = ALGO_BYTES / (kernel_ms * 1e-3) / 1e9
+        line = {"metric": "Mtexels/s at 4K RGBA 6x6 -medium", "value": value, "unit": "Mtexels/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "e2e": {"value": texels / (e2e_ms * 1e-3) / 1e6, "unit": "Mtexels/s", "h2d_bytes_per_step": DIM * DIM * 4, "d2h_bytes_per_step": payload,
+                        "ms_per_step": e2e_ms},
+                "gpu_launches": launches,
+                "clocks": clocks,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_from_profile(),
+                             "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)", "kernel": "astc_compress_kernel", "kernel_ms": kernel_ms,
+                             "algorithmic_bytes_per_launch": ALGO_BYTES,
+                             "note": "the search is fp32-issue/latency bound, not bandwidth bound; frac is reported against the HBM roofline as the tier requires"},
+                "wall_ms_per_step": wall * 1e3 / K}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(image)
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

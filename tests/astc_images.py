@@ -14,7 +14,51 @@ def _value_noise(rng, h, w, cell, channels):
     return (a * (1 - fx) + b * fx) * (1 - fy) + (c * (1 - fx) + d * fx) * fy
 
 
+def _jitter_voronoi(rng, h, w, cell, channels):
+    gh, gw = h // cell + 3, w // cell + 3
+    py = (np.arange(gh)[:, None] - 1 + rng.random((gh, gw))) * cell
+    px = (np.arange(gw)[None, :] - 1 + rng.random((gh, gw))) * cell
+    cols = rng.random((gh, gw, channels)).astype(np.float32)
+    yy = np.arange(h, dtype=np.float32)[:, None]
+    xx = np.arange(w, dtype=np.float32)[None, :]
+    cy = (np.arange(h) // cell + 1)[:, None]
+    cx = (np.arange(w) // cell + 1)[None, :]
+    best = np.full((h, w), 1e30, np.float32)
+    out = np.zeros((h, w, channels), np.float32)
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            iy = np.broadcast_to(cy + dy, (h, w))
+            ix = np.broadcast_to(cx + dx, (h, w))
+            d = (yy - py[iy, ix]) ** 2 + (xx - px[iy, ix]) ** 2
+            m = d < best
+            best = np.where(m, d, best)
+            out[m] = cols[iy, ix][m]
+    return out
+
+
 def photo_like(h, w, seed=1234):
+    """Texture-like content. Images larger than 1024 in either axis are a mirrored tiling of a 1024-sized
+    base image (keeps generation fast; block statistics are those of the base image)."""
+    if h > 1024 or w > 1024:
+        bh, bw = min(h, 1024), min(w, 1024)
+        base = _photo_like_base(bh, bw, seed)
+        ny, nx = (h + bh - 1) // bh, (w + bw - 1) // bw
+        rows = []
+        for ty in range(ny):
+            row = []
+            for tx in range(nx):
+                t = base
+                if ty & 1:
+                    t = t[::-1]
+                if tx & 1:
+                    t = t[:, ::-1]
+                row.append(t)
+            rows.append(np.concatenate(row, axis=1))
+        return np.ascontiguousarray(np.concatenate(rows, axis=0)[:h, :w])
+    return _photo_like_base(h, w, seed)
+
+
+def _photo_like_base(h, w, seed=1234):
     """Multi-octave colour noise + Voronoi edges + flat patches + partly varying alpha: a mix of block types
     (constant, smooth, edge, textured) comparable to real texture content."""
     rng = np.random.default_rng(seed)
@@ -26,20 +70,10 @@ def photo_like(h, w, seed=1234):
             tot += amp
         amp *= 0.5
     img /= max(tot, 1e-6)
-    # Voronoi cells with per-cell tint -> hard edges
-    n = max(4, (h * w) // (48 * 48))
-    pts = rng.random((n, 2)) * [h, w]
-    cols = rng.random((n, 4)).astype(np.float32)
-    step = 64
-    yy, xx = np.mgrid[0:h, 0:w]
-    lab = np.zeros((h, w), np.int32)
-    best = np.full((h, w), 1e30, np.float32)
-    for i in range(n):
-        d = (yy - pts[i, 0]) ** 2 + (xx - pts[i, 1]) ** 2
-        m = d < best
-        best[m] = d[m]; lab[m] = i
+    # jittered-grid Voronoi cells with per-cell tint -> hard edges (9-neighbour search, vectorised)
+    lab_cols = _jitter_voronoi(rng, h, w, 48, 4)
     mix = _value_noise(rng, h, w, 128, 1)
-    img = img * (0.55 + 0.45 * mix) + cols[lab] * (0.45 * (1 - mix))
+    img = img * (0.55 + 0.45 * mix) + lab_cols * (0.45 * (1 - mix))
     # flat patches and opaque alpha regions
     flat = _value_noise(rng, h, w, 96, 1)[..., 0] > 0.72
     img[flat] = np.round(img[flat] * 6) / 6
