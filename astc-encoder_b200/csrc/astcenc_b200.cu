@@ -243,6 +243,15 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			ctx->warps_per_cta = warps;
 			ctx->grid = prop.multiProcessorCount * 2;
 		}
+		// tuning overrides (experiments): warps per CTA and CTAs per SM
+		if (const char* e = getenv("ASTCENC_B200_WARPS")) {
+			int v = atoi(e);
+			if (v >= 1 && v <= warps && (!ctx->arena_in_smem || arena * v <= smem_limit)) ctx->warps_per_cta = v;
+		}
+		if (const char* e = getenv("ASTCENC_B200_CTAS_PER_SM")) {
+			int v = atoi(e);
+			if (v >= 1 && v <= 8) ctx->grid = prop.multiProcessorCount * v;
+		}
 		ctx->smem_bytes = ctx->arena_in_smem ? arena * ctx->warps_per_cta : 0;
 		if (ctx->smem_bytes > 48 * 1024) {
 			CUDA_TRY(cudaFuncSetAttribute(astc_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
