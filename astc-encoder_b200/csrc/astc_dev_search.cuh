@@ -5,9 +5,11 @@
 #include "astc_dev_core.cuh"
 
 // su (union scratch) sub-layouts. Each phase owns the whole union while it runs.
-//   quantise+error pass : per-lane quantised weight rows                  UQ_ROW_STRIDE * 32
-//   endpoint formats    : best_error/format tables, combined tables       see EF_* below
-//   refinement          : undecimated weights, int weights, realign staging
+//   decimation          : infilled[2][T]
+//   angular search      : table rows, pair ranges, step records         (see compute_angular_endpoints)
+//   quantise+error pass : per-lane quantised weight rows                 UQ_ROW_STRIDE * 32
+//   endpoint formats    : best_error/format tables, combined tables     (EfTables)
+//   refinement          : undecimated weights, int weights, chain staging tile (RefineScratch)
 //   partition search    : mismatch counts, ordering, histogram, k-means state, candidate errors
 #define UQ_ROW_STRIDE 68    /* 17 words: conflict-free lane-private rows */
 
@@ -16,85 +18,78 @@
 // (astcenc_compress_symbolic.cpp:434-485 / :803-868 + ideal_endpoints.cpp:688-842, :974-1080).
 // Lanes over block modes; the texel error sum keeps the reference's 4-lane accumulator order per mode.
 // =============================================================================================
-ASTC_COOP void quantize_and_score_modes(WCtx& w, unsigned int start_mode, unsigned int end_mode, int nplanes, unsigned int partition_count,
+ASTC_COOP void quantize_and_score_modes(WCtx w, unsigned int start_mode, unsigned int end_mode, int nplanes, unsigned int partition_count,
                                         int max_weight_quant, float min_wt_cutoff1, float min_wt_cutoff2) {
-	const DevBsd& bsd = *w.bsd;
-	const int8_t free_bits_for_partition_count[4] = {115 - 4, 111 - 4 - 10, 108 - 4 - 10, 105 - 4 - 10};
-	uint8_t* uqrow = w.su + w.lane * UQ_ROW_STRIDE;
+	int free_bits = partition_count == 1 ? 115 - 4 : partition_count == 2 ? 111 - 4 - 10 : partition_count == 3 ? 108 - 4 - 10 : 105 - 4 - 10;
+	SPtr<uint8_t> uqrow = sptr<uint8_t>(su_of(w) + (uint32_t)w.lane * UQ_ROW_STRIDE);
+	SPtr<float> mode_err = mode_err_of(w);
+	SPtr<float> dwi = dwi_of(w);
+	SPtr<float> eiw1 = eiw_of(w, 0), eis1 = eis_of(w, 0), eiw2 = eiw_of(w, 1), eis2 = eis_of(w, 1);
 	int T = w.T;
+	ASTC_NOUNROLL
 	for (unsigned int i = start_mode + (unsigned int)w.lane; i < end_mode; i += ASTC_WARP) {
-		const DevBlockMode bm = bsd.block_modes[i];
-		if (bm.quant_mode > max_weight_quant) {
-			w.mode_err[i] = 1e38f;
+		const DevBlockMode* bmp = BSD.block_modes + i;
+		int quant_mode = ASTC_LDG(&bmp->quant_mode);
+		int dmode = ASTC_LDG(&bmp->decimation_mode);
+		if (quant_mode > max_weight_quant) {
+			mode_err[(int)i] = 1e38f;
 			continue;
 		}
 		if (nplanes == 1) {
-			int bitcount = free_bits_for_partition_count[partition_count - 1] - bm.weight_bits;
+			int bitcount = free_bits - (int)ASTC_LDG(&bmp->weight_bits);
 			if (bitcount <= 0) {
-				w.mode_err[i] = 1e38f;
+				mode_err[(int)i] = 1e38f;
 				continue;
 			}
 		}
-		DecView di = dec_view(bsd, bm.decimation_mode);
+		DecView di = dec_view((unsigned int)dmode);
 		int W = di.W;
 		float low1, high1, low2 = 0.0f, high2 = 1.0f;
-		mode_low_high(w, bm, 0, min_wt_cutoff1, low1, high1);
-		WeightQuantizer z1 = make_weight_quantizer(low1, high1, bm.quant_mode);
-		WeightQuantizer z2 = z1;
-		const float* ideal1 = w.dwi + di.dm->dwi_offset;
+		mode_low_high(w, dmode, quant_mode, 0, min_wt_cutoff1, low1, high1);
+		WeightQuantizer z1 = make_weight_quantizer(low1, high1, quant_mode);
+		float rscale2 = z1.rscale, lowb2 = z1.low_bound;
+		SPtr<float> ideal1 = dwi + di.dwi_offset;
+		ASTC_NOUNROLL
 		for (int k = 0; k < W; k++) {
 			uqrow[k] = (uint8_t)quantize_weight(z1, ideal1[k]);
 		}
 		if (nplanes == 2) {
-			mode_low_high(w, bm, 1, min_wt_cutoff2, low2, high2);
-			z2 = make_weight_quantizer(low2, high2, bm.quant_mode);
-			const float* ideal2 = ideal1 + W;
+			mode_low_high(w, dmode, quant_mode, 1, min_wt_cutoff2, low2, high2);
+			WeightQuantizer z2 = make_weight_quantizer(low2, high2, quant_mode);
+			rscale2 = z2.rscale;
+			lowb2 = z2.low_bound;
+			SPtr<float> ideal2 = ideal1 + W;
+			ASTC_NOUNROLL
 			for (int k = 0; k < W; k++) {
 				uqrow[32 + k] = (uint8_t)quantize_weight(z2, ideal2[k]);
 			}
 		}
-		// compute_error_of_weight_set_1plane / _2planes
-		float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-		const float* eiw1 = w.eiw[0];
-		const float* eis1 = w.eis[0];
-		const float* eiw2 = w.eiw[1];
-		const float* eis2 = w.eis[1];
+		// compute_error_of_weight_set_1plane / _2planes: texel t feeds accumulator lane t & 3
+		float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+		float rscale1 = z1.rscale, lowb1 = z1.low_bound;
+		ASTC_NOUNROLL
 		for (int t = 0; t < T; t++) {
-			float cur1, cur2 = 0.0f;
-			if (di.max_twc > 2) {
-				cur1 = (quantized_weight_value(z1, uqrow[di.tw[t]]) * contrib_f(di.tc[t]) +
-				        quantized_weight_value(z1, uqrow[di.tw[T + t]]) * contrib_f(di.tc[T + t])) +
-				       (quantized_weight_value(z1, uqrow[di.tw[2 * T + t]]) * contrib_f(di.tc[2 * T + t]) +
-				        quantized_weight_value(z1, uqrow[di.tw[3 * T + t]]) * contrib_f(di.tc[3 * T + t]));
-				if (nplanes == 2) {
-					cur2 = (quantized_weight_value(z2, uqrow[32 + di.tw[t]]) * contrib_f(di.tc[t]) +
-					        quantized_weight_value(z2, uqrow[32 + di.tw[T + t]]) * contrib_f(di.tc[T + t])) +
-					       (quantized_weight_value(z2, uqrow[32 + di.tw[2 * T + t]]) * contrib_f(di.tc[2 * T + t]) +
-					        quantized_weight_value(z2, uqrow[32 + di.tw[3 * T + t]]) * contrib_f(di.tc[3 * T + t]));
-				}
-			} else if (di.max_twc > 1) {
-				cur1 = (quantized_weight_value(z1, uqrow[di.tw[t]]) * contrib_f(di.tc[t]) +
-				        quantized_weight_value(z1, uqrow[di.tw[T + t]]) * contrib_f(di.tc[T + t]));
-				if (nplanes == 2) {
-					cur2 = (quantized_weight_value(z2, uqrow[32 + di.tw[t]]) * contrib_f(di.tc[t]) +
-					        quantized_weight_value(z2, uqrow[32 + di.tw[T + t]]) * contrib_f(di.tc[T + t]));
-				}
-			} else {
-				cur1 = quantized_weight_value(z1, uqrow[t]);
-				if (nplanes == 2) {
-					cur2 = quantized_weight_value(z2, uqrow[32 + t]);
-				}
-			}
+			int i0 = ASTC_LDG(&di.tw[t]), i1 = ASTC_LDG(&di.tw[T + t]), i2 = ASTC_LDG(&di.tw[2 * T + t]), i3 = ASTC_LDG(&di.tw[3 * T + t]);
+			float c0 = contrib_f(ASTC_LDG(&di.tc[t])), c1 = contrib_f(ASTC_LDG(&di.tc[T + t])), c2 = contrib_f(ASTC_LDG(&di.tc[2 * T + t])),
+			      c3 = contrib_f(ASTC_LDG(&di.tc[3 * T + t]));
+			float cur1 = ((static_cast<float>(uqrow[i0]) * rscale1 + lowb1) * c0 + (static_cast<float>(uqrow[i1]) * rscale1 + lowb1) * c1) +
+			             ((static_cast<float>(uqrow[i2]) * rscale1 + lowb1) * c2 + (static_cast<float>(uqrow[i3]) * rscale1 + lowb1) * c3);
 			float diff = cur1 - eiw1[t];
 			float error = diff * diff * eis1[t];
 			if (nplanes == 2) {
+				float cur2 = ((static_cast<float>(uqrow[32 + i0]) * rscale2 + lowb2) * c0 + (static_cast<float>(uqrow[32 + i1]) * rscale2 + lowb2) * c1) +
+				             ((static_cast<float>(uqrow[32 + i2]) * rscale2 + lowb2) * c2 + (static_cast<float>(uqrow[32 + i3]) * rscale2 + lowb2) * c3);
 				float diff2 = cur2 - eiw2[t];
 				float error2 = diff2 * diff2 * eis2[t];
 				error = error + error2;
 			}
-			acc[t & 3] = acc[t & 3] + error;
+			int a = t & 3;
+			if (a == 0) acc0 = acc0 + error;
+			else if (a == 1) acc1 = acc1 + error;
+			else if (a == 2) acc2 = acc2 + error;
+			else acc3 = acc3 + error;
 		}
-		w.mode_err[i] = (acc[0] + acc[2]) + (acc[1] + acc[3]);
+		mode_err[(int)i] = (acc0 + acc2) + (acc1 + acc3);
 	}
 	wsync();
 }
@@ -105,11 +100,6 @@ ASTC_COOP void quantize_and_score_modes(WCtx& w, unsigned int start_mode, unsign
 struct EncodingChoiceErrors {
 	float rgb_scale_error, rgb_luma_error, luminance_error, alpha_drop_error;
 	bool can_offset_encode, can_blue_contract;
-};
-
-struct ProcessedLine {
-	f4 amod;
-	f4 bs;
 };
 
 ASTC_FN f4 dot3_splat(f4 a, f4 b) {
@@ -124,100 +114,126 @@ struct EfTables {
 	uint8_t format_of_choice[4][21][4];
 	uint8_t combined_format[21][13][4];
 };
+#define EF_OF(w) (*reinterpret_cast<EfTables*>(astc_smem + su_of(w)))
+// (the chain staging tile of compute_encoding_choice_errors uses the same bytes first: its sums are done
+//  before the tables are written)
 
 // compute_encoding_choice_errors :222-312 with compute_error_squared_rgb_single_partition :72-219.
-// One chain per (partition, accumulator a, texel index mod 4).
-ASTC_COOP void compute_encoding_choice_errors(WCtx& w, const PartView& pi, int ep0slot, int ep1slot, EncodingChoiceErrors eci[4]) {
+// Terms per texel: 0 alpha drop, 1 uncorrelated line, 2 same-chroma line, 3 rgb-luma line, 4 luminance line;
+// one chain per (partition, term, texel index mod 4).
+ASTC_COOP void compute_encoding_choice_errors(WCtx w, const PartView& pi, int ep0slot, int ep1slot, EncodingChoiceErrors eci[4]) {
 	int pc = (int)pi.partition_count;
 	PartitionMetrics pms[4];
 	compute_avgs_and_dirs_3_comp_rgb(w, pi, pms);
-	ProcessedLine uncor[4], samec[4], rgbl[4], lum[4];
-	for (int i = 0; i < pc; i++) {
-		f4 uncor_a = pms[i].avg;
-		f4 uncor_b = normalize_safe4(pms[i].dir, unit3());
-		f4 samec_b = normalize_safe4(pms[i].avg, unit3());
-		f4 luma_a = pms[i].avg;
-		f4 luma_b = unit3();
-		uncor[i].amod = uncor_a - uncor_b * dot3_splat(uncor_a, uncor_b);
-		uncor[i].bs = uncor_b;
-		samec[i].amod = splat4(0.0f);
-		samec[i].bs = samec_b;
-		rgbl[i].amod = luma_a - luma_b * dot3_splat(luma_a, luma_b);
-		rgbl[i].bs = luma_b;
-		lum[i].amod = splat4(0.0f);
-		lum[i].bs = unit3();
-	}
-	f4 ews = w.bi.channel_weight;
-	float default_a = default_alpha(w);
-	int nchains = pc * 20;
-	for (int id = w.lane; id < nchains; id += ASTC_WARP) {
-		int p = id / 20;
-		int r = id - p * 20;
-		int a = r >> 2;
-		int l = r & 3;
-		const uint8_t* tix = pi.texels + pi.start[p];
-		int n = pi.count[p];
-		f4 amod, bs;
-		if (a == 1) { amod = uncor[p].amod; bs = uncor[p].bs; }
-		else if (a == 2) { amod = samec[p].amod; bs = samec[p].bs; }
-		else if (a == 3) { amod = rgbl[p].amod; bs = rgbl[p].bs; }
-		else { amod = lum[p].amod; bs = lum[p].bs; }
-		float s = 0.0f;
-		for (int j = l; j < n; j += 4) {
-			int t = tix[j];
-			float term;
-			if (a == 0) {
-				float alpha_diff = w.blk[3][t] - default_a;
-				term = alpha_diff * alpha_diff;
-			} else {
-				float dr = w.blk[0][t], dg = w.blk[1][t], db = w.blk[2][t];
-				float param = dr * bs.x + dg * bs.y + db * bs.z;
-				float dist0, dist1, dist2;
-				if (a == 1 || a == 3) {
-					dist0 = (amod.x + param * bs.x) - dr;
-					dist1 = (amod.y + param * bs.y) - dg;
-					dist2 = (amod.z + param * bs.z) - db;
-				} else {
-					dist0 = (param * bs.x) - dr;
-					dist1 = (param * bs.y) - dg;
-					dist2 = (param * bs.z) - db;
-				}
-				term = dist0 * dist0 * ews.x + dist1 * dist1 * ews.y + dist2 * dist2 * ews.z;
-			}
-			s = s + term;
+	SPtr<float> tmpf = tmpf_of(w);
+	SPtr<float> lines = tmpf + 80;          // per partition: uncor.amod[3] uncor.bs[3] samec.bs[3] rgbl.amod[3]
+	if (w.lane == 0) {
+		for (int i = 0; i < pc; i++) {
+			f4 uncor_a = pms[i].avg;
+			f4 uncor_b = normalize_safe4(pms[i].dir, unit3());
+			f4 samec_b = normalize_safe4(pms[i].avg, unit3());
+			f4 luma_a = pms[i].avg;
+			f4 luma_b = unit3();
+			f4 uncor_amod = uncor_a - uncor_b * dot3_splat(uncor_a, uncor_b);
+			f4 rgbl_amod = luma_a - luma_b * dot3_splat(luma_a, luma_b);
+			SPtr<float> l = lines + i * 12;
+			l[0] = uncor_amod.x; l[1] = uncor_amod.y; l[2] = uncor_amod.z;
+			l[3] = uncor_b.x; l[4] = uncor_b.y; l[5] = uncor_b.z;
+			l[6] = samec_b.x; l[7] = samec_b.y; l[8] = samec_b.z;
+			l[9] = rgbl_amod.x; l[10] = rgbl_amod.y; l[11] = rgbl_amod.z;
 		}
-		w.tmpf[id] = s;
+	}
+	int nchains = pc * 20;
+	ASTC_NOUNROLL
+	for (int id = w.lane; id < nchains; id += ASTC_WARP) {
+		tmpf[id] = 0.0f;
 	}
 	wsync();
+	f4 ews = bi_of(w).channel_weight;
+	float default_a = default_alpha(w);
+	SPtr<float> br = blk_of(w, 0), bg = blk_of(w, 1), bb = blk_of(w, 2), ba = blk_of(w, 3);
+	const float u3 = 0.577350258827209473f;
+	chain_sums<5>(w, w.T, su_of(w), tmpf, nchains,
+		[&](int pos, float* term) {
+			int t = ASTC_LDG(&pi.texels[pos]);
+			int p = pc > 1 ? (int)ASTC_LDG(&pi.partition_of_texel[t]) : 0;
+			SPtr<float> l = lines + p * 12;
+			float dr = br[t], dg = bg[t], db = bb[t];
+			float alpha_diff = ba[t] - default_a;
+			term[0] = alpha_diff * alpha_diff;
+			{
+				float bx = l[3], by = l[4], bz = l[5];
+				float param = dr * bx + dg * by + db * bz;
+				float dist0 = (l[0] + param * bx) - dr;
+				float dist1 = (l[1] + param * by) - dg;
+				float dist2 = (l[2] + param * bz) - db;
+				term[1] = dist0 * dist0 * ews.x + dist1 * dist1 * ews.y + dist2 * dist2 * ews.z;
+			}
+			{
+				float bx = l[6], by = l[7], bz = l[8];
+				float param = dr * bx + dg * by + db * bz;
+				float dist0 = (param * bx) - dr;
+				float dist1 = (param * by) - dg;
+				float dist2 = (param * bz) - db;
+				term[2] = dist0 * dist0 * ews.x + dist1 * dist1 * ews.y + dist2 * dist2 * ews.z;
+			}
+			{
+				float param = dr * u3 + dg * u3 + db * u3;
+				float dist0 = (l[9] + param * u3) - dr;
+				float dist1 = (l[10] + param * u3) - dg;
+				float dist2 = (l[11] + param * u3) - db;
+				term[3] = dist0 * dist0 * ews.x + dist1 * dist1 * ews.y + dist2 * dist2 * ews.z;
+				float e0 = (param * u3) - dr;
+				float e1 = (param * u3) - dg;
+				float e2 = (param * u3) - db;
+				term[4] = e0 * e0 * ews.x + e1 * e1 * ews.y + e2 * e2 * ews.z;
+			}
+		},
+		[&](int id, int& k, int& lo, int& hi, int& step) {
+			int p = id / 20;
+			int r = id - p * 20;
+			k = r >> 2;
+			lo = pv_start(pi, (unsigned int)p) + (r & 3);
+			hi = pv_start(pi, (unsigned int)p) + pv_count(pi, (unsigned int)p);
+			step = 4;
+		});
+	SPtr<f4> ep = ep_of(w);
+	bool blue_contract = !is_luminance(w);
 	for (int i = 0; i < pc; i++) {
-		const float* a = w.tmpf + i * 20;
+		SPtr<float> a = tmpf + i * 20;
 		float alpha_drop_error = ((a[0] + a[2]) + (a[1] + a[3])) * ews.w;
 		float uncorr_rgb_error = (a[4] + a[6]) + (a[5] + a[7]);
 		float samechroma_rgb_error = (a[8] + a[10]) + (a[9] + a[11]);
 		float rgb_luma_error = (a[12] + a[14]) + (a[13] + a[15]);
 		float luminance_rgb_error = (a[16] + a[18]) + (a[17] + a[19]);
-		f4 d = w.ep[ep1slot + i] - w.ep[ep0slot + i];
+		f4 d = ep[ep1slot + i] - ep[ep0slot + i];
 		const float lim = 0.12f * 65535.0f;
 		eci[i].can_offset_encode = (absf(d.x) < lim) && (absf(d.y) < lim) && (absf(d.z) < lim);
 		eci[i].rgb_scale_error = (samechroma_rgb_error - uncorr_rgb_error) * 0.7f;
 		eci[i].rgb_luma_error = (rgb_luma_error - uncorr_rgb_error) * 1.5f;
 		eci[i].luminance_error = (luminance_rgb_error - uncorr_rgb_error) * 3.0f;
 		eci[i].alpha_drop_error = alpha_drop_error * 3.0f;
-		eci[i].can_blue_contract = !is_luminance(w);
+		eci[i].can_blue_contract = blue_contract;
 	}
 	wsync();
 }
 
+// 5^2 7^2 9^2 11^2 15^2 19^2 23^2 31^2 39^2 47^2 63^2 79^2 95^2 127^2 159^2 191^2 255^2: (levels - 1)^2 from QUANT_6 up
+ASTC_FN float quant_den(int q) {
+	float m = static_cast<float>(quant_level_count(q) - 1u);
+	return m * m;
+}
+
 // compute_color_error_for_every_integer_count_and_quant_level :315-675. Lanes over quant levels.
-ASTC_COOP void compute_color_error_tables(WCtx& w, const PartView& pi, int partition_index, const EncodingChoiceErrors& eci, int ep0slot, int ep1slot, EfTables* ef) {
-	bool encode_hdr_rgb = w.bi.rgb_lns0 != 0;
-	bool encode_hdr_alpha = w.bi.alpha_lns0 != 0;
-	f4 error_weight = w.bi.channel_weight;
-	int partition_size = pi.count[partition_index];
-	const float den[17] = {5 * 5, 7 * 7, 9 * 9, 11 * 11, 15 * 15, 19 * 19, 23 * 23, 31 * 31, 39 * 39, 47 * 47,
-	                       63 * 63, 79 * 79, 95 * 95, 127 * 127, 159 * 159, 191 * 191, 255 * 255};
-	f4 ep0 = w.ep[ep0slot + partition_index];
-	f4 ep1 = w.ep[ep1slot + partition_index];
+ASTC_COOP void compute_color_error_tables(WCtx w, int partition_size, int partition_index, const EncodingChoiceErrors& eci, int ep0slot, int ep1slot) {
+	const BlkInfo& bi = bi_of(w);
+	EfTables& ef = EF_OF(w);
+	bool encode_hdr_rgb = bi.rgb_lns0 != 0;
+	bool encode_hdr_alpha = bi.alpha_lns0 != 0;
+	f4 error_weight = bi.channel_weight;
+	SPtr<f4> ep = ep_of(w);
+	f4 ep0 = ep[ep0slot + partition_index];
+	f4 ep1 = ep[ep1slot + partition_index];
 	float ep1_min = hmin_s(mk4(ep1.x, ep1.y, ep1.z, ep1.x));
 	ep1_min = maxf(ep1_min, 0.0f);
 	float error_weight_rgbsum = hadd_rgb_s(error_weight);
@@ -232,8 +248,8 @@ ASTC_COOP void compute_color_error_tables(WCtx& w, const PartView& pi, int parti
 	f4 sum_range_error = (ep0_low * ep0_low) + (ep1_low * ep1_low) + (ep0_high * ep0_high) + (ep1_high * ep1_high);
 	float rgb_range_error = dot3_s(sum_range_error, error_weight) * 0.5f * static_cast<float>(partition_size);
 	float alpha_range_error = sum_range_error.w * error_weight.w * 0.5f * static_cast<float>(partition_size);
-	float (*best_error)[4] = ef->best_error[partition_index];
-	uint8_t (*format_of_choice)[4] = ef->format_of_choice[partition_index];
+	float (*best_error)[4] = ef.best_error[partition_index];
+	uint8_t (*format_of_choice)[4] = ef.format_of_choice[partition_index];
 
 	if (encode_hdr_rgb) {
 		float af, cf;
@@ -278,6 +294,7 @@ ASTC_COOP void compute_color_error_tables(WCtx& w, const PartView& pi, int parti
 		float lumdif = lum_high - lum_low;
 		float mode23mult = lumdif < 960 ? 4.0f : lumdif < 3968 ? 16.0f : 128.0f;
 		mode23mult *= 0.0005f;
+		ASTC_NOUNROLL
 		for (int i = w.lane; i <= QUANT_256; i += ASTC_WARP) {
 			format_of_choice[i][3] = static_cast<uint8_t>(encode_hdr_alpha ? FMT_HDR_RGBA : FMT_HDR_RGB_LDR_ALPHA);
 			format_of_choice[i][2] = FMT_HDR_RGB;
@@ -290,7 +307,7 @@ ASTC_COOP void compute_color_error_tables(WCtx& w, const PartView& pi, int parti
 				best_error[i][0] = ERROR_CALC_DEFAULT;
 				continue;
 			}
-			float base_quant_error = ((65536.0f * 65536.0f / 18.0f) / den[i - QUANT_6]) * static_cast<float>(partition_size);
+			float base_quant_error = ((65536.0f * 65536.0f / 18.0f) / quant_den(i)) * static_cast<float>(partition_size);
 			float rgb_quantization_error = error_weight_rgbsum * base_quant_error * 2.0f;
 			float alpha_quantization_error = error_weight.w * base_quant_error * 2.0f;
 			float rgba_quantization_error = rgb_quantization_error + alpha_quantization_error;
@@ -305,6 +322,7 @@ ASTC_COOP void compute_color_error_tables(WCtx& w, const PartView& pi, int parti
 		float base_quant_error_rgba = base_quant_error_rgb + base_quant_error_a;
 		float error_scale_bc_rgba = eci.can_blue_contract ? 0.625f : 1.0f;
 		float error_scale_bc_rgb = eci.can_blue_contract ? 0.5f : 1.0f;
+		ASTC_NOUNROLL
 		for (int i = w.lane; i <= QUANT_256; i += ASTC_WARP) {
 			if (i < QUANT_6) {
 				best_error[i][3] = ERROR_CALC_DEFAULT;
@@ -323,7 +341,7 @@ ASTC_COOP void compute_color_error_tables(WCtx& w, const PartView& pi, int parti
 				error_scale_oe_rgba = 1.0f;
 				error_scale_oe_rgb = 1.0f;
 			}
-			float base_quant_error = (65536.0f * 65536.0f / 18.0f) / den[i - QUANT_6];
+			float base_quant_error = (65536.0f * 65536.0f / 18.0f) / quant_den(i);
 			float quant_error_rgb = base_quant_error_rgb * base_quant_error;
 			float quant_error_rgba = base_quant_error_rgba * base_quant_error;
 			best_error[i][3] = quant_error_rgba * error_scale_bc_rgba * error_scale_oe_rgba + rgb_range_error + alpha_range_error;
@@ -354,66 +372,56 @@ ASTC_COOP void compute_color_error_tables(WCtx& w, const PartView& pi, int parti
 }
 
 // N-partition combination tables (:728-1093): lanes over quant levels, the combination scan inside a
-// level is sequential (the reference's "<=" update order matters).
-ASTC_COOP void multi_partition_find_best_combination(WCtx& w, int pc, EfTables* ef) {
+// level is sequential (the reference's "<=" update order matters). The reference walks nested loops over the
+// per-partition integer counts and prunes every prefix whose counts differ by more than one; the tuples that
+// survive are listed here in the same (lexicographic) order, 2 bits per partition, first partition on top.
+#if defined(ASTC_HOSTSIM)
+	#define ASTC_DEV_TABLE static const
+#else
+	#define ASTC_DEV_TABLE __constant__ const
+#endif
+ASTC_DEV_TABLE uint8_t g_combo_tuples[10 + 22 + 46] = {
+	0, 1, 4, 5, 6, 9, 10, 11, 14, 15,
+	0, 1, 4, 5, 16, 17, 20, 21, 22, 25, 26, 37, 38, 41, 42, 43, 46, 47, 58, 59, 62, 63,
+	0, 1, 4, 5, 16, 17, 20, 21, 64, 65, 68, 69, 80, 81, 84, 85, 86, 89, 90, 101, 102, 105, 106, 149, 150, 153, 154, 165, 166, 169, 170,
+	171, 174, 175, 186, 187, 190, 191, 234, 235, 238, 239, 250, 251, 254, 255};
+
+ASTC_COOP void multi_partition_find_best_combination(WCtx w, int pc) {
+	EfTables& ef = EF_OF(w);
 	int width = pc == 2 ? 7 : pc == 3 ? 10 : 13;
+	int combos = pc == 2 ? 10 : pc == 3 ? 22 : 46;
+	const uint8_t* tuples = g_combo_tuples + (pc == 2 ? 0 : pc == 3 ? 10 : 32);
+	ASTC_NOUNROLL
 	for (int quant = w.lane; quant <= QUANT_256; quant += ASTC_WARP) {
+		ASTC_NOUNROLL
 		for (int j = 0; j < width; j++) {
-			ef->combined_error[quant][j] = ERROR_CALC_DEFAULT;
+			ef.combined_error[quant][j] = ERROR_CALC_DEFAULT;
 		}
 		if (quant < QUANT_6) {
 			continue;
 		}
-		for (int i = 0; i < 4; i++) {
-			for (int j = 0; j < 4; j++) {
-				int low2 = mini(i, j);
-				int high2 = maxi(i, j);
-				if ((high2 - low2) > 1) {
-					continue;
-				}
-				if (pc == 2) {
-					int intcnt = i + j;
-					float errorterm = minf(ef->best_error[0][quant][i] + ef->best_error[1][quant][j], 1e10f);
-					if (errorterm <= ef->combined_error[quant][intcnt]) {
-						ef->combined_error[quant][intcnt] = errorterm;
-						ef->combined_format[quant][intcnt][0] = ef->format_of_choice[0][quant][i];
-						ef->combined_format[quant][intcnt][1] = ef->format_of_choice[1][quant][j];
-					}
-					continue;
-				}
-				for (int k = 0; k < 4; k++) {
-					int low3 = mini(k, low2);
-					int high3 = maxi(k, high2);
-					if ((high3 - low3) > 1) {
-						continue;
-					}
-					if (pc == 3) {
-						int intcnt = i + j + k;
-						float errorterm = minf(ef->best_error[0][quant][i] + ef->best_error[1][quant][j] + ef->best_error[2][quant][k], 1e10f);
-						if (errorterm <= ef->combined_error[quant][intcnt]) {
-							ef->combined_error[quant][intcnt] = errorterm;
-							ef->combined_format[quant][intcnt][0] = ef->format_of_choice[0][quant][i];
-							ef->combined_format[quant][intcnt][1] = ef->format_of_choice[1][quant][j];
-							ef->combined_format[quant][intcnt][2] = ef->format_of_choice[2][quant][k];
-						}
-						continue;
-					}
-					for (int l = 0; l < 4; l++) {
-						int low4 = mini(l, low3);
-						int high4 = maxi(l, high3);
-						if ((high4 - low4) > 1) {
-							continue;
-						}
-						int intcnt = i + j + k + l;
-						float errorterm = minf(ef->best_error[0][quant][i] + ef->best_error[1][quant][j] + ef->best_error[2][quant][k] + ef->best_error[3][quant][l], 1e10f);
-						if (errorterm <= ef->combined_error[quant][intcnt]) {
-							ef->combined_error[quant][intcnt] = errorterm;
-							ef->combined_format[quant][intcnt][0] = ef->format_of_choice[0][quant][i];
-							ef->combined_format[quant][intcnt][1] = ef->format_of_choice[1][quant][j];
-							ef->combined_format[quant][intcnt][2] = ef->format_of_choice[2][quant][k];
-							ef->combined_format[quant][intcnt][3] = ef->format_of_choice[3][quant][l];
-						}
-					}
+		ASTC_NOUNROLL
+		for (int n = 0; n < combos; n++) {
+			unsigned int tup = tuples[n];
+			int sh = 2 * (pc - 1);
+			int dg = (int)(tup >> sh) & 3;
+			float errorterm = ef.best_error[0][quant][dg];
+			int intcnt = dg;
+			ASTC_NOUNROLL
+			for (int k = 1; k < pc; k++) {
+				sh -= 2;
+				dg = (int)(tup >> sh) & 3;
+				errorterm = errorterm + ef.best_error[k][quant][dg];
+				intcnt += dg;
+			}
+			errorterm = minf(errorterm, 1e10f);
+			if (errorterm <= ef.combined_error[quant][intcnt]) {
+				ef.combined_error[quant][intcnt] = errorterm;
+				sh = 2 * pc;
+				ASTC_NOUNROLL
+				for (int k = 0; k < pc; k++) {
+					sh -= 2;
+					ef.combined_format[quant][intcnt][k] = ef.format_of_choice[k][quant][(tup >> sh) & 3];
 				}
 			}
 		}
@@ -422,28 +430,30 @@ ASTC_COOP void multi_partition_find_best_combination(WCtx& w, int pc, EfTables* 
 }
 
 // one_partition_/N-partition _find_best_combination_for_bitcount (:678-725, :768-1093)
-ASTC_NOINLINE float find_best_combination_for_bitcount(int pc, const EfTables* ef, int bits_available, uint8_t& best_quant_level, uint8_t& best_quant_level_mod, uint8_t* best_formats) {
+ASTC_NOINLINE float find_best_combination_for_bitcount(int pc, uint32_t ef_off, int bits_available, uint8_t& best_quant_level, uint8_t& best_quant_level_mod, uint8_t* best_formats) {
 	const DevConstTables* ct = ASTC_CT;
+	const EfTables& ef = *reinterpret_cast<const EfTables*>(astc_smem + ef_off);
 	if (pc == 1) {
 		int best_integer_count = 0;
 		float best_integer_count_error = ERROR_CALC_DEFAULT;
+		ASTC_NOUNROLL
 		for (int integer_count = 1; integer_count <= 4; integer_count++) {
-			int quant_level = ct->quant_mode_table[integer_count][bits_available];
+			int quant_level = ASTC_LDG(&ct->quant_mode_table[integer_count][bits_available]);
 			if (quant_level < QUANT_6) {
 				continue;
 			}
-			float integer_count_error = ef->best_error[0][quant_level][integer_count - 1];
+			float integer_count_error = ef.best_error[0][quant_level][integer_count - 1];
 			if (integer_count_error < best_integer_count_error) {
 				best_integer_count_error = integer_count_error;
 				best_integer_count = integer_count - 1;
 			}
 		}
-		int ql = ct->quant_mode_table[best_integer_count + 1][bits_available];
+		int ql = ASTC_LDG(&ct->quant_mode_table[best_integer_count + 1][bits_available]);
 		best_quant_level = static_cast<uint8_t>(ql);
 		best_quant_level_mod = best_quant_level;
 		best_formats[0] = FMT_LUMINANCE;
 		if (ql >= QUANT_6) {
-			best_formats[0] = ef->format_of_choice[0][ql][best_integer_count];
+			best_formats[0] = ef.format_of_choice[0][ql][best_integer_count];
 		}
 		return best_integer_count_error;
 	}
@@ -452,24 +462,25 @@ ASTC_NOINLINE float find_best_combination_for_bitcount(int pc, const EfTables* e
 	int first = pc;
 	int last = pc == 2 ? 8 : 9;
 	int mod_bits = pc == 2 ? 2 : pc == 3 ? 5 : 8;
+	ASTC_NOUNROLL
 	for (int integer_count = first; integer_count <= last; integer_count++) {
-		int quant_level = ct->quant_mode_table[integer_count][bits_available];
+		int quant_level = ASTC_LDG(&ct->quant_mode_table[integer_count][bits_available]);
 		if (quant_level < QUANT_6) {
 			break;
 		}
-		float integer_count_error = ef->combined_error[quant_level][integer_count - first];
+		float integer_count_error = ef.combined_error[quant_level][integer_count - first];
 		if (integer_count_error < best_integer_count_error) {
 			best_integer_count_error = integer_count_error;
 			best_integer_count = integer_count;
 		}
 	}
-	int ql = ct->quant_mode_table[best_integer_count][bits_available];
-	int ql_mod = ct->quant_mode_table[best_integer_count][bits_available + mod_bits];
+	int ql = ASTC_LDG(&ct->quant_mode_table[best_integer_count][bits_available]);
+	int ql_mod = ASTC_LDG(&ct->quant_mode_table[best_integer_count][bits_available + mod_bits]);
 	best_quant_level = static_cast<uint8_t>(ql);
 	best_quant_level_mod = static_cast<uint8_t>(ql_mod);
 	if (ql >= QUANT_6) {
 		for (int i = 0; i < pc; i++) {
-			best_formats[i] = ef->combined_format[ql][best_integer_count - first][i];
+			best_formats[i] = ef.combined_format[ql][best_integer_count - first][i];
 		}
 	} else {
 		for (int i = 0; i < pc; i++) {
@@ -479,53 +490,57 @@ ASTC_NOINLINE float find_best_combination_for_bitcount(int pc, const EfTables* e
 	return best_integer_count_error;
 }
 
-// candidate record kept in w.cand (8 bytes each)
+// candidate record kept in the arena (8 bytes each)
 struct Candidate {
 	uint16_t block_mode;       // packed index
 	uint8_t quant_level, quant_level_mod;
 	uint8_t formats[4];
 };
+ASTC_FN SPtr<Candidate> cand_of(const WCtx& w) { return sptr<Candidate>(w.base + A_CAND); }
 
-ASTC_FN int mode_bitcount(const DevBlockMode& bm, int nplanes, int pc) {
-	const int8_t free_bits_for_partition_count[4] = {115 - 4, 111 - 4 - 10, 108 - 4 - 10, 105 - 4 - 10};
-	return nplanes == 2 ? 109 - bm.weight_bits : free_bits_for_partition_count[pc - 1] - bm.weight_bits;
+ASTC_FN int mode_bitcount(int weight_bits, int nplanes, int pc) {
+	int free_bits = pc == 1 ? 115 - 4 : pc == 2 ? 111 - 4 - 10 : pc == 3 ? 108 - 4 - 10 : 105 - 4 - 10;
+	return nplanes == 2 ? 109 - weight_bits : free_bits - weight_bits;
 }
 
-// compute_ideal_endpoint_formats :1096-1357. Returns the candidate count; candidates go to w.cand.
-ASTC_COOP unsigned int compute_ideal_endpoint_formats(WCtx& w, const PartView& pi, int ep0slot, int ep1slot, int nplanes,
+// compute_ideal_endpoint_formats :1096-1357. Returns the candidate count; candidates go to the arena.
+ASTC_COOP unsigned int compute_ideal_endpoint_formats(WCtx w, const PartView& pi, int ep0slot, int ep1slot, int nplanes,
                                                       unsigned int start_block_mode, unsigned int end_block_mode) {
-	const DevBsd& bsd = *w.bsd;
 	int pc = (int)pi.partition_count;
 	EncodingChoiceErrors eci[4];
 	compute_encoding_choice_errors(w, pi, ep0slot, ep1slot, eci);
-	EfTables* ef = reinterpret_cast<EfTables*>(w.su);
 	for (int i = 0; i < pc; i++) {
-		compute_color_error_tables(w, pi, i, eci[i], ep0slot, ep1slot, ef);
+		compute_color_error_tables(w, pv_count(pi, (unsigned int)i), i, eci[i], ep0slot, ep1slot);
 	}
 	if (pc >= 2) {
-		multi_partition_find_best_combination(w, pc, ef);
+		multi_partition_find_best_combination(w, pc);
 	}
+	uint32_t ef_off = su_of(w);
+	SPtr<float> mode_err = mode_err_of(w);
 	// total error per mode (overwrites the weight error in place)
+	ASTC_NOUNROLL
 	for (unsigned int i = start_block_mode + (unsigned int)w.lane; i < end_block_mode; i += ASTC_WARP) {
-		float qwt = w.mode_err[i];
+		float qwt = mode_err[(int)i];
 		if (qwt >= ERROR_CALC_DEFAULT) {
-			w.mode_err[i] = ERROR_CALC_DEFAULT;
+			mode_err[(int)i] = ERROR_CALC_DEFAULT;
 			continue;
 		}
 		uint8_t ql, qlm, fmts[4];
-		float error_of_best = find_best_combination_for_bitcount(pc, ef, mode_bitcount(bsd.block_modes[i], nplanes, pc), ql, qlm, fmts);
-		w.mode_err[i] = error_of_best + qwt;
+		float error_of_best = find_best_combination_for_bitcount(pc, ef_off, mode_bitcount(ASTC_LDG(&BSD.block_modes[i].weight_bits), nplanes, pc), ql, qlm, fmts);
+		mode_err[(int)i] = error_of_best + qwt;
 	}
 	wsync();
 	// the tune_candidate_limit lowest totals, lowest index first among equals (:1286-1333)
-	unsigned int limit = w.cfg->tune_candidate_limit;
+	unsigned int limit = CFG.tune_candidate_limit;
 	unsigned int count = 0;
-	Candidate* cands = reinterpret_cast<Candidate*>(w.cand);
+	SPtr<Candidate> cands = cand_of(w);
+	ASTC_NOUNROLL
 	for (unsigned int k = 0; k < limit; k++) {
 		float best = ERROR_CALC_DEFAULT;
 		int best_idx = 0x7FFFFFFF;
+		ASTC_NOUNROLL
 		for (unsigned int i = start_block_mode + (unsigned int)w.lane; i < end_block_mode; i += ASTC_WARP) {
-			float e = w.mode_err[i];
+			float e = mode_err[(int)i];
 			if (e < best) {
 				best = e;
 				best_idx = (int)i;
@@ -536,12 +551,12 @@ ASTC_COOP unsigned int compute_ideal_endpoint_formats(WCtx& w, const PartView& p
 			break;
 		}
 		if (w.lane == 0) {
-			w.mode_err[best_idx] = ERROR_CALC_DEFAULT;
+			mode_err[best_idx] = ERROR_CALC_DEFAULT;
 			Candidate c;
 			c.block_mode = (uint16_t)best_idx;
 			c.formats[0] = c.formats[1] = c.formats[2] = c.formats[3] = 0;
-			find_best_combination_for_bitcount(pc, ef, mode_bitcount(bsd.block_modes[best_idx], nplanes, pc), c.quant_level, c.quant_level_mod, c.formats);
-			cands[k] = c;
+			find_best_combination_for_bitcount(pc, ef_off, mode_bitcount(ASTC_LDG(&BSD.block_modes[best_idx].weight_bits), nplanes, pc), c.quant_level, c.quant_level_mod, c.formats);
+			cands[(int)k] = c;
 		}
 		count++;
 		wsync();
@@ -587,161 +602,200 @@ ASTC_FN void rgbo_fallback(f4& rgbo, const f4& v0, const f4& v1) {
 	}
 }
 
-// refinement scratch inside su, laid out from the block size at run time
+// refinement scratch inside su (byte offsets in the shared window), laid out from the block size
 struct RefineScratch {
-	float* undec[2];      // [T] undecimated float weights per plane
-	float* texel_err;     // [T] per-texel error terms for the ordered sums
-	float* uqf;           // [64] realign: float copy of the quantised weights
-	float* stage;         // [12][stage_stride] realign: per-texel error vectors of one weight
-	int stage_stride;
-	uint8_t* iw[2];       // [T] integer undecimated weights (0..64) per plane
+	uint32_t undec[2];    // float[T] undecimated float weights per plane
+	uint32_t texel_err;   // float[T] per-texel error terms for the ordered sums
+	uint32_t uqf;         // float[64] realign: float copy of the quantised weights
+	uint32_t iw[2];       // u8[T] integer undecimated weights (0..64) per plane
+	uint32_t tile;        // chain staging tile: 20 x CHAIN_STRIDE floats
 };
+#define REFINE_TILE_BYTES (20 * CHAIN_STRIDE * 4)
 
 ASTC_FN RefineScratch make_refine_scratch(const WCtx& w) {
 	RefineScratch r;
-	int Tp = (w.T + 3) & ~3;
-	float* f = reinterpret_cast<float*>(w.su);
+	uint32_t t4 = tp4(w);
+	uint32_t f = su_of(w);
 	r.undec[0] = f;
-	r.undec[1] = f + Tp;
-	r.texel_err = f + 2 * Tp;
-	r.uqf = f + 3 * Tp;
-	r.stage = f + 3 * Tp + 64;
-	r.stage_stride = (int)w.bsd->max_weight_texel_count;
-	uint8_t* b = reinterpret_cast<uint8_t*>(r.stage + 12 * r.stage_stride);
-	r.iw[0] = b;
-	r.iw[1] = b + Tp;
+	r.undec[1] = f + t4;
+	r.texel_err = f + 2 * t4;
+	r.uqf = f + 3 * t4;
+	r.tile = f + 3 * t4 + 256;
+	r.iw[0] = r.tile + REFINE_TILE_BYTES;
+	r.iw[1] = r.iw[0] + (t4 >> 2);
 	return r;
 }
 
 // undecimate the quantised weights of `planes` planes: lanes over texels
-ASTC_COOP void undecimate_weights(WCtx& w, const DecView& di, const uint8_t* uquant, int planes, RefineScratch* rs) {
+ASTC_COOP void undecimate_weights(WCtx w, unsigned int d, int planes) {
+	RefineScratch rs = make_refine_scratch(w);
+	DecView di = dec_view(d);
 	int T = w.T;
+	SPtr<uint8_t> uquant = work_weights_of(w);
+	ASTC_NOUNROLL
 	for (int id = w.lane; id < T * planes; id += ASTC_WARP) {
 		int pl = id >= T ? 1 : 0;
 		int t = id - pl * T;
-		const uint8_t* uq = uquant + pl * 32;
+		SPtr<uint8_t> uq = uquant + pl * 32;
 		float v;
 		if (di.max_twc == 1) {
 			v = static_cast<float>(uq[t]) * (1.0f / 64.0f);
-		} else if (di.max_twc <= 2) {
-			v = (static_cast<float>(uq[di.tw[t]]) * (1.0f / 64.0f)) * contrib_f(di.tc[t]) +
-			    (static_cast<float>(uq[di.tw[T + t]]) * (1.0f / 64.0f)) * contrib_f(di.tc[T + t]);
 		} else {
-			v = ((static_cast<float>(uq[di.tw[t]]) * (1.0f / 64.0f)) * contrib_f(di.tc[t]) +
-			     (static_cast<float>(uq[di.tw[T + t]]) * (1.0f / 64.0f)) * contrib_f(di.tc[T + t])) +
-			    ((static_cast<float>(uq[di.tw[2 * T + t]]) * (1.0f / 64.0f)) * contrib_f(di.tc[2 * T + t]) +
-			     (static_cast<float>(uq[di.tw[3 * T + t]]) * (1.0f / 64.0f)) * contrib_f(di.tc[3 * T + t]));
+			v = ((static_cast<float>(uq[ASTC_LDG(&di.tw[t])]) * (1.0f / 64.0f)) * contrib_f(ASTC_LDG(&di.tc[t])) +
+			     (static_cast<float>(uq[ASTC_LDG(&di.tw[T + t])]) * (1.0f / 64.0f)) * contrib_f(ASTC_LDG(&di.tc[T + t]))) +
+			    ((static_cast<float>(uq[ASTC_LDG(&di.tw[2 * T + t])]) * (1.0f / 64.0f)) * contrib_f(ASTC_LDG(&di.tc[2 * T + t])) +
+			     (static_cast<float>(uq[ASTC_LDG(&di.tw[3 * T + t])]) * (1.0f / 64.0f)) * contrib_f(ASTC_LDG(&di.tc[3 * T + t])));
 		}
-		rs->undec[pl][t] = v;
+		sptr<float>(rs.undec[pl])[t] = v;
 	}
 	wsync();
 }
 
-// recompute_ideal_colors_1plane :1146-1366. Chains per partition:
-//   0 left, 1 middle, 2 right, 3 weight_weight, 4-7 color_vec_x, 8-11 color_vec_y, 12-13 scale_vec, 14-17 rgba_sum
-ASTC_COOP void recompute_ideal_colors_1plane(WCtx& w, const PartView& pi, const DecView& di, RefineScratch* rs) {
+// recompute_ideal_colors_1plane :1146-1366. Per-texel terms (in partition-texel order):
+//   0 left, 1 middle, 2 right, 3 weight_weight, 4-7 color_vec_x, 8-11 color_vec_y, 12-13 scale_vec;
+// one chain per (partition, term).
+ASTC_COOP void recompute_ideal_colors_1plane(WCtx w, const PartView& pi, unsigned int d) {
+	RefineScratch rs = make_refine_scratch(w);
 	unsigned int pc = pi.partition_count;
-	undecimate_weights(w, di, w.work_weights, 1, rs);
-	const float* undec = rs->undec[0];
-	f4 color_weight = w.bi.channel_weight;
+	undecimate_weights(w, d, 1);
+	SPtr<float> undec = sptr<float>(rs.undec[0]);
+	SPtr<float> tmpf = tmpf_of(w);
+	SPtr<float> sdv = tmpf + 64;            // scale_dir per partition, 4 floats each
+	const BlkInfo& bi = bi_of(w);
+	f4 color_weight = bi.channel_weight;
 	float ls_weight = hadd_rgb_s(color_weight);
-	// phase A: per-partition colour sums (needed for scale_dir) - chains 14-17
+	SPtr<float> b0 = blk_of(w, 0);
+	uint32_t cs = tp4(w);
+	// phase A: per-partition colour sums (needed for scale_dir)
 	if (pc > 1) {
+		ASTC_NOUNROLL
 		for (int id = w.lane; id < (int)pc * 4; id += ASTC_WARP) {
-			int p = id >> 2;
+			unsigned int p = (unsigned int)id >> 2;
 			int c = id & 3;
-			const uint8_t* tix = pi.texels + pi.start[p];
-			int n = pi.count[p];
-			const float* d = w.blk[c];
+			const uint8_t* tix = pi.texels + pv_start(pi, p);
+			int n = pv_count(pi, p);
+			SPtr<float> dch = sptr<float>(b0.off + (uint32_t)c * cs);
 			float s = 0.0f;
+			ASTC_NOUNROLL
 			for (int j = 0; j < n; j++) {
-				s = s + d[tix[j]];
+				s = s + dch[ASTC_LDG(&tix[j])];
 			}
-			w.tmpf[96 + id] = s;
+			tmpf[96 + id] = s;
 		}
 		wsync();
 	}
-	f4 scale_dir[4], rgba_weight_sum[4];
-	for (unsigned int p = 0; p < pc; p++) {
-		f4 rgba_sum = pc > 1 ? mk4(w.tmpf[96 + p * 4], w.tmpf[96 + p * 4 + 1], w.tmpf[96 + p * 4 + 2], w.tmpf[96 + p * 4 + 3])
-		                     : w.bi.data_mean * static_cast<float>(w.T);
-		rgba_sum = rgba_sum * color_weight;
-		rgba_weight_sum[p] = max4(color_weight * static_cast<float>(pi.count[p]), splat4(1e-17f));
-		f4 q = rgba_sum / rgba_weight_sum[p];
-		scale_dir[p] = normalize4(mk4(q.x, q.y, q.z, 0.0f));
+	// scale_dir per partition -> sdv (shared), read back by the term and solve phases
+	if (w.lane == 0) {
+		ASTC_NOUNROLL
+		for (unsigned int p = 0; p < pc; p++) {
+			f4 rgba_sum = pc > 1 ? mk4(tmpf[96 + (int)p * 4], tmpf[96 + (int)p * 4 + 1], tmpf[96 + (int)p * 4 + 2], tmpf[96 + (int)p * 4 + 3])
+			                     : bi.data_mean * static_cast<float>(w.T);
+			rgba_sum = rgba_sum * color_weight;
+			f4 rws = max4(color_weight * static_cast<float>(pv_count(pi, p)), splat4(1e-17f));
+			f4 q = rgba_sum / rws;
+			f4 sd = normalize4(mk4(q.x, q.y, q.z, 0.0f));
+			sdv[(int)p * 4] = sd.x;
+			sdv[(int)p * 4 + 1] = sd.y;
+			sdv[(int)p * 4 + 2] = sd.z;
+			sdv[(int)p * 4 + 3] = sd.w;
+		}
 	}
-	// phase B: the weighted sums - 14 chains per partition; min/max terms by lanes over texels
-	for (int id = w.lane; id < (int)pc * 14; id += ASTC_WARP) {
-		int p = id / 14;
-		int ch = id - p * 14;
-		const uint8_t* tix = pi.texels + pi.start[p];
-		int n = pi.count[p];
-		f4 sd = scale_dir[p];
-		float s = ch == 3 ? 1e-17f : 0.0f;
-		for (int j = 0; j < n; j++) {
-			int t = tix[j];
+	int nchains = (int)pc * 14;
+	ASTC_NOUNROLL
+	for (int id = w.lane; id < nchains; id += ASTC_WARP) {
+		tmpf[id] = (id % 14) == 3 ? 1e-17f : 0.0f;
+	}
+	wsync();
+	// phase B: the weighted sums
+	chain_sums<14>(w, w.T, rs.tile, tmpf, nchains,
+		[&](int pos, float* term) {
+			int t = ASTC_LDG(&pi.texels[pos]);
+			int p = pc > 1 ? (int)ASTC_LDG(&pi.partition_of_texel[t]) : 0;
 			float idx0 = undec[t];
 			float om_idx0 = 1.0f - idx0;
-			float term;
-			if (ch == 0) term = om_idx0 * om_idx0;
-			else if (ch == 1) term = om_idx0 * idx0;
-			else if (ch == 2) term = idx0 * idx0;
-			else if (ch == 3) term = idx0;
-			else if (ch < 8) {
-				float cw = w.blk[ch - 4][t];
-				float cwi = cw * idx0;
-				term = cw - cwi;
-			} else if (ch < 12) {
-				term = w.blk[ch - 8][t] * idx0;
-			} else {
-				f4 rgba = texel4(w, t);
-				float scale = dot3_s(sd, rgba);
-				term = (ch == 12 ? om_idx0 : idx0) * (scale * ls_weight);
-			}
-			s = s + term;
-		}
-		w.tmpf[id] = s;
-	}
-	float wmin1[4], wmax1[4], scale_min[4], scale_max[4];
+			SPtr<float> tx = b0 + t;
+			float r = tx[0], g = sptr<float>(tx.off + cs)[0], b = sptr<float>(tx.off + 2 * cs)[0], a = sptr<float>(tx.off + 3 * cs)[0];
+			term[0] = om_idx0 * om_idx0;
+			term[1] = om_idx0 * idx0;
+			term[2] = idx0 * idx0;
+			term[3] = idx0;
+			float ri = r * idx0, gi = g * idx0, bi2 = b * idx0, ai = a * idx0;
+			term[4] = r - ri;
+			term[5] = g - gi;
+			term[6] = b - bi2;
+			term[7] = a - ai;
+			term[8] = ri;
+			term[9] = gi;
+			term[10] = bi2;
+			term[11] = ai;
+			SPtr<float> sd = sdv + p * 4;
+			float scale = (sd[0] * r + sd[1] * g) + sd[2] * b;
+			term[12] = om_idx0 * (scale * ls_weight);
+			term[13] = idx0 * (scale * ls_weight);
+		},
+		[&](int id, int& k, int& lo, int& hi, int& step) {
+			int p = id / 14;
+			k = id - p * 14;
+			lo = pv_start(pi, (unsigned int)p);
+			hi = lo + pv_count(pi, (unsigned int)p);
+			step = 1;
+		});
+	SPtr<float> mm = tmpf + 112;            // per partition: weight min, weight max, scale min, scale max
+	ASTC_NOUNROLL
 	for (unsigned int p = 0; p < pc; p++) {
-		const uint8_t* tix = pi.texels + pi.start[p];
-		int n = pi.count[p];
-		float a = 1.0f, b = 0.0f, c = 1e10f, d = 0.0f;
+		const uint8_t* tix = pi.texels + pv_start(pi, p);
+		int n = pv_count(pi, p);
+		SPtr<float> sdp = sdv + (int)p * 4;
+		f4 sd = mk4(sdp[0], sdp[1], sdp[2], sdp[3]);
+		float a = 1.0f, b = 0.0f, c = 1e10f, dd = 0.0f;
+		ASTC_NOUNROLL
 		for (int j = w.lane; j < n; j += ASTC_WARP) {
-			int t = tix[j];
+			int t = ASTC_LDG(&tix[j]);
 			float idx0 = undec[t];
 			a = minf(idx0, a);
 			b = maxf(idx0, b);
-			float scale = dot3_s(scale_dir[p], texel4(w, t));
+			float scale = dot3_s(sd, texel4(w, t));
 			c = minf(scale, c);
-			d = maxf(scale, d);
+			dd = maxf(scale, dd);
 		}
-		wmin1[p] = wmin_f(a);
-		wmax1[p] = wmax_f(b);
-		scale_min[p] = wmin_f(c);
-		scale_max[p] = wmax_f(d);
+		a = wmin_f(a);
+		b = wmax_f(b);
+		c = wmin_f(c);
+		dd = wmax_f(dd);
+		if (w.lane == 0) {
+			mm[(int)p * 4] = a;
+			mm[(int)p * 4 + 1] = b;
+			mm[(int)p * 4 + 2] = c;
+			mm[(int)p * 4 + 3] = dd;
+		}
 	}
 	wsync();
 	// phase C: the solves, one lane per partition
+	SPtr<f4> ep = ep_of(w);
+	ASTC_NOUNROLL
 	for (unsigned int i = (unsigned int)w.lane; i < pc; i += ASTC_WARP) {
-		const float* a = w.tmpf + i * 14;
+		SPtr<float> a = tmpf + (int)i * 14;
 		float left_sum_s = a[0], middle_sum_s = a[1], right_sum_s = a[2], weight_weight_sum_s = a[3];
 		f4 color_vec_x = mk4(a[4], a[5], a[6], a[7]);
 		f4 color_vec_y = mk4(a[8], a[9], a[10], a[11]);
 		f4 scale_vec = mk4(a[12], a[13], 0.0f, 0.0f);
+		SPtr<float> sdp = sdv + (int)i * 4;
+		f4 sdir = mk4(sdp[0], sdp[1], sdp[2], sdp[3]);
+		f4 rws = max4(color_weight * static_cast<float>(pv_count(pi, i)), splat4(1e-17f));
+		float wmn = mm[(int)i * 4], wmx = mm[(int)i * 4 + 1], smn = mm[(int)i * 4 + 2], smx = mm[(int)i * 4 + 3];
 		f4 left_sum = splat4(left_sum_s) * color_weight;
 		f4 middle_sum = splat4(middle_sum_s) * color_weight;
 		f4 right_sum = splat4(right_sum_s) * color_weight;
 		f4 lmrs_sum = mk4(left_sum_s, middle_sum_s, right_sum_s, 0.0f) * ls_weight;
 		color_vec_x = color_vec_x * color_weight;
 		color_vec_y = color_vec_y * color_weight;
-		float scalediv = scale_min[i] / maxf(scale_max[i], 1e-10f);
+		float scalediv = smn / maxf(smx, 1e-10f);
 		scalediv = clamp1f(scalediv);
-		f4 sds = scale_dir[i] * scale_max[i];
+		f4 sds = sdir * smx;
 		f4 rgbs = mk4(sds.x, sds.y, sds.z, scalediv);
-		f4 e0 = w.ep[EP_WORK_0 + i], e1 = w.ep[EP_WORK_1 + i];
-		if (wmin1[i] >= wmax1[i] * 0.999f) {
-			f4 avg = (color_vec_x + color_vec_y) / rgba_weight_sum[i];
+		f4 e0 = ep[EP_WORK_0 + (int)i], e1 = ep[EP_WORK_1 + (int)i];
+		if (wmn >= wmx * 0.999f) {
+			f4 avg = (color_vec_x + color_vec_y) / rws;
 			e0 = sel4(e0, avg, avg.x == avg.x, avg.y == avg.y, avg.z == avg.z, avg.w == avg.w);
 			e1 = sel4(e1, avg, avg.x == avg.x, avg.y == avg.y, avg.z == avg.z, avg.w == avg.w);
 			rgbs = mk4(sds.x, sds.y, sds.z, 1.0f);
@@ -755,85 +809,101 @@ ASTC_COOP void recompute_ideal_colors_1plane(WCtx& w, const PartView& pi, const 
 			f4 ep0 = (right_sum * color_vec_x - middle_sum * color_vec_y) * color_rdet1;
 			f4 ep1 = (left_sum * color_vec_y - middle_sum * color_vec_x) * color_rdet1;
 			f4 thr = color_mss1 * 1e-4f;
-			bool m[4];
-			for (int c = 0; c < 4; c++) {
-				bool det = absf(lane(color_det1, c)) > lane(thr, c);
-				bool notnan = (lane(ep0, c) == lane(ep0, c)) && (lane(ep1, c) == lane(ep1, c));
-				m[c] = det && notnan;
-			}
-			e0 = sel4(e0, ep0, m[0], m[1], m[2], m[3]);
-			e1 = sel4(e1, ep1, m[0], m[1], m[2], m[3]);
+			bool m0 = absf(color_det1.x) > thr.x && ep0.x == ep0.x && ep1.x == ep1.x;
+			bool m1 = absf(color_det1.y) > thr.y && ep0.y == ep0.y && ep1.y == ep1.y;
+			bool m2 = absf(color_det1.z) > thr.z && ep0.z == ep0.z && ep1.z == ep1.z;
+			bool m3 = absf(color_det1.w) > thr.w && ep0.w == ep0.w && ep1.w == ep1.w;
+			e0 = sel4(e0, ep0, m0, m1, m2, m3);
+			e1 = sel4(e1, ep1, m0, m1, m2, m3);
 			float scale_ep0 = (lmrs_sum.z * scale_vec.x - lmrs_sum.y * scale_vec.y) * ls_rdet1;
 			float scale_ep1 = (lmrs_sum.x * scale_vec.y - lmrs_sum.y * scale_vec.x) * ls_rdet1;
 			if (fabsf(ls_det1) > (ls_mss1 * 1e-4f) && scale_ep0 == scale_ep0 && scale_ep1 == scale_ep1 && scale_ep0 < scale_ep1) {
 				float scalediv2 = scale_ep0 / scale_ep1;
-				f4 sdsm = scale_dir[i] * scale_ep1;
+				f4 sdsm = sdir * scale_ep1;
 				rgbs = mk4(sdsm.x, sdsm.y, sdsm.z, scalediv2);
 			}
 		}
-		w.ep[EP_WORK_0 + i] = e0;
-		w.ep[EP_WORK_1 + i] = e1;
-		w.ep[EP_RGBS + i] = rgbs;
-		if (w.bi.rgb_lns0 || w.bi.alpha_lns0) {
+		ep[EP_WORK_0 + (int)i] = e0;
+		ep[EP_WORK_1 + (int)i] = e1;
+		ep[EP_RGBS + (int)i] = rgbs;
+		if (bi.rgb_lns0 || bi.alpha_lns0) {
 			f4 weight_weight_sum = splat4(weight_weight_sum_s) * color_weight;
 			float psum = right_sum_s * hadd_rgb_s(color_weight);
 			f4 rgbq_sum = color_vec_x + color_vec_y;
 			rgbq_sum.w = hadd_rgb_s(color_vec_y);
-			f4 rgbovec = compute_rgbo_vector(rgba_weight_sum[i], weight_weight_sum, rgbq_sum, psum);
+			f4 rgbovec = compute_rgbo_vector(rws, weight_weight_sum, rgbq_sum, psum);
 			rgbo_fallback(rgbovec, e0, e1);
-			w.ep[EP_RGBO + i] = rgbovec;
+			ep[EP_RGBO + (int)i] = rgbovec;
 		}
 	}
 	wsync();
 }
 
-// recompute_ideal_colors_2planes :1369-1650. Chains:
+// recompute_ideal_colors_2planes :1369-1650. Per-texel terms (texel order):
 //   0-2 left/middle/right plane 1, 3-5 plane 2, 6-9 color_vec_x, 10-13 color_vec_y, 14-15 scale_vec, 16-19 weight_weight_sum
-ASTC_COOP void recompute_ideal_colors_2planes(WCtx& w, const DecView& di, int plane2_component, RefineScratch* rs) {
+ASTC_COOP void recompute_ideal_colors_2planes(WCtx w, unsigned int d, int plane2_component) {
+	RefineScratch rs = make_refine_scratch(w);
 	int T = w.T;
-	undecimate_weights(w, di, w.work_weights, 2, rs);
-	const float* undec1 = rs->undec[0];
-	const float* undec2 = rs->undec[1];
-	f4 color_weight = w.bi.channel_weight;
+	undecimate_weights(w, d, 2);
+	SPtr<float> undec1 = sptr<float>(rs.undec[0]);
+	SPtr<float> undec2 = sptr<float>(rs.undec[1]);
+	SPtr<float> tmpf = tmpf_of(w);
+	const BlkInfo& bi = bi_of(w);
+	f4 color_weight = bi.channel_weight;
 	float ls_weight = hadd_rgb_s(color_weight);
 	f4 rgba_weight_sum = max4(color_weight * static_cast<float>(T), splat4(1e-17f));
-	f4 scale_dir = normalize4(mk4(w.bi.data_mean.x, w.bi.data_mean.y, w.bi.data_mean.z, 0.0f));
-	for (int ch = w.lane; ch < 20; ch += ASTC_WARP) {
-		float s = ch >= 16 ? 1e-17f : 0.0f;
-		for (int j = 0; j < T; j++) {
+	f4 dmean = bi.data_mean;
+	f4 scale_dir = normalize4(mk4(dmean.x, dmean.y, dmean.z, 0.0f));
+	SPtr<float> b0 = blk_of(w, 0);
+	uint32_t cs = tp4(w);
+	ASTC_NOUNROLL
+	for (int id = w.lane; id < 20; id += ASTC_WARP) {
+		tmpf[id] = id >= 16 ? 1e-17f : 0.0f;
+	}
+	wsync();
+	chain_sums<20>(w, T, rs.tile, tmpf, 20,
+		[&](int j, float* term) {
 			float idx0 = undec1[j];
 			float om_idx0 = 1.0f - idx0;
 			float idx1 = undec2[j];
 			float om_idx1 = 1.0f - idx1;
-			float term;
-			if (ch == 0) term = om_idx0 * om_idx0;
-			else if (ch == 1) term = om_idx0 * idx0;
-			else if (ch == 2) term = idx0 * idx0;
-			else if (ch == 3) term = om_idx1 * om_idx1;
-			else if (ch == 4) term = om_idx1 * idx1;
-			else if (ch == 5) term = idx1 * idx1;
-			else if (ch < 10) {
-				int c = ch - 6;
-				float color_idx = c == plane2_component ? idx1 : idx0;
-				float cw = w.blk[c][j];
-				float cwi = cw * color_idx;
-				term = cw - cwi;
-			} else if (ch < 14) {
-				int c = ch - 10;
-				float color_idx = c == plane2_component ? idx1 : idx0;
-				term = w.blk[c][j] * color_idx;
-			} else if (ch < 16) {
-				float scale = dot3_s(scale_dir, texel4(w, j));
-				term = (ch == 14 ? om_idx0 : idx0) * (ls_weight * scale);
-			} else {
-				int c = ch - 16;
-				term = c == plane2_component ? idx1 : idx0;
-			}
-			s = s + term;
-		}
-		w.tmpf[ch] = s;
-	}
-	float a = 1.0f, b = 0.0f, a2 = 1.0f, b2 = 0.0f, c = 1e10f, d = 0.0f;
+			SPtr<float> tx = b0 + j;
+			float r = tx[0], g = sptr<float>(tx.off + cs)[0], b = sptr<float>(tx.off + 2 * cs)[0], a = sptr<float>(tx.off + 3 * cs)[0];
+			term[0] = om_idx0 * om_idx0;
+			term[1] = om_idx0 * idx0;
+			term[2] = idx0 * idx0;
+			term[3] = om_idx1 * om_idx1;
+			term[4] = om_idx1 * idx1;
+			term[5] = idx1 * idx1;
+			float i_r = plane2_component == 0 ? idx1 : idx0;
+			float i_g = plane2_component == 1 ? idx1 : idx0;
+			float i_b = plane2_component == 2 ? idx1 : idx0;
+			float i_a = plane2_component == 3 ? idx1 : idx0;
+			float ri = r * i_r, gi = g * i_g, bi2 = b * i_b, ai = a * i_a;
+			term[6] = r - ri;
+			term[7] = g - gi;
+			term[8] = b - bi2;
+			term[9] = a - ai;
+			term[10] = ri;
+			term[11] = gi;
+			term[12] = bi2;
+			term[13] = ai;
+			float scale = (scale_dir.x * r + scale_dir.y * g) + scale_dir.z * b;
+			term[14] = om_idx0 * (ls_weight * scale);
+			term[15] = idx0 * (ls_weight * scale);
+			term[16] = i_r;
+			term[17] = i_g;
+			term[18] = i_b;
+			term[19] = i_a;
+		},
+		[&](int id, int& k, int& lo, int& hi, int& step) {
+			k = id;
+			lo = 0;
+			hi = T;
+			step = 1;
+		});
+	float a = 1.0f, b = 0.0f, a2 = 1.0f, b2 = 0.0f, c = 1e10f, dd = 0.0f;
+	ASTC_NOUNROLL
 	for (int j = w.lane; j < T; j += ASTC_WARP) {
 		float idx0 = undec1[j];
 		float idx1 = undec2[j];
@@ -843,14 +913,15 @@ ASTC_COOP void recompute_ideal_colors_2planes(WCtx& w, const DecView& di, int pl
 		b2 = maxf(idx1, b2);
 		float scale = dot3_s(scale_dir, texel4(w, j));
 		c = minf(scale, c);
-		d = maxf(scale, d);
+		dd = maxf(scale, dd);
 	}
 	float wmin1 = wmin_f(a), wmax1 = wmax_f(b), wmin2 = wmin_f(a2), wmax2 = wmax_f(b2);
-	float scale_min = wmin_f(c), scale_max = wmax_f(d);
+	float scale_min = wmin_f(c), scale_max = wmax_f(dd);
 	wsync();
 	if (w.lane == 0) {
-		const float* t = w.tmpf;
-		bool p2[4] = {plane2_component == 0, plane2_component == 1, plane2_component == 2, plane2_component == 3};
+		SPtr<float> t = tmpf;
+		SPtr<f4> ep = ep_of(w);
+		bool p20 = plane2_component == 0, p21 = plane2_component == 1, p22 = plane2_component == 2, p23 = plane2_component == 3;
 		float left1_sum_s = t[0], middle1_sum_s = t[1], right1_sum_s = t[2];
 		float left2_sum_s = t[3], middle2_sum_s = t[4], right2_sum_s = t[5];
 		f4 color_vec_x = mk4(t[6], t[7], t[8], t[9]);
@@ -870,15 +941,12 @@ ASTC_COOP void recompute_ideal_colors_2planes(WCtx& w, const DecView& di, int pl
 		scalediv = clamp1f(scalediv);
 		f4 sds = scale_dir * scale_max;
 		f4 rgbs_vector = mk4(sds.x, sds.y, sds.z, scalediv);
-		f4 e0 = w.ep[EP_WORK_0], e1 = w.ep[EP_WORK_1];
+		f4 e0 = ep[EP_WORK_0], e1 = ep[EP_WORK_1];
 		if (wmin1 >= wmax1 * 0.999f) {
 			f4 avg = (color_vec_x + color_vec_y) / rgba_weight_sum;
-			bool m[4];
-			for (int k = 0; k < 4; k++) {
-				m[k] = !p2[k] && (lane(avg, k) == lane(avg, k));
-			}
-			e0 = sel4(e0, avg, m[0], m[1], m[2], m[3]);
-			e1 = sel4(e1, avg, m[0], m[1], m[2], m[3]);
+			bool m0 = !p20 && avg.x == avg.x, m1 = !p21 && avg.y == avg.y, m2 = !p22 && avg.z == avg.z, m3 = !p23 && avg.w == avg.w;
+			e0 = sel4(e0, avg, m0, m1, m2, m3);
+			e1 = sel4(e1, avg, m0, m1, m2, m3);
 			rgbs_vector = mk4(sds.x, sds.y, sds.z, 1.0f);
 		} else {
 			f4 color_det1 = (left1_sum * right1_sum) - (middle1_sum * middle1_sum);
@@ -892,14 +960,12 @@ ASTC_COOP void recompute_ideal_colors_2planes(WCtx& w, const DecView& di, int pl
 			float scale_ep0 = (lmrs_sum.z * scale_vec.x - lmrs_sum.y * scale_vec.y) * ls_rdet1;
 			float scale_ep1 = (lmrs_sum.x * scale_vec.y - lmrs_sum.y * scale_vec.x) * ls_rdet1;
 			f4 thr = color_mss1 * 1e-4f;
-			bool m[4];
-			for (int k = 0; k < 4; k++) {
-				bool det = absf(lane(color_det1, k)) > lane(thr, k);
-				bool notnan = (lane(ep0, k) == lane(ep0, k)) && (lane(ep1, k) == lane(ep1, k));
-				m[k] = !p2[k] && det && notnan;
-			}
-			e0 = sel4(e0, ep0, m[0], m[1], m[2], m[3]);
-			e1 = sel4(e1, ep1, m[0], m[1], m[2], m[3]);
+			bool m0 = !p20 && absf(color_det1.x) > thr.x && ep0.x == ep0.x && ep1.x == ep1.x;
+			bool m1 = !p21 && absf(color_det1.y) > thr.y && ep0.y == ep0.y && ep1.y == ep1.y;
+			bool m2 = !p22 && absf(color_det1.z) > thr.z && ep0.z == ep0.z && ep1.z == ep1.z;
+			bool m3 = !p23 && absf(color_det1.w) > thr.w && ep0.w == ep0.w && ep1.w == ep1.w;
+			e0 = sel4(e0, ep0, m0, m1, m2, m3);
+			e1 = sel4(e1, ep1, m0, m1, m2, m3);
 			if (fabsf(ls_det1) > (ls_mss1 * 1e-4f) && scale_ep0 == scale_ep0 && scale_ep1 == scale_ep1 && scale_ep0 < scale_ep1) {
 				float scalediv2 = scale_ep0 / scale_ep1;
 				f4 sdsm = scale_dir * scale_ep1;
@@ -908,12 +974,9 @@ ASTC_COOP void recompute_ideal_colors_2planes(WCtx& w, const DecView& di, int pl
 		}
 		if (wmin2 >= wmax2 * 0.999f) {
 			f4 avg = (color_vec_x + color_vec_y) / rgba_weight_sum;
-			bool m[4];
-			for (int k = 0; k < 4; k++) {
-				m[k] = p2[k] && (lane(avg, k) == lane(avg, k));
-			}
-			e0 = sel4(e0, avg, m[0], m[1], m[2], m[3]);
-			e1 = sel4(e1, avg, m[0], m[1], m[2], m[3]);
+			bool m0 = p20 && avg.x == avg.x, m1 = p21 && avg.y == avg.y, m2 = p22 && avg.z == avg.z, m3 = p23 && avg.w == avg.w;
+			e0 = sel4(e0, avg, m0, m1, m2, m3);
+			e1 = sel4(e1, avg, m0, m1, m2, m3);
 		} else {
 			f4 color_det2 = (left2_sum * right2_sum) - (middle2_sum * middle2_sum);
 			f4 color_rdet2 = splat4(1.0f) / color_det2;
@@ -921,28 +984,26 @@ ASTC_COOP void recompute_ideal_colors_2planes(WCtx& w, const DecView& di, int pl
 			f4 ep0 = (right2_sum * color_vec_x - middle2_sum * color_vec_y) * color_rdet2;
 			f4 ep1 = (left2_sum * color_vec_y - middle2_sum * color_vec_x) * color_rdet2;
 			f4 thr = color_mss2 * 1e-4f;
-			bool m[4];
-			for (int k = 0; k < 4; k++) {
-				bool det = absf(lane(color_det2, k)) > lane(thr, k);
-				bool notnan = (lane(ep0, k) == lane(ep0, k)) && (lane(ep1, k) == lane(ep1, k));
-				m[k] = p2[k] && det && notnan;
-			}
-			e0 = sel4(e0, ep0, m[0], m[1], m[2], m[3]);
-			e1 = sel4(e1, ep1, m[0], m[1], m[2], m[3]);
+			bool m0 = p20 && absf(color_det2.x) > thr.x && ep0.x == ep0.x && ep1.x == ep1.x;
+			bool m1 = p21 && absf(color_det2.y) > thr.y && ep0.y == ep0.y && ep1.y == ep1.y;
+			bool m2 = p22 && absf(color_det2.z) > thr.z && ep0.z == ep0.z && ep1.z == ep1.z;
+			bool m3 = p23 && absf(color_det2.w) > thr.w && ep0.w == ep0.w && ep1.w == ep1.w;
+			e0 = sel4(e0, ep0, m0, m1, m2, m3);
+			e1 = sel4(e1, ep1, m0, m1, m2, m3);
 		}
-		w.ep[EP_WORK_0] = e0;
-		w.ep[EP_WORK_1] = e1;
-		w.ep[EP_RGBS] = rgbs_vector;
-		if (w.bi.rgb_lns0 || w.bi.alpha_lns0) {
+		ep[EP_WORK_0] = e0;
+		ep[EP_WORK_1] = e1;
+		ep[EP_RGBS] = rgbs_vector;
+		if (bi.rgb_lns0 || bi.alpha_lns0) {
 			weight_weight_sum = weight_weight_sum * color_weight;
-			f4 rsel = mk4(p2[0] ? right2_sum.x : right1_sum.x, p2[1] ? right2_sum.y : right1_sum.y, p2[2] ? right2_sum.z : right1_sum.z,
-			              p2[3] ? right2_sum.w : right1_sum.w);
+			f4 rsel = mk4(p20 ? right2_sum.x : right1_sum.x, p21 ? right2_sum.y : right1_sum.y, p22 ? right2_sum.z : right1_sum.z,
+			              p23 ? right2_sum.w : right1_sum.w);
 			float psum = dot3_s(rsel, color_weight);
 			f4 rgbq_sum = color_vec_x + color_vec_y;
 			rgbq_sum.w = hadd_rgb_s(color_vec_y);
 			f4 rgbo_vector = compute_rgbo_vector(rgba_weight_sum, weight_weight_sum, rgbq_sum, psum);
 			rgbo_fallback(rgbo_vector, e0, e1);
-			w.ep[EP_RGBO] = rgbo_vector;
+			ep[EP_RGBO] = rgbo_vector;
 		}
 	}
 	wsync();
@@ -951,7 +1012,7 @@ ASTC_COOP void recompute_ideal_colors_2planes(WCtx& w, const DecView& di, int pl
 // =============================================================================================
 // Decompress-and-diff scoring (astcenc_decompress_symbolic.cpp:89-618)
 // =============================================================================================
-ASTC_FN bool u8_mask(const WCtx& w) { return w.bi.decode_unorm8 || w.cfg->profile == PRF_LDR_SRGB; }
+ASTC_FN bool u8_mask(const WCtx& w) { return bi_of(w).decode_unorm8 || CFG.profile == PRF_LDR_SRGB; }
 
 ASTC_FN int lerp1(bool u8, int c0, int c1, int w1) {   // lerp_color_int :37-61
 	int w0 = 64 - w1;
@@ -963,58 +1024,68 @@ ASTC_FN int lerp1(bool u8, int c0, int c1, int w1) {   // lerp_color_int :37-61
 	return color;
 }
 
-// unpack_weights :89-167: integer infill into rs->iw
-ASTC_COOP void unpack_weights(WCtx& w, const DecView& di, const uint8_t* weights, int planes, RefineScratch* rs) {
-	int T = w.T;
-	for (int id = w.lane; id < T * planes; id += ASTC_WARP) {
-		int pl = id >= T ? 1 : 0;
-		int t = id - pl * T;
-		const uint8_t* uq = weights + pl * 32;
-		int s = 8;
-		s += uq[di.tw[t]] * di.tc[t];
-		s += uq[di.tw[T + t]] * di.tc[T + t];
-		s += uq[di.tw[2 * T + t]] * di.tc[2 * T + t];
-		s += uq[di.tw[3 * T + t]] * di.tc[3 * T + t];
-		rs->iw[pl][t] = (uint8_t)(s >> 4);
+// Unpack the integer endpoints of the work candidate into the arena: ends[p * 8 + 0..3] = endpoint 0 (rgba), + 4..7 = endpoint 1.
+ASTC_COOP void unpack_work_endpoints(WCtx w, unsigned int pc, uint32_t formats, uint32_t ends_off) {
+	SPtr<int> ends = sptr<int>(ends_off);
+	SPtr<uint8_t> wc = work_colors_of(w);
+	ASTC_NOUNROLL
+	for (unsigned int p = (unsigned int)w.lane; p < pc; p += ASTC_WARP) {
+		uint8_t in[8];
+		for (int k = 0; k < 8; k++) {
+			in[k] = wc[(int)p * 8 + k];
+		}
+		bool rgb_lns, a_lns;
+		i4 e0, e1;
+		unpack_color_endpoints(CFG.profile, (int)((formats >> (8 * p)) & 0xFF), in, rgb_lns, a_lns, e0, e1);
+		SPtr<int> o = ends + (int)p * 8;
+		o[0] = e0.x; o[1] = e0.y; o[2] = e0.z; o[3] = e0.w;
+		o[4] = e1.x; o[5] = e1.y; o[6] = e1.z; o[7] = e1.w;
 	}
 	wsync();
 }
+ASTC_FN uint32_t pack_formats(const ScbHdr& h) {
+	return (uint32_t)h.color_formats[0] | ((uint32_t)h.color_formats[1] << 8) | ((uint32_t)h.color_formats[2] << 16) | ((uint32_t)h.color_formats[3] << 24);
+}
+// the unpacked endpoints live in tmpf[96..128) (32 ints) during scoring / realignment
+ASTC_FN uint32_t ends_off_of(const WCtx& w) { return w.base + A_TMPF + 96 * 4; }
 
-// compute_symbolic_block_difference_{2plane,1plane,1plane_1partition} (:313-618) on the candidate in
-// w.work_weights / w.work_colors with header hdr. Per-texel terms by lanes over texels, then the
-// reference's summation order: 4-lane accumulator (1 partition, 1 plane, no RGBM) or one scalar chain.
-ASTC_COOP float compute_symbolic_block_difference(WCtx& w, const ScbHdr& hdr, const PartView& pi, const DecView& di, bool dual, RefineScratch* rs) {
-	if (hdr.block_type == SYM_BTYPE_ERROR) {
-		return ERROR_CALC_DEFAULT;
-	}
-	const DevConfig& cfg = *w.cfg;
+// compute_symbolic_block_difference_{2plane,1plane,1plane_1partition} (:313-618) on the work candidate.
+// Per-texel terms by lanes over texels (integer infill :89-167 inlined), then the reference's summation order:
+// 4-lane accumulator (1 partition, 1 plane, no RGBM) or one scalar chain.
+ASTC_COOP float compute_symbolic_block_difference(WCtx w, unsigned int pc, uint32_t formats, int plane2_component, const PartView& pi, unsigned int d, bool dual) {
+	RefineScratch rs = make_refine_scratch(w);
+	DecView di = dec_view(d);
 	int T = w.T;
-	unsigned int pc = hdr.partition_count;
-	bool rgbm = (cfg.flags & FLG_MAP_RGBM) != 0;
+	bool rgbm = (CFG.flags & FLG_MAP_RGBM) != 0;
+	float rgbm_scale = CFG.rgbm_m_scale;
 	bool fast = !dual && pc == 1 && !rgbm;
-	unpack_weights(w, di, w.work_weights, dual ? 2 : 1, rs);
 	bool u8 = u8_mask(w);
-	i4 ep0[4], ep1[4];
-	for (unsigned int p = 0; p < pc; p++) {
-		bool rgb_lns, a_lns;
-		unpack_color_endpoints(cfg.profile, hdr.color_formats[p], w.work_colors + p * 8, rgb_lns, a_lns, ep0[p], ep1[p]);
-	}
-	f4 cw = w.bi.channel_weight;
+	unpack_work_endpoints(w, pc, formats, ends_off_of(w));
+	SPtr<int> ends = sptr<int>(ends_off_of(w));
+	SPtr<uint8_t> uq = work_weights_of(w);
+	SPtr<float> texel_err = sptr<float>(rs.texel_err);
+	SPtr<float> tmpf = tmpf_of(w);
+	f4 cw = bi_of(w).channel_weight;
+	SPtr<float> b0 = blk_of(w, 0);
+	uint32_t cs = tp4(w);
 	bool reject = false;
+	ASTC_NOUNROLL
 	for (int t = w.lane; t < T; t += ASTC_WARP) {
-		int p = pc > 1 ? pi.partition_of_texel[t] : 0;
-		int w1 = rs->iw[0][t];
-		int w2 = dual ? rs->iw[1][t] : w1;
-		int pc2 = hdr.plane2_component;
-		i4 e0 = ep0[0], e1 = ep1[0];
-		if (p == 1) { e0 = ep0[1]; e1 = ep1[1]; }
-		else if (p == 2) { e0 = ep0[2]; e1 = ep1[2]; }
-		else if (p == 3) { e0 = ep0[3]; e1 = ep1[3]; }
-		float cr = (float)lerp1(u8, e0.x, e1.x, (dual && pc2 == 0) ? w2 : w1);
-		float cg = (float)lerp1(u8, e0.y, e1.y, (dual && pc2 == 1) ? w2 : w1);
-		float cb = (float)lerp1(u8, e0.z, e1.z, (dual && pc2 == 2) ? w2 : w1);
-		float ca = (float)lerp1(u8, e0.w, e1.w, (dual && pc2 == 3) ? w2 : w1);
-		float orr = w.blk[0][t], og = w.blk[1][t], ob = w.blk[2][t], oa = w.blk[3][t];
+		int i0 = ASTC_LDG(&di.tw[t]), i1 = ASTC_LDG(&di.tw[T + t]), i2 = ASTC_LDG(&di.tw[2 * T + t]), i3 = ASTC_LDG(&di.tw[3 * T + t]);
+		int c0 = ASTC_LDG(&di.tc[t]), c1 = ASTC_LDG(&di.tc[T + t]), c2 = ASTC_LDG(&di.tc[2 * T + t]), c3 = ASTC_LDG(&di.tc[3 * T + t]);
+		int w1 = (8 + uq[i0] * c0 + uq[i1] * c1 + uq[i2] * c2 + uq[i3] * c3) >> 4;
+		int w2 = w1;
+		if (dual) {
+			w2 = (8 + uq[32 + i0] * c0 + uq[32 + i1] * c1 + uq[32 + i2] * c2 + uq[32 + i3] * c3) >> 4;
+		}
+		int p = pc > 1 ? (int)ASTC_LDG(&pi.partition_of_texel[t]) : 0;
+		SPtr<int> e = ends + p * 8;
+		float cr = (float)lerp1(u8, e[0], e[4], plane2_component == 0 ? w2 : w1);
+		float cg = (float)lerp1(u8, e[1], e[5], plane2_component == 1 ? w2 : w1);
+		float cb = (float)lerp1(u8, e[2], e[6], plane2_component == 2 ? w2 : w1);
+		float ca = (float)lerp1(u8, e[3], e[7], plane2_component == 3 ? w2 : w1);
+		SPtr<float> tx = b0 + t;
+		float orr = tx[0], og = sptr<float>(tx.off + cs)[0], ob = sptr<float>(tx.off + 2 * cs)[0], oa = sptr<float>(tx.off + 3 * cs)[0];
 		float metric;
 		if (fast) {
 			float er = minf(absf(orr - cr), 1e15f);
@@ -1033,15 +1104,15 @@ ASTC_COOP float compute_symbolic_block_difference(WCtx& w, const ScbHdr& hdr, co
 				if (color.w == 0.0f) {
 					reject = true;
 				}
-				color = mk4(color.x * color.w * cfg.rgbm_m_scale, color.y * color.w * cfg.rgbm_m_scale, color.z * color.w * cfg.rgbm_m_scale, 1.0f);
-				old = mk4(old.x * old.w * cfg.rgbm_m_scale, old.y * old.w * cfg.rgbm_m_scale, old.z * old.w * cfg.rgbm_m_scale, 1.0f);
+				color = mk4(color.x * color.w * rgbm_scale, color.y * color.w * rgbm_scale, color.z * color.w * rgbm_scale, 1.0f);
+				old = mk4(old.x * old.w * rgbm_scale, old.y * old.w * rgbm_scale, old.z * old.w * rgbm_scale, 1.0f);
 			}
 			f4 error = old - color;
 			error = min4(mk4(absf(error.x), absf(error.y), absf(error.z), absf(error.w)), splat4(1e15f));
 			error = error * error;
 			metric = minf(dot_s(error, cw), ERROR_CALC_DEFAULT);
 		}
-		rs->texel_err[t] = metric;
+		texel_err[t] = metric;
 	}
 	// The reference returns -1e30 at the first texel (in its iteration order) whose decoded alpha is 0; any
 	// such texel makes the result -1e30, so the order does not matter for the rejection itself.
@@ -1051,33 +1122,37 @@ ASTC_COOP float compute_symbolic_block_difference(WCtx& w, const ScbHdr& hdr, co
 		return -ERROR_CALC_DEFAULT;
 	}
 	if (fast) {
+		ASTC_NOUNROLL
 		for (int l = w.lane; l < 4; l += ASTC_WARP) {
 			float s = 0.0f;
+			ASTC_NOUNROLL
 			for (int t = l; t < T; t += 4) {
-				s = s + rs->texel_err[t];
+				s = s + texel_err[t];
 			}
-			w.tmpf[l] = s;
+			tmpf[l] = s;
 		}
 		wsync();
-		float r = (w.tmpf[0] + w.tmpf[2]) + (w.tmpf[1] + w.tmpf[3]);
+		float r = (tmpf[0] + tmpf[2]) + (tmpf[1] + tmpf[3]);
 		wsync();
 		return r;
 	}
 	if (w.lane == 0) {
 		float summa = 0.0f;
 		if (dual || pc == 1) {
+			ASTC_NOUNROLL
 			for (int t = 0; t < T; t++) {
-				summa += rs->texel_err[t];
+				summa += texel_err[t];
 			}
 		} else {
+			ASTC_NOUNROLL
 			for (int t = 0; t < T; t++) {
-				summa += rs->texel_err[pi.texels[t]];
+				summa += texel_err[ASTC_LDG(&pi.texels[t])];
 			}
 		}
-		w.tmpf[0] = summa;
+		tmpf[0] = summa;
 	}
 	wsync();
-	float r = w.tmpf[0];
+	float r = tmpf[0];
 	wsync();
 	return r;
 }
@@ -1085,143 +1160,185 @@ ASTC_COOP float compute_symbolic_block_difference(WCtx& w, const ScbHdr& hdr, co
 // =============================================================================================
 // Weight realignment (astcenc_compress_symbolic.cpp:69-350)
 // =============================================================================================
-ASTC_COOP bool realign_weights(WCtx& w, const ScbHdr& hdr, const PartView& pi, const DevBlockMode& bm, const DecView& di, RefineScratch* rs) {
+// Decimated grids (:188-350): weights are visited in order and a changed weight feeds the following ones, so
+// the outer loop is sequential. Per weight, lane = (texel slot 0..7, channel 0..3): eight of the weight's texels
+// at a time compute their squared channel differences for the current / previous / next quantised value into a
+// [12][8] tile; twelve chain lanes (3 candidates x 4 channels) then add them in texel order.
+ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int plane2_component, const PartView& pi, int quant_mode, bool is_dual, unsigned int d) {
 	const DevConstTables* ct = ASTC_CT;
-	const DevConfig& cfg = *w.cfg;
-	unsigned int pc = hdr.partition_count;
-	const uint16_t* prev_next = ct->wq_prev_next[bm.quant_mode];
+	RefineScratch rs = make_refine_scratch(w);
+	DecView di = dec_view(d);
+	const uint16_t* prev_next = ct->wq_prev_next[quant_mode];
 	int weight_count = di.W;
 	int T = w.T;
 	bool decimated = weight_count != T;
-	unsigned int max_plane = bm.is_dual_plane;
-	int plane2_component = hdr.plane2_component;
-	i4 endpnt0[4], endpnt1[4];
-	for (unsigned int p = 0; p < pc; p++) {
-		bool rgb_hdr, alpha_hdr;
-		unpack_color_endpoints(cfg.profile, hdr.color_formats[p], w.work_colors + p * 8, rgb_hdr, alpha_hdr, endpnt0[p], endpnt1[p]);
-	}
-	f4 ew = w.bi.channel_weight;
+	unsigned int max_plane = is_dual ? 1u : 0u;
+	unpack_work_endpoints(w, pc, formats, ends_off_of(w));
+	SPtr<int> ends = sptr<int>(ends_off_of(w));
+	f4 ew = bi_of(w).channel_weight;
+	SPtr<float> uqf = sptr<float>(rs.uqf);
+	SPtr<float> tile = sptr<float>(rs.tile);
+	SPtr<float> tmpf = tmpf_of(w);
+	SPtr<float> b0 = blk_of(w, 0);
+	uint32_t cs = tp4(w);
 	bool adjustments = false;
-	uint8_t* dec_weights_uquant = w.work_weights;
+	ASTC_NOUNROLL
 	for (unsigned int pl = 0; pl <= max_plane; pl++) {
-		// plane_mask lanes are zeroed: for plane 1 that is the plane-2 component, for plane 2 all others
-		f4 endpnt0f[4], offset[4];
-		for (unsigned int p = 0; p < pc; p++) {
-			i4 epd = mki4(endpnt1[p].x - endpnt0[p].x, endpnt1[p].y - endpnt0[p].y, endpnt1[p].z - endpnt0[p].z, endpnt1[p].w - endpnt0[p].w);
-			bool m0 = (plane2_component == 0) != (pl == 1);
-			bool m1 = (plane2_component == 1) != (pl == 1);
-			bool m2 = (plane2_component == 2) != (pl == 1);
-			bool m3 = (plane2_component == 3) != (pl == 1);
-			if (m0) epd.x = 0;
-			if (m1) epd.y = 0;
-			if (m2) epd.z = 0;
-			if (m3) epd.w = 0;
-			endpnt0f[p] = mk4((float)endpnt0[p].x, (float)endpnt0[p].y, (float)endpnt0[p].z, (float)endpnt0[p].w);
-			offset[p] = mk4((float)epd.x, (float)epd.y, (float)epd.z, (float)epd.w) * (1.0f / 64.0f);
-		}
+		SPtr<uint8_t> dec_weights_uquant = work_weights_of(w) + (int)pl * 32;
+		// plane_mask: for plane 1 the plane-2 component is zeroed, for plane 2 all others
 		if (!decimated) {
 			// realign_weights_undecimated :69-185 - texels are independent
+			ASTC_NOUNROLL
 			for (int texel = w.lane; texel < T; texel += ASTC_WARP) {
 				int uqw = dec_weights_uquant[texel];
-				uint32_t pn = prev_next[uqw];
+				uint32_t pn = ASTC_LDG(&prev_next[uqw]);
 				int uqw_down = pn & 0xFF;
 				int uqw_up = (pn >> 8) & 0xFF;
 				float weight_base = static_cast<float>(uqw);
 				float weight_down = static_cast<float>(uqw_down - uqw);
 				float weight_up = static_cast<float>(uqw_up - uqw);
-				int partition = pc > 1 ? pi.partition_of_texel[texel] : 0;
-				f4 color_offset = offset[0], color_base = endpnt0f[0];
-				if (partition == 1) { color_offset = offset[1]; color_base = endpnt0f[1]; }
-				else if (partition == 2) { color_offset = offset[2]; color_base = endpnt0f[2]; }
-				else if (partition == 3) { color_offset = offset[3]; color_base = endpnt0f[3]; }
-				f4 color = color_base + color_offset * weight_base;
-				f4 orig_color = texel4(w, texel);
-				f4 color_diff = color - orig_color;
-				f4 color_diff_down = color_diff + color_offset * weight_down;
-				f4 color_diff_up = color_diff + color_offset * weight_up;
-				float error_base = dot_s(color_diff * color_diff, ew);
-				float error_down = dot_s(color_diff_down * color_diff_down, ew);
-				float error_up = dot_s(color_diff_up * color_diff_up, ew);
-				if ((error_up < error_base) && (error_up < error_down) && (uqw < 64)) {
+				int partition = pc > 1 ? (int)ASTC_LDG(&pi.partition_of_texel[texel]) : 0;
+				SPtr<int> e = ends + partition * 8;
+				float eb = 0.0f, ed = 0.0f, eu = 0.0f;     // dot_s: (x + z) + (y + w) below
+				float t0[4], t1[4], t2[4];
+				for (int c = 0; c < 4; c++) {
+					int e0 = e[c], e1 = e[4 + c];
+					bool masked = (plane2_component == c) != (pl == 1);
+					float color_offset = static_cast<float>(masked ? 0 : e1 - e0) * (1.0f / 64.0f);
+					float color_base = static_cast<float>(e0);
+					float color = color_base + color_offset * weight_base;
+					float orig = sptr<float>(b0.off + (uint32_t)c * cs)[texel];
+					float color_diff = color - orig;
+					float color_diff_down = color_diff + color_offset * weight_down;
+					float color_diff_up = color_diff + color_offset * weight_up;
+					float ewc = lane(ew, c);
+					t0[c] = color_diff * color_diff * ewc;
+					t1[c] = color_diff_down * color_diff_down * ewc;
+					t2[c] = color_diff_up * color_diff_up * ewc;
+				}
+				eb = (t0[0] + t0[2]) + (t0[1] + t0[3]);
+				ed = (t1[0] + t1[2]) + (t1[1] + t1[3]);
+				eu = (t2[0] + t2[2]) + (t2[1] + t2[3]);
+				if ((eu < eb) && (eu < ed) && (uqw < 64)) {
 					dec_weights_uquant[texel] = static_cast<uint8_t>(uqw_up);
 					adjustments = true;
-				} else if ((error_down < error_base) && (uqw > 0)) {
+				} else if ((ed < eb) && (uqw > 0)) {
 					dec_weights_uquant[texel] = static_cast<uint8_t>(uqw_down);
 					adjustments = true;
 				}
 			}
 			wsync();
-		} else {
-			// realign_weights_decimated :188-350 - weights are visited in order; a changed weight feeds the
-			// following ones. Per weight: lanes over its texels, then 12 ordered chains (3 vectors x 4 lanes).
-			for (int we = w.lane; we < weight_count; we += ASTC_WARP) {
-				rs->uqf[we] = static_cast<float>(dec_weights_uquant[we]);
+			continue;
+		}
+		ASTC_NOUNROLL
+		for (int we = w.lane; we < weight_count; we += ASTC_WARP) {
+			uqf[we] = static_cast<float>(dec_weights_uquant[we]);
+		}
+		wsync();
+#if ASTC_WARP == 1
+		const int slot_lanes = 1, slot = 0;
+#else
+		const int slot_lanes = 8;
+		int slot = w.lane >> 2;
+#endif
+		ASTC_NOUNROLL
+		for (int we = 0; we < weight_count; we++) {
+			int uqw = dec_weights_uquant[we];
+			uint32_t pn = ASTC_LDG(&prev_next[uqw]);
+			float uqw_base = uqf[we];
+			float uqw_down = static_cast<float>(pn & 0xFF);
+			float uqw_up = static_cast<float>((pn >> 8) & 0xFF);
+			float uqw_diff_down = uqw_down - uqw_base;
+			float uqw_diff_up = uqw_up - uqw_base;
+			int off = ASTC_LDG(&di.wto[we]);
+			int cnt = ASTC_LDG(&di.wto[we + 1]) - off;
+			float sum = 0.0f;                  // chain lanes 0..11: (candidate, channel)
+			ASTC_NOUNROLL
+			for (int te0 = 0; te0 < cnt; te0 += 8) {
+				ASTC_NOUNROLL
+				for (int s8 = slot; s8 < 8; s8 += slot_lanes) {
+					int te = te0 + s8;
+					if (te < cnt) {
+						int texel = ASTC_LDG(&di.wt[off + te]);
+						float tw_base = contrib_f(ASTC_LDG(&di.wc[off + te]));
+						float weight_base = (uqf[ASTC_LDG(&di.tw[texel])] * contrib_f(ASTC_LDG(&di.tc[texel])) +
+						                     uqf[ASTC_LDG(&di.tw[T + texel])] * contrib_f(ASTC_LDG(&di.tc[T + texel]))) +
+						                    (uqf[ASTC_LDG(&di.tw[2 * T + texel])] * contrib_f(ASTC_LDG(&di.tc[2 * T + texel])) +
+						                     uqf[ASTC_LDG(&di.tw[3 * T + texel])] * contrib_f(ASTC_LDG(&di.tc[3 * T + texel])));
+						float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
+						float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
+						int partition = pc > 1 ? (int)ASTC_LDG(&pi.partition_of_texel[texel]) : 0;
+						SPtr<int> e = ends + partition * 8;
+#if ASTC_WARP == 1
+						for (int c = 0; c < 4; c++)
+#else
+						int c = w.lane & 3;
+#endif
+						{
+							int e0 = e[c], e1 = e[4 + c];
+							bool masked = (plane2_component == c) != (pl == 1);
+							float color_offset = static_cast<float>(masked ? 0 : e1 - e0) * (1.0f / 64.0f);
+							float color = static_cast<float>(e0) + color_offset * weight_base;
+							float orig = sptr<float>(b0.off + (uint32_t)c * cs)[texel];
+							float color_diff = color - orig;
+							float color_down_diff = color_diff + color_offset * weight_down;
+							float color_up_diff = color_diff + color_offset * weight_up;
+							tile[c * 9 + s8] = color_diff * color_diff;
+							tile[(4 + c) * 9 + s8] = color_down_diff * color_down_diff;
+							tile[(8 + c) * 9 + s8] = color_up_diff * color_up_diff;
+						}
+					}
+				}
+				wsync();
+				int m = cnt - te0 < 8 ? cnt - te0 : 8;
+#if ASTC_WARP == 1
+				ASTC_NOUNROLL
+				for (int ch = 0; ch < 12; ch++) {
+					float s = te0 == 0 ? 0.0f : tmpf[16 + ch];
+					for (int k = 0; k < m; k++) {
+						s = s + tile[ch * 9 + k];
+					}
+					tmpf[16 + ch] = s;
+				}
+#else
+				if (w.lane < 12) {
+					SPtr<float> row = tile + w.lane * 9;
+					ASTC_NOUNROLL
+					for (int k = 0; k < m; k++) {
+						sum = sum + row[k];
+					}
+				}
+#endif
+				wsync();
+			}
+#if ASTC_WARP == 1
+			for (int ch = 0; ch < 12; ch++) {
+				tmpf[ch] = tmpf[16 + ch] * lane(ew, ch & 3);
+			}
+#else
+			if (w.lane < 12) {
+				tmpf[w.lane] = sum * lane(ew, w.lane & 3);
+			}
+#endif
+			wsync();
+			float error_base = (tmpf[0] + tmpf[2]) + (tmpf[1] + tmpf[3]);
+			float error_down = (tmpf[4] + tmpf[6]) + (tmpf[5] + tmpf[7]);
+			float error_up = (tmpf[8] + tmpf[10]) + (tmpf[9] + tmpf[11]);
+			if ((error_up < error_base) && (error_up < error_down) && (uqw < 64)) {
+				if (w.lane == 0) {
+					uqf[we] = uqw_up;
+					dec_weights_uquant[we] = static_cast<uint8_t>(uqw_up);
+				}
+				adjustments = true;
+			} else if ((error_down < error_base) && (uqw > 0)) {
+				if (w.lane == 0) {
+					uqf[we] = uqw_down;
+					dec_weights_uquant[we] = static_cast<uint8_t>(uqw_down);
+				}
+				adjustments = true;
 			}
 			wsync();
-			for (int we = 0; we < weight_count; we++) {
-				int uqw = dec_weights_uquant[we];
-				uint32_t pn = prev_next[uqw];
-				float uqw_base = rs->uqf[we];
-				float uqw_down = static_cast<float>(pn & 0xFF);
-				float uqw_up = static_cast<float>((pn >> 8) & 0xFF);
-				float uqw_diff_down = uqw_down - uqw_base;
-				float uqw_diff_up = uqw_up - uqw_base;
-				int off = di.wto[we];
-				int cnt = di.wto[we + 1] - off;
-				for (int te = w.lane; te < cnt; te += ASTC_WARP) {
-					int texel = di.wt[off + te];
-					float tw_base = contrib_f(di.wc[off + te]);
-					float weight_base = (rs->uqf[di.tw[texel]] * contrib_f(di.tc[texel]) + rs->uqf[di.tw[T + texel]] * contrib_f(di.tc[T + texel])) +
-					                    (rs->uqf[di.tw[2 * T + texel]] * contrib_f(di.tc[2 * T + texel]) + rs->uqf[di.tw[3 * T + texel]] * contrib_f(di.tc[3 * T + texel]));
-					float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
-					float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
-					int partition = pc > 1 ? pi.partition_of_texel[texel] : 0;
-					f4 color_offset = offset[0], color_base = endpnt0f[0];
-					if (partition == 1) { color_offset = offset[1]; color_base = endpnt0f[1]; }
-					else if (partition == 2) { color_offset = offset[2]; color_base = endpnt0f[2]; }
-					else if (partition == 3) { color_offset = offset[3]; color_base = endpnt0f[3]; }
-					f4 color = color_base + color_offset * weight_base;
-					f4 orig_color = texel4(w, texel);
-					f4 color_diff = color - orig_color;
-					f4 color_down_diff = color_diff + color_offset * weight_down;
-					f4 color_up_diff = color_diff + color_offset * weight_up;
-					f4 b = color_diff * color_diff;
-					f4 dn = color_down_diff * color_down_diff;
-					f4 up = color_up_diff * color_up_diff;
-					rs->stage[0 * rs->stage_stride + te] = b.x; rs->stage[1 * rs->stage_stride + te] = b.y; rs->stage[2 * rs->stage_stride + te] = b.z; rs->stage[3 * rs->stage_stride + te] = b.w;
-					rs->stage[4 * rs->stage_stride + te] = dn.x; rs->stage[5 * rs->stage_stride + te] = dn.y; rs->stage[6 * rs->stage_stride + te] = dn.z; rs->stage[7 * rs->stage_stride + te] = dn.w;
-					rs->stage[8 * rs->stage_stride + te] = up.x; rs->stage[9 * rs->stage_stride + te] = up.y; rs->stage[10 * rs->stage_stride + te] = up.z; rs->stage[11 * rs->stage_stride + te] = up.w;
-				}
-				wsync();
-				for (int ch = w.lane; ch < 12; ch += ASTC_WARP) {
-					float s = 0.0f;
-					for (int te = 0; te < cnt; te++) {
-						s = s + rs->stage[ch * rs->stage_stride + te];
-					}
-					w.tmpf[ch] = s * lane(ew, ch & 3);
-				}
-				wsync();
-				const float* t = w.tmpf;
-				float error_base = (t[0] + t[2]) + (t[1] + t[3]);
-				float error_down = (t[4] + t[6]) + (t[5] + t[7]);
-				float error_up = (t[8] + t[10]) + (t[9] + t[11]);
-				if ((error_up < error_base) && (error_up < error_down) && (uqw < 64)) {
-					if (w.lane == 0) {
-						rs->uqf[we] = uqw_up;
-						dec_weights_uquant[we] = static_cast<uint8_t>(uqw_up);
-					}
-					adjustments = true;
-				} else if ((error_down < error_base) && (uqw > 0)) {
-					if (w.lane == 0) {
-						rs->uqf[we] = uqw_down;
-						dec_weights_uquant[we] = static_cast<uint8_t>(uqw_down);
-					}
-					adjustments = true;
-				}
-				wsync();
-			}
 		}
-		dec_weights_uquant += 32;
 	}
 	return wany(adjustments);
 }
@@ -1261,65 +1378,91 @@ ASTC_FN uint64_t brev64(uint64_t v) {
 #endif
 }
 
-// encode_ise (astcenc_integer_sequence.cpp:493-648); get(i) yields the i-th value to encode
-template <typename GetFn>
-ASTC_FN void encode_ise(int quant_level, unsigned int character_count, GetFn get, Bits128& out, unsigned int bit_offset) {
+// Source of the values of one integer sequence: the block's weights (scrambled quantised values, planes
+// interleaved for dual-plane modes :127-150) or its colour values (partition after partition :268-285).
+struct IseSource {
+	uint32_t arr;                    // shared offset of best_weights / best_colors
+	const uint8_t* table;            // scramble map / uquant -> scrambled pquant
+	float weight_quant_levels_m1;    // weights only
+	int is_dual_plane;               // weights only
+	int is_color;
+	uint32_t n0, n1, n2;             // colours only: values in partitions 0, 1, 2
+};
+
+ASTC_NOINLINE unsigned int ise_value(const IseSource& s, unsigned int i, unsigned int count) {
+	if (i >= count) {
+		return 0u;
+	}
+	SPtr<uint8_t> a = sptr<uint8_t>(s.arr);
+	if (!s.is_color) {
+		unsigned int src = s.is_dual_plane ? ((i >> 1) + ((i & 1) ? 32u : 0u)) : i;
+		float uqw = static_cast<float>(a[(int)src]);
+		float qw = (uqw / 64.0f) * s.weight_quant_levels_m1;
+		int qwi = static_cast<int>(qw + 0.5f);
+		return ASTC_LDG(&s.table[qwi]);
+	}
+	unsigned int p = 0;
+	if (i >= s.n0) { i -= s.n0; p = 1; if (i >= s.n1) { i -= s.n1; p = 2; if (i >= s.n2) { i -= s.n2; p = 3; } } }
+	return ASTC_LDG(&s.table[a[(int)(p * 8 + i)]]);
+}
+
+// encode_ise (astcenc_integer_sequence.cpp:493-648)
+ASTC_NOINLINE void encode_ise(int quant_level, unsigned int character_count, const IseSource& src, Bits128& out, unsigned int bit_offset) {
 	const DevConstTables* ct = ASTC_CT;
 	unsigned int bits, trits, quints;
 	ise_btq(quant_level, bits, trits, quints);
 	unsigned int mask = (1u << bits) - 1;
 	if (trits) {
-		unsigned int i = 0;
-		while (i < character_count) {
-			unsigned int v0 = get(i);
-			unsigned int v1 = (i + 1 < character_count) ? get(i + 1) : 0u;
-			unsigned int v2 = (i + 2 < character_count) ? get(i + 2) : 0u;
-			unsigned int v3 = (i + 3 < character_count) ? get(i + 3) : 0u;
-			unsigned int v4 = (i + 4 < character_count) ? get(i + 4) : 0u;
-			unsigned int T = ct->integer_of_trits[(((((v4 >> bits) * 3 + (v3 >> bits)) * 3 + (v2 >> bits)) * 3 + (v1 >> bits)) * 3) + (v0 >> bits)];
-			put_bits(out, (v0 & mask) | (((T >> 0) & 3) << bits), bits + 2, bit_offset);
-			bit_offset += bits + 2;
-			if (++i >= character_count) break;
-			put_bits(out, (v1 & mask) | (((T >> 2) & 3) << bits), bits + 2, bit_offset);
-			bit_offset += bits + 2;
-			if (++i >= character_count) break;
-			put_bits(out, (v2 & mask) | (((T >> 4) & 1) << bits), bits + 1, bit_offset);
-			bit_offset += bits + 1;
-			if (++i >= character_count) break;
-			put_bits(out, (v3 & mask) | (((T >> 5) & 3) << bits), bits + 2, bit_offset);
-			bit_offset += bits + 2;
-			if (++i >= character_count) break;
-			put_bits(out, (v4 & mask) | (((T >> 7) & 1) << bits), bits + 1, bit_offset);
-			bit_offset += bits + 1;
-			++i;
+		// five values share one packed trit byte T; element j carries T bits [sh, sh + n): 2 2 1 2 1
+		ASTC_NOUNROLL
+		for (unsigned int i = 0; i < character_count; i += 5) {
+			unsigned int v[5];
+			unsigned int tr = 0;
+			for (int j = 4; j >= 0; j--) {
+				v[j] = ise_value(src, i + (unsigned int)j, character_count);
+				tr = tr * 3 + (v[j] >> bits);
+			}
+			unsigned int T = ASTC_LDG(&ct->integer_of_trits[tr]);
+			unsigned int sh = 0;
+			for (int j = 0; j < 5; j++) {
+				if (i + (unsigned int)j >= character_count) break;
+				unsigned int n = (j == 2 || j == 4) ? 1u : 2u;
+				put_bits(out, (v[j] & mask) | (((T >> sh) & ((1u << n) - 1)) << bits), bits + n, bit_offset);
+				bit_offset += bits + n;
+				sh += n;
+			}
 		}
 	} else if (quints) {
-		unsigned int i = 0;
-		while (i < character_count) {
-			unsigned int v0 = get(i);
-			unsigned int v1 = (i + 1 < character_count) ? get(i + 1) : 0u;
-			unsigned int v2 = (i + 2 < character_count) ? get(i + 2) : 0u;
-			unsigned int Q = ct->integer_of_quints[((v2 >> bits) * 5 + (v1 >> bits)) * 5 + (v0 >> bits)];
-			put_bits(out, (v0 & mask) | (((Q >> 0) & 7) << bits), bits + 3, bit_offset);
-			bit_offset += bits + 3;
-			if (++i >= character_count) break;
-			put_bits(out, (v1 & mask) | (((Q >> 3) & 3) << bits), bits + 2, bit_offset);
-			bit_offset += bits + 2;
-			if (++i >= character_count) break;
-			put_bits(out, (v2 & mask) | (((Q >> 5) & 3) << bits), bits + 2, bit_offset);
-			bit_offset += bits + 2;
-			++i;
+		// three values share one packed quint byte Q; element j carries Q bits: 3 2 2
+		ASTC_NOUNROLL
+		for (unsigned int i = 0; i < character_count; i += 3) {
+			unsigned int v[3];
+			unsigned int qv = 0;
+			for (int j = 2; j >= 0; j--) {
+				v[j] = ise_value(src, i + (unsigned int)j, character_count);
+				qv = qv * 5 + (v[j] >> bits);
+			}
+			unsigned int Q = ASTC_LDG(&ct->integer_of_quints[qv]);
+			unsigned int sh = 0;
+			for (int j = 0; j < 3; j++) {
+				if (i + (unsigned int)j >= character_count) break;
+				unsigned int n = j == 0 ? 3u : 2u;
+				put_bits(out, (v[j] & mask) | (((Q >> sh) & ((1u << n) - 1)) << bits), bits + n, bit_offset);
+				bit_offset += bits + n;
+				sh += n;
+			}
 		}
 	} else {
+		ASTC_NOUNROLL
 		for (unsigned int i = 0; i < character_count; i++) {
-			put_bits(out, get(i), bits, bit_offset);
+			put_bits(out, ise_value(src, i, character_count), bits, bit_offset);
 			bit_offset += bits;
 		}
 	}
 }
 
-// Writes the 16 physical bytes of the best block (header hdr, arrays in w.best_*) to out. Lane 0 only.
-ASTC_NOINLINE void symbolic_to_physical(const WCtx& w, const ScbHdr& scb, uint8_t* out) {
+// Writes the 16 physical bytes of the best block (header scb, arrays in the arena's best_* slots) to out. Lane 0 only.
+ASTC_NOINLINE void symbolic_to_physical(WCtx w, const ScbHdr& scb, uint8_t* out) {
 	Bits128 pcb;
 	pcb.lo = 0;
 	pcb.hi = 0;
@@ -1329,30 +1472,25 @@ ASTC_NOINLINE void symbolic_to_physical(const WCtx& w, const ScbHdr& scb, uint8_
 		pcb.hi = ((uint64_t)(scb.constant_color[0] & 0xFFFF)) | ((uint64_t)(scb.constant_color[1] & 0xFFFF) << 16) |
 		         ((uint64_t)(scb.constant_color[2] & 0xFFFF) << 32) | ((uint64_t)(scb.constant_color[3] & 0xFFFF) << 48);
 	} else {
-		const DevBsd& bsd = *w.bsd;
 		const DevConstTables* ct = ASTC_CT;
 		unsigned int partition_count = scb.partition_count;
-		const DevBlockMode bm = bsd.block_modes[bsd.block_mode_packed_index[scb.block_mode]];
-		int weight_count = bsd.dec_modes[bm.decimation_mode].weight_count;
-		int weight_quant_method = bm.quant_mode;
-		float weight_quant_levels = static_cast<float>(quant_level_count(weight_quant_method));
-		int is_dual_plane = bm.is_dual_plane;
-		const uint8_t* scramble = ct->wq_scramble_map[weight_quant_method];
+		const DevBlockMode* bm = BSD.block_modes + ASTC_LDG(&BSD.block_mode_packed_index[scb.block_mode]);
+		int weight_count = ASTC_LDG(&BSD.dec_modes[ASTC_LDG(&bm->decimation_mode)].weight_count);
+		int weight_quant_method = ASTC_LDG(&bm->quant_mode);
+		int is_dual_plane = ASTC_LDG(&bm->is_dual_plane);
 		int real_weight_count = is_dual_plane ? 2 * weight_count : weight_count;
 		int bits_for_weights = (int)ise_sequence_bitcount((unsigned int)real_weight_count, weight_quant_method);
-		const uint8_t* bw = w.best_weights;
-		// the i-th weight in transmission order: planes interleave for dual-plane modes (:127-150)
-		auto get_weight = [&](unsigned int i) -> unsigned int {
-			unsigned int src = is_dual_plane ? ((i >> 1) + ((i & 1) ? 32u : 0u)) : i;
-			float uqw = static_cast<float>(bw[src]);
-			float qw = (uqw / 64.0f) * (weight_quant_levels - 1.0f);
-			int qwi = static_cast<int>(qw + 0.5f);
-			return scramble[qwi];
-		};
+		IseSource ws;
+		ws.arr = best_weights_of(w).off;
+		ws.table = ct->wq_scramble_map[weight_quant_method];
+		ws.weight_quant_levels_m1 = static_cast<float>(quant_level_count(weight_quant_method)) - 1.0f;
+		ws.is_dual_plane = is_dual_plane;
+		ws.is_color = 0;
+		ws.n0 = ws.n1 = ws.n2 = 0;
 		Bits128 wb;
 		wb.lo = 0;
 		wb.hi = 0;
-		encode_ise(weight_quant_method, (unsigned int)real_weight_count, get_weight, wb, 0);
+		encode_ise(weight_quant_method, (unsigned int)real_weight_count, ws, wb, 0);
 		// the weight stream is stored bit-reversed from the top of the block (:153-156)
 		pcb.lo = brev64(wb.hi);
 		pcb.hi = brev64(wb.lo);
@@ -1400,23 +1538,23 @@ ASTC_NOINLINE void symbolic_to_physical(const WCtx& w, const ScbHdr& scb, uint8_
 			put_bits(pcb, (unsigned int)scb.plane2_component, 2, (unsigned int)(below_weights_pos - 2));
 		}
 		// colour values: partition after partition, 2 * (class + 1) values each (:268-285)
-		const uint8_t* pack_table = ct->color_uquant_to_scrambled_pquant[scb.quant_mode - QUANT_6];
-		unsigned int n0 = 2u * (scb.color_formats[0] >> 2) + 2u;
-		unsigned int n1 = partition_count > 1 ? 2u * (scb.color_formats[1] >> 2) + 2u : 0u;
-		unsigned int n2 = partition_count > 2 ? 2u * (scb.color_formats[2] >> 2) + 2u : 0u;
+		IseSource cs;
+		cs.arr = best_colors_of(w).off;
+		cs.table = ct->color_uquant_to_scrambled_pquant[scb.quant_mode - QUANT_6];
+		cs.weight_quant_levels_m1 = 0.0f;
+		cs.is_dual_plane = 0;
+		cs.is_color = 1;
+		cs.n0 = 2u * (scb.color_formats[0] >> 2) + 2u;
+		cs.n1 = partition_count > 1 ? 2u * (scb.color_formats[1] >> 2) + 2u : 0u;
+		cs.n2 = partition_count > 2 ? 2u * (scb.color_formats[2] >> 2) + 2u : 0u;
 		unsigned int n3 = partition_count > 3 ? 2u * (scb.color_formats[3] >> 2) + 2u : 0u;
-		const uint8_t* bc = w.best_colors;
-		auto get_color = [&](unsigned int i) -> unsigned int {
-			unsigned int p = 0;
-			if (i >= n0) { i -= n0; p = 1; if (i >= n1) { i -= n1; p = 2; if (i >= n2) { i -= n2; p = 3; } } }
-			return pack_table[bc[p * 8 + i]];
-		};
-		encode_ise(scb.quant_mode, n0 + n1 + n2 + n3, get_color, pcb, scb.partition_count == 1 ? 17 : 19 + 10);
+		encode_ise(scb.quant_mode, cs.n0 + cs.n1 + cs.n2 + n3, cs, pcb, scb.partition_count == 1 ? 17 : 19 + 10);
 	}
-	for (int i = 0; i < 8; i++) {
-		out[i] = (uint8_t)(pcb.lo >> (8 * i));
-		out[8 + i] = (uint8_t)(pcb.hi >> (8 * i));
-	}
+	uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
+	o32[0] = (uint32_t)pcb.lo;
+	o32[1] = (uint32_t)(pcb.lo >> 32);
+	o32[2] = (uint32_t)pcb.hi;
+	o32[3] = (uint32_t)(pcb.hi >> 32);
 }
 
 #include "astc_dev_partition.cuh"

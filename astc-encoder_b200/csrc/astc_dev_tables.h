@@ -84,10 +84,12 @@ struct DevBsd {
 	const uint16_t* partitioning_packed_index[3];
 	const uint64_t* coverage_bitmaps[5];        // [pc][packed * pc + p]
 	uint8_t kmeans_texels[ASTC_MAX_KMEANS_TEXELS];
-	// per-warp arena layout (byte offsets, 16-byte aligned) and size
+	// per-warp arena layout (byte offsets from the arena base, 16-byte aligned) and size. The fixed part
+	// (state, endpoint slots, symbolic block arrays, chain results, candidates, block texels, ideal weights) is
+	// laid out by astc_dev_core.cuh (A_* constants); the block-size dependent tail is planned by the host.
 	uint32_t arena_bytes;
-	uint32_t off_blk, off_ei, off_ep, off_dwi, off_lowhigh, off_mode_err, off_scb, off_scratch;
-	uint32_t scratch_bytes;
+	uint32_t off_dwi, off_lowhigh, off_mode_err, off_scratch;
+	uint32_t scratch_bytes;      // size of the union scratch at off_scratch
 };
 
 // The search configuration consumed on the device (subset of astcenc_config, astcenc.h:427-605).

@@ -191,32 +191,32 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 		}
 	}
 
-	// ---- per-warp arena plan ----
+	// ---- per-warp arena plan (fixed head: see the A_* constants in astc_dev_core.cuh) ----
 	const uint32_t Tp = (T + 3u) & ~3u;
-	uint32_t o = 0;
-	b.off_blk = o;        o = align16(o + 16 * Tp);
-	b.off_ei = o;         o = align16(o + 16 * Tp);
-	b.off_ep = o;         o = align16(o + 16 * 40);
+	uint32_t o = 1536;                                                          // A_BLK
+	o = align16(o + 16 * Tp);                                                   // block texels [4][Tp]
+	o = align16(o + 16 * Tp);                                                   // ideal weights / error scales, 2 planes
 	b.off_dwi = o;        o = align16(o + 4 * (dwi_total ? dwi_total : 4));
 	b.off_lowhigh = o;    o = align16(o + 128 * t.decimation_mode_count_selected);
 	b.off_mode_err = o;   o = align16(o + 4 * t.block_mode_count_1plane_2plane_selected);
-	b.off_scb = o;        o = align16(o + 224);
 	b.off_scratch = o;
 	// union scratch: the largest of the phase layouts (see astc_dev_search.cuh / astc_dev_partition.cuh)
 	uint32_t su = 32 * 68;                                                      // quantise+score rows
 	uint32_t ef = 4 * 21 * 4 * 4 + 21 * 13 * 4 + 4 * 21 * 4 + 21 * 13 * 4;      // EfTables
 	if (ef > su) su = ef;
-	uint32_t rf = 4 * (3 * Tp + 64 + 12 * max_wtc) + 2 * Tp;                    // RefineScratch
+	uint32_t rf = 4 * 3 * Tp + 256 + 20 * 33 * 4 + 2 * Tp;                      // RefineScratch incl. the chain tile
 	if (rf > su) su = rf;
 	uint32_t inf = 8 * Tp;                                                      // infilled[2][T]
 	if (inf > su) su = inf;
+	uint32_t ang = align16(dwi_total) + 288 + 25 * 96;                          // angular search: >= 96 step records per round
+	if (ang > su) su = ang;
 	for (unsigned int pc = 2; pc <= 4; pc++) {
 		unsigned int n = t.partitioning_count_selected[pc - 1];
 		unsigned int L = partition_index_limit[pc - 2] < n ? partition_index_limit[pc - 2] : n;
 		uint32_t ps = 4 * Tp + 8 * L + 8 + 32 + 2 * ((L + 1) & ~1u) + 128 + Tp + n + 16;
 		if (ps > su) su = ps;
 	}
-	b.scratch_bytes = 512 + 64 + align16(su);
+	b.scratch_bytes = align16(su);
 	b.arena_bytes = align16(b.off_scratch + b.scratch_bytes);
 }
 

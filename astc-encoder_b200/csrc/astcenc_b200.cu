@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstddef>
 #include <new>
 
 #include "astc_dev_search.cuh"
@@ -25,20 +26,37 @@
 // The kernel: persistent warps, one block per warp at a time, dynamic ticket scheduling (the GPU analogue
 // of the reference's ParallelManager::get_task_assignment ticket counter).
 // ---------------------------------------------------------------------------------------------
-#define ASTC_CTA_THREADS 256
+#define ASTC_CTA_THREADS_MAX 512
 
-__global__ void __launch_bounds__(ASTC_CTA_THREADS, 2)
+// Shared window: [0, ASTC_SMEM_HDR) launch constants, then one arena per warp.
+__global__ void __launch_bounds__(ASTC_CTA_THREADS_MAX, 1)
 astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img,
-                     unsigned int* __restrict__ ticket, uint8_t* __restrict__ global_arena, int arena_in_smem) {
-	extern __shared__ __align__(16) uint8_t smem[];
+                     unsigned int* __restrict__ ticket) {
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
-	const int warps_per_cta = blockDim.x >> 5;
-	uint8_t* arena = arena_in_smem ? smem + (size_t)warp * bsd.arena_bytes
-	                               : global_arena + ((size_t)blockIdx.x * warps_per_cta + warp) * bsd.arena_bytes;
+	{
+		// all threads help copy the launch constants from the parameter bank
+		uint32_t* dst = reinterpret_cast<uint32_t*>(astc_smem);
+		const uint32_t* s0 = reinterpret_cast<const uint32_t*>(&bsd);
+		const uint32_t* s1 = reinterpret_cast<const uint32_t*>(&cfg);
+		const uint32_t* s2 = reinterpret_cast<const uint32_t*>(&img);
+		for (unsigned int i = threadIdx.x; i < sizeof(DevBsd) / 4; i += blockDim.x) {
+			dst[offsetof(SmemHdr, bsd) / 4 + i] = s0[i];
+		}
+		for (unsigned int i = threadIdx.x; i < sizeof(DevConfig) / 4; i += blockDim.x) {
+			dst[offsetof(SmemHdr, cfg) / 4 + i] = s1[i];
+		}
+		for (unsigned int i = threadIdx.x; i < sizeof(DevImage) / 4; i += blockDim.x) {
+			dst[offsetof(SmemHdr, img) / 4 + i] = s2[i];
+		}
+	}
+	__syncthreads();
 	WCtx w;
-	init_wctx(w, lane, &bsd, &cfg, arena);
+	w.lane = lane;
+	w.base = ASTC_SMEM_HDR + (uint32_t)warp * bsd.arena_bytes;
+	w.T = bsd.texel_count;
 	const unsigned int total = img.blocks_x * img.block_rows;
+	const unsigned int blocks_x = img.blocks_x;
 #if defined(ASTC_DEBUG_SINGLE_LANE)
 	if (lane != 0) {
 		return;
@@ -55,10 +73,10 @@ astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__
 		if (b >= total) {
 			break;
 		}
-		unsigned int by = b / img.blocks_x;
-		unsigned int bx = b - by * img.blocks_x;
-		load_block(w, img, bx * bsd.dim_x, (by + img.block_row0) * bsd.dim_y);
-		compress_block(w, img.out + (size_t)b * 16);
+		unsigned int by = b / blocks_x;
+		unsigned int bx = b - by * blocks_x;
+		load_block(w, bx * BSD.dim_x, (by + IMG.block_row0) * BSD.dim_y);
+		compress_block(w, IMG.out + (size_t)b * 16);
 	}
 }
 
@@ -84,8 +102,6 @@ struct astcenc_context {
 	cudaStream_t stream;
 	cudaEvent_t ev0, ev1;
 	unsigned int* d_ticket;
-	uint8_t* d_arena;            // only when the arena does not fit shared memory
-	int arena_in_smem;
 	int warps_per_cta;
 	int grid;
 	size_t smem_bytes;
@@ -170,7 +186,6 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	ctx->stream = nullptr;
 	ctx->ev0 = ctx->ev1 = nullptr;
 	ctx->d_ticket = nullptr;
-	ctx->d_arena = nullptr;
 	ctx->d_image = nullptr;
 	ctx->d_out = nullptr;
 	ctx->d_image_bytes = ctx->d_out_bytes = 0;
@@ -219,47 +234,31 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	if (!(cfg.flags & ASTCENC_FLG_DECOMPRESS_ONLY)) {
 		cudaDeviceProp prop;
 		CUDA_TRY(cudaGetDeviceProperties(&prop, device), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+		// The per-warp arena lives in shared memory only: one CTA per SM with as many warps as fit (at most 16).
 		size_t smem_limit = prop.sharedMemPerBlockOptin;
 		size_t arena = ctx->tables->bsd.arena_bytes;
-		const char* force_global = getenv("ASTCENC_B200_ARENA_GLOBAL");
-		int warps = ASTC_CTA_THREADS / 32;
-		// two CTAs per SM when both arenas fit (the SM has ~228 KB, 1 KB reserved per CTA)
-		size_t per_sm = prop.sharedMemPerMultiprocessor;
-		if (!force_global && arena * warps + 1024 <= per_sm / 2 && arena * warps <= smem_limit) {
-			ctx->arena_in_smem = 1;
-			ctx->warps_per_cta = warps;
-			ctx->grid = prop.multiProcessorCount * 2;
-		} else if (!force_global && arena * warps <= smem_limit) {
-			ctx->arena_in_smem = 1;
-			ctx->warps_per_cta = warps;
-			ctx->grid = prop.multiProcessorCount;
-		} else if (!force_global && arena * 4 <= smem_limit) {
-			ctx->arena_in_smem = 1;
-			ctx->warps_per_cta = (int)(smem_limit / arena);
-			if (ctx->warps_per_cta > warps) ctx->warps_per_cta = warps;
-			ctx->grid = prop.multiProcessorCount;
-		} else {
-			ctx->arena_in_smem = 0;
-			ctx->warps_per_cta = warps;
-			ctx->grid = prop.multiProcessorCount * 2;
+		int warps = (int)((smem_limit - ASTC_SMEM_HDR) / arena);
+		if (warps > ASTC_CTA_THREADS_MAX / 32) warps = ASTC_CTA_THREADS_MAX / 32;
+		if (warps < 1) {
+			// block sizes / presets whose working set exceeds one SM's shared memory are not supported by this build
+			release_tables(ctx->tables);
+			delete ctx;
+			return ASTCENC_ERR_NOT_IMPLEMENTED;
 		}
+		ctx->warps_per_cta = warps;
+		ctx->grid = prop.multiProcessorCount;
 		// tuning overrides (experiments): warps per CTA and CTAs per SM
 		if (const char* e = getenv("ASTCENC_B200_WARPS")) {
 			int v = atoi(e);
-			if (v >= 1 && v <= warps && (!ctx->arena_in_smem || arena * v <= smem_limit)) ctx->warps_per_cta = v;
+			if (v >= 1 && v <= warps) ctx->warps_per_cta = v;
 		}
 		if (const char* e = getenv("ASTCENC_B200_CTAS_PER_SM")) {
 			int v = atoi(e);
 			if (v >= 1 && v <= 8) ctx->grid = prop.multiProcessorCount * v;
 		}
-		ctx->smem_bytes = ctx->arena_in_smem ? arena * ctx->warps_per_cta : 0;
-		if (ctx->smem_bytes > 48 * 1024) {
-			CUDA_TRY(cudaFuncSetAttribute(astc_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
-			         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
-		}
-		if (!ctx->arena_in_smem) {
-			CUDA_TRY(cudaMalloc(&ctx->d_arena, arena * ctx->warps_per_cta * ctx->grid), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
-		}
+		ctx->smem_bytes = ASTC_SMEM_HDR + arena * ctx->warps_per_cta;
+		CUDA_TRY(cudaFuncSetAttribute(astc_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
+		         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
 		CUDA_TRY(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
 	}
 	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
@@ -276,7 +275,6 @@ void astcenc_context_free(astcenc_context* ctx) {
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	cudaFree(ctx->d_ticket);
-	cudaFree(ctx->d_arena);
 	cudaFree(ctx->d_image);
 	cudaFree(ctx->d_out);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -332,7 +330,7 @@ static astcenc_error launch_slab(astcenc_context* ctx, const void* d_pixels, int
 	if ((size_t)grid > needed) {
 		grid = (int)(needed ? needed : 1);
 	}
-	astc_compress_kernel<<<grid, ctx->warps_per_cta * 32, ctx->smem_bytes, stream>>>(bsd, ctx->dcfg, img, ctx->d_ticket, ctx->d_arena, ctx->arena_in_smem);
+	astc_compress_kernel<<<grid, ctx->warps_per_cta * 32, ctx->smem_bytes, stream>>>(bsd, ctx->dcfg, img, ctx->d_ticket);
 	CUDA_TRY(cudaGetLastError(), return ASTCENC_ERR_BAD_CONTEXT);
 	ctx->launches++;
 	return ASTCENC_SUCCESS;

@@ -24,7 +24,9 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	g_astc_ct = &pk.consts;
 	DevConfig dcfg;
 	astc_host::make_device_config(cfg, dcfg);
-	std::vector<uint8_t> arena(pk.bsd.arena_bytes + 64, 0xCD);
+	// the simulated shared window: launch constants, then one arena (16-byte aligned like the device's)
+	std::vector<uint8_t> window(ASTC_SMEM_HDR + pk.bsd.arena_bytes + 64, 0xCD);
+	astc_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(window.data()) + 15) & ~(uintptr_t)15);
 	DevImage img;
 	img.data = data;
 	img.data_type = data_type;
@@ -35,11 +37,17 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	img.block_rows = (dim_y + by - 1) / by;
 	for (int i = 0; i < 4; i++) img.swz[i] = swz ? swz[i] : i;
 	img.out = out;
+	SmemHdr* hdr = reinterpret_cast<SmemHdr*>(astc_smem);
+	hdr->bsd = pk.bsd;
+	hdr->cfg = dcfg;
+	hdr->img = img;
 	WCtx w;
-	init_wctx(w, 0, &pk.bsd, &dcfg, arena.data());
+	w.lane = 0;
+	w.base = ASTC_SMEM_HDR;
+	w.T = pk.bsd.texel_count;
 	for (unsigned int y = 0; y < img.block_rows; y++) {
 		for (unsigned int x = 0; x < img.blocks_x; x++) {
-			load_block(w, img, x * bx, y * by);
+			load_block(w, x * bx, y * by);
 			compress_block(w, out + ((size_t)y * img.blocks_x + x) * 16);
 		}
 	}
