@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <string.h>
+#include <stddef.h>
 #include "astc_dev_tables.h"
 
 #if defined(ASTC_HOSTSIM)
@@ -177,6 +178,7 @@ struct BlkInfo {
 	uint8_t grayscale, decode_unorm8, rgb_lns0, alpha_lns0;
 	uint8_t ei_const_wes[2];
 	uint8_t pad[10];
+	uint16_t partition_list[8];   // partition candidates of the current partition count (lockstep driver)
 };
 
 struct ScbHdr {            // scalar part of symbolic_compressed_block (arrays live in the arena)
@@ -199,14 +201,15 @@ struct WCtx {
 // Fixed part of the arena (byte offsets from base); the block-size dependent part follows at A_BLK
 // (layout planned by the host: astc_host_pack.h plan_arena, offsets in DevBsd).
 enum {
-	A_STATE = 0,           // BlkInfo (96)
-	A_EP = 96,             // f4[EP_COUNT] endpoint slots (640)
-	A_SCB = 736,           // best_weights[64] best_colors[32] work_weights[64] work_colors[32] mod_colors[32] (224)
-	A_TMPF = 960,          // float[128] chain results / partial sums
-	A_CAND = 1472,         // Candidate[8]
-	A_BLK = 1536           // float[4][Tp] block texels, then ei, dwi, lowhigh, mode_err, su
+	A_STATE = 0,           // BlkInfo (112)
+	A_EP = 112,            // f4[EP_COUNT] endpoint slots (640)
+	A_SCB = 752,           // best_weights[64] best_colors[32] work_weights[64] work_colors[32] mod_colors[32] (224)
+	A_TMPF = 976,          // float[128] chain results / partial sums
+	A_CAND = 1488,         // Candidate[8]
+	A_BLK = ASTC_ARENA_FIXED   // float[4][Tp] block texels, then ei, dwi, lowhigh, mode_err, su
 };
-static_assert(sizeof(BlkInfo) == 96, "BlkInfo layout");
+static_assert(sizeof(BlkInfo) == 112, "BlkInfo layout");
+static_assert(A_CAND + 64 == A_BLK, "arena head layout");
 
 // endpoint slots (f4 units)
 enum { EP_EI1_0 = 0, EP_EI1_1 = 4, EP_EI2_0 = 8, EP_EI2_1 = 12, EP_WORK_0 = 16, EP_WORK_1 = 20, EP_RGBS = 24, EP_RGBO = 28, EP_BASE_0 = 32, EP_BASE_1 = 36, EP_COUNT = 40 };

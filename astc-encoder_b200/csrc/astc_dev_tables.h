@@ -15,6 +15,7 @@
 #define ASTC_MAX_BLOCK_MODES 2048
 #define ASTC_MAX_DECIMATION_MODES 87
 #define ASTC_MAX_KMEANS_TEXELS 64
+#define ASTC_ARENA_FIXED 1552      /* bytes of the per-warp arena before the block-size dependent part (astc_dev_core.cuh A_*) */
 #define ASTC_ANGULAR_STEPS 12     /* TUNE_MAX_ANGULAR_QUANT = 7 -> at most 12 steps are ever evaluated */
 
 enum { QUANT_2 = 0, QUANT_3, QUANT_4, QUANT_5, QUANT_6, QUANT_8, QUANT_10, QUANT_12, QUANT_16, QUANT_20, QUANT_24,

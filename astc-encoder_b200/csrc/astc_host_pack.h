@@ -193,7 +193,7 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 
 	// ---- per-warp arena plan (fixed head: see the A_* constants in astc_dev_core.cuh) ----
 	const uint32_t Tp = (T + 3u) & ~3u;
-	uint32_t o = 1536;                                                          // A_BLK
+	uint32_t o = ASTC_ARENA_FIXED;                                              // A_BLK
 	o = align16(o + 16 * Tp);                                                   // block texels [4][Tp]
 	o = align16(o + 16 * Tp);                                                   // ideal weights / error scales, 2 planes
 	b.off_dwi = o;        o = align16(o + 4 * (dwi_total ? dwi_total : 4));

@@ -31,7 +31,7 @@
 // Shared window: [0, ASTC_SMEM_HDR) launch constants, then one arena per warp.
 __global__ void __launch_bounds__(ASTC_CTA_THREADS_MAX, 1)
 astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img,
-                     unsigned int* __restrict__ ticket) {
+                     unsigned int* __restrict__ ticket, int coherence_probe, int lockstep) {
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	{
@@ -62,14 +62,37 @@ astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__
 		return;
 	}
 #endif
+	if (lockstep) {
+		BlockFeed feed;
+		feed.ticket = ticket;
+		feed.total = total;
+		feed.blocks_x = blocks_x;
+		compress_blocks_lockstep(w, feed);
+		return;
+	}
 	while (true) {
 		unsigned int b = 0;
-		if (lane == 0) {
-			b = atomicAdd(ticket, 1u);
-		}
 #if !defined(ASTC_DEBUG_SINGLE_LANE)
-		b = __shfl_sync(0xffffffffu, b, 0);
+		if (coherence_probe) {
+			// experiment only: every warp of the CTA compresses the SAME block (measures what instruction-cache
+			// sharing between phase-aligned warps is worth); results are identical, so the duplicate stores are benign
+			unsigned int* cta_ticket = reinterpret_cast<unsigned int*>(astc_smem + ASTC_SMEM_HDR - 4);
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				*cta_ticket = atomicAdd(ticket, 1u);
+			}
+			__syncthreads();
+			b = *cta_ticket;
+		} else
 #endif
+		{
+			if (lane == 0) {
+				b = atomicAdd(ticket, 1u);
+			}
+#if !defined(ASTC_DEBUG_SINGLE_LANE)
+			b = __shfl_sync(0xffffffffu, b, 0);
+#endif
+		}
 		if (b >= total) {
 			break;
 		}
@@ -105,6 +128,7 @@ struct astcenc_context {
 	int warps_per_cta;
 	int grid;
 	size_t smem_bytes;
+	int lockstep;                // phase-aligned CTA driver (default) or the independent per-warp driver
 	// staging buffers for the host-pointer API, grown on demand
 	uint8_t* d_image;
 	size_t d_image_bytes;
@@ -256,6 +280,10 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			int v = atoi(e);
 			if (v >= 1 && v <= 8) ctx->grid = prop.multiProcessorCount * v;
 		}
+		ctx->lockstep = 1;
+		if (const char* e = getenv("ASTCENC_B200_LOCKSTEP")) {
+			ctx->lockstep = atoi(e) != 0;
+		}
 		ctx->smem_bytes = ASTC_SMEM_HDR + arena * ctx->warps_per_cta;
 		CUDA_TRY(cudaFuncSetAttribute(astc_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
 		         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
@@ -330,7 +358,7 @@ static astcenc_error launch_slab(astcenc_context* ctx, const void* d_pixels, int
 	if ((size_t)grid > needed) {
 		grid = (int)(needed ? needed : 1);
 	}
-	astc_compress_kernel<<<grid, ctx->warps_per_cta * 32, ctx->smem_bytes, stream>>>(bsd, ctx->dcfg, img, ctx->d_ticket);
+	astc_compress_kernel<<<grid, ctx->warps_per_cta * 32, ctx->smem_bytes, stream>>>(bsd, ctx->dcfg, img, ctx->d_ticket, getenv("ASTCENC_B200_COHERENCE_PROBE") ? 1 : 0, ctx->lockstep);
 	CUDA_TRY(cudaGetLastError(), return ASTCENC_ERR_BAD_CONTEXT);
 	ctx->launches++;
 	return ASTCENC_SUCCESS;

@@ -8,6 +8,7 @@
 #include "../../astc-encoder_b200/csrc/astc_host_config.h"
 #include <vector>
 #include <cstdio>
+#include <cstdlib>
 
 extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int by, float quality, unsigned int flags,
                                       const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, const int* swz, uint8_t* out) {
@@ -45,11 +46,20 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	w.lane = 0;
 	w.base = ASTC_SMEM_HDR;
 	w.T = pk.bsd.texel_count;
-	for (unsigned int y = 0; y < img.block_rows; y++) {
-		for (unsigned int x = 0; x < img.blocks_x; x++) {
-			load_block(w, x * bx, y * by);
-			compress_block(w, out + ((size_t)y * img.blocks_x + x) * 16);
+	if (getenv("HOSTSIM_PER_WARP_DRIVER")) {
+		for (unsigned int y = 0; y < img.block_rows; y++) {
+			for (unsigned int x = 0; x < img.blocks_x; x++) {
+				load_block(w, x * bx, y * by);
+				compress_block(w, out + ((size_t)y * img.blocks_x + x) * 16);
+			}
 		}
+	} else {
+		unsigned int counter = 0;
+		BlockFeed feed;
+		feed.ticket = &counter;
+		feed.total = img.blocks_x * img.block_rows;
+		feed.blocks_x = img.blocks_x;
+		compress_blocks_lockstep(w, feed);
 	}
 	astc_host::free_block_size_tables(t);
 	return 0;
