@@ -198,21 +198,27 @@ struct WCtx {
 	int T;                 // texels per block
 };
 
-// Fixed part of the arena (byte offsets from base); the block-size dependent part follows at A_BLK
-// (layout planned by the host: astc_host_pack.h plan_arena, offsets in DevBsd).
+// Head of the arena (byte offsets from base). [0, A_PERSIST) plus the block texels at A_BLK are a block's record:
+// what has to survive from one stage kernel to the next. The block-size dependent tail follows at A_BLK
+// (layout planned by the host: astc_host_pack.h, offsets in DevBsd): block texels, union scratch, and - for the
+// trial-setup kernel only - ideal weights, decimated weights, angular ranges, per-mode errors.
 enum {
 	A_STATE = 0,           // BlkInfo (112)
-	A_EP = 112,            // f4[EP_COUNT] endpoint slots (640)
-	A_SCB = 752,           // best_weights[64] best_colors[32] work_weights[64] work_colors[32] mod_colors[32] (224)
-	A_TMPF = 976,          // float[128] chain results / partial sums
-	A_CAND = 1488,         // Candidate[8]
-	A_BLK = ASTC_ARENA_FIXED   // float[4][Tp] block texels, then ei, dwi, lowhigh, mode_err, su
+	A_SEARCH = 112,        // BlockSearch (128): where the block's decision tree stands
+	A_TRIAL = 240,         // Trial (64): the trial in flight
+	A_SCB = 304,           // best_weights[64] best_colors[32] work_weights[64] work_colors[32] mod_colors[32] (224)
+	A_CAND = 528,          // Candidate[8]
+	A_CANDW = 592,         // quantised weights of the candidates, 8 x 64
+	A_EP = 1104,           // f4[EP_COUNT] endpoint slots (640), the trial's base endpoints first
+	A_PERSIST = ASTC_ARENA_PERSIST_HEAD,   // = A_EP + 128
+	A_TMPF = 1744,         // float[128] chain results / partial sums
+	A_BLK = ASTC_ARENA_FIXED   // float[4][Tp] block texels
 };
 static_assert(sizeof(BlkInfo) == 112, "BlkInfo layout");
-static_assert(A_CAND + 64 == A_BLK, "arena head layout");
+static_assert(A_TMPF + 512 == A_BLK && A_EP + 128 == A_PERSIST && A_EP + 640 == A_TMPF, "arena head layout");
 
 // endpoint slots (f4 units)
-enum { EP_EI1_0 = 0, EP_EI1_1 = 4, EP_EI2_0 = 8, EP_EI2_1 = 12, EP_WORK_0 = 16, EP_WORK_1 = 20, EP_RGBS = 24, EP_RGBO = 28, EP_BASE_0 = 32, EP_BASE_1 = 36, EP_COUNT = 40 };
+enum { EP_BASE_0 = 0, EP_BASE_1 = 4, EP_EI1_0 = 8, EP_EI1_1 = 12, EP_EI2_0 = 16, EP_EI2_1 = 20, EP_WORK_0 = 24, EP_WORK_1 = 28, EP_RGBS = 32, EP_RGBO = 36, EP_COUNT = 40 };
 
 ASTC_FN uint32_t tp4(const WCtx& w) { return (uint32_t)((w.T + 3) & ~3) * 4u; }
 ASTC_FN BlkInfo& bi_of(const WCtx& w) { return *reinterpret_cast<BlkInfo*>(astc_smem + w.base + A_STATE); }
@@ -224,8 +230,8 @@ ASTC_FN SPtr<uint8_t> work_colors_of(const WCtx& w) { return sptr<uint8_t>(w.bas
 ASTC_FN SPtr<uint8_t> mod_colors_of(const WCtx& w) { return sptr<uint8_t>(w.base + A_SCB + 192); }
 ASTC_FN SPtr<float> tmpf_of(const WCtx& w) { return sptr<float>(w.base + A_TMPF); }
 ASTC_FN SPtr<float> blk_of(const WCtx& w, int c) { return sptr<float>(w.base + A_BLK + (uint32_t)c * tp4(w)); }
-ASTC_FN SPtr<float> eiw_of(const WCtx& w, int pl) { return sptr<float>(w.base + A_BLK + (uint32_t)(4 + 2 * pl) * tp4(w)); }
-ASTC_FN SPtr<float> eis_of(const WCtx& w, int pl) { return sptr<float>(w.base + A_BLK + (uint32_t)(5 + 2 * pl) * tp4(w)); }
+ASTC_FN SPtr<float> eiw_of(const WCtx& w, int pl) { return sptr<float>(w.base + BSD.off_ei + (uint32_t)(2 * pl) * tp4(w)); }
+ASTC_FN SPtr<float> eis_of(const WCtx& w, int pl) { return sptr<float>(w.base + BSD.off_ei + (uint32_t)(2 * pl + 1) * tp4(w)); }
 ASTC_FN SPtr<float> dwi_of(const WCtx& w) { return sptr<float>(w.base + BSD.off_dwi); }
 ASTC_FN SPtr<float> lowhigh_of(const WCtx& w) { return sptr<float>(w.base + BSD.off_lowhigh); }
 ASTC_FN SPtr<float> mode_err_of(const WCtx& w) { return sptr<float>(w.base + BSD.off_mode_err); }

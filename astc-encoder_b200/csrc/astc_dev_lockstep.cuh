@@ -108,9 +108,13 @@ ASTC_FN void block_search_begin(const WCtx& w, BlockSearch& s) {
 	s.skip_two_plane = false;
 }
 
-// Pick the next trial of the block (compress_block :1236-1443 unrolled into a state machine). Returns false when the
-// search is over. Runs the block statistics / partition search when a phase needs them.
-ASTC_COOP bool block_search_next(WCtx w, BlockSearch& s, Trial& t) {
+// Pick the next trial of the block (compress_block :1236-1443 unrolled into a state machine).
+//   NEXT_TRIAL    : t describes the trial to run
+//   NEXT_PREPARE  : the phase just entered needs the block statistics (2 planes) or the partition search first
+//   NEXT_FINISHED : the search is over
+enum { NEXT_TRIAL = 0, NEXT_PREPARE = 1, NEXT_FINISHED = 2 };
+
+ASTC_FN int block_search_advance(const WCtx& w, BlockSearch& s, Trial& t) {
 	const BlkInfo& bi = bi_of(w);
 	while (true) {
 		if (s.phase == 0) {
@@ -124,8 +128,8 @@ ASTC_COOP bool block_search_next(WCtx w, BlockSearch& s, Trial& t) {
 				t.plane2_component = -1;
 				t.tune_errorval_threshold = s.error_threshold * mult * s.errorval_overshoot;
 				t.done_threshold = s.error_threshold * mult;
-				t.max_weight_quant = mini((int)QUANT_32, (int)QUANT_32);
-				return true;
+				t.max_weight_quant = (int)QUANT_32;
+				return NEXT_TRIAL;
 			}
 			s.phase = 1;
 			s.idx = 3;
@@ -134,9 +138,7 @@ ASTC_COOP bool block_search_next(WCtx w, BlockSearch& s, Trial& t) {
 		}
 		if (s.phase == 1) {
 			if (!s.phase_entered) {
-				float lowest_correl = prepare_block_statistics(w);
-				s.skip_two_plane = lowest_correl > CFG.tune_2plane_early_out_limit_correlation;
-				s.phase_entered = true;
+				return NEXT_PREPARE;
 			}
 			bool found = false;
 			while (s.idx >= 0) {
@@ -158,7 +160,7 @@ ASTC_COOP bool block_search_next(WCtx w, BlockSearch& s, Trial& t) {
 				t.tune_errorval_threshold = s.error_threshold * s.errorval_overshoot;
 				t.done_threshold = s.error_threshold;
 				t.max_weight_quant = mini((int)QUANT_32, s.quant_limit);
-				return true;
+				return NEXT_TRIAL;
 			}
 			s.phase = 2;
 			s.pc = 2;
@@ -172,23 +174,7 @@ ASTC_COOP bool block_search_next(WCtx w, BlockSearch& s, Trial& t) {
 				continue;
 			}
 			if (!s.phase_entered) {
-				unsigned int partition_indices[8];
-				unsigned int requested_indices = CFG.tune_partition_index_limit[s.pc - 2];
-				unsigned int requested_trials = CFG.tune_partitioning_candidate_limit[s.pc - 2];
-				requested_trials = requested_trials < requested_indices ? requested_trials : requested_indices;
-				s.actual_trials = find_best_partition_candidates(w, (unsigned int)s.pc, requested_indices, partition_indices, requested_trials);
-				SPtr<uint16_t> pl = partition_list_of(w);
-				if (w.lane == 0) {
-					for (unsigned int k = 0; k < 8; k++) {
-						if (k < s.actual_trials) {
-							pl[(int)k] = (uint16_t)partition_indices[k];
-						}
-					}
-				}
-				wsync();
-				s.best_error_cur = ERROR_CALC_DEFAULT;
-				s.idx = 0;
-				s.phase_entered = true;
+				return NEXT_PREPARE;
 			}
 			if ((unsigned int)s.idx < s.actual_trials) {
 				t.dual = 0;
@@ -200,7 +186,7 @@ ASTC_COOP bool block_search_next(WCtx w, BlockSearch& s, Trial& t) {
 				t.tune_errorval_threshold = s.error_threshold * s.errorval_overshoot;
 				t.done_threshold = s.error_threshold;
 				t.max_weight_quant = mini((int)QUANT_32, s.quant_limit);
-				return true;
+				return NEXT_TRIAL;
 			}
 			// all trials of this partition count done (:1434-1441)
 			float exit_threshold = s.pc == 2 ? CFG.tune_2partition_early_out_limit_factor : s.pc == 3 ? CFG.tune_3partition_early_out_limit_factor : 0.0f;
@@ -213,7 +199,46 @@ ASTC_COOP bool block_search_next(WCtx w, BlockSearch& s, Trial& t) {
 			s.phase_entered = false;
 			continue;
 		}
-		return false;
+		return NEXT_FINISHED;
+	}
+}
+
+// The work a phase needs before its first trial: block statistics (2 planes, :1283-1289) or the partition search
+// of the current partition count (:1341-1360).
+ASTC_COOP void block_search_prepare(WCtx w, BlockSearch& s) {
+	if (s.phase == 1) {
+		float lowest_correl = prepare_block_statistics(w);
+		s.skip_two_plane = lowest_correl > CFG.tune_2plane_early_out_limit_correlation;
+		s.phase_entered = true;
+		return;
+	}
+	unsigned int partition_indices[8];
+	unsigned int requested_indices = CFG.tune_partition_index_limit[s.pc - 2];
+	unsigned int requested_trials = CFG.tune_partitioning_candidate_limit[s.pc - 2];
+	requested_trials = requested_trials < requested_indices ? requested_trials : requested_indices;
+	s.actual_trials = find_best_partition_candidates(w, (unsigned int)s.pc, requested_indices, partition_indices, requested_trials);
+	SPtr<uint16_t> pl = partition_list_of(w);
+	if (w.lane == 0) {
+		for (unsigned int k = 0; k < 8; k++) {
+			if (k < s.actual_trials) {
+				pl[(int)k] = (uint16_t)partition_indices[k];
+			}
+		}
+	}
+	wsync();
+	s.best_error_cur = ERROR_CALC_DEFAULT;
+	s.idx = 0;
+	s.phase_entered = true;
+}
+
+ASTC_COOP bool block_search_next(WCtx w, BlockSearch& s, Trial& t) {
+	while (true) {
+		int k = block_search_advance(w, s, t);
+		if (k == NEXT_PREPARE) {
+			block_search_prepare(w, s);
+			continue;
+		}
+		return k == NEXT_TRIAL;
 	}
 }
 
@@ -391,6 +416,7 @@ struct Refine {
 	int dmode, qmode, quant_level, quant_level_mod;
 	uint16_t mode_index;
 	bool adjustments;
+	bool from_candw;                // candidate weights were quantised by the setup kernel (A_CANDW) instead of being derived here
 };
 
 // start candidate r.i (quantise its weights, reset the work endpoints): the part of the candidate loop before `for l`
@@ -403,7 +429,17 @@ ASTC_COOP void refine_begin_candidate(WCtx w, const Trial& t, Refine& r) {
 	r.quant_level = cd.quant_level;
 	r.quant_level_mod = cd.quant_level_mod;
 	r.cd_formats = (uint32_t)cd.formats[0] | ((uint32_t)cd.formats[1] << 8) | ((uint32_t)cd.formats[2] << 16) | ((uint32_t)cd.formats[3] << 24);
-	quantize_candidate_weights(w, r.dmode, r.qmode, t.dual ? 2 : 1, t.cutoff1, t.cutoff2);
+	if (r.from_candw) {
+		SPtr<uint32_t> ww = sptr<uint32_t>(work_weights_of(w).off);
+		SPtr<uint32_t> cw = sptr<uint32_t>(w.base + A_CANDW + r.i * 64u);
+		ASTC_NOUNROLL
+		for (int k = w.lane; k < 16; k += ASTC_WARP) {
+			ww[k] = cw[k];
+		}
+		wsync();
+	} else {
+		quantize_candidate_weights(w, r.dmode, r.qmode, t.dual ? 2 : 1, t.cutoff1, t.cutoff2);
+	}
 	SPtr<f4> ep = ep_of(w);
 	ASTC_NOUNROLL
 	for (int k = w.lane; k < 4; k += ASTC_WARP) {
@@ -574,6 +610,11 @@ ASTC_FN void refine_second_score(WCtx w, const Trial& t, Refine& r, BlockSearch&
 	}
 }
 
+#if defined(ASTC_HOSTSIM) && defined(ASTC_TRIAL_STATS)
+#include <stdio.h>
+static unsigned int g_trial_steps;
+#endif
+
 // The CTA main loop. Every warp of the CTA must call this (barriers inside).
 ASTC_COOP void compress_blocks_lockstep(WCtx w, BlockFeed feed) {
 	BlockSearch s;
@@ -638,9 +679,16 @@ ASTC_COOP void compress_blocks_lockstep(WCtx w, BlockFeed feed) {
 		r.best_errorval_in_mode = ERROR_CALC_DEFAULT;
 		r.best_errorval_in_scb = s.scb.errorval;
 		r.adjustments = false;
+		r.from_candw = false;
+#if defined(ASTC_HOSTSIM) && defined(ASTC_TRIAL_STATS)
+		g_trial_steps = 0;
+#endif
 		while (cta_any(r.running)) {
 			if (r.running) {
 				r.in_step = true;
+#if defined(ASTC_HOSTSIM) && defined(ASTC_TRIAL_STATS)
+				g_trial_steps++;
+#endif
 				refine_recompute(w, t, r);
 			}
 			cta_sync();
@@ -655,6 +703,11 @@ ASTC_COOP void compress_blocks_lockstep(WCtx w, BlockFeed feed) {
 			cta_sync();
 			if (r.running && r.in_step) refine_second_score(w, t, r, s);
 		}
+#if defined(ASTC_HOSTSIM) && defined(ASTC_TRIAL_STATS)
+		if (active) {
+			fprintf(stderr, "TRIAL blk=%u dual=%d pc=%u cands=%u steps=%u\n", s.out_index, t.dual, t.partition_count, t.candidate_count, g_trial_steps);
+		}
+#endif
 		if (active) {
 			block_search_after_trial(w, s, t, r.best_errorval_in_mode);
 		}

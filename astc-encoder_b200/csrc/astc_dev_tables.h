@@ -15,7 +15,10 @@
 #define ASTC_MAX_BLOCK_MODES 2048
 #define ASTC_MAX_DECIMATION_MODES 87
 #define ASTC_MAX_KMEANS_TEXELS 64
-#define ASTC_ARENA_FIXED 1552      /* bytes of the per-warp arena before the block-size dependent part (astc_dev_core.cuh A_*) */
+/* Per-warp arena head (astc_dev_core.cuh A_*): bytes before the block texels, and the part of it that, together with the
+   block texels, forms a block's persistent record between stage kernels */
+#define ASTC_ARENA_FIXED 2256
+#define ASTC_ARENA_PERSIST_HEAD 1232
 #define ASTC_ANGULAR_STEPS 12     /* TUNE_MAX_ANGULAR_QUANT = 7 -> at most 12 steps are ever evaluated */
 
 enum { QUANT_2 = 0, QUANT_3, QUANT_4, QUANT_5, QUANT_6, QUANT_8, QUANT_10, QUANT_12, QUANT_16, QUANT_20, QUANT_24,
@@ -88,9 +91,11 @@ struct DevBsd {
 	// per-warp arena layout (byte offsets from the arena base, 16-byte aligned) and size. The fixed part
 	// (state, endpoint slots, symbolic block arrays, chain results, candidates, block texels, ideal weights) is
 	// laid out by astc_dev_core.cuh (A_* constants); the block-size dependent tail is planned by the host.
-	uint32_t arena_bytes;
-	uint32_t off_dwi, off_lowhigh, off_mode_err, off_scratch;
+	uint32_t arena_bytes;        // everything (the trial-setup kernel)
+	uint32_t arena_bytes_small;  // up to the end of the union scratch (refinement / partition-search kernels)
+	uint32_t off_scratch, off_ei, off_dwi, off_lowhigh, off_mode_err;
 	uint32_t scratch_bytes;      // size of the union scratch at off_scratch
+	uint32_t record_bytes;       // ASTC_ARENA_PERSIST_HEAD + 16 * Tp, rounded to 16
 };
 
 // The search configuration consumed on the device (subset of astcenc_config, astcenc.h:427-605).

@@ -1,0 +1,330 @@
+// B200-native ASTC block compressor: the stage-kernel ("wave") pipeline.
+//
+// The per-block search is a chain of trials; every trial is [setup: ideal endpoints/weights, decimated weights,
+// angular ranges, per-mode errors, endpoint formats] followed by [refinement steps]. Running the whole chain in one
+// kernel leaves the SMs starved for instructions (each warp is somewhere else in ~150 KB of code); aligning the
+// warps of a CTA on a common stage list fixes the fetch problem but makes them wait for each other, because blocks
+// need different numbers of refinement steps. So the chain is cut into four kernels that exchange small per-block
+// records through HBM, and every kernel only ever runs ONE kind of work:
+//
+//   setup    (S) : one trial setup per popped item, warps of a CTA phase-aligned stage by stage
+//   refine   (R) : refinement steps; a warp pops the next item as soon as its trial ends - every step is the same
+//                  code, so warps never wait for a slower block's extra steps; then the block's decision tree
+//                  (compress_block) picks what comes next and routes the block to the matching queue
+//   prepare  (P) : block statistics / partition search for blocks entering the 2-plane / n-partition phases
+//   emit     (E) : symbolic -> physical packing, one block per LANE
+//
+// One "wave" = S, R, P over the blocks still searching; the host enqueues as many waves as a block can have trials
+// (kernels whose queue is empty return at once) and one E at the end. A block's record is the persistent head of
+// its arena plus its texels (DevBsd::record_bytes, ~1.8 KB at 6x6): 466 k blocks x ~7 KB moved per trial is
+// noise next to 6.5 TB/s of HBM. Results are bit-identical to the single-kernel drivers.
+#pragma once
+
+#define ASTC_MAX_WAVES 64
+enum { Q_SETUP = 0, Q_REFINE = 1, Q_PREPARE = 2, Q_EMIT = 3 };
+
+struct WaveArgs {
+	uint8_t* records;            // [blocks] x record_bytes
+	uint32_t* queue[4];          // item lists (block indices), capacity = blocks each
+	uint32_t* count;             // [4][ASTC_MAX_WAVES] items pushed (Q_EMIT uses wave slot 0)
+	uint32_t* head;              // [4][ASTC_MAX_WAVES] items popped
+	unsigned int total;          // blocks in this launch
+	unsigned int blocks_x;
+	int wave;
+};
+
+#if defined(ASTC_HOSTSIM)
+ASTC_FN uint32_t q_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+ASTC_FN uint32_t q_load(const uint32_t* p) { return *p; }
+#else
+ASTC_FN uint32_t q_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+ASTC_FN uint32_t q_load(const uint32_t* p) { return __ldcg(p); }
+#endif
+
+ASTC_FN uint32_t wbroadcast0(const WCtx& w, uint32_t v) {
+#if defined(ASTC_HOSTSIM) || defined(ASTC_DEBUG_SINGLE_LANE)
+	(void)w;
+	return v;
+#else
+	(void)w;
+	return __shfl_sync(0xffffffffu, v, 0);
+#endif
+}
+
+ASTC_FN bool q_pop(const WCtx& w, const WaveArgs& a, int kind, int wave, unsigned int& b) {
+	uint32_t i = 0;
+	if (w.lane == 0) {
+		i = q_atomic_add(a.head + kind * ASTC_MAX_WAVES + wave, 1u);
+	}
+	i = wbroadcast0(w, i);
+	if (i >= q_load(a.count + kind * ASTC_MAX_WAVES + wave)) {
+		return false;
+	}
+	b = q_load(a.queue[kind] + i);
+	return true;
+}
+
+ASTC_FN void q_push(const WCtx& w, const WaveArgs& a, int kind, int wave, unsigned int b) {
+	if (w.lane == 0) {
+		uint32_t i = q_atomic_add(a.count + kind * ASTC_MAX_WAVES + wave, 1u);
+		a.queue[kind][i] = b;
+	}
+}
+
+// record <-> arena: [0, A_PERSIST) and the block texels, 16 bytes per lane and trip
+struct alignas(16) U128 {
+	uint32_t x, y, z, w;
+};
+ASTC_FN void record_copy(const WCtx& w, const WaveArgs& a, unsigned int b, bool save) {
+	U128* g = reinterpret_cast<U128*>(a.records + (size_t)b * BSD.record_bytes);
+	const int n1 = A_PERSIST / 16;
+	int n2 = (w.T + 3) & ~3;              // 4 channels x Tp floats = Tp x 16 bytes
+	SPtr<U128> h = sptr<U128>(w.base);
+	SPtr<U128> t = sptr<U128>(w.base + A_BLK);
+	ASTC_NOUNROLL
+	for (int i = w.lane; i < n1 + n2; i += ASTC_WARP) {
+		if (save) {
+			g[i] = i < n1 ? h[i] : t[i - n1];
+		} else {
+			U128 v = g[i];
+			if (i < n1) h[i] = v;
+			else t[i - n1] = v;
+		}
+	}
+	wsync();
+}
+
+ASTC_FN BlockSearch& search_of(const WCtx& w) { return *reinterpret_cast<BlockSearch*>(astc_smem + w.base + A_SEARCH); }
+ASTC_FN Trial& trial_of(const WCtx& w) { return *reinterpret_cast<Trial*>(astc_smem + w.base + A_TRIAL); }
+static_assert(sizeof(BlockSearch) <= 128 && sizeof(Trial) <= 64, "search state must fit its arena slots");
+
+// park the search state in the arena and write the record
+ASTC_FN void record_save(const WCtx& w, const WaveArgs& a, unsigned int b, const BlockSearch& s, const Trial& t) {
+	if (w.lane == 0) {
+		search_of(w) = s;
+		trial_of(w) = t;
+	}
+	wsync();
+	record_copy(w, a, b, true);
+}
+ASTC_FN void record_restore(const WCtx& w, const WaveArgs& a, unsigned int b, BlockSearch& s, Trial& t) {
+	record_copy(w, a, b, false);
+	s = search_of(w);
+	t = trial_of(w);
+}
+
+// where a block goes after its state machine advanced
+ASTC_FN void route_block(const WCtx& w, const WaveArgs& a, unsigned int b, int next) {
+	if (next == NEXT_TRIAL) {
+		q_push(w, a, Q_SETUP, a.wave + 1, b);
+	} else if (next == NEXT_PREPARE) {
+		q_push(w, a, Q_PREPARE, a.wave, b);
+	} else {
+		q_push(w, a, Q_EMIT, 0, b);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// S: trial setup. Wave 0 reads the image (load_block, constant-colour blocks are emitted on the spot).
+// ---------------------------------------------------------------------------------------------
+ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
+	BlockSearch s;
+	Trial t;
+	BlockFeed feed;
+	feed.ticket = a.head + Q_SETUP * ASTC_MAX_WAVES;      // wave 0 has no queue: its head counter is the image ticket
+	feed.total = a.total;
+	feed.blocks_x = a.blocks_x;
+	while (true) {
+		bool active = false;
+		unsigned int b = 0;
+		if (a.wave == 0) {
+			while (feed_next(w, feed, b)) {
+				unsigned int by = b / a.blocks_x;
+				unsigned int bx = b - by * a.blocks_x;
+				load_block(w, bx * BSD.dim_x, (by + IMG.block_row0) * BSD.dim_y);
+				if (emit_if_constant(w, b)) {
+					continue;
+				}
+				block_search_begin(w, s);
+				s.out_index = b;
+				block_search_advance(w, s, t);       // phase 0 always yields a trial
+				active = true;
+				break;
+			}
+		} else if (q_pop(w, a, Q_SETUP, a.wave, b)) {
+			record_restore(w, a, b, s, t);
+			active = true;
+		}
+		if (!cta_any(active)) {
+			break;
+		}
+		if (active) stage_ideal(w, t);
+		cta_sync();
+		if (active) stage_decimate(w, t);
+		cta_sync();
+		if (active) {
+			trial_cutoffs(w, t);
+			compute_angular_endpoints(w, t.only_always != 0, t.dual ? 2 : 1, (unsigned int)t.max_weight_quant);
+		}
+		cta_sync();
+		if (active) quantize_and_score_modes(w, t.start_mode, t.end_mode, t.dual ? 2 : 1, t.partition_count, t.max_weight_quant, t.cutoff1, t.cutoff2);
+		cta_sync();
+		if (active) {
+			stage_formats(w, t);
+			// the refinement kernel has no decimated ideal weights: quantise every candidate's weights now
+			SPtr<uint32_t> ww = sptr<uint32_t>(work_weights_of(w).off);
+			SPtr<uint32_t> cw = sptr<uint32_t>(w.base + A_CANDW);
+			ASTC_NOUNROLL
+			for (unsigned int i = 0; i < t.candidate_count; i++) {
+				Candidate cd = cand_of(w)[(int)i];
+				const DevBlockMode* bm = BSD.block_modes + cd.block_mode;
+				quantize_candidate_weights(w, ASTC_LDG(&bm->decimation_mode), ASTC_LDG(&bm->quant_mode), t.dual ? 2 : 1, t.cutoff1, t.cutoff2);
+				ASTC_NOUNROLL
+				for (int k = w.lane; k < 16; k += ASTC_WARP) {
+					cw[(int)i * 16 + k] = ww[k];
+				}
+				wsync();
+			}
+			record_save(w, a, b, s, t);
+			q_push(w, a, Q_REFINE, a.wave, b);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// R: refinement steps + the decision what the block does next.
+// ---------------------------------------------------------------------------------------------
+ASTC_COOP void wave_finish_trial(WCtx w, const WaveArgs& a, unsigned int b, BlockSearch& s, Trial& t, float errorval) {
+	block_search_after_trial(w, s, t, errorval);
+	int next = block_search_advance(w, s, t);
+	record_save(w, a, b, s, t);
+	route_block(w, a, b, next);
+}
+
+ASTC_COOP void wave_refine(WCtx w, WaveArgs a) {
+	BlockSearch s;
+	Trial t;
+	Refine r;
+	bool has_item = false;
+	bool drained = false;
+	unsigned int b = 0;
+	r.running = false;
+	t.dual = 0;
+	t.partition_count = 1;
+	t.packed = 0;
+	while (true) {
+		while (!has_item && !drained) {
+			if (!q_pop(w, a, Q_REFINE, a.wave, b)) {
+				drained = true;
+				break;
+			}
+			record_restore(w, a, b, s, t);
+			r.i = 0;
+			r.l = 0;
+			r.running = t.candidate_count > 0;
+			r.in_step = false;
+			r.best_errorval_in_mode = ERROR_CALC_DEFAULT;
+			r.best_errorval_in_scb = s.scb.errorval;
+			r.adjustments = false;
+			r.from_candw = true;
+			if (!r.running) {
+				wave_finish_trial(w, a, b, s, t, r.best_errorval_in_mode);
+				continue;
+			}
+			has_item = true;
+		}
+		if (!cta_any(has_item)) {
+			break;
+		}
+		if (has_item) {
+			r.in_step = true;
+			refine_recompute(w, t, r);
+		}
+		cta_sync();
+		if (has_item) refine_pack(w, t, r);
+		cta_sync();
+		if (has_item && r.l == 0) refine_first_score(w, t, r, s);
+		cta_sync();
+		if (has_item && r.running && r.in_step) {
+			PartView pi = part_view_packed(t.partition_count, t.packed);
+			r.adjustments = realign_weights(w, t.partition_count, r.formats, t.plane2_component, pi, r.qmode, t.dual != 0, (unsigned int)r.dmode);
+		}
+		cta_sync();
+		if (has_item && r.running && r.in_step) refine_second_score(w, t, r, s);
+		if (has_item && !r.running) {
+			wave_finish_trial(w, a, b, s, t, r.best_errorval_in_mode);
+			has_item = false;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// P: block statistics / partition search.
+// ---------------------------------------------------------------------------------------------
+ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
+	BlockSearch s;
+	Trial t;
+	while (true) {
+		unsigned int b = 0;
+		bool active = q_pop(w, a, Q_PREPARE, a.wave, b);
+		if (!cta_any(active)) {
+			break;
+		}
+		if (active) {
+			record_restore(w, a, b, s, t);
+			int next;
+			do {
+				block_search_prepare(w, s);
+				next = block_search_advance(w, s, t);
+			} while (next == NEXT_PREPARE);
+			record_save(w, a, b, s, t);
+			route_block(w, a, b, next);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// E: symbolic -> physical, one block per lane. Each lane gets a private 96-byte slice holding its block's
+// best_weights / best_colors, addressed through a lane-private context so symbolic_to_physical() runs unchanged.
+// ---------------------------------------------------------------------------------------------
+#define EMIT_SLICE 96
+ASTC_COOP void wave_emit(int lane, uint32_t slices_base, WaveArgs a) {
+	uint32_t n = q_load(a.count + Q_EMIT * ASTC_MAX_WAVES);
+	while (true) {
+		uint32_t i0 = 0;
+		if (lane == 0) {
+			i0 = q_atomic_add(a.head + Q_EMIT * ASTC_MAX_WAVES, (uint32_t)ASTC_WARP);
+		}
+		WCtx wl;
+		wl.lane = lane;
+		wl.T = BSD.texel_count;
+		i0 = wbroadcast0(wl, i0);
+		if (i0 >= n) {
+			break;
+		}
+		uint32_t i = i0 + (uint32_t)lane;
+		if (i < n) {
+			unsigned int b = q_load(a.queue[Q_EMIT] + i);
+			const uint8_t* rec = a.records + (size_t)b * BSD.record_bytes;
+			uint32_t slice = slices_base + (uint32_t)lane * EMIT_SLICE;
+			const uint32_t* src = reinterpret_cast<const uint32_t*>(rec + A_SCB);
+			SPtr<uint32_t> dst = sptr<uint32_t>(slice);
+			ASTC_NOUNROLL
+			for (int k = 0; k < EMIT_SLICE / 4; k++) {
+				dst[k] = src[k];
+			}
+			ScbHdr scb = reinterpret_cast<const BlockSearch*>(rec + A_SEARCH)->scb;
+			if (scb.block_type == SYM_BTYPE_ERROR) {
+				f4 ot = reinterpret_cast<const BlkInfo*>(rec + A_STATE)->origin_texel;
+				scb.block_type = SYM_BTYPE_CONST_U16;
+				f4 c = vclamp4(0.0f, 1.0f, ot) * 65535.0f;
+				scb.constant_color[0] = f2i_rtn(c.x);
+				scb.constant_color[1] = f2i_rtn(c.y);
+				scb.constant_color[2] = f2i_rtn(c.z);
+				scb.constant_color[3] = f2i_rtn(c.w);
+			}
+			wl.base = slice - A_SCB;
+			symbolic_to_physical(wl, scb, IMG.out + (size_t)b * 16);
+		}
+	}
+}

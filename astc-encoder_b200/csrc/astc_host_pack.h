@@ -195,10 +195,7 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 	const uint32_t Tp = (T + 3u) & ~3u;
 	uint32_t o = ASTC_ARENA_FIXED;                                              // A_BLK
 	o = align16(o + 16 * Tp);                                                   // block texels [4][Tp]
-	o = align16(o + 16 * Tp);                                                   // ideal weights / error scales, 2 planes
-	b.off_dwi = o;        o = align16(o + 4 * (dwi_total ? dwi_total : 4));
-	b.off_lowhigh = o;    o = align16(o + 128 * t.decimation_mode_count_selected);
-	b.off_mode_err = o;   o = align16(o + 4 * t.block_mode_count_1plane_2plane_selected);
+	b.record_bytes = align16(ASTC_ARENA_PERSIST_HEAD + 16 * Tp);
 	b.off_scratch = o;
 	// union scratch: the largest of the phase layouts (see astc_dev_search.cuh / astc_dev_partition.cuh)
 	uint32_t su = 32 * 68;                                                      // quantise+score rows
@@ -217,7 +214,13 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 		if (ps > su) su = ps;
 	}
 	b.scratch_bytes = align16(su);
-	b.arena_bytes = align16(b.off_scratch + b.scratch_bytes);
+	o = align16(b.off_scratch + b.scratch_bytes);
+	b.arena_bytes_small = o;
+	b.off_ei = o;         o = align16(o + 16 * Tp);                             // ideal weights / error scales, 2 planes
+	b.off_dwi = o;        o = align16(o + 4 * (dwi_total ? dwi_total : 4));
+	b.off_lowhigh = o;    o = align16(o + 128 * t.decimation_mode_count_selected);
+	b.off_mode_err = o;   o = align16(o + 4 * t.block_mode_count_1plane_2plane_selected);
+	b.arena_bytes = o;
 }
 
 static inline void relocate_bsd(DevBsd& b, const uint8_t* base) {

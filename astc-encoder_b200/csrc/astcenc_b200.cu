@@ -29,28 +29,81 @@
 #define ASTC_CTA_THREADS_MAX 512
 
 // Shared window: [0, ASTC_SMEM_HDR) launch constants, then one arena per warp.
+static __device__ __forceinline__ void stage_launch_constants(const DevBsd& bsd, const DevConfig& cfg, const DevImage& img) {
+	// all threads help copy the launch constants from the parameter bank
+	uint32_t* dst = reinterpret_cast<uint32_t*>(astc_smem);
+	const uint32_t* s0 = reinterpret_cast<const uint32_t*>(&bsd);
+	const uint32_t* s1 = reinterpret_cast<const uint32_t*>(&cfg);
+	const uint32_t* s2 = reinterpret_cast<const uint32_t*>(&img);
+	for (unsigned int i = threadIdx.x; i < sizeof(DevBsd) / 4; i += blockDim.x) {
+		dst[offsetof(SmemHdr, bsd) / 4 + i] = s0[i];
+	}
+	for (unsigned int i = threadIdx.x; i < sizeof(DevConfig) / 4; i += blockDim.x) {
+		dst[offsetof(SmemHdr, cfg) / 4 + i] = s1[i];
+	}
+	for (unsigned int i = threadIdx.x; i < sizeof(DevImage) / 4; i += blockDim.x) {
+		dst[offsetof(SmemHdr, img) / 4 + i] = s2[i];
+	}
+	__syncthreads();
+}
+
+// ---- the stage kernels of the wave pipeline (astc_dev_wave.cuh) ----
+#define ASTC_SETUP_THREADS_MAX 512
+#define ASTC_REFINE_THREADS_MAX 768
+#define ASTC_EMIT_THREADS 256
+
+__global__ void __launch_bounds__(ASTC_SETUP_THREADS_MAX, 1)
+astc_wave_setup_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img, const __grid_constant__ WaveArgs a) {
+	if (a.wave != 0 && __ldcg(a.count + Q_SETUP * ASTC_MAX_WAVES + a.wave) == 0) {
+		return;
+	}
+	stage_launch_constants(bsd, cfg, img);
+	WCtx w;
+	w.lane = threadIdx.x & 31;
+	w.base = ASTC_SMEM_HDR + (uint32_t)(threadIdx.x >> 5) * bsd.arena_bytes;
+	w.T = bsd.texel_count;
+	wave_setup(w, a);
+}
+
+__global__ void __launch_bounds__(ASTC_REFINE_THREADS_MAX, 1)
+astc_wave_refine_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img, const __grid_constant__ WaveArgs a) {
+	if (__ldcg(a.count + Q_REFINE * ASTC_MAX_WAVES + a.wave) == 0) {
+		return;
+	}
+	stage_launch_constants(bsd, cfg, img);
+	WCtx w;
+	w.lane = threadIdx.x & 31;
+	w.base = ASTC_SMEM_HDR + (uint32_t)(threadIdx.x >> 5) * bsd.arena_bytes_small;
+	w.T = bsd.texel_count;
+	wave_refine(w, a);
+}
+
+__global__ void __launch_bounds__(ASTC_REFINE_THREADS_MAX, 1)
+astc_wave_prepare_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img, const __grid_constant__ WaveArgs a) {
+	if (__ldcg(a.count + Q_PREPARE * ASTC_MAX_WAVES + a.wave) == 0) {
+		return;
+	}
+	stage_launch_constants(bsd, cfg, img);
+	WCtx w;
+	w.lane = threadIdx.x & 31;
+	w.base = ASTC_SMEM_HDR + (uint32_t)(threadIdx.x >> 5) * bsd.arena_bytes_small;
+	w.T = bsd.texel_count;
+	wave_prepare(w, a);
+}
+
+__global__ void __launch_bounds__(ASTC_EMIT_THREADS, 1)
+astc_wave_emit_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img, const __grid_constant__ WaveArgs a) {
+	stage_launch_constants(bsd, cfg, img);
+	wave_emit(threadIdx.x & 31, ASTC_SMEM_HDR + (uint32_t)(threadIdx.x >> 5) * (32 * EMIT_SLICE), a);
+}
+
+// ---- the single-kernel drivers (kept for A/B measurements: ASTCENC_B200_DRIVER=lockstep|warp) ----
 __global__ void __launch_bounds__(ASTC_CTA_THREADS_MAX, 1)
 astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img,
                      unsigned int* __restrict__ ticket, int coherence_probe, int lockstep) {
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
-	{
-		// all threads help copy the launch constants from the parameter bank
-		uint32_t* dst = reinterpret_cast<uint32_t*>(astc_smem);
-		const uint32_t* s0 = reinterpret_cast<const uint32_t*>(&bsd);
-		const uint32_t* s1 = reinterpret_cast<const uint32_t*>(&cfg);
-		const uint32_t* s2 = reinterpret_cast<const uint32_t*>(&img);
-		for (unsigned int i = threadIdx.x; i < sizeof(DevBsd) / 4; i += blockDim.x) {
-			dst[offsetof(SmemHdr, bsd) / 4 + i] = s0[i];
-		}
-		for (unsigned int i = threadIdx.x; i < sizeof(DevConfig) / 4; i += blockDim.x) {
-			dst[offsetof(SmemHdr, cfg) / 4 + i] = s1[i];
-		}
-		for (unsigned int i = threadIdx.x; i < sizeof(DevImage) / 4; i += blockDim.x) {
-			dst[offsetof(SmemHdr, img) / 4 + i] = s2[i];
-		}
-	}
-	__syncthreads();
+	stage_launch_constants(bsd, cfg, img);
 	WCtx w;
 	w.lane = lane;
 	w.base = ASTC_SMEM_HDR + (uint32_t)warp * bsd.arena_bytes;
@@ -128,7 +181,17 @@ struct astcenc_context {
 	int warps_per_cta;
 	int grid;
 	size_t smem_bytes;
-	int lockstep;                // phase-aligned CTA driver (default) or the independent per-warp driver
+	int lockstep;                // single-kernel drivers: phase-aligned CTA (1) or independent warps (0)
+	int driver;                  // 0 = wave pipeline (default), 1 = single kernel
+	int warps_setup, warps_small;   // warps per CTA of the setup / refine+prepare kernels
+	size_t smem_setup, smem_small;
+	int max_waves;
+	// wave pipeline buffers, grown on demand
+	uint8_t* d_records;
+	size_t d_records_bytes;
+	uint32_t* d_queues;          // 4 x capacity
+	size_t queue_capacity;
+	uint32_t* d_counters;        // count[4][MAX_WAVES] head[4][MAX_WAVES]
 	// staging buffers for the host-pointer API, grown on demand
 	uint8_t* d_image;
 	size_t d_image_bytes;
@@ -210,6 +273,11 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	ctx->stream = nullptr;
 	ctx->ev0 = ctx->ev1 = nullptr;
 	ctx->d_ticket = nullptr;
+	ctx->d_records = nullptr;
+	ctx->d_records_bytes = 0;
+	ctx->d_queues = nullptr;
+	ctx->queue_capacity = 0;
+	ctx->d_counters = nullptr;
 	ctx->d_image = nullptr;
 	ctx->d_out = nullptr;
 	ctx->d_image_bytes = ctx->d_out_bytes = 0;
@@ -281,12 +349,49 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			if (v >= 1 && v <= 8) ctx->grid = prop.multiProcessorCount * v;
 		}
 		ctx->lockstep = 1;
-		if (const char* e = getenv("ASTCENC_B200_LOCKSTEP")) {
-			ctx->lockstep = atoi(e) != 0;
+		ctx->driver = 0;
+		if (const char* e = getenv("ASTCENC_B200_DRIVER")) {
+			if (!strcmp(e, "lockstep")) { ctx->driver = 1; ctx->lockstep = 1; }
+			else if (!strcmp(e, "warp")) { ctx->driver = 1; ctx->lockstep = 0; }
 		}
 		ctx->smem_bytes = ASTC_SMEM_HDR + arena * ctx->warps_per_cta;
 		CUDA_TRY(cudaFuncSetAttribute(astc_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
 		         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+		// wave pipeline: the setup kernel needs the full arena, refinement / preparation only up to the union scratch
+		{
+			size_t arena_small = ctx->tables->bsd.arena_bytes_small;
+			int ws = (int)((smem_limit - ASTC_SMEM_HDR) / arena);
+			if (ws > ASTC_SETUP_THREADS_MAX / 32) ws = ASTC_SETUP_THREADS_MAX / 32;
+			int wr = (int)((smem_limit - ASTC_SMEM_HDR) / arena_small);
+			if (wr > ASTC_REFINE_THREADS_MAX / 32) wr = ASTC_REFINE_THREADS_MAX / 32;
+			if (const char* e = getenv("ASTCENC_B200_WARPS_SETUP")) {
+				int v = atoi(e);
+				if (v >= 1 && v <= ws) ws = v;
+			}
+			if (const char* e = getenv("ASTCENC_B200_WARPS_REFINE")) {
+				int v = atoi(e);
+				if (v >= 1 && v <= wr) wr = v;
+			}
+			ctx->warps_setup = ws;
+			ctx->warps_small = wr;
+			ctx->smem_setup = ASTC_SMEM_HDR + arena * ws;
+			ctx->smem_small = ASTC_SMEM_HDR + arena_small * wr;
+			CUDA_TRY(cudaFuncSetAttribute(astc_wave_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
+			         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+			CUDA_TRY(cudaFuncSetAttribute(astc_wave_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
+			         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+			CUDA_TRY(cudaFuncSetAttribute(astc_wave_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
+			         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+			// a block runs at most this many trials (compress_block: mode-0 + full 1-plane, 4 two-plane, then the partition candidates)
+			int waves = 2 + 4;
+			const unsigned int cl[3] = {cfg.tune_2partitioning_candidate_limit, cfg.tune_3partitioning_candidate_limit, cfg.tune_4partitioning_candidate_limit};
+			for (unsigned int pc = 2; pc <= cfg.tune_partition_count_limit && pc <= 4; pc++) {
+				waves += (int)cl[pc - 2];
+			}
+			if (waves > ASTC_MAX_WAVES - 1) waves = ASTC_MAX_WAVES - 1;
+			ctx->max_waves = waves;
+			CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(uint32_t) * 2 * 4 * ASTC_MAX_WAVES), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
+		}
 		CUDA_TRY(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
 	}
 	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
@@ -303,6 +408,9 @@ void astcenc_context_free(astcenc_context* ctx) {
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	cudaFree(ctx->d_ticket);
+	cudaFree(ctx->d_records);
+	cudaFree(ctx->d_queues);
+	cudaFree(ctx->d_counters);
 	cudaFree(ctx->d_image);
 	cudaFree(ctx->d_out);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -351,8 +459,49 @@ static astcenc_error launch_slab(astcenc_context* ctx, const void* d_pixels, int
 		img.swz[i] = swz[i];
 	}
 	img.out = d_out;
-	CUDA_TRY(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), stream), return ASTCENC_ERR_BAD_CONTEXT);
 	size_t total = (size_t)img.blocks_x * block_rows;
+	if (ctx->driver == 0) {
+		// ---- wave pipeline ----
+		if (total > ctx->queue_capacity) {
+			cudaFree(ctx->d_queues);
+			ctx->d_queues = nullptr;
+			ctx->queue_capacity = 0;
+			CUDA_TRY(cudaMalloc(&ctx->d_queues, sizeof(uint32_t) * 4 * total), return ASTCENC_ERR_OUT_OF_MEM);
+			ctx->queue_capacity = total;
+		}
+		size_t rec_bytes = total * (size_t)bsd.record_bytes;
+		if (rec_bytes > ctx->d_records_bytes) {
+			cudaFree(ctx->d_records);
+			ctx->d_records = nullptr;
+			ctx->d_records_bytes = 0;
+			CUDA_TRY(cudaMalloc(&ctx->d_records, rec_bytes), return ASTCENC_ERR_OUT_OF_MEM);
+			ctx->d_records_bytes = rec_bytes;
+		}
+		CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, sizeof(uint32_t) * 2 * 4 * ASTC_MAX_WAVES, stream), return ASTCENC_ERR_BAD_CONTEXT);
+		WaveArgs a;
+		a.records = ctx->d_records;
+		for (int k = 0; k < 4; k++) {
+			a.queue[k] = ctx->d_queues + (size_t)k * ctx->queue_capacity;
+		}
+		a.count = ctx->d_counters;
+		a.head = ctx->d_counters + 4 * ASTC_MAX_WAVES;
+		a.total = (unsigned int)total;
+		a.blocks_x = img.blocks_x;
+		int grid = ctx->grid;
+		for (int wave = 0; wave < ctx->max_waves; wave++) {
+			a.wave = wave;
+			astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
+			astc_wave_refine_kernel<<<grid, ctx->warps_small * 32, ctx->smem_small, stream>>>(bsd, ctx->dcfg, img, a);
+			astc_wave_prepare_kernel<<<grid, ctx->warps_small * 32, ctx->smem_small, stream>>>(bsd, ctx->dcfg, img, a);
+			ctx->launches += 3;
+		}
+		a.wave = 0;
+		astc_wave_emit_kernel<<<grid, ASTC_EMIT_THREADS, ASTC_SMEM_HDR + (ASTC_EMIT_THREADS / 32) * 32 * EMIT_SLICE, stream>>>(bsd, ctx->dcfg, img, a);
+		ctx->launches++;
+		CUDA_TRY(cudaGetLastError(), return ASTCENC_ERR_BAD_CONTEXT);
+		return ASTCENC_SUCCESS;
+	}
+	CUDA_TRY(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), stream), return ASTCENC_ERR_BAD_CONTEXT);
 	int grid = ctx->grid;
 	size_t needed = (total + ctx->warps_per_cta - 1) / ctx->warps_per_cta;
 	if ((size_t)grid > needed) {

@@ -8,6 +8,7 @@
 #include "../../astc-encoder_b200/csrc/astc_host_config.h"
 #include <vector>
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 
 extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int by, float quality, unsigned int flags,
@@ -26,7 +27,7 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	DevConfig dcfg;
 	astc_host::make_device_config(cfg, dcfg);
 	// the simulated shared window: launch constants, then one arena (16-byte aligned like the device's)
-	std::vector<uint8_t> window(ASTC_SMEM_HDR + pk.bsd.arena_bytes + 64, 0xCD);
+	std::vector<uint8_t> window(ASTC_SMEM_HDR + pk.bsd.arena_bytes + 64 + 32 * EMIT_SLICE, 0xCD);
 	astc_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(window.data()) + 15) & ~(uintptr_t)15);
 	DevImage img;
 	img.data = data;
@@ -46,20 +47,43 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	w.lane = 0;
 	w.base = ASTC_SMEM_HDR;
 	w.T = pk.bsd.texel_count;
-	if (getenv("HOSTSIM_PER_WARP_DRIVER")) {
+	const char* driver = getenv("HOSTSIM_DRIVER");
+	if (driver && !strcmp(driver, "warp")) {
 		for (unsigned int y = 0; y < img.block_rows; y++) {
 			for (unsigned int x = 0; x < img.blocks_x; x++) {
 				load_block(w, x * bx, y * by);
 				compress_block(w, out + ((size_t)y * img.blocks_x + x) * 16);
 			}
 		}
-	} else {
+	} else if (driver && !strcmp(driver, "lockstep")) {
 		unsigned int counter = 0;
 		BlockFeed feed;
 		feed.ticket = &counter;
 		feed.total = img.blocks_x * img.block_rows;
 		feed.blocks_x = img.blocks_x;
 		compress_blocks_lockstep(w, feed);
+	} else {
+		// the wave pipeline, driven like the CUDA host code does (one simulated warp per "kernel")
+		unsigned int total = img.blocks_x * img.block_rows;
+		std::vector<uint8_t> records((size_t)total * pk.bsd.record_bytes + 16);
+		std::vector<uint32_t> queues((size_t)4 * total);
+		std::vector<uint32_t> counters(2 * 4 * ASTC_MAX_WAVES, 0);
+		WaveArgs a;
+		a.records = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(records.data()) + 15) & ~(uintptr_t)15);
+		for (int k = 0; k < 4; k++) a.queue[k] = queues.data() + (size_t)k * total;
+		a.count = counters.data();
+		a.head = counters.data() + 4 * ASTC_MAX_WAVES;
+		a.total = total;
+		a.blocks_x = img.blocks_x;
+		for (int wave = 0; wave < ASTC_MAX_WAVES - 1; wave++) {
+			a.wave = wave;
+			if (wave != 0 && a.count[Q_SETUP * ASTC_MAX_WAVES + wave] == 0) break;
+			wave_setup(w, a);
+			wave_refine(w, a);
+			wave_prepare(w, a);
+		}
+		a.wave = 0;
+		wave_emit(0, ASTC_SMEM_HDR + pk.bsd.arena_bytes, a);
 	}
 	astc_host::free_block_size_tables(t);
 	return 0;
