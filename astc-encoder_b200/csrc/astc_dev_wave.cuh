@@ -31,6 +31,7 @@ struct WaveArgs {
 	unsigned int total;          // blocks in this launch
 	unsigned int blocks_x;
 	int wave;
+	unsigned int sync_mask;      // tuning: which stage barriers are active (bit i = i-th barrier of the kernel loop)
 };
 
 #if defined(ASTC_HOSTSIM)
@@ -159,16 +160,16 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 			break;
 		}
 		if (active) stage_ideal(w, t);
-		cta_sync();
+		if (a.sync_mask & 1) cta_sync();
 		if (active) stage_decimate(w, t);
-		cta_sync();
+		if (a.sync_mask & 2) cta_sync();
 		if (active) {
 			trial_cutoffs(w, t);
 			compute_angular_endpoints(w, t.only_always != 0, t.dual ? 2 : 1, (unsigned int)t.max_weight_quant);
 		}
-		cta_sync();
+		if (a.sync_mask & 4) cta_sync();
 		if (active) quantize_and_score_modes(w, t.start_mode, t.end_mode, t.dual ? 2 : 1, t.partition_count, t.max_weight_quant, t.cutoff1, t.cutoff2);
-		cta_sync();
+		if (a.sync_mask & 8) cta_sync();
 		if (active) {
 			stage_formats(w, t);
 			// the refinement kernel has no decimated ideal weights: quantise every candidate's weights now
@@ -240,16 +241,16 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a) {
 			r.in_step = true;
 			refine_recompute(w, t, r);
 		}
-		cta_sync();
+		if (a.sync_mask & 16) cta_sync();
 		if (has_item) refine_pack(w, t, r);
-		cta_sync();
+		if (a.sync_mask & 32) cta_sync();
 		if (has_item && r.l == 0) refine_first_score(w, t, r, s);
-		cta_sync();
+		if (a.sync_mask & 64) cta_sync();
 		if (has_item && r.running && r.in_step) {
 			PartView pi = part_view_packed(t.partition_count, t.packed);
 			r.adjustments = realign_weights(w, t.partition_count, r.formats, t.plane2_component, pi, r.qmode, t.dual != 0, (unsigned int)r.dmode);
 		}
-		cta_sync();
+		if (a.sync_mask & 128) cta_sync();
 		if (has_item && r.running && r.in_step) refine_second_score(w, t, r, s);
 		if (has_item && !r.running) {
 			wave_finish_trial(w, a, b, s, t, r.best_errorval_in_mode);

@@ -487,6 +487,10 @@ static astcenc_error launch_slab(astcenc_context* ctx, const void* d_pixels, int
 		a.head = ctx->d_counters + 4 * ASTC_MAX_WAVES;
 		a.total = (unsigned int)total;
 		a.blocks_x = img.blocks_x;
+		a.sync_mask = 0;      // measured: once every kernel runs one kind of work, the stage barriers no longer pay (110.7 -> 106.5 ms)
+		if (const char* e = getenv("ASTCENC_B200_SYNC_MASK")) {
+			a.sync_mask = (unsigned int)strtoul(e, nullptr, 0);
+		}
 		int grid = ctx->grid;
 		for (int wave = 0; wave < ctx->max_waves; wave++) {
 			a.wave = wave;

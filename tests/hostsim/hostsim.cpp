@@ -75,6 +75,7 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 		a.head = counters.data() + 4 * ASTC_MAX_WAVES;
 		a.total = total;
 		a.blocks_x = img.blocks_x;
+		a.sync_mask = 0xFF;
 		for (int wave = 0; wave < ASTC_MAX_WAVES - 1; wave++) {
 			a.wave = wave;
 			if (wave != 0 && a.count[Q_SETUP * ASTC_MAX_WAVES + wave] == 0) break;

@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
 """Aggregate an ncu source page by device function (dev tool).
-   python tools/ncu_by_function.py report.ncu-rep lib.so [blocks]"""
+   python tools/ncu_by_function.py report.ncu-rep lib.so [blocks] [kernel-substring]"""
 import csv, subprocess, sys, re
 rep, lib = sys.argv[1], sys.argv[2]
 blocks = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+kern = sys.argv[4] if len(sys.argv) > 4 else ""
 elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
 syms = []
 insym = False
@@ -24,15 +25,20 @@ for l in elf.splitlines():
             short = name
             if m2:
                 short = m2.group(2)[:int(m2.group(1))]
-            if size and not name.startswith("_Z20"):
+            if size and name.startswith("$") and kern in name.split("$")[1]:
                 syms.append((off, size, short))
 syms.sort()
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
+# several kernels may be in the report: take the first whose name matches
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+sel = next(i for i in starts if kern in rows[i][1])
+end = next((i for i in starts if i > sel), len(rows))
+rows = rows[sel:end]
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 ci = {n: i for i, n in enumerate(hdr)}
-data = rows[hi + 1:]
+data = [r for r in rows[hi + 1:] if r and r[0].startswith("0x")]
 base = int(data[0][0], 16)
 agg = {}
 def fn_of(off):
