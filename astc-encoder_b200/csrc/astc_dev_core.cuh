@@ -103,6 +103,8 @@ struct SmemHdr {
 };
 #define ASTC_SMEM_HDR 512
 static_assert(sizeof(SmemHdr) <= ASTC_SMEM_HDR, "launch constants must fit the shared header");
+// kernels that run the angular search also stage its sin/cos tables behind the header (6 KB, shared by the CTA)
+#define ASTC_SMEM_SINCOS_BYTES (2 * 64 * ASTC_ANGULAR_STEPS * 4)
 #define BSD (reinterpret_cast<const SmemHdr*>(astc_smem)->bsd)
 #define CFG (reinterpret_cast<const SmemHdr*>(astc_smem)->cfg)
 #define IMG (reinterpret_cast<const SmemHdr*>(astc_smem)->img)
@@ -265,11 +267,11 @@ ASTC_FN bool is_luminancealpha(const WCtx& w) {
 // Table accessors (global memory, read-only)
 // ---------------------------------------------------------------------------------------------
 struct DecView {
-	const uint8_t* tw;        // [4][T] texel -> grid weight
-	const uint8_t* tc;        // [4][T] contribution in 1/16ths
+	const float* tcf;         // [T][4] contributions as floats
+	const uint32_t* twi;      // [T] 4 x u8 grid weight indices
+	const uint32_t* tci;      // [T] 4 x u8 contributions in 1/16ths
 	const uint16_t* wto;      // [W + 1]
-	const uint8_t* wt;
-	const uint8_t* wc;
+	const uint16_t* wtc;      // [E] texel | contribution << 8
 	int T, W, max_twc, dwi_offset;
 };
 
@@ -281,12 +283,23 @@ ASTC_FN DecView dec_view(unsigned int d) {
 	v.W = ASTC_LDG(&dm->weight_count);
 	v.max_twc = ASTC_LDG(&dm->max_texel_weight_count);
 	v.dwi_offset = ASTC_LDG(&dm->dwi_offset);
-	v.tw = blob;
-	v.tc = blob + 4 * v.T;
-	v.wto = reinterpret_cast<const uint16_t*>(blob + ASTC_LDG(&dm->wto_offset));
-	v.wt = blob + ASTC_LDG(&dm->wt_offset);
-	v.wc = blob + ASTC_LDG(&dm->wc_offset);
+	v.tcf = reinterpret_cast<const float*>(blob);
+	v.twi = reinterpret_cast<const uint32_t*>(blob + 16 * v.T);
+	v.tci = reinterpret_cast<const uint32_t*>(blob + 20 * v.T);
+	v.wto = reinterpret_cast<const uint16_t*>(blob + 24 * v.T);
+	v.wtc = reinterpret_cast<const uint16_t*>(blob + ASTC_LDG(&dm->wtc_offset));
 	return v;
+}
+
+// the four float contributions of texel t
+ASTC_FN f4 dec_contribs(const DecView& di, int t) {
+#if defined(ASTC_HOSTSIM)
+	const float* p = di.tcf + 4 * t;
+	return mk4(p[0], p[1], p[2], p[3]);
+#else
+	float4 v = __ldg(reinterpret_cast<const float4*>(di.tcf) + t);
+	return mk4(v.x, v.y, v.z, v.w);
+#endif
 }
 
 struct PartView {
@@ -916,16 +929,11 @@ ASTC_COOP void compute_ideal_colors_and_weights_2planes(WCtx w, unsigned int pla
 // bilinear infill (:38-104): (w0*c0 + w1*c1) + (w2*c2 + w3*c3); contributions are exact multiples of 1/16.
 // Grids whose texels touch at most two weights skip the second pair in the reference; adding its (+0.0 + +0.0)
 // here leaves the non-negative sum unchanged bit for bit, so one form serves every grid.
-ASTC_FN float contrib_f(uint32_t c) { return static_cast<float>(c) * (1.0f / 16.0f); }
-
 ASTC_FN float bilinear_infill(const DecView& di, SPtr<float> weights, int t) {
-	int T = di.T;
-	return (weights[ASTC_LDG(&di.tw[t])] * contrib_f(ASTC_LDG(&di.tc[t])) + weights[ASTC_LDG(&di.tw[T + t])] * contrib_f(ASTC_LDG(&di.tc[T + t]))) +
-	       (weights[ASTC_LDG(&di.tw[2 * T + t])] * contrib_f(ASTC_LDG(&di.tc[2 * T + t])) + weights[ASTC_LDG(&di.tw[3 * T + t])] * contrib_f(ASTC_LDG(&di.tc[3 * T + t])));
-}
-ASTC_FN float bilinear_infill_2(const DecView& di, SPtr<float> weights, int t) {
-	int T = di.T;
-	return (weights[ASTC_LDG(&di.tw[t])] * contrib_f(ASTC_LDG(&di.tc[t])) + weights[ASTC_LDG(&di.tw[T + t])] * contrib_f(ASTC_LDG(&di.tc[T + t])));
+	uint32_t ix = ASTC_LDG(&di.twi[t]);
+	f4 c = dec_contribs(di, t);
+	return (weights[(int)(ix & 0xFF)] * c.x + weights[(int)((ix >> 8) & 0xFF)] * c.y) +
+	       (weights[(int)((ix >> 16) & 0xFF)] * c.z + weights[(int)(ix >> 24)] * c.w);
 }
 
 // compute_ideal_weights_for_decimation (:845-971) for one grid; nplanes = 1 or 2 (second plane: ei slot 1,
@@ -964,8 +972,9 @@ ASTC_COOP void compute_ideal_weights_for_decimation(WCtx w, unsigned int d, int 
 		int end = ASTC_LDG(&di.wto[i + 1]);
 		ASTC_NOUNROLL
 		for (int j = off; j < end; j++) {
-			int texel = ASTC_LDG(&di.wt[j]);
-			float weight = static_cast<float>(ASTC_LDG(&di.wc[j]));
+			uint32_t e = ASTC_LDG(&di.wtc[j]);
+			int texel = (int)(e & 0xFF);
+			float weight = static_cast<float>(e >> 8);
 			float wes = constant_wes ? wes0 : eis[texel];
 			float contrib_weight = weight * wes;
 			weight_weight += contrib_weight;
@@ -999,8 +1008,9 @@ ASTC_COOP void compute_ideal_weights_for_decimation(WCtx w, unsigned int d, int 
 		int end = ASTC_LDG(&di.wto[i + 1]);
 		ASTC_NOUNROLL
 		for (int j = off; j < end; j++) {
-			int texel = ASTC_LDG(&di.wt[j]);
-			float contrib_weight = static_cast<float>(ASTC_LDG(&di.wc[j]));
+			uint32_t e = ASTC_LDG(&di.wtc[j]);
+			int texel = (int)(e & 0xFF);
+			float contrib_weight = static_cast<float>(e >> 8);
 			float wes = constant_wes ? wes0 : eis[texel];
 			float scale = wes * contrib_weight;
 			float old_weight = inf[texel];
@@ -1050,7 +1060,6 @@ ASTC_FN int angular_steps_of(unsigned int d, int nplanes, uint16_t mask, unsigne
 
 // compute_angular_endpoints_1plane / _2planes (:358-500)
 ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, unsigned int max_weight_quant) {
-	const DevConstTables* ct = ASTC_CT;
 	unsigned int max_dm = (nplanes == 1 && only_always) ? BSD.decimation_mode_count_always : BSD.decimation_mode_count_selected;
 	uint16_t mask = (uint16_t)((1u << (max_weight_quant + 1)) - 1);
 	int pairs = (int)max_dm * nplanes;
@@ -1143,13 +1152,13 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 			SPtr<uint8_t> is = isamp + pdoff;
 			// compute_angular_offsets :94-157
 			float anglesum_x = 0.0f, anglesum_y = 0.0f;
-			const float* cosp = &ct->cos_table[0][sp];
-			const float* sinp = &ct->sin_table[0][sp];
+			SPtr<float> cosp = sptr<float>(ASTC_SMEM_HDR) + sp;
+			SPtr<float> sinp = cosp + 64 * ASTC_ANGULAR_STEPS;
 			ASTC_NOUNROLL
 			for (int j = 0; j < pW; j++) {
 				int row = is[j] * ASTC_ANGULAR_STEPS;
-				anglesum_x += ASTC_LDG(cosp + row);
-				anglesum_y += ASTC_LDG(sinp + row);
+				anglesum_x += cosp[row];
+				anglesum_y += sinp[row];
 			}
 			float angle = approx_atan2(anglesum_y, anglesum_x);
 			angle = (angle == angle) ? angle : 0.0f;

@@ -69,9 +69,10 @@ ASTC_COOP void quantize_and_score_modes(WCtx w, unsigned int start_mode, unsigne
 		float rscale1 = z1.rscale, lowb1 = z1.low_bound;
 		ASTC_NOUNROLL
 		for (int t = 0; t < T; t++) {
-			int i0 = ASTC_LDG(&di.tw[t]), i1 = ASTC_LDG(&di.tw[T + t]), i2 = ASTC_LDG(&di.tw[2 * T + t]), i3 = ASTC_LDG(&di.tw[3 * T + t]);
-			float c0 = contrib_f(ASTC_LDG(&di.tc[t])), c1 = contrib_f(ASTC_LDG(&di.tc[T + t])), c2 = contrib_f(ASTC_LDG(&di.tc[2 * T + t])),
-			      c3 = contrib_f(ASTC_LDG(&di.tc[3 * T + t]));
+			uint32_t ix = ASTC_LDG(&di.twi[t]);
+			f4 cf = dec_contribs(di, t);
+			int i0 = (int)(ix & 0xFF), i1 = (int)((ix >> 8) & 0xFF), i2 = (int)((ix >> 16) & 0xFF), i3 = (int)(ix >> 24);
+			float c0 = cf.x, c1 = cf.y, c2 = cf.z, c3 = cf.w;
 			float cur1 = ((static_cast<float>(uqrow[i0]) * rscale1 + lowb1) * c0 + (static_cast<float>(uqrow[i1]) * rscale1 + lowb1) * c1) +
 			             ((static_cast<float>(uqrow[i2]) * rscale1 + lowb1) * c2 + (static_cast<float>(uqrow[i3]) * rscale1 + lowb1) * c3);
 			float diff = cur1 - eiw1[t];
@@ -641,10 +642,10 @@ ASTC_COOP void undecimate_weights(WCtx w, unsigned int d, int planes) {
 		if (di.max_twc == 1) {
 			v = static_cast<float>(uq[t]) * (1.0f / 64.0f);
 		} else {
-			v = ((static_cast<float>(uq[ASTC_LDG(&di.tw[t])]) * (1.0f / 64.0f)) * contrib_f(ASTC_LDG(&di.tc[t])) +
-			     (static_cast<float>(uq[ASTC_LDG(&di.tw[T + t])]) * (1.0f / 64.0f)) * contrib_f(ASTC_LDG(&di.tc[T + t]))) +
-			    ((static_cast<float>(uq[ASTC_LDG(&di.tw[2 * T + t])]) * (1.0f / 64.0f)) * contrib_f(ASTC_LDG(&di.tc[2 * T + t])) +
-			     (static_cast<float>(uq[ASTC_LDG(&di.tw[3 * T + t])]) * (1.0f / 64.0f)) * contrib_f(ASTC_LDG(&di.tc[3 * T + t])));
+			uint32_t ix = ASTC_LDG(&di.twi[t]);
+			f4 c = dec_contribs(di, t);
+			v = ((static_cast<float>(uq[(int)(ix & 0xFF)]) * (1.0f / 64.0f)) * c.x + (static_cast<float>(uq[(int)((ix >> 8) & 0xFF)]) * (1.0f / 64.0f)) * c.y) +
+			    ((static_cast<float>(uq[(int)((ix >> 16) & 0xFF)]) * (1.0f / 64.0f)) * c.z + (static_cast<float>(uq[(int)(ix >> 24)]) * (1.0f / 64.0f)) * c.w);
 		}
 		sptr<float>(rs.undec[pl])[t] = v;
 	}
@@ -1071,8 +1072,10 @@ ASTC_COOP float compute_symbolic_block_difference(WCtx w, unsigned int pc, uint3
 	bool reject = false;
 	ASTC_NOUNROLL
 	for (int t = w.lane; t < T; t += ASTC_WARP) {
-		int i0 = ASTC_LDG(&di.tw[t]), i1 = ASTC_LDG(&di.tw[T + t]), i2 = ASTC_LDG(&di.tw[2 * T + t]), i3 = ASTC_LDG(&di.tw[3 * T + t]);
-		int c0 = ASTC_LDG(&di.tc[t]), c1 = ASTC_LDG(&di.tc[T + t]), c2 = ASTC_LDG(&di.tc[2 * T + t]), c3 = ASTC_LDG(&di.tc[3 * T + t]);
+		uint32_t ix = ASTC_LDG(&di.twi[t]);
+		uint32_t cx = ASTC_LDG(&di.tci[t]);
+		int i0 = (int)(ix & 0xFF), i1 = (int)((ix >> 8) & 0xFF), i2 = (int)((ix >> 16) & 0xFF), i3 = (int)(ix >> 24);
+		int c0 = (int)(cx & 0xFF), c1 = (int)((cx >> 8) & 0xFF), c2 = (int)((cx >> 16) & 0xFF), c3 = (int)(cx >> 24);
 		int w1 = (8 + uq[i0] * c0 + uq[i1] * c1 + uq[i2] * c2 + uq[i3] * c3) >> 4;
 		int w2 = w1;
 		if (dual) {
@@ -1163,7 +1166,9 @@ ASTC_COOP float compute_symbolic_block_difference(WCtx w, unsigned int pc, uint3
 // Decimated grids (:188-350): weights are visited in order and a changed weight feeds the following ones, so
 // the outer loop is sequential. Per weight, lane = (texel slot 0..7, channel 0..3): eight of the weight's texels
 // at a time compute their squared channel differences for the current / previous / next quantised value into a
-// [12][8] tile; twelve chain lanes (3 candidates x 4 channels) then add them in texel order.
+// [12][8] tile; twelve chain lanes (3 candidates x 4 channels) then add them in texel order, and a few shuffles fold
+// the channel sums the way the reference's dot product does. The bilinear infill of every texel (wb) is kept
+// current instead of being rebuilt for every weight: it only changes for the texels of a weight that moved.
 ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int plane2_component, const PartView& pi, int quant_mode, bool is_dual, unsigned int d) {
 	const DevConstTables* ct = ASTC_CT;
 	RefineScratch rs = make_refine_scratch(w);
@@ -1177,8 +1182,11 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 	SPtr<int> ends = sptr<int>(ends_off_of(w));
 	f4 ew = bi_of(w).channel_weight;
 	SPtr<float> uqf = sptr<float>(rs.uqf);
+	SPtr<float> wb = sptr<float>(rs.undec[0]);        // per-texel infill of uqf (free here: recompute rebuilds its own)
 	SPtr<float> tile = sptr<float>(rs.tile);
 	SPtr<float> tmpf = tmpf_of(w);
+	SPtr<float> eb = tmpf + 32;                       // endpoint 0 as float, [partition][channel]
+	SPtr<float> eo = tmpf + 48;                       // (endpoint 1 - endpoint 0) / 64, plane-masked
 	SPtr<float> b0 = blk_of(w, 0);
 	uint32_t cs = tp4(w);
 	bool adjustments = false;
@@ -1186,6 +1194,15 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 	for (unsigned int pl = 0; pl <= max_plane; pl++) {
 		SPtr<uint8_t> dec_weights_uquant = work_weights_of(w) + (int)pl * 32;
 		// plane_mask: for plane 1 the plane-2 component is zeroed, for plane 2 all others
+		ASTC_NOUNROLL
+		for (int k = w.lane; k < (int)pc * 4; k += ASTC_WARP) {
+			int p = k >> 2, c = k & 3;
+			int e0 = ends[p * 8 + c], e1 = ends[p * 8 + 4 + c];
+			bool masked = (plane2_component == c) != (pl == 1);
+			eb[k] = static_cast<float>(e0);
+			eo[k] = static_cast<float>(masked ? 0 : e1 - e0) * (1.0f / 64.0f);
+		}
+		wsync();
 		if (!decimated) {
 			// realign_weights_undecimated :69-185 - texels are independent
 			ASTC_NOUNROLL
@@ -1198,15 +1215,10 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 				float weight_down = static_cast<float>(uqw_down - uqw);
 				float weight_up = static_cast<float>(uqw_up - uqw);
 				int partition = pc > 1 ? (int)ASTC_LDG(&pi.partition_of_texel[texel]) : 0;
-				SPtr<int> e = ends + partition * 8;
-				float eb = 0.0f, ed = 0.0f, eu = 0.0f;     // dot_s: (x + z) + (y + w) below
 				float t0[4], t1[4], t2[4];
 				for (int c = 0; c < 4; c++) {
-					int e0 = e[c], e1 = e[4 + c];
-					bool masked = (plane2_component == c) != (pl == 1);
-					float color_offset = static_cast<float>(masked ? 0 : e1 - e0) * (1.0f / 64.0f);
-					float color_base = static_cast<float>(e0);
-					float color = color_base + color_offset * weight_base;
+					float color_offset = eo[partition * 4 + c];
+					float color = eb[partition * 4 + c] + color_offset * weight_base;
 					float orig = sptr<float>(b0.off + (uint32_t)c * cs)[texel];
 					float color_diff = color - orig;
 					float color_diff_down = color_diff + color_offset * weight_down;
@@ -1216,13 +1228,13 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 					t1[c] = color_diff_down * color_diff_down * ewc;
 					t2[c] = color_diff_up * color_diff_up * ewc;
 				}
-				eb = (t0[0] + t0[2]) + (t0[1] + t0[3]);
-				ed = (t1[0] + t1[2]) + (t1[1] + t1[3]);
-				eu = (t2[0] + t2[2]) + (t2[1] + t2[3]);
-				if ((eu < eb) && (eu < ed) && (uqw < 64)) {
+				float ebs = (t0[0] + t0[2]) + (t0[1] + t0[3]);      // dot_s: (x + z) + (y + w)
+				float ed = (t1[0] + t1[2]) + (t1[1] + t1[3]);
+				float eu = (t2[0] + t2[2]) + (t2[1] + t2[3]);
+				if ((eu < ebs) && (eu < ed) && (uqw < 64)) {
 					dec_weights_uquant[texel] = static_cast<uint8_t>(uqw_up);
 					adjustments = true;
-				} else if ((ed < eb) && (uqw > 0)) {
+				} else if ((ed < ebs) && (uqw > 0)) {
 					dec_weights_uquant[texel] = static_cast<uint8_t>(uqw_down);
 					adjustments = true;
 				}
@@ -1235,11 +1247,18 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 			uqf[we] = static_cast<float>(dec_weights_uquant[we]);
 		}
 		wsync();
+		ASTC_NOUNROLL
+		for (int t = w.lane; t < T; t += ASTC_WARP) {
+			wb[t] = bilinear_infill(di, uqf, t);
+		}
+		wsync();
 #if ASTC_WARP == 1
 		const int slot_lanes = 1, slot = 0;
 #else
 		const int slot_lanes = 8;
 		int slot = w.lane >> 2;
+		int lc = w.lane & 3;
+		float ew_c = lane(ew, lc);
 #endif
 		ASTC_NOUNROLL
 		for (int we = 0; we < weight_count; we++) {
@@ -1259,26 +1278,21 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 				for (int s8 = slot; s8 < 8; s8 += slot_lanes) {
 					int te = te0 + s8;
 					if (te < cnt) {
-						int texel = ASTC_LDG(&di.wt[off + te]);
-						float tw_base = contrib_f(ASTC_LDG(&di.wc[off + te]));
-						float weight_base = (uqf[ASTC_LDG(&di.tw[texel])] * contrib_f(ASTC_LDG(&di.tc[texel])) +
-						                     uqf[ASTC_LDG(&di.tw[T + texel])] * contrib_f(ASTC_LDG(&di.tc[T + texel]))) +
-						                    (uqf[ASTC_LDG(&di.tw[2 * T + texel])] * contrib_f(ASTC_LDG(&di.tc[2 * T + texel])) +
-						                     uqf[ASTC_LDG(&di.tw[3 * T + texel])] * contrib_f(ASTC_LDG(&di.tc[3 * T + texel])));
+						uint32_t e = ASTC_LDG(&di.wtc[off + te]);
+						int texel = (int)(e & 0xFF);
+						float tw_base = static_cast<float>(e >> 8) * (1.0f / 16.0f);
+						float weight_base = wb[texel];
 						float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
 						float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
 						int partition = pc > 1 ? (int)ASTC_LDG(&pi.partition_of_texel[texel]) : 0;
-						SPtr<int> e = ends + partition * 8;
 #if ASTC_WARP == 1
 						for (int c = 0; c < 4; c++)
 #else
-						int c = w.lane & 3;
+						int c = lc;
 #endif
 						{
-							int e0 = e[c], e1 = e[4 + c];
-							bool masked = (plane2_component == c) != (pl == 1);
-							float color_offset = static_cast<float>(masked ? 0 : e1 - e0) * (1.0f / 64.0f);
-							float color = static_cast<float>(e0) + color_offset * weight_base;
+							float color_offset = eo[partition * 4 + c];
+							float color = eb[partition * 4 + c] + color_offset * weight_base;
 							float orig = sptr<float>(b0.off + (uint32_t)c * cs)[texel];
 							float color_diff = color - orig;
 							float color_down_diff = color_diff + color_offset * weight_down;
@@ -1311,33 +1325,49 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 #endif
 				wsync();
 			}
+			float error_base, error_down, error_up;
 #if ASTC_WARP == 1
-			for (int ch = 0; ch < 12; ch++) {
-				tmpf[ch] = tmpf[16 + ch] * lane(ew, ch & 3);
+			{
+				float t[12];
+				for (int ch = 0; ch < 12; ch++) {
+					t[ch] = tmpf[16 + ch] * lane(ew, ch & 3);
+				}
+				error_base = (t[0] + t[2]) + (t[1] + t[3]);
+				error_down = (t[4] + t[6]) + (t[5] + t[7]);
+				error_up = (t[8] + t[10]) + (t[9] + t[11]);
 			}
 #else
-			if (w.lane < 12) {
-				tmpf[w.lane] = sum * lane(ew, w.lane & 3);
+			{
+				// lanes 0-3 / 4-7 / 8-11 hold the weighted channel sums of base / down / up: (x + z) + (y + w)
+				float v = sum * ew_c;
+				float a2 = v + __shfl_down_sync(0xffffffffu, v, 2);
+				float a1 = a2 + __shfl_down_sync(0xffffffffu, a2, 1);
+				error_base = __shfl_sync(0xffffffffu, a1, 0);
+				error_down = __shfl_sync(0xffffffffu, a1, 4);
+				error_up = __shfl_sync(0xffffffffu, a1, 8);
 			}
 #endif
-			wsync();
-			float error_base = (tmpf[0] + tmpf[2]) + (tmpf[1] + tmpf[3]);
-			float error_down = (tmpf[4] + tmpf[6]) + (tmpf[5] + tmpf[7]);
-			float error_up = (tmpf[8] + tmpf[10]) + (tmpf[9] + tmpf[11]);
+			float new_uqw = -1.0f;
 			if ((error_up < error_base) && (error_up < error_down) && (uqw < 64)) {
-				if (w.lane == 0) {
-					uqf[we] = uqw_up;
-					dec_weights_uquant[we] = static_cast<uint8_t>(uqw_up);
-				}
-				adjustments = true;
+				new_uqw = uqw_up;
 			} else if ((error_down < error_base) && (uqw > 0)) {
+				new_uqw = uqw_down;
+			}
+			if (new_uqw >= 0.0f) {
 				if (w.lane == 0) {
-					uqf[we] = uqw_down;
-					dec_weights_uquant[we] = static_cast<uint8_t>(uqw_down);
+					uqf[we] = new_uqw;
+					dec_weights_uquant[we] = static_cast<uint8_t>(new_uqw);
 				}
 				adjustments = true;
+				wsync();
+				// the infill changed for this weight's texels only
+				ASTC_NOUNROLL
+				for (int te = w.lane; te < cnt; te += ASTC_WARP) {
+					int texel = (int)(ASTC_LDG(&di.wtc[off + te]) & 0xFF);
+					wb[texel] = bilinear_infill(di, uqf, texel);
+				}
+				wsync();
 			}
-			wsync();
 		}
 	}
 	return wany(adjustments);

@@ -45,14 +45,15 @@ struct DevBlockMode {
 	uint8_t is_dual_plane;
 };
 
-// Per weight grid. The bilinear tables live in a byte blob:
-//   tw[4][T] u8      texel -> up to 4 grid weights              (texel_weights_tr)
-//   tc[4][T] u8      their contributions in 1/16ths (0 = unused) (texel_weight_contribs_int_tr)
+// Per weight grid. The bilinear tables live in a blob (16-byte aligned), packed so that one texel / one list
+// entry is one load:
+//   tcf[T] float4    the (up to) 4 contributions of a texel as floats, c / 16 (0 = unused)   (texel_weight_contribs_float_tr)
+//   twi[T] u32       the 4 grid weights a texel reads, one byte each                          (texel_weights_tr)
+//   tci[T] u32       the 4 contributions in 1/16ths, one byte each                            (texel_weight_contribs_int_tr)
 //   wto[W+1] u16     CSR offsets of the weight -> texel lists
-//   wt[E] u8         texel of each list entry                   (weight_texels_tr)
-//   wc[E] u8         contribution of that entry in 1/16ths      (weights_texel_contribs_tr, texel_contrib_for_weight)
-// Float contributions are rebuilt as float(c) * (1/16) resp. float(c): both are exact, so the values equal
-// the reference's stored floats bit for bit.
+//   wtc[E] u16       list entries: texel | contribution-in-1/16ths << 8    (weight_texels_tr, weights_texel_contribs_tr)
+// Float contributions are c * (1/16) resp. float(c): both are exact, so the values equal the reference's
+// stored floats bit for bit.
 struct DevDecMode {
 	int8_t maxprec_1plane;
 	int8_t maxprec_2planes;
@@ -63,9 +64,9 @@ struct DevDecMode {
 	uint8_t weight_y;
 	uint8_t max_texel_weight_count;
 	uint16_t dwi_offset;      // float offset of this grid's ideal weights in the per-warp arena
-	uint16_t wto_offset;      // byte offset of wto inside the blob
-	uint16_t wt_offset;       // byte offset of wt
-	uint16_t wc_offset;       // byte offset of wc
+	uint16_t wto_offset;      // byte offset of wto inside the blob (= 24 * T)
+	uint16_t wtc_offset;      // byte offset of wtc
+	uint16_t pad0;
 	uint32_t blob_offset;     // byte offset of the blob in dec_blob
 };
 

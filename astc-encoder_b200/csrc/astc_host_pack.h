@@ -110,23 +110,34 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 		const unsigned int W = di.weight_count;
 		const unsigned int E = di.weight_texel_offset[W];
 		size_t base = (dblob.size() + 15) / 16 * 16;
-		size_t wto_off = (8 * T + 1) & ~(size_t)1;
-		size_t wt_off = wto_off + 2 * (W + 1);
-		size_t wc_off = wt_off + E;
-		size_t total = wc_off + E;
+		size_t twi_off = 16 * (size_t)T;
+		size_t tci_off = 20 * (size_t)T;
+		size_t wto_off = 24 * (size_t)T;
+		size_t wtc_off = wto_off + 2 * (W + 1);
+		size_t total = wtc_off + 2 * (size_t)E;
 		dblob.resize(base + total, 0);
 		uint8_t* p = dblob.data() + base;
-		for (unsigned int k = 0; k < 4; k++) {
-			memcpy(p + k * T, di.texel_weights[k], T);
-			memcpy(p + 4 * T + k * T, di.texel_weight_contribs_int[k], T);
+		float* tcf = reinterpret_cast<float*>(p);
+		uint32_t* twi = reinterpret_cast<uint32_t*>(p + twi_off);
+		uint32_t* tci = reinterpret_cast<uint32_t*>(p + tci_off);
+		for (unsigned int i = 0; i < T; i++) {
+			uint32_t wi = 0, ci = 0;
+			for (unsigned int k = 0; k < 4; k++) {
+				uint32_t c = di.texel_weight_contribs_int[k][i];
+				wi |= (uint32_t)di.texel_weights[k][i] << (8 * k);
+				ci |= c << (8 * k);
+				tcf[4 * i + k] = static_cast<float>(c) * (1.0f / 16.0f);
+			}
+			twi[i] = wi;
+			tci[i] = ci;
 		}
 		uint16_t* wto = reinterpret_cast<uint16_t*>(p + wto_off);
 		for (unsigned int i = 0; i <= W; i++) {
 			wto[i] = di.weight_texel_offset[i];
 		}
+		uint16_t* wtc = reinterpret_cast<uint16_t*>(p + wtc_off);
 		for (unsigned int e = 0; e < E; e++) {
-			p[wt_off + e] = di.weight_texels[e];
-			p[wc_off + e] = (uint8_t)di.weight_texel_contribs[e];
+			wtc[e] = (uint16_t)(di.weight_texels[e] | ((unsigned int)di.weight_texel_contribs[e] << 8));
 		}
 		for (unsigned int i = 0; i < W; i++) {
 			if (di.weight_texel_count[i] > max_wtc) {
@@ -135,8 +146,8 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 		}
 		dm.blob_offset = (uint32_t)base;
 		dm.wto_offset = (uint16_t)wto_off;
-		dm.wt_offset = (uint16_t)wt_off;
-		dm.wc_offset = (uint16_t)wc_off;
+		dm.wtc_offset = (uint16_t)wtc_off;
+		dm.pad0 = 0;
 		// arena slot for the decimated ideal weights (only grids the search can reference)
 		dm.dwi_offset = (uint16_t)dwi_total;
 		if (d < t.decimation_mode_count_selected) {

@@ -47,6 +47,19 @@ static __device__ __forceinline__ void stage_launch_constants(const DevBsd& bsd,
 	__syncthreads();
 }
 
+// cos_table then sin_table, [64][ASTC_ANGULAR_STEPS] each, right behind the header (kernels that run the angular search)
+static __device__ __forceinline__ void stage_sincos_tables() {
+	float* dst = reinterpret_cast<float*>(astc_smem + ASTC_SMEM_HDR);
+	const DevConstTables* ct = ASTC_CT;
+	const float* c = &ct->cos_table[0][0];
+	const float* sn = &ct->sin_table[0][0];
+	for (unsigned int i = threadIdx.x; i < 64 * ASTC_ANGULAR_STEPS; i += blockDim.x) {
+		dst[i] = __ldg(c + i);
+		dst[64 * ASTC_ANGULAR_STEPS + i] = __ldg(sn + i);
+	}
+	__syncthreads();
+}
+
 // ---- the stage kernels of the wave pipeline (astc_dev_wave.cuh) ----
 #define ASTC_SETUP_THREADS_MAX 512
 #define ASTC_REFINE_THREADS_MAX 768
@@ -58,9 +71,10 @@ astc_wave_setup_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant
 		return;
 	}
 	stage_launch_constants(bsd, cfg, img);
+	stage_sincos_tables();
 	WCtx w;
 	w.lane = threadIdx.x & 31;
-	w.base = ASTC_SMEM_HDR + (uint32_t)(threadIdx.x >> 5) * bsd.arena_bytes;
+	w.base = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + (uint32_t)(threadIdx.x >> 5) * bsd.arena_bytes;
 	w.T = bsd.texel_count;
 	wave_setup(w, a);
 }
@@ -104,9 +118,10 @@ astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	stage_launch_constants(bsd, cfg, img);
+	stage_sincos_tables();
 	WCtx w;
 	w.lane = lane;
-	w.base = ASTC_SMEM_HDR + (uint32_t)warp * bsd.arena_bytes;
+	w.base = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + (uint32_t)warp * bsd.arena_bytes;
 	w.T = bsd.texel_count;
 	const unsigned int total = img.blocks_x * img.block_rows;
 	const unsigned int blocks_x = img.blocks_x;
@@ -329,7 +344,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 		// The per-warp arena lives in shared memory only: one CTA per SM with as many warps as fit (at most 16).
 		size_t smem_limit = prop.sharedMemPerBlockOptin;
 		size_t arena = ctx->tables->bsd.arena_bytes;
-		int warps = (int)((smem_limit - ASTC_SMEM_HDR) / arena);
+		int warps = (int)((smem_limit - ASTC_SMEM_HDR - ASTC_SMEM_SINCOS_BYTES) / arena);
 		if (warps > ASTC_CTA_THREADS_MAX / 32) warps = ASTC_CTA_THREADS_MAX / 32;
 		if (warps < 1) {
 			// block sizes / presets whose working set exceeds one SM's shared memory are not supported by this build
@@ -354,13 +369,13 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			if (!strcmp(e, "lockstep")) { ctx->driver = 1; ctx->lockstep = 1; }
 			else if (!strcmp(e, "warp")) { ctx->driver = 1; ctx->lockstep = 0; }
 		}
-		ctx->smem_bytes = ASTC_SMEM_HDR + arena * ctx->warps_per_cta;
+		ctx->smem_bytes = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + arena * ctx->warps_per_cta;
 		CUDA_TRY(cudaFuncSetAttribute(astc_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
 		         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
 		// wave pipeline: the setup kernel needs the full arena, refinement / preparation only up to the union scratch
 		{
 			size_t arena_small = ctx->tables->bsd.arena_bytes_small;
-			int ws = (int)((smem_limit - ASTC_SMEM_HDR) / arena);
+			int ws = (int)((smem_limit - ASTC_SMEM_HDR - ASTC_SMEM_SINCOS_BYTES) / arena);
 			if (ws > ASTC_SETUP_THREADS_MAX / 32) ws = ASTC_SETUP_THREADS_MAX / 32;
 			int wr = (int)((smem_limit - ASTC_SMEM_HDR) / arena_small);
 			if (wr > ASTC_REFINE_THREADS_MAX / 32) wr = ASTC_REFINE_THREADS_MAX / 32;
@@ -374,7 +389,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			}
 			ctx->warps_setup = ws;
 			ctx->warps_small = wr;
-			ctx->smem_setup = ASTC_SMEM_HDR + arena * ws;
+			ctx->smem_setup = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + arena * ws;
 			ctx->smem_small = ASTC_SMEM_HDR + arena_small * wr;
 			CUDA_TRY(cudaFuncSetAttribute(astc_wave_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
 			         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });

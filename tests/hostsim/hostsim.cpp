@@ -27,7 +27,7 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	DevConfig dcfg;
 	astc_host::make_device_config(cfg, dcfg);
 	// the simulated shared window: launch constants, then one arena (16-byte aligned like the device's)
-	std::vector<uint8_t> window(ASTC_SMEM_HDR + pk.bsd.arena_bytes + 64 + 32 * EMIT_SLICE, 0xCD);
+	std::vector<uint8_t> window(ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + pk.bsd.arena_bytes + 64 + 32 * EMIT_SLICE, 0xCD);
 	astc_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(window.data()) + 15) & ~(uintptr_t)15);
 	DevImage img;
 	img.data = data;
@@ -45,7 +45,16 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	hdr->img = img;
 	WCtx w;
 	w.lane = 0;
-	w.base = ASTC_SMEM_HDR;
+	w.base = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES;
+	{
+		float* sc = reinterpret_cast<float*>(astc_smem + ASTC_SMEM_HDR);
+		for (int j = 0; j < 64; j++) {
+			for (int i = 0; i < ASTC_ANGULAR_STEPS; i++) {
+				sc[j * ASTC_ANGULAR_STEPS + i] = pk.consts.cos_table[j][i];
+				sc[64 * ASTC_ANGULAR_STEPS + j * ASTC_ANGULAR_STEPS + i] = pk.consts.sin_table[j][i];
+			}
+		}
+	}
 	w.T = pk.bsd.texel_count;
 	const char* driver = getenv("HOSTSIM_DRIVER");
 	if (driver && !strcmp(driver, "warp")) {
@@ -84,7 +93,7 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 			wave_prepare(w, a);
 		}
 		a.wave = 0;
-		wave_emit(0, ASTC_SMEM_HDR + pk.bsd.arena_bytes, a);
+		wave_emit(0, ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + pk.bsd.arena_bytes, a);
 	}
 	astc_host::free_block_size_tables(t);
 	return 0;
