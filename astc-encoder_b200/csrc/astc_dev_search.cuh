@@ -1183,7 +1183,6 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 	f4 ew = bi_of(w).channel_weight;
 	SPtr<float> uqf = sptr<float>(rs.uqf);
 	SPtr<float> wb = sptr<float>(rs.undec[0]);        // per-texel infill of uqf (free here: recompute rebuilds its own)
-	SPtr<float> tile = sptr<float>(rs.tile);
 	SPtr<float> tmpf = tmpf_of(w);
 	SPtr<float> eb = tmpf + 32;                       // endpoint 0 as float, [partition][channel]
 	SPtr<float> eo = tmpf + 48;                       // (endpoint 1 - endpoint 0) / 64, plane-masked
@@ -1242,109 +1241,131 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 			wsync();
 			continue;
 		}
+		// Stage everything the sequential weight loop reads in shared memory (the staging tile is free here), so an
+		// iteration never waits for global memory: per weight its previous/next quantised value and list range,
+		// the list entries, the partition of every texel.
+		SPtr<uint16_t> s_pn = sptr<uint16_t>(rs.tile);                       // [64]
+		SPtr<uint16_t> s_wto = sptr<uint16_t>(rs.tile + 128);                // [65]
+		SPtr<uint8_t> s_pot = sptr<uint8_t>(rs.tile + 128 + 136);           // [T] (<= 144)
+		SPtr<uint16_t> s_wtc = sptr<uint16_t>(rs.tile + 128 + 136 + 144);    // [E] (<= 4 T)
 		ASTC_NOUNROLL
-		for (int we = w.lane; we < weight_count; we += ASTC_WARP) {
-			uqf[we] = static_cast<float>(dec_weights_uquant[we]);
+		for (int we = w.lane; we <= weight_count; we += ASTC_WARP) {
+			s_wto[we] = ASTC_LDG(&di.wto[we]);
+			if (we < weight_count) {
+				int uq = dec_weights_uquant[we];
+				uqf[we] = static_cast<float>(uq);
+				s_pn[we] = ASTC_LDG(&prev_next[uq]);
+			}
+		}
+		ASTC_NOUNROLL
+		for (int t = w.lane; t < T; t += ASTC_WARP) {
+			s_pot[t] = pc > 1 ? ASTC_LDG(&pi.partition_of_texel[t]) : (uint8_t)0;
 		}
 		wsync();
+		int E = s_wto[weight_count];
+		ASTC_NOUNROLL
+		for (int e = w.lane; e < E; e += ASTC_WARP) {
+			s_wtc[e] = ASTC_LDG(&di.wtc[e]);
+		}
 		ASTC_NOUNROLL
 		for (int t = w.lane; t < T; t += ASTC_WARP) {
 			wb[t] = bilinear_infill(di, uqf, t);
 		}
 		wsync();
 #if ASTC_WARP == 1
-		const int slot_lanes = 1, slot = 0;
+		const int slot = 0;
 #else
-		const int slot_lanes = 8;
 		int slot = w.lane >> 2;
 		int lc = w.lane & 3;
 		float ew_c = lane(ew, lc);
 #endif
 		ASTC_NOUNROLL
 		for (int we = 0; we < weight_count; we++) {
-			int uqw = dec_weights_uquant[we];
-			uint32_t pn = ASTC_LDG(&prev_next[uqw]);
+			uint32_t pn = s_pn[we];
 			float uqw_base = uqf[we];
+			int uqw = (int)uqw_base;
 			float uqw_down = static_cast<float>(pn & 0xFF);
 			float uqw_up = static_cast<float>((pn >> 8) & 0xFF);
 			float uqw_diff_down = uqw_down - uqw_base;
 			float uqw_diff_up = uqw_up - uqw_base;
-			int off = ASTC_LDG(&di.wto[we]);
-			int cnt = ASTC_LDG(&di.wto[we + 1]) - off;
-			float sum = 0.0f;                  // chain lanes 0..11: (candidate, channel)
-			ASTC_NOUNROLL
-			for (int te0 = 0; te0 < cnt; te0 += 8) {
+			int off = s_wto[we];
+			int cnt = s_wto[we + 1] - off;
+			float error_base, error_down, error_up;
+#if ASTC_WARP == 1
+			{
+				// serial form: 12 ordered channel sums, then the weighted (x + z) + (y + w) fold
+				float acc[12];
+				for (int k = 0; k < 12; k++) acc[k] = 0.0f;
+				for (int te = 0; te < cnt; te++) {
+					uint32_t e = s_wtc[off + te];
+					int texel = (int)(e & 0xFF);
+					float tw_base = static_cast<float>(e >> 8) * (1.0f / 16.0f);
+					float weight_base = wb[texel];
+					float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
+					float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
+					int partition = s_pot[texel];
+					for (int c = 0; c < 4; c++) {
+						float color_offset = eo[partition * 4 + c];
+						float color = eb[partition * 4 + c] + color_offset * weight_base;
+						float orig = sptr<float>(b0.off + (uint32_t)c * cs)[texel];
+						float color_diff = color - orig;
+						float color_down_diff = color_diff + color_offset * weight_down;
+						float color_up_diff = color_diff + color_offset * weight_up;
+						acc[c] = acc[c] + color_diff * color_diff;
+						acc[4 + c] = acc[4 + c] + color_down_diff * color_down_diff;
+						acc[8 + c] = acc[8 + c] + color_up_diff * color_up_diff;
+					}
+				}
+				for (int k = 0; k < 12; k++) acc[k] = acc[k] * lane(ew, k & 3);
+				error_base = (acc[0] + acc[2]) + (acc[1] + acc[3]);
+				error_down = (acc[4] + acc[6]) + (acc[5] + acc[7]);
+				error_up = (acc[8] + acc[10]) + (acc[9] + acc[11]);
+			}
+			(void)slot;
+#else
+			{
+				// lane (slot, c): channel c of the slot-th texel of the current chunk of 8; every lane then gathers the
+				// chunk's terms of ITS channel in texel order, so all lanes of a channel hold the same ordered sums
+				float sb = 0.0f, sd = 0.0f, su = 0.0f;
 				ASTC_NOUNROLL
-				for (int s8 = slot; s8 < 8; s8 += slot_lanes) {
-					int te = te0 + s8;
+				for (int te0 = 0; te0 < cnt; te0 += 8) {
+					int te = te0 + slot;
+					float xb = 0.0f, xd = 0.0f, xu = 0.0f;
 					if (te < cnt) {
-						uint32_t e = ASTC_LDG(&di.wtc[off + te]);
+						uint32_t e = s_wtc[off + te];
 						int texel = (int)(e & 0xFF);
 						float tw_base = static_cast<float>(e >> 8) * (1.0f / 16.0f);
 						float weight_base = wb[texel];
 						float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
 						float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
-						int partition = pc > 1 ? (int)ASTC_LDG(&pi.partition_of_texel[texel]) : 0;
-#if ASTC_WARP == 1
-						for (int c = 0; c < 4; c++)
-#else
-						int c = lc;
-#endif
-						{
-							float color_offset = eo[partition * 4 + c];
-							float color = eb[partition * 4 + c] + color_offset * weight_base;
-							float orig = sptr<float>(b0.off + (uint32_t)c * cs)[texel];
-							float color_diff = color - orig;
-							float color_down_diff = color_diff + color_offset * weight_down;
-							float color_up_diff = color_diff + color_offset * weight_up;
-							tile[c * 9 + s8] = color_diff * color_diff;
-							tile[(4 + c) * 9 + s8] = color_down_diff * color_down_diff;
-							tile[(8 + c) * 9 + s8] = color_up_diff * color_up_diff;
-						}
+						int pidx = s_pot[texel] * 4 + lc;
+						float color_offset = eo[pidx];
+						float color = eb[pidx] + color_offset * weight_base;
+						float orig = sptr<float>(b0.off + (uint32_t)lc * cs)[texel];
+						float color_diff = color - orig;
+						float color_down_diff = color_diff + color_offset * weight_down;
+						float color_up_diff = color_diff + color_offset * weight_up;
+						xb = color_diff * color_diff;
+						xd = color_down_diff * color_down_diff;
+						xu = color_up_diff * color_up_diff;
 					}
-				}
-				wsync();
-				int m = cnt - te0 < 8 ? cnt - te0 : 8;
-#if ASTC_WARP == 1
-				ASTC_NOUNROLL
-				for (int ch = 0; ch < 12; ch++) {
-					float s = te0 == 0 ? 0.0f : tmpf[16 + ch];
-					for (int k = 0; k < m; k++) {
-						s = s + tile[ch * 9 + k];
-					}
-					tmpf[16 + ch] = s;
-				}
-#else
-				if (w.lane < 12) {
-					SPtr<float> row = tile + w.lane * 9;
+					int m = cnt - te0 < 8 ? cnt - te0 : 8;
 					ASTC_NOUNROLL
 					for (int k = 0; k < m; k++) {
-						sum = sum + row[k];
+						int src = k * 4 + lc;
+						sb = sb + __shfl_sync(0xffffffffu, xb, src);
+						sd = sd + __shfl_sync(0xffffffffu, xd, src);
+						su = su + __shfl_sync(0xffffffffu, xu, src);
 					}
 				}
-#endif
-				wsync();
-			}
-			float error_base, error_down, error_up;
-#if ASTC_WARP == 1
-			{
-				float t[12];
-				for (int ch = 0; ch < 12; ch++) {
-					t[ch] = tmpf[16 + ch] * lane(ew, ch & 3);
-				}
-				error_base = (t[0] + t[2]) + (t[1] + t[3]);
-				error_down = (t[4] + t[6]) + (t[5] + t[7]);
-				error_up = (t[8] + t[10]) + (t[9] + t[11]);
-			}
-#else
-			{
-				// lanes 0-3 / 4-7 / 8-11 hold the weighted channel sums of base / down / up: (x + z) + (y + w)
-				float v = sum * ew_c;
-				float a2 = v + __shfl_down_sync(0xffffffffu, v, 2);
-				float a1 = a2 + __shfl_down_sync(0xffffffffu, a2, 1);
-				error_base = __shfl_sync(0xffffffffu, a1, 0);
-				error_down = __shfl_sync(0xffffffffu, a1, 4);
-				error_up = __shfl_sync(0xffffffffu, a1, 8);
+				// dot with the channel weights: (x + z) + (y + w); fp addition commutes, so every lane gets the same bits
+				float vb = sb * ew_c, vd = sd * ew_c, vu = su * ew_c;
+				vb = vb + __shfl_xor_sync(0xffffffffu, vb, 2);
+				vd = vd + __shfl_xor_sync(0xffffffffu, vd, 2);
+				vu = vu + __shfl_xor_sync(0xffffffffu, vu, 2);
+				error_base = vb + __shfl_xor_sync(0xffffffffu, vb, 1);
+				error_down = vd + __shfl_xor_sync(0xffffffffu, vd, 1);
+				error_up = vu + __shfl_xor_sync(0xffffffffu, vu, 1);
 			}
 #endif
 			float new_uqw = -1.0f;
@@ -1363,7 +1384,7 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 				// the infill changed for this weight's texels only
 				ASTC_NOUNROLL
 				for (int te = w.lane; te < cnt; te += ASTC_WARP) {
-					int texel = (int)(ASTC_LDG(&di.wtc[off + te]) & 0xFF);
+					int texel = (int)(s_wtc[off + te] & 0xFF);
 					wb[texel] = bilinear_infill(di, uqf, texel);
 				}
 				wsync();

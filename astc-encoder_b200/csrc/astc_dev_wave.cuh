@@ -156,6 +156,8 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 			record_restore(w, a, b, s, t);
 			active = true;
 		}
+		// one CTA-wide vote per round: it doubles as the barrier that keeps the warps loosely phase-aligned
+		// (without it: 95.6 -> 126 ms at 4K 6x6 medium)
 		if (!cta_any(active)) {
 			break;
 		}
