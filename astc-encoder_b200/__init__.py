@@ -99,6 +99,8 @@ def lib():
         l.astcenc_b200_launch_count.restype = C.c_ulonglong
         l.astcenc_b200_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         l.astcenc_b200_last_timing.restype = C.c_int
+        l.astcenc_b200_stage_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint)]
+        l.astcenc_b200_stage_timing.restype = C.c_int
         _lib = l
     return _lib
 
@@ -170,6 +172,16 @@ class Context:
 
     def launch_count(self):
         return int(lib().astcenc_b200_launch_count(self.handle))
+
+    def stage_timing(self, enable, fetch=False):
+        """Enable / disable per-launch events; with fetch=True also return ({kernel: ms}, {kernel: launches}) of the last call."""
+        names = ("setup", "refine", "prepare", "emit")
+        if fetch:
+            ms = (C.c_float * 4)(); n = (C.c_uint * 4)()
+            lib().astcenc_b200_stage_timing(self.handle, 1 if enable else 0, ms, n)
+            return {k: float(ms[i]) for i, k in enumerate(names)}, {k: int(n[i]) for i, k in enumerate(names)}
+        lib().astcenc_b200_stage_timing(self.handle, 1 if enable else 0, None, None)
+        return None
 
     def last_timing(self):
         ms = C.c_float(); a = C.c_size_t(); b = C.c_size_t()

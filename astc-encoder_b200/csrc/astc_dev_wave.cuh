@@ -76,10 +76,11 @@ ASTC_FN void q_push(const WCtx& w, const WaveArgs& a, int kind, int wave, unsign
 struct alignas(16) U128 {
 	uint32_t x, y, z, w;
 };
-ASTC_FN void record_copy(const WCtx& w, const WaveArgs& a, unsigned int b, bool save) {
+// (the texels never change after the first save: later saves write the head only)
+ASTC_FN void record_copy(const WCtx& w, const WaveArgs& a, unsigned int b, bool save, bool with_texels = true) {
 	U128* g = reinterpret_cast<U128*>(a.records + (size_t)b * BSD.record_bytes);
 	const int n1 = A_PERSIST / 16;
-	int n2 = (w.T + 3) & ~3;              // 4 channels x Tp floats = Tp x 16 bytes
+	int n2 = with_texels ? ((w.T + 3) & ~3) : 0;      // 4 channels x Tp floats = Tp x 16 bytes
 	SPtr<U128> h = sptr<U128>(w.base);
 	SPtr<U128> t = sptr<U128>(w.base + A_BLK);
 	ASTC_NOUNROLL
@@ -100,13 +101,13 @@ ASTC_FN Trial& trial_of(const WCtx& w) { return *reinterpret_cast<Trial*>(astc_s
 static_assert(sizeof(BlockSearch) <= 128 && sizeof(Trial) <= 64, "search state must fit its arena slots");
 
 // park the search state in the arena and write the record
-ASTC_FN void record_save(const WCtx& w, const WaveArgs& a, unsigned int b, const BlockSearch& s, const Trial& t) {
+ASTC_FN void record_save(const WCtx& w, const WaveArgs& a, unsigned int b, const BlockSearch& s, const Trial& t, bool with_texels = false) {
 	if (w.lane == 0) {
 		search_of(w) = s;
 		trial_of(w) = t;
 	}
 	wsync();
-	record_copy(w, a, b, true);
+	record_copy(w, a, b, true, with_texels);
 }
 ASTC_FN void record_restore(const WCtx& w, const WaveArgs& a, unsigned int b, BlockSearch& s, Trial& t) {
 	record_copy(w, a, b, false);
@@ -188,7 +189,7 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 				}
 				wsync();
 			}
-			record_save(w, a, b, s, t);
+			record_save(w, a, b, s, t, a.wave == 0);
 			q_push(w, a, Q_REFINE, a.wave, b);
 		}
 	}

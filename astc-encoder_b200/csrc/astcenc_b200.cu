@@ -207,6 +207,10 @@ struct astcenc_context {
 	uint32_t* d_queues;          // 4 x capacity
 	size_t queue_capacity;
 	uint32_t* d_counters;        // count[4][MAX_WAVES] head[4][MAX_WAVES]
+	// optional per-stage timing (astcenc_b200_stage_timing): an event after every launch of the next call
+	int stage_timing;
+	std::vector<cudaEvent_t> stage_events;
+	std::vector<int> stage_kinds;
 	// staging buffers for the host-pointer API, grown on demand
 	uint8_t* d_image;
 	size_t d_image_bytes;
@@ -293,6 +297,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	ctx->d_queues = nullptr;
 	ctx->queue_capacity = 0;
 	ctx->d_counters = nullptr;
+	ctx->stage_timing = 0;
 	ctx->d_image = nullptr;
 	ctx->d_out = nullptr;
 	ctx->d_image_bytes = ctx->d_out_bytes = 0;
@@ -426,6 +431,9 @@ void astcenc_context_free(astcenc_context* ctx) {
 	cudaFree(ctx->d_records);
 	cudaFree(ctx->d_queues);
 	cudaFree(ctx->d_counters);
+	for (cudaEvent_t e : ctx->stage_events) {
+		cudaEventDestroy(e);
+	}
 	cudaFree(ctx->d_image);
 	cudaFree(ctx->d_out);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -507,15 +515,43 @@ static astcenc_error launch_slab(astcenc_context* ctx, const void* d_pixels, int
 			a.sync_mask = (unsigned int)strtoul(e, nullptr, 0);
 		}
 		int grid = ctx->grid;
+		size_t ev_used = 0;
+		auto mark = [&](int kind) {
+			if (!ctx->stage_timing) {
+				return;
+			}
+			if (ev_used == ctx->stage_events.size()) {
+				cudaEvent_t e;
+				if (cudaEventCreate(&e) != cudaSuccess) {
+					return;
+				}
+				ctx->stage_events.push_back(e);
+				ctx->stage_kinds.push_back(kind);
+			}
+			ctx->stage_kinds[ev_used] = kind;
+			cudaEventRecord(ctx->stage_events[ev_used++], stream);
+		};
+		if (ctx->stage_timing) {
+			ctx->stage_kinds.clear();
+			ctx->stage_kinds.resize(ctx->stage_events.size(), -1);
+		}
+		mark(-1);
 		for (int wave = 0; wave < ctx->max_waves; wave++) {
 			a.wave = wave;
 			astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
+			mark(0);
 			astc_wave_refine_kernel<<<grid, ctx->warps_small * 32, ctx->smem_small, stream>>>(bsd, ctx->dcfg, img, a);
+			mark(1);
 			astc_wave_prepare_kernel<<<grid, ctx->warps_small * 32, ctx->smem_small, stream>>>(bsd, ctx->dcfg, img, a);
+			mark(2);
 			ctx->launches += 3;
 		}
 		a.wave = 0;
 		astc_wave_emit_kernel<<<grid, ASTC_EMIT_THREADS, ASTC_SMEM_HDR + (ASTC_EMIT_THREADS / 32) * 32 * EMIT_SLICE, stream>>>(bsd, ctx->dcfg, img, a);
+		mark(3);
+		if (ctx->stage_timing) {
+			ctx->stage_kinds.resize(ev_used);
+		}
 		ctx->launches++;
 		CUDA_TRY(cudaGetLastError(), return ASTCENC_ERR_BAD_CONTEXT);
 		return ASTCENC_SUCCESS;
@@ -721,6 +757,32 @@ astcenc_error astcenc_b200_compress_device(astcenc_context* ctx, const void* d_p
 	int swz[4] = {(int)swizzle->r, (int)swizzle->g, (int)swizzle->b, (int)swizzle->a};
 	cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
 	return launch_slab(ctx, d_pixels, (int)data_type, dim_x, dim_y, swz, block_row0, block_rows, d_out, s);
+}
+
+astcenc_error astcenc_b200_stage_timing(astcenc_context* ctx, int enable, float stage_ms[4], unsigned int stage_launches[4]) {
+	if (!ctx) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	cudaSetDevice(ctx->device);
+	if (stage_ms && stage_launches && ctx->stage_timing && ctx->stage_kinds.size() > 1) {
+		// durations of the launches of the last astcenc_b200_compress_device() call, summed per kernel
+		cudaEventSynchronize(ctx->stage_events[ctx->stage_kinds.size() - 1]);
+		for (int k = 0; k < 4; k++) {
+			stage_ms[k] = 0.0f;
+			stage_launches[k] = 0;
+		}
+		for (size_t i = 1; i < ctx->stage_kinds.size(); i++) {
+			float ms = 0.0f;
+			cudaEventElapsedTime(&ms, ctx->stage_events[i - 1], ctx->stage_events[i]);
+			int k = ctx->stage_kinds[i];
+			if (k >= 0 && k < 4) {
+				stage_ms[k] += ms;
+				stage_launches[k]++;
+			}
+		}
+	}
+	ctx->stage_timing = enable ? 1 : 0;
+	return ASTCENC_SUCCESS;
 }
 
 unsigned long long astcenc_b200_launch_count(astcenc_context* ctx) {

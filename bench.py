@@ -138,9 +138,10 @@ def cpu_baseline(image, max_seconds=20.0):
 
 
 def traffic_from_profile():
+    """DRAM bytes of one pipeline pass (all stage-kernel launches of one image), summed from the committed ncu capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            return json.load(f).get("dram_bytes_per_pass")
     except Exception:
         return None
 
@@ -247,6 +248,12 @@ def main():
         b.record(stream)
     torch.cuda.synchronize()
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
+    # one more pass with an event after every launch: how the pass splits over the four stage kernels
+    ctx.stage_timing(True)
+    flush.zero_()
+    ctx.compress_device(d_img.data_ptr(), pkg.TYPE_U8, DIM, DIM, d_out.data_ptr(), stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+    stage_ms, stage_launches = ctx.stage_timing(False, fetch=True)
 
     # end to end through the C ABI with pinned host buffers (H2D + kernel + D2H inside the timed region)
     pin_in = torch.empty((DIM, DIM, 4), dtype=torch.uint8, pin_memory=True)
@@ -283,9 +290,14 @@ def main():
                 "gpu_launches": launches,
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_from_profile(),
-                             "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)", "kernel": "astc_compress_kernel", "kernel_ms": kernel_ms,
-                             "algorithmic_bytes_per_launch": ALGO_BYTES,
-                             "note": "the search is fp32-issue/latency bound, not bandwidth bound; frac is reported against the HBM roofline as the tier requires"},
+                             "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)",
+                             "kernel": "wave pipeline = astc_wave_{setup,refine,prepare,emit}_kernel, one pass over the image (%d launches)" % sum(stage_launches.values()),
+                             "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": ALGO_BYTES,
+                             "stage_ms": stage_ms, "stage_launches": stage_launches,
+                             "dominant_kernel": "astc_wave_%s_kernel" % max(stage_ms, key=stage_ms.get),
+                             "note": "achieved = (texels in + blocks out) / duration of one pipeline pass (CUDA events on the launching stream); traffic = DRAM bytes "
+                                     "of the same pass from ncu, it includes the per-block records the stage kernels exchange; the search is issue/latency "
+                                     "bound, not bandwidth bound - frac is reported against the HBM roofline as the tier requires"},
                 "wall_ms_per_step": wall * 1e3 / K}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(image)

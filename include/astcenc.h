@@ -192,6 +192,14 @@ ASTCENC_PUBLIC enum astcenc_error astcenc_b200_compress_device(struct astcenc_co
 /* Number of kernel launches issued by this context so far (bench.py reports it as gpu_launches). */
 ASTCENC_PUBLIC unsigned long long astcenc_b200_launch_count(struct astcenc_context* context);
 
+/**
+ * Per-stage timing of the wave pipeline (measurement aid). enable != 0 makes the following
+ * astcenc_b200_compress_device() calls record a CUDA event after every kernel launch; a later call with non-NULL
+ * arrays returns, for the last such call, the summed launch durations and launch counts per kernel
+ * (0 setup, 1 refine, 2 prepare, 3 emit). Leave it off for production use.
+ */
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_stage_timing(struct astcenc_context* context, int enable, float stage_ms[4], unsigned int stage_launches[4]);
+
 /* Milliseconds of device time (CUDA events on the launching stream) spent in the compress kernel by the most
  * recent astcenc_compress_image() call on this context, and its H2D / D2H byte counts. */
 ASTCENC_PUBLIC enum astcenc_error astcenc_b200_last_timing(struct astcenc_context* context, float* kernel_ms, size_t* h2d_bytes, size_t* d2h_bytes);
