@@ -211,9 +211,11 @@ enum {
 	A_SCB = 304,           // best_weights[64] best_colors[32] work_weights[64] work_colors[32] mod_colors[32] (224)
 	A_CAND = 528,          // Candidate[8]
 	A_CANDW = 592,         // quantised weights of the candidates, 8 x 64
-	A_EP = 1104,           // f4[EP_COUNT] endpoint slots (640), the trial's base endpoints first
+	A_CAND2 = 1104,        // candidates + weights of the FOLLOWING trial when one set-up serves two trials
+	A_CANDW2 = 1168,       //   (the mode-0 trial and the full 1-plane trial share everything but the mode range)
+	A_EP = 1680,           // f4[EP_COUNT] endpoint slots (640), the trial's base endpoints first
 	A_PERSIST = ASTC_ARENA_PERSIST_HEAD,   // = A_EP + 128
-	A_TMPF = 1744,         // float[128] chain results / partial sums
+	A_TMPF = 2320,         // float[128] chain results / partial sums
 	A_BLK = ASTC_ARENA_FIXED   // float[4][Tp] block texels
 };
 static_assert(sizeof(BlkInfo) == 112, "BlkInfo layout");

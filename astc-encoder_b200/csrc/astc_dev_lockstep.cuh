@@ -73,6 +73,7 @@ struct Trial {
 	float cutoff1, cutoff2;
 	unsigned int start_mode, end_mode;
 	unsigned int candidate_count;
+	unsigned int candidate_count_next;   // wave pipeline: candidates already selected for the following trial (A_CAND2), 0 = none
 };
 
 ASTC_FN SPtr<uint16_t> partition_list_of(const WCtx& w) { return sptr<uint16_t>(w.base + A_STATE + (uint32_t)offsetof(BlkInfo, partition_list)); }

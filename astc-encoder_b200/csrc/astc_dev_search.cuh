@@ -504,9 +504,10 @@ ASTC_FN int mode_bitcount(int weight_bits, int nplanes, int pc) {
 	return nplanes == 2 ? 109 - weight_bits : free_bits - weight_bits;
 }
 
-// compute_ideal_endpoint_formats :1096-1357. Returns the candidate count; candidates go to the arena.
-ASTC_COOP unsigned int compute_ideal_endpoint_formats(WCtx w, const PartView& pi, int ep0slot, int ep1slot, int nplanes,
-                                                      unsigned int start_block_mode, unsigned int end_block_mode) {
+// compute_ideal_endpoint_formats :1096-1357, in two parts.
+// Part 1: error tables + the total error of every block mode in [start, end) (overwrites the weight error in place).
+ASTC_COOP void endpoint_formats_prepare(WCtx w, const PartView& pi, int ep0slot, int ep1slot, int nplanes,
+                                        unsigned int start_block_mode, unsigned int end_block_mode) {
 	int pc = (int)pi.partition_count;
 	EncodingChoiceErrors eci[4];
 	compute_encoding_choice_errors(w, pi, ep0slot, ep1slot, eci);
@@ -518,7 +519,6 @@ ASTC_COOP unsigned int compute_ideal_endpoint_formats(WCtx w, const PartView& pi
 	}
 	uint32_t ef_off = su_of(w);
 	SPtr<float> mode_err = mode_err_of(w);
-	// total error per mode (overwrites the weight error in place)
 	ASTC_NOUNROLL
 	for (unsigned int i = start_block_mode + (unsigned int)w.lane; i < end_block_mode; i += ASTC_WARP) {
 		float qwt = mode_err[(int)i];
@@ -531,10 +531,18 @@ ASTC_COOP unsigned int compute_ideal_endpoint_formats(WCtx w, const PartView& pi
 		mode_err[(int)i] = error_of_best + qwt;
 	}
 	wsync();
-	// the tune_candidate_limit lowest totals, lowest index first among equals (:1286-1333)
+}
+
+// Part 2: the tune_candidate_limit lowest totals of [start, end), lowest index first among equals (:1286-1333), written
+// to the Candidate array at cand_off. With keep_errors the totals survive (a second selection over another range follows).
+ASTC_COOP unsigned int endpoint_formats_select(WCtx w, int pc, int nplanes, unsigned int start_block_mode, unsigned int end_block_mode,
+                                               uint32_t cand_off, bool keep_errors) {
+	uint32_t ef_off = su_of(w);
+	SPtr<float> mode_err = mode_err_of(w);
 	unsigned int limit = CFG.tune_candidate_limit;
 	unsigned int count = 0;
-	SPtr<Candidate> cands = cand_of(w);
+	SPtr<Candidate> cands = sptr<Candidate>(cand_off);
+	SPtr<float> taken = tmpf_of(w);             // [8] x (index, value) of the entries knocked out
 	ASTC_NOUNROLL
 	for (unsigned int k = 0; k < limit; k++) {
 		float best = ERROR_CALC_DEFAULT;
@@ -552,6 +560,8 @@ ASTC_COOP unsigned int compute_ideal_endpoint_formats(WCtx w, const PartView& pi
 			break;
 		}
 		if (w.lane == 0) {
+			taken[2 * (int)k] = ASTC_U2F((uint32_t)best_idx);
+			taken[2 * (int)k + 1] = best;
 			mode_err[best_idx] = ERROR_CALC_DEFAULT;
 			Candidate c;
 			c.block_mode = (uint16_t)best_idx;
@@ -562,8 +572,19 @@ ASTC_COOP unsigned int compute_ideal_endpoint_formats(WCtx w, const PartView& pi
 		count++;
 		wsync();
 	}
+	if (keep_errors && w.lane == 0) {
+		for (unsigned int k = 0; k < count; k++) {
+			mode_err[(int)ASTC_F2U(taken[2 * (int)k])] = taken[2 * (int)k + 1];
+		}
+	}
 	wsync();
 	return count;
+}
+
+ASTC_COOP unsigned int compute_ideal_endpoint_formats(WCtx w, const PartView& pi, int ep0slot, int ep1slot, int nplanes,
+                                                      unsigned int start_block_mode, unsigned int end_block_mode) {
+	endpoint_formats_prepare(w, pi, ep0slot, ep1slot, nplanes, start_block_mode, end_block_mode);
+	return endpoint_formats_select(w, (int)pi.partition_count, nplanes, start_block_mode, end_block_mode, w.base + A_CAND, false);
 }
 
 // =============================================================================================

@@ -17,8 +17,8 @@
 #define ASTC_MAX_KMEANS_TEXELS 64
 /* Per-warp arena head (astc_dev_core.cuh A_*): bytes before the block texels, and the part of it that, together with the
    block texels, forms a block's persistent record between stage kernels */
-#define ASTC_ARENA_FIXED 2256
-#define ASTC_ARENA_PERSIST_HEAD 1232
+#define ASTC_ARENA_FIXED 2832
+#define ASTC_ARENA_PERSIST_HEAD 1808
 #define ASTC_ANGULAR_STEPS 12     /* TUNE_MAX_ANGULAR_QUANT = 7 -> at most 12 steps are ever evaluated */
 
 enum { QUANT_2 = 0, QUANT_3, QUANT_4, QUANT_5, QUANT_6, QUANT_8, QUANT_10, QUANT_12, QUANT_16, QUANT_20, QUANT_24,

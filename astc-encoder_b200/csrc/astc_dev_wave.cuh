@@ -162,32 +162,66 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 		if (!cta_any(active)) {
 			break;
 		}
-		if (active) stage_ideal(w, t);
+		// The mode-0 trial (only the "always" modes) and the full 1-plane trial that follows it differ in nothing but
+		// the range of grids / block modes they look at: ideal weights, decimated weights, angular ranges and per-mode
+		// errors of the shared modes are identical (compress_symbolic.cpp:1243-1270 runs the same code twice).
+		// One set-up over the full range therefore serves both; the second candidate list waits in A_CAND2.
+		bool shared = active && !t.dual && t.only_always && t.partition_count == 1;
+		Trial tf = t;
+		if (shared) {
+			tf.only_always = 0;
+		}
+		if (active) stage_ideal(w, tf);
 		if (a.sync_mask & 1) cta_sync();
-		if (active) stage_decimate(w, t);
+		if (active) stage_decimate(w, tf);
 		if (a.sync_mask & 2) cta_sync();
 		if (active) {
-			trial_cutoffs(w, t);
-			compute_angular_endpoints(w, t.only_always != 0, t.dual ? 2 : 1, (unsigned int)t.max_weight_quant);
+			trial_cutoffs(w, tf);
+			compute_angular_endpoints(w, tf.only_always != 0, tf.dual ? 2 : 1, (unsigned int)tf.max_weight_quant);
 		}
 		if (a.sync_mask & 4) cta_sync();
-		if (active) quantize_and_score_modes(w, t.start_mode, t.end_mode, t.dual ? 2 : 1, t.partition_count, t.max_weight_quant, t.cutoff1, t.cutoff2);
+		if (active) quantize_and_score_modes(w, tf.start_mode, tf.end_mode, tf.dual ? 2 : 1, tf.partition_count, tf.max_weight_quant, tf.cutoff1, tf.cutoff2);
 		if (a.sync_mask & 8) cta_sync();
 		if (active) {
-			stage_formats(w, t);
-			// the refinement kernel has no decimated ideal weights: quantise every candidate's weights now
-			SPtr<uint32_t> ww = sptr<uint32_t>(work_weights_of(w).off);
-			SPtr<uint32_t> cw = sptr<uint32_t>(w.base + A_CANDW);
-			ASTC_NOUNROLL
-			for (unsigned int i = 0; i < t.candidate_count; i++) {
-				Candidate cd = cand_of(w)[(int)i];
-				const DevBlockMode* bm = BSD.block_modes + cd.block_mode;
-				quantize_candidate_weights(w, ASTC_LDG(&bm->decimation_mode), ASTC_LDG(&bm->quant_mode), t.dual ? 2 : 1, t.cutoff1, t.cutoff2);
+			t.cutoff1 = tf.cutoff1;
+			t.cutoff2 = tf.cutoff2;
+			t.start_mode = tf.start_mode;
+			t.end_mode = tf.end_mode;
+			t.candidate_count_next = 0;
+			if (shared) {
+				PartView pi = part_view_packed(1, 0);
+				SPtr<f4> ep = ep_of(w);
+				endpoint_formats_prepare(w, pi, EP_EI1_0, EP_EI1_1, 1, 0, tf.end_mode);
+				t.end_mode = BSD.block_mode_count_1plane_always;
+				t.candidate_count = endpoint_formats_select(w, 1, 1, 0, t.end_mode, w.base + A_CAND, true);
+				t.candidate_count_next = endpoint_formats_select(w, 1, 1, 0, tf.end_mode, w.base + A_CAND2, false);
 				ASTC_NOUNROLL
-				for (int k = w.lane; k < 16; k += ASTC_WARP) {
-					cw[(int)i * 16 + k] = ww[k];
+				for (int k = w.lane; k < 4; k += ASTC_WARP) {
+					ep[EP_BASE_0 + k] = ep[EP_EI1_0 + k];
+					ep[EP_BASE_1 + k] = ep[EP_EI1_1 + k];
 				}
 				wsync();
+			} else {
+				stage_formats(w, t);
+			}
+			// the refinement kernel has no decimated ideal weights: quantise every candidate's weights now
+			SPtr<uint32_t> ww = sptr<uint32_t>(work_weights_of(w).off);
+			ASTC_NOUNROLL
+			for (int list = 0; list < 2; list++) {
+				unsigned int n = list == 0 ? t.candidate_count : t.candidate_count_next;
+				SPtr<Candidate> cl = sptr<Candidate>(w.base + (list == 0 ? A_CAND : A_CAND2));
+				SPtr<uint32_t> cw = sptr<uint32_t>(w.base + (list == 0 ? A_CANDW : A_CANDW2));
+				ASTC_NOUNROLL
+				for (unsigned int i = 0; i < n; i++) {
+					Candidate cd = cl[(int)i];
+					const DevBlockMode* bm = BSD.block_modes + cd.block_mode;
+					quantize_candidate_weights(w, ASTC_LDG(&bm->decimation_mode), ASTC_LDG(&bm->quant_mode), t.dual ? 2 : 1, t.cutoff1, t.cutoff2);
+					ASTC_NOUNROLL
+					for (int k = w.lane; k < 16; k += ASTC_WARP) {
+						cw[(int)i * 16 + k] = ww[k];
+					}
+					wsync();
+				}
 			}
 			record_save(w, a, b, s, t, a.wave == 0);
 			q_push(w, a, Q_REFINE, a.wave, b);
@@ -199,8 +233,24 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 // R: refinement steps + the decision what the block does next.
 // ---------------------------------------------------------------------------------------------
 ASTC_COOP void wave_finish_trial(WCtx w, const WaveArgs& a, unsigned int b, BlockSearch& s, Trial& t, float errorval) {
+	unsigned int ready = t.candidate_count_next;
 	block_search_after_trial(w, s, t, errorval);
 	int next = block_search_advance(w, s, t);
+	t.candidate_count_next = 0;
+	if (ready != 0 && next == NEXT_TRIAL && s.phase == 0) {
+		// the set-up of the trial just finished already selected this trial's candidates: go straight to refinement
+		SPtr<uint32_t> dst = sptr<uint32_t>(w.base + A_CAND);
+		SPtr<uint32_t> src = sptr<uint32_t>(w.base + A_CAND2);
+		ASTC_NOUNROLL
+		for (int k = w.lane; k < (64 + 512) / 4; k += ASTC_WARP) {
+			dst[k] = src[k];
+		}
+		wsync();
+		t.candidate_count = ready;
+		record_save(w, a, b, s, t);
+		q_push(w, a, Q_REFINE, a.wave + 1, b);
+		return;
+	}
 	record_save(w, a, b, s, t);
 	route_block(w, a, b, next);
 }

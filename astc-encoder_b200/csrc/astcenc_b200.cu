@@ -775,6 +775,9 @@ astcenc_error astcenc_b200_stage_timing(astcenc_context* ctx, int enable, float 
 			float ms = 0.0f;
 			cudaEventElapsedTime(&ms, ctx->stage_events[i - 1], ctx->stage_events[i]);
 			int k = ctx->stage_kinds[i];
+			if (getenv("ASTCENC_B200_STAGE_PRINT")) {
+				fprintf(stderr, "launch %zu kind %d %.3f ms\n", i - 1, k, ms);
+			}
 			if (k >= 0 && k < 4) {
 				stage_ms[k] += ms;
 				stage_launches[k]++;

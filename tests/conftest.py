@@ -64,7 +64,7 @@ def hostsim():
     srcs = [os.path.join(HERE, "hostsim", "hostsim.cpp"), os.path.join(ROOT, "astc-encoder_b200", "csrc", "astc_host_tables.cpp"),
             os.path.join(ROOT, "astc-encoder_b200", "csrc", "astc_host_config.cpp")]
     csrc = os.path.join(ROOT, "astc-encoder_b200", "csrc")
-    newest = max(os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc))
+    newest = max([os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc)] + [os.path.getmtime(srcs[0])])
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         os.makedirs(os.path.dirname(so), exist_ok=True)
         _run(["g++", "-std=c++14", "-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-shared", "-x", "c++"] + srcs + ["-o", so])

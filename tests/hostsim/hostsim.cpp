@@ -87,7 +87,6 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 		a.sync_mask = 0xFF;
 		for (int wave = 0; wave < ASTC_MAX_WAVES - 1; wave++) {
 			a.wave = wave;
-			if (wave != 0 && a.count[Q_SETUP * ASTC_MAX_WAVES + wave] == 0) break;
 			wave_setup(w, a);
 			wave_refine(w, a);
 			wave_prepare(w, a);
