@@ -467,8 +467,37 @@ static size_t block_count_axis(size_t dim, size_t blk) {
 	return n;
 }
 
+static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
+                                  unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream);
+
+// A slab of block rows is processed in batches of at most ~1 M blocks: the per-block search records (a few KB each)
+// are the only buffer that grows with the image, and the batches reuse them in stream order.
 static astcenc_error launch_slab(astcenc_context* ctx, const void* d_pixels, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
                                  unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream) {
+	const DevBsd& bsd = ctx->tables->bsd;
+	size_t blocks_x = (dim_x + bsd.dim_x - 1) / bsd.dim_x;
+	size_t batch_blocks = (size_t)1 << 20;
+	if (const char* e = getenv("ASTCENC_B200_BATCH_BLOCKS")) {
+		long v = atol(e);
+		if (v > 0) batch_blocks = (size_t)v;
+	}
+	size_t rows_per_batch = batch_blocks / (blocks_x ? blocks_x : 1);
+	if (rows_per_batch < 1) rows_per_batch = 1;
+	unsigned int done = 0;
+	while (done < block_rows) {
+		unsigned int rows = block_rows - done;
+		if ((size_t)rows > rows_per_batch) rows = (unsigned int)rows_per_batch;
+		astcenc_error st = launch_batch(ctx, d_pixels, data_type, dim_x, dim_y, swz, block_row0 + done, rows, d_out + (size_t)done * blocks_x * 16, stream);
+		if (st != ASTCENC_SUCCESS) {
+			return st;
+		}
+		done += rows;
+	}
+	return ASTCENC_SUCCESS;
+}
+
+static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
+                                  unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream) {
 	const DevBsd& bsd = ctx->tables->bsd;
 	DevImage img;
 	img.data = d_pixels;

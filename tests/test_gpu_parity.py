@@ -246,10 +246,29 @@ def test_volume_of_2d_slices(gpu, oracle):
     assert np.array_equal(got, want)
 
 
-def test_global_memory_arena_fallback(gpu, oracle, monkeypatch):
-    """Configs whose per-warp arena exceeds shared memory run from a global-memory arena with identical results."""
-    monkeypatch.setenv("ASTCENC_B200_ARENA_GLOBAL", "1")
+@pytest.mark.parametrize("driver", ["lockstep", "warp"])
+def test_single_kernel_drivers_agree(gpu, oracle, monkeypatch, driver):
+    """The single-kernel drivers kept for A/B measurements (ASTCENC_B200_DRIVER) produce the same bytes as the wave pipeline."""
+    monkeypatch.setenv("ASTCENC_B200_DRIVER", driver)
     img = I.photo_like(96, 96, seed=12)
     want = oracle.compress(img, PRF_LDR, 6, 6, PRE_MEDIUM, S)
     got = gpu_compress(gpu, img, PRF_LDR, 6, 6, PRE_MEDIUM, S)
     assert np.array_equal(got, want)
+
+
+def test_batched_slabs_and_stage_barriers(gpu, oracle, monkeypatch):
+    """Small record batches (several pipeline passes per image) and the optional stage barriers change nothing."""
+    img = I.photo_like(192, 160, seed=13)
+    want = oracle.compress(img, PRF_LDR, 6, 6, PRE_MEDIUM, S)
+    monkeypatch.setenv("ASTCENC_B200_BATCH_BLOCKS", "100")
+    assert np.array_equal(gpu_compress(gpu, img, PRF_LDR, 6, 6, PRE_MEDIUM, S), want)
+    monkeypatch.setenv("ASTCENC_B200_SYNC_MASK", "0xFF")
+    assert np.array_equal(gpu_compress(gpu, img, PRF_LDR, 6, 6, PRE_MEDIUM, S), want)
+
+
+def test_mode0_disabled_and_partition_limits(gpu, oracle):
+    """Presets without the mode-0 trial (thorough and up) and with 1..4 partitions take the unshared set-up path."""
+    img = I.voronoi_flat(96, 96, seed=5)
+    for q in (PRE_THOROUGH, PRE_FASTEST):
+        want = oracle.compress(img, PRF_LDR, 5, 5, q, S)
+        assert np.array_equal(gpu_compress(gpu, img, PRF_LDR, 5, 5, q, S), want)
