@@ -1293,6 +1293,153 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 			wb[t] = bilinear_infill(di, uqf, t);
 		}
 		wsync();
+		// Dense grids (every weight touches only a few texels) leave most lanes of the per-weight scheme idle and
+		// are dominated by its sequential overhead. Weights (x, y) and (x', y') only interact when they are grid
+		// neighbours, and the reference's index order lets (x, y) see exactly its neighbours (x-1, y), (x-1, y-1),
+		// (x, y-1), (x+1, y-1) updated - which is what the anti-diagonal order k = x + 2 y guarantees as well. So all
+		// weights of one k are processed at once, one per group of four lanes (one lane per channel), each group
+		// walking its weight's texels in order. Same decisions, about half the sequential steps.
+		const DevDecMode* dmp = BSD.dec_modes + d;
+		int gw = ASTC_LDG(&dmp->weight_x), gh = ASTC_LDG(&dmp->weight_y);
+		if (ASTC_LDG(&dmp->max_weight_texels) <= 6) {
+#if ASTC_WARP == 1
+			const int groups = 1;
+#else
+			const int groups = 8;
+			int lc = w.lane & 3;
+			float ew_c = lane(ew, lc);
+#endif
+			ASTC_NOUNROLL
+			for (int k = 0; k <= (gw - 1) + 2 * (gh - 1); k++) {
+				int y0 = k > gw - 1 ? (k - (gw - 1) + 1) >> 1 : 0;
+				int y1 = (k >> 1) < gh - 1 ? (k >> 1) : gh - 1;
+				int n = y1 - y0 + 1;
+				ASTC_NOUNROLL
+				for (int j0 = 0; j0 < n; j0 += groups) {
+#if ASTC_WARP == 1
+					int j = j0;
+#else
+					int j = j0 + (w.lane >> 2);
+#endif
+					bool act = j < n;
+					int we = 0, off = 0, cnt = 0, uqw = 0;
+					float uqw_down = 0.0f, uqw_up = 0.0f, uqw_diff_down = 0.0f, uqw_diff_up = 0.0f;
+					if (act) {
+						int y = y0 + j;
+						we = y * gw + (k - 2 * y);
+						uint32_t pn = s_pn[we];
+						float uqw_base = uqf[we];
+						uqw = (int)uqw_base;
+						uqw_down = static_cast<float>(pn & 0xFF);
+						uqw_up = static_cast<float>((pn >> 8) & 0xFF);
+						uqw_diff_down = uqw_down - uqw_base;
+						uqw_diff_up = uqw_up - uqw_base;
+						off = s_wto[we];
+						cnt = s_wto[we + 1] - off;
+					}
+					float error_base, error_down, error_up;
+#if ASTC_WARP == 1
+					{
+						float acc[12];
+						for (int q = 0; q < 12; q++) acc[q] = 0.0f;
+						for (int te = 0; te < cnt; te++) {
+							uint32_t e = s_wtc[off + te];
+							int texel = (int)(e & 0xFF);
+							float tw_base = static_cast<float>(e >> 8) * (1.0f / 16.0f);
+							float weight_base = wb[texel];
+							float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
+							float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
+							int partition = s_pot[texel];
+							for (int c = 0; c < 4; c++) {
+								float color_offset = eo[partition * 4 + c];
+								float color = eb[partition * 4 + c] + color_offset * weight_base;
+								float orig = sptr<float>(b0.off + (uint32_t)c * cs)[texel];
+								float color_diff = color - orig;
+								float color_down_diff = color_diff + color_offset * weight_down;
+								float color_up_diff = color_diff + color_offset * weight_up;
+								acc[c] = acc[c] + color_diff * color_diff;
+								acc[4 + c] = acc[4 + c] + color_down_diff * color_down_diff;
+								acc[8 + c] = acc[8 + c] + color_up_diff * color_up_diff;
+							}
+						}
+						for (int q = 0; q < 12; q++) acc[q] = acc[q] * lane(ew, q & 3);
+						error_base = (acc[0] + acc[2]) + (acc[1] + acc[3]);
+						error_down = (acc[4] + acc[6]) + (acc[5] + acc[7]);
+						error_up = (acc[8] + acc[10]) + (acc[9] + acc[11]);
+					}
+#else
+					{
+						float sb = 0.0f, sd = 0.0f, su = 0.0f;
+						ASTC_NOUNROLL
+						for (int te = 0; te < cnt; te++) {
+							uint32_t e = s_wtc[off + te];
+							int texel = (int)(e & 0xFF);
+							float tw_base = static_cast<float>(e >> 8) * (1.0f / 16.0f);
+							float weight_base = wb[texel];
+							float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
+							float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
+							int pidx = s_pot[texel] * 4 + lc;
+							float color_offset = eo[pidx];
+							float color = eb[pidx] + color_offset * weight_base;
+							float orig = sptr<float>(b0.off + (uint32_t)lc * cs)[texel];
+							float color_diff = color - orig;
+							float color_down_diff = color_diff + color_offset * weight_down;
+							float color_up_diff = color_diff + color_offset * weight_up;
+							sb = sb + color_diff * color_diff;
+							sd = sd + color_down_diff * color_down_diff;
+							su = su + color_up_diff * color_up_diff;
+						}
+						float vb = sb * ew_c, vd = sd * ew_c, vu = su * ew_c;
+						vb = vb + __shfl_xor_sync(0xffffffffu, vb, 2);
+						vd = vd + __shfl_xor_sync(0xffffffffu, vd, 2);
+						vu = vu + __shfl_xor_sync(0xffffffffu, vu, 2);
+						error_base = vb + __shfl_xor_sync(0xffffffffu, vb, 1);
+						error_down = vd + __shfl_xor_sync(0xffffffffu, vd, 1);
+						error_up = vu + __shfl_xor_sync(0xffffffffu, vu, 1);
+					}
+#endif
+					float new_uqw = -1.0f;
+					if (act) {
+						if ((error_up < error_base) && (error_up < error_down) && (uqw < 64)) {
+							new_uqw = uqw_up;
+						} else if ((error_down < error_base) && (uqw > 0)) {
+							new_uqw = uqw_down;
+						}
+					}
+					bool changed = new_uqw >= 0.0f;
+#if ASTC_WARP == 1
+					if (changed) {
+						uqf[we] = new_uqw;
+						dec_weights_uquant[we] = static_cast<uint8_t>(new_uqw);
+						adjustments = true;
+						for (int te = 0; te < cnt; te++) {
+							int texel = (int)(s_wtc[off + te] & 0xFF);
+							wb[texel] = bilinear_infill(di, uqf, texel);
+						}
+					}
+#else
+					if (wany(changed)) {
+						adjustments = true;
+						if (changed && lc == 0) {
+							uqf[we] = new_uqw;
+							dec_weights_uquant[we] = static_cast<uint8_t>(new_uqw);
+						}
+						wsync();
+						if (changed) {
+							// the four lanes of the group share the texels whose infill moved
+							ASTC_NOUNROLL
+							for (int te = lc; te < cnt; te += 4) {
+								int texel = (int)(s_wtc[off + te] & 0xFF);
+								wb[texel] = bilinear_infill(di, uqf, texel);
+							}
+						}
+						wsync();
+					}
+#endif
+				}
+			}
+			continue;
+		}
 #if ASTC_WARP == 1
 		const int slot = 0;
 #else

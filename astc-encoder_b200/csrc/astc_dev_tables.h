@@ -66,7 +66,7 @@ struct DevDecMode {
 	uint16_t dwi_offset;      // float offset of this grid's ideal weights in the per-warp arena
 	uint16_t wto_offset;      // byte offset of wto inside the blob (= 24 * T)
 	uint16_t wtc_offset;      // byte offset of wtc
-	uint16_t pad0;
+	uint16_t max_weight_texels;   // longest weight -> texel list of this grid
 	uint32_t blob_offset;     // byte offset of the blob in dec_blob
 };
 

@@ -139,15 +139,19 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 		for (unsigned int e = 0; e < E; e++) {
 			wtc[e] = (uint16_t)(di.weight_texels[e] | ((unsigned int)di.weight_texel_contribs[e] << 8));
 		}
+		unsigned int grid_max_wtc = 0;
 		for (unsigned int i = 0; i < W; i++) {
 			if (di.weight_texel_count[i] > max_wtc) {
 				max_wtc = di.weight_texel_count[i];
+			}
+			if (di.weight_texel_count[i] > grid_max_wtc) {
+				grid_max_wtc = di.weight_texel_count[i];
 			}
 		}
 		dm.blob_offset = (uint32_t)base;
 		dm.wto_offset = (uint16_t)wto_off;
 		dm.wtc_offset = (uint16_t)wtc_off;
-		dm.pad0 = 0;
+		dm.max_weight_texels = (uint16_t)grid_max_wtc;
 		// arena slot for the decimated ideal weights (only grids the search can reference)
 		dm.dwi_offset = (uint16_t)dwi_total;
 		if (d < t.decimation_mode_count_selected) {
