@@ -266,6 +266,8 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a) {
 	t.dual = 0;
 	t.partition_count = 1;
 	t.packed = 0;
+	unsigned int round = 0;
+	const unsigned int vote_mask = (1u << ((a.sync_mask >> 8) & 7)) - 1u;
 	while (true) {
 		while (!has_item && !drained) {
 			if (!q_pop(w, a, Q_REFINE, a.wave, b)) {
@@ -287,8 +289,11 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a) {
 			}
 			has_item = true;
 		}
-		if (!cta_any(has_item)) {
-			break;
+		// (vote_period: tuning knob - vote only every 2^n-th round)
+		if ((round++ & vote_mask) == 0) {
+			if (!cta_any(has_item)) {
+				break;
+			}
 		}
 		if (has_item) {
 			r.in_step = true;
