@@ -27,6 +27,9 @@ ERROR_NAMES = ["ASTCENC_SUCCESS", "ASTCENC_ERR_OUT_OF_MEM", "ASTCENC_ERR_BAD_CPU
                "ASTCENC_ERR_NOT_IMPLEMENTED", "ASTCENC_ERR_BAD_DECODE_MODE"]
 
 
+ERR_OUT_OF_MEM, ERR_BAD_PARAM, ERR_BAD_SWIZZLE, ERR_BAD_CONTEXT, ERR_NOT_IMPLEMENTED = 1, 3, 7, 9, 10
+
+
 class AstcencError(RuntimeError):
     def __init__(self, code, what):
         self.code = code
@@ -87,6 +90,8 @@ def lib():
         l.astcenc_compress_image.restype = C.c_int
         l.astcenc_compress_reset.argtypes = [C.c_void_p]
         l.astcenc_compress_reset.restype = C.c_int
+        l.astcenc_decompress_image.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Image), C.POINTER(Swizzle), C.c_uint]
+        l.astcenc_decompress_image.restype = C.c_int
         l.astcenc_compress_cancel.argtypes = [C.c_void_p]
         l.astcenc_compress_cancel.restype = C.c_int
         l.astcenc_context_free.argtypes = [C.c_void_p]
@@ -158,6 +163,18 @@ class Context:
         if err:
             raise AstcencError(err, "astcenc_compress_image")
         return out
+
+    def decompress_image(self, blocks, dim_x, dim_y, dtype=np.uint8, swizzle=(0, 1, 2, 3), dim_z=1, thread_index=0):
+        """astcenc_decompress_image: 16-byte blocks -> (H, W, 4) (or (D, H, W, 4)) array of uint8 / float16 / float32."""
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+        out = np.zeros((dim_z, dim_y, dim_x, 4), dtype=dtype)
+        slices = (C.c_void_p * dim_z)(*[out[z].ctypes.data for z in range(dim_z)])
+        image = Image(dim_x, dim_y, dim_z, _DTYPES[np.dtype(dtype)], slices)
+        sw = Swizzle(*swizzle)
+        err = lib().astcenc_decompress_image(self.handle, blocks.ctypes.data, blocks.nbytes, C.byref(image), C.byref(sw), thread_index)
+        if err:
+            raise AstcencError(err, "astcenc_decompress_image")
+        return out[0] if dim_z == 1 else out
 
     def compress_device(self, d_pixels_ptr, data_type, dim_x, dim_y, d_out_ptr, block_row0=0, block_rows=None, swizzle=(0, 1, 2, 3), stream=0):
         """Device-resident path (astcenc_b200_compress_device): raw device pointers, enqueued on `stream`, no sync."""

@@ -33,6 +33,11 @@ struct DevConstTables {
 	uint8_t wq_quant_to_unquant[12][32];
 	uint8_t wq_scramble_map[12][32];
 	uint16_t wq_prev_next[12][65];
+	// decompression only
+	uint8_t trits_of_integer[256][5];
+	uint8_t quints_of_integer[128][3];
+	uint8_t wq_unscramble_and_unquant[12][32];
+	uint8_t color_scrambled_pquant_to_uquant[17][256];
 	float sin_table[64][ASTC_ANGULAR_STEPS];
 	float cos_table[64][ASTC_ANGULAR_STEPS];
 };

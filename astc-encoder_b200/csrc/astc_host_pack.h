@@ -42,10 +42,14 @@ static inline void fill_dev_const_tables(DevConstTables& d) {
 	memcpy(d.color_unquant_to_uquant, ct.color_unquant_to_uquant, sizeof(d.color_unquant_to_uquant));
 	memcpy(d.color_uquant_to_scrambled_pquant, ct.color_uquant_to_scrambled_pquant, sizeof(d.color_uquant_to_scrambled_pquant));
 	memcpy(d.quant_mode_table, ct.quant_mode_table, sizeof(d.quant_mode_table));
+	memcpy(d.trits_of_integer, ct.trits_of_integer, sizeof(d.trits_of_integer));
+	memcpy(d.quints_of_integer, ct.quints_of_integer, sizeof(d.quints_of_integer));
+	memcpy(d.color_scrambled_pquant_to_uquant, ct.color_scrambled_pquant_to_uquant, sizeof(d.color_scrambled_pquant_to_uquant));
 	for (int q = 0; q < 12; q++) {
 		memcpy(d.wq_quant_to_unquant[q], ct.weight_quant[q].quant_to_unquant, 32);
 		memcpy(d.wq_scramble_map[q], ct.weight_quant[q].scramble_map, 32);
 		memcpy(d.wq_prev_next[q], ct.weight_quant[q].prev_next_values, sizeof(uint16_t) * 65);
+		memcpy(d.wq_unscramble_and_unquant[q], ct.weight_quant[q].unscramble_and_unquant_map, 32);
 	}
 	for (int j = 0; j < 64; j++) {
 		for (int i = 0; i < ASTC_ANGULAR_STEPS; i++) {

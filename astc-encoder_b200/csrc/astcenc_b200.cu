@@ -111,6 +111,22 @@ astc_wave_emit_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant_
 	wave_emit(threadIdx.x & 31, ASTC_SMEM_HDR + (uint32_t)(threadIdx.x >> 5) * (32 * EMIT_SLICE), a);
 }
 
+// ---- decompression: one warp per block, grid-stride ----
+#define ASTC_DECODE_THREADS 256
+__global__ void __launch_bounds__(ASTC_DECODE_THREADS, 2)
+astc_decompress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img,
+                       const uint8_t* __restrict__ blocks, unsigned int block_count) {
+	stage_launch_constants(bsd, cfg, img);
+	const int lane = threadIdx.x & 31;
+	const unsigned int warps_per_cta = blockDim.x >> 5;
+	const uint32_t slice = ASTC_SMEM_HDR + (threadIdx.x >> 5) * D_SLICE;
+	for (unsigned int b = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); b < block_count; b += gridDim.x * warps_per_cta) {
+		unsigned int by = b / img.blocks_x;
+		unsigned int bx = b - by * img.blocks_x;
+		decompress_block(lane, slice, blocks + (size_t)b * 16, bx, by);
+	}
+}
+
 // ---- the single-kernel drivers (kept for A/B measurements: ASTCENC_B200_DRIVER=lockstep|warp) ----
 __global__ void __launch_bounds__(ASTC_CTA_THREADS_MAX, 1)
 astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img,
@@ -221,6 +237,8 @@ struct astcenc_context {
 	std::condition_variable cv;
 	int state;                   // 0 idle, 1 running, 2 done
 	astcenc_error result;
+	int dstate;                  // the same for decompression
+	astcenc_error dresult;
 	std::atomic<bool> cancel;
 	// stats
 	unsigned long long launches;
@@ -303,6 +321,8 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	ctx->d_image_bytes = ctx->d_out_bytes = 0;
 	ctx->state = 0;
 	ctx->result = ASTCENC_SUCCESS;
+	ctx->dstate = 0;
+	ctx->dresult = ASTCENC_SUCCESS;
 	ctx->cancel = false;
 	ctx->launches = 0;
 	ctx->last_kernel_ms = 0.0f;
@@ -724,18 +744,123 @@ astcenc_error astcenc_compress_cancel(astcenc_context* ctx) {
 	return ASTCENC_SUCCESS;
 }
 
-astcenc_error astcenc_decompress_image(astcenc_context* ctx, const uint8_t* data, size_t data_len, astcenc_image* image_out, const astcenc_swizzle* swizzle,
+static astcenc_error validate_decompression_swizzle(const astcenc_swizzle& s) {   // astcenc_entry.cpp:279-300: r,g,b,a,0,1 and Z
+	const int v[4] = {(int)s.r, (int)s.g, (int)s.b, (int)s.a};
+	for (int i = 0; i < 4; i++) {
+		if (v[i] < ASTCENC_SWZ_R || v[i] > ASTCENC_SWZ_Z) {
+			return ASTCENC_ERR_BAD_SWIZZLE;
+		}
+	}
+	return ASTCENC_SUCCESS;
+}
+
+static astcenc_error decompress_image_gpu(astcenc_context* ctx, const uint8_t* data, astcenc_image& image, const astcenc_swizzle& swizzle) {
+	const DevBsd& bsd = ctx->tables->bsd;
+	CUDA_TRY(cudaSetDevice(ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
+	size_t bpt = image.data_type == ASTCENC_TYPE_U8 ? 4 : image.data_type == ASTCENC_TYPE_F16 ? 8 : 16;
+	size_t slice_bytes = (size_t)image.dim_x * image.dim_y * bpt;
+	size_t blocks_x = block_count_axis(image.dim_x, bsd.dim_x);
+	size_t blocks_y = block_count_axis(image.dim_y, bsd.dim_y);
+	size_t in_bytes = blocks_x * blocks_y * 16;
+	if (ctx->d_image_bytes < slice_bytes) {
+		cudaFree(ctx->d_image);
+		ctx->d_image = nullptr;
+		ctx->d_image_bytes = 0;
+		CUDA_TRY(cudaMalloc(&ctx->d_image, slice_bytes), return ASTCENC_ERR_OUT_OF_MEM);
+		ctx->d_image_bytes = slice_bytes;
+	}
+	if (ctx->d_out_bytes < in_bytes) {
+		cudaFree(ctx->d_out);
+		ctx->d_out = nullptr;
+		ctx->d_out_bytes = 0;
+		CUDA_TRY(cudaMalloc(&ctx->d_out, in_bytes), return ASTCENC_ERR_OUT_OF_MEM);
+		ctx->d_out_bytes = in_bytes;
+	}
+	DevImage img;
+	img.data = ctx->d_image;
+	img.data_type = (int)image.data_type;
+	img.dim_x = image.dim_x;
+	img.dim_y = image.dim_y;
+	img.blocks_x = (unsigned int)blocks_x;
+	img.block_row0 = 0;
+	img.block_rows = (unsigned int)blocks_y;
+	img.swz[0] = (int)swizzle.r;
+	img.swz[1] = (int)swizzle.g;
+	img.swz[2] = (int)swizzle.b;
+	img.swz[3] = (int)swizzle.a;
+	img.out = nullptr;
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
+	unsigned int nblocks = (unsigned int)(blocks_x * blocks_y);
+	int warps = ASTC_DECODE_THREADS / 32;
+	int grid = (int)((nblocks + warps - 1) / warps);
+	if (grid > prop.multiProcessorCount * 8) {
+		grid = prop.multiProcessorCount * 8;
+	}
+	// 3D images with 2D blocks are an array of independent 2D slices; blocks of slice z follow those of slice z - 1
+	for (unsigned int z = 0; z < image.dim_z; z++) {
+		CUDA_TRY(cudaMemcpyAsync(ctx->d_out, data + (size_t)z * in_bytes, in_bytes, cudaMemcpyHostToDevice, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		astc_decompress_kernel<<<grid, ASTC_DECODE_THREADS, ASTC_SMEM_HDR + warps * D_SLICE, ctx->stream>>>(bsd, ctx->dcfg, img, ctx->d_out, nblocks);
+		CUDA_TRY(cudaGetLastError(), return ASTCENC_ERR_BAD_CONTEXT);
+		ctx->launches++;
+		CUDA_TRY(cudaMemcpyAsync(image.data[z], ctx->d_image, slice_bytes, cudaMemcpyDeviceToHost, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		CUDA_TRY(cudaStreamSynchronize(ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+	}
+	return ASTCENC_SUCCESS;
+}
+
+// astcenc_decompress_image (astcenc_entry.cpp:1274-1385): same check order; the decode mode follows the output type
+astcenc_error astcenc_decompress_image(astcenc_context* ctx, const uint8_t* data, size_t data_len, astcenc_image* image_outp, const astcenc_swizzle* swizzle,
                                        unsigned int thread_index) {
-	(void)data; (void)data_len; (void)image_out; (void)swizzle;
 	if (thread_index >= ctx->thread_count) {
 		return ASTCENC_ERR_BAD_PARAM;
 	}
-	// Decompression is the first "next" row of the scope table; not built yet.
-	return ASTCENC_ERR_NOT_IMPLEMENTED;
+	astcenc_error status = validate_decompression_swizzle(*swizzle);
+	if (status != ASTCENC_SUCCESS) {
+		return status;
+	}
+	astcenc_image& image = *image_outp;
+	bool overflow = false;
+	size_t texel_count = mul_safe(mul_safe(image.dim_x, image.dim_y, overflow), image.dim_z, overflow);
+	if (overflow || texel_count == 0) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	size_t blocks_x = block_count_axis(image.dim_x, ctx->config.block_x);
+	size_t blocks_y = block_count_axis(image.dim_y, ctx->config.block_y);
+	size_t blocks_z = block_count_axis(image.dim_z, ctx->config.block_z);
+	overflow = false;
+	size_t block_count = mul_safe(mul_safe(blocks_x, blocks_y, overflow), blocks_z, overflow);
+	mul_safe(block_count, 16, overflow);
+	if (overflow || block_count == 0) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	if (data_len < block_count * 16) {
+		return ASTCENC_ERR_OUT_OF_MEM;
+	}
+	// any subset of the thread_count callers may call; the image is decoded once, everybody returns when it is done
+	if (ctx->thread_count == 1) {
+		astcenc_decompress_reset(ctx);
+	}
+	std::unique_lock<std::mutex> lk(ctx->mtx);
+	if (ctx->dstate == 0) {
+		ctx->dstate = 1;
+		lk.unlock();
+		astcenc_error r = decompress_image_gpu(ctx, data, image, *swizzle);
+		lk.lock();
+		ctx->dresult = r;
+		ctx->dstate = 2;
+		ctx->cv.notify_all();
+		return r;
+	}
+	ctx->cv.wait(lk, [ctx] { return ctx->dstate == 2; });
+	return ctx->dresult;
 }
 
 astcenc_error astcenc_decompress_reset(astcenc_context* ctx) {
-	(void)ctx;
+	std::lock_guard<std::mutex> lk(ctx->mtx);
+	if (ctx->dstate != 1) {
+		ctx->dstate = 0;
+	}
 	return ASTCENC_SUCCESS;
 }
 

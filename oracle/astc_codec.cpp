@@ -1157,5 +1157,6 @@ static void compute_angular_endpoints_2planes(const BlockSizeTables& bsd, const 
 }
 
 #include "astc_codec_part2.inl"
+#include "astc_decode.inl"
 
 }  // namespace ao

@@ -88,6 +88,8 @@ void load_block(const Context& ctx, const void* data, int data_type, unsigned in
 void compress_block(const Context& ctx, const ImageBlock& blk, uint8_t pcb[16]);
 
 // whole-image loop of compress_image (astcenc_entry.cpp:891-1043), single slice
+// astcenc_decompress_image (astcenc_entry.cpp:1274-1385), single slice; swz uses astcenc_swz numbering (6 = Z)
+void decompress_image(const Context& ctx, const uint8_t* data, void* out, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4]);
 void compress_image(const Context& ctx, const void* data, int data_type, unsigned int dim_x, unsigned int dim_y,
                     const int swz[4], uint8_t* out);
 

@@ -34,6 +34,13 @@ int oracle_compress_image(void* ctx, const void* data, int data_type, unsigned i
 	return 0;
 }
 
+// blocks -> image. out has dim_x * dim_y * 4 components of data_type (0 = U8, 1 = F16, 2 = F32)
+int oracle_decompress_image(void* ctx, const uint8_t* data, void* out, int data_type, unsigned int dim_x, unsigned int dim_y, const int* swz) {
+	static const int ident[4] = {0, 1, 2, 3};
+	decompress_image(*static_cast<Context*>(ctx), data, out, data_type, dim_x, dim_y, swz ? swz : ident);
+	return 0;
+}
+
 // Copy the finalized config (as floats/uints in declaration order) for host-logic tests.
 void oracle_get_config(void* ctx, Config* out) {
 	*out = static_cast<Context*>(ctx)->config;

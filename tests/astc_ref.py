@@ -49,6 +49,8 @@ def _bind(lib):
     lib.astcenc_context_alloc.restype = C.c_int
     lib.astcenc_compress_image.argtypes = [C.c_void_p, C.POINTER(Image), C.POINTER(Swizzle), C.c_void_p, C.c_size_t, C.c_uint]
     lib.astcenc_compress_image.restype = C.c_int
+    lib.astcenc_decompress_image.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Image), C.POINTER(Swizzle), C.c_uint]
+    lib.astcenc_decompress_image.restype = C.c_int
     lib.astcenc_compress_reset.argtypes = [C.c_void_p]
     lib.astcenc_compress_reset.restype = C.c_int
     lib.astcenc_context_free.argtypes = [C.c_void_p]
@@ -114,6 +116,29 @@ class AstcencLib:
         return out
 
 
+    NP_TYPES = {TYPE_U8: np.uint8, TYPE_F16: np.float16, TYPE_F32: np.float32}
+
+    def decompress(self, blocks, w, h, profile, bx, by, out_type=TYPE_U8, flags=0, swz=(0, 1, 2, 3), quality=PRE_MEDIUM):
+        """blocks: uint8 array of 16-byte blocks. Returns a numpy (h, w, 4) image of out_type; raises on API errors."""
+        cfg = self.config(profile, bx, by, quality, flags)
+        ctx = C.c_void_p()
+        err = self.lib.astcenc_context_alloc(C.byref(cfg), 1, C.byref(ctx), None)
+        if err:
+            raise RuntimeError("context_alloc failed: %d" % err)
+        try:
+            blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+            out = np.zeros((h, w, 4), dtype=self.NP_TYPES[out_type])
+            slices = (C.c_void_p * 1)(out.ctypes.data)
+            image = Image(w, h, 1, out_type, slices)
+            sw = Swizzle(*swz)
+            err = self.lib.astcenc_decompress_image(ctx, blocks.ctypes.data, blocks.nbytes, C.byref(image), C.byref(sw), 0)
+            if err:
+                raise RuntimeError("decompress_image failed: %d" % err)
+            return out
+        finally:
+            self.lib.astcenc_context_free(ctx)
+
+
 def have_ref():
     return os.path.exists(REF_SO)
 
@@ -147,7 +172,22 @@ class Oracle:
         lib.oracle_compress_image.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.POINTER(C.c_int), C.c_void_p]
         lib.oracle_compress_image.restype = C.c_int
         lib.oracle_get_config.argtypes = [C.c_void_p, C.POINTER(OracleConfig)]
+        lib.oracle_decompress_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.POINTER(C.c_int)]
+        lib.oracle_decompress_image.restype = C.c_int
         self.lib = lib
+
+    def decompress(self, blocks, w, h, profile, bx, by, out_type=TYPE_U8, flags=0, swz=None, quality=PRE_MEDIUM):
+        ctx = self.lib.oracle_context_create(profile, bx, by, quality, flags, None)
+        if not ctx:
+            raise RuntimeError("oracle context failed")
+        try:
+            blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+            out = np.zeros((h, w, 4), dtype=AstcencLib.NP_TYPES[out_type])
+            sw = (C.c_int * 4)(*swz) if swz is not None else None
+            self.lib.oracle_decompress_image(ctx, blocks.ctypes.data, out.ctypes.data, out_type, w, h, sw)
+            return out
+        finally:
+            self.lib.oracle_context_destroy(ctx)
 
     def compress(self, img, profile, bx, by, quality, flags=0, swz=None, partition_count_limit=0, plane2_correlation=-1.0):
         img = np.ascontiguousarray(img)

@@ -98,6 +98,47 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	return 0;
 }
 
+// decompression through the device source (one simulated lane). swz uses astcenc_swz numbering.
+extern "C" int hostsim_decompress_image(int profile, unsigned int bx, unsigned int by, unsigned int flags, const uint8_t* blocks, void* out, int data_type,
+                                        unsigned int dim_x, unsigned int dim_y, const int* swz) {
+	astcenc_config cfg;
+	if (astc_host::config_init((astcenc_profile)profile, bx, by, 1, 60.0f, flags, &cfg) != ASTCENC_SUCCESS) return 1;
+	if (astc_host::validate_config(cfg) != ASTCENC_SUCCESS) return 2;
+	astc_host::BlockSizeTables* t = astc_host::build_block_size_tables(bx, by, (flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0, cfg.tune_partition_count_limit,
+	                                                                   static_cast<float>(cfg.tune_block_mode_limit) / 100.0f);
+	astc_host::PackedTables pk;
+	unsigned int lim[3] = {cfg.tune_2partition_index_limit, cfg.tune_3partition_index_limit, cfg.tune_4partition_index_limit};
+	astc_host::pack_device_tables(*t, lim, pk);
+	astc_host::relocate_bsd(pk.bsd, pk.blob.data());
+	astc_host::fill_dev_const_tables(pk.consts);
+	g_astc_ct = &pk.consts;
+	DevConfig dcfg;
+	astc_host::make_device_config(cfg, dcfg);
+	std::vector<uint8_t> window(ASTC_SMEM_HDR + D_SLICE + 64, 0xCD);
+	astc_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(window.data()) + 15) & ~(uintptr_t)15);
+	DevImage img;
+	img.data = out;
+	img.data_type = data_type;
+	img.dim_x = dim_x;
+	img.dim_y = dim_y;
+	img.blocks_x = (dim_x + bx - 1) / bx;
+	img.block_row0 = 0;
+	img.block_rows = (dim_y + by - 1) / by;
+	for (int i = 0; i < 4; i++) img.swz[i] = swz ? swz[i] : i;
+	img.out = nullptr;
+	SmemHdr* hdr = reinterpret_cast<SmemHdr*>(astc_smem);
+	hdr->bsd = pk.bsd;
+	hdr->cfg = dcfg;
+	hdr->img = img;
+	for (unsigned int y = 0; y < img.block_rows; y++) {
+		for (unsigned int x = 0; x < img.blocks_x; x++) {
+			decompress_block(0, ASTC_SMEM_HDR, blocks + ((size_t)y * img.blocks_x + x) * 16, x, y);
+		}
+	}
+	astc_host::free_block_size_tables(t);
+	return 0;
+}
+
 extern "C" unsigned int hostsim_arena_bytes(int profile, unsigned int bx, unsigned int by, float quality, unsigned int flags) {
 	astcenc_config cfg;
 	if (astc_host::config_init((astcenc_profile)profile, bx, by, 1, quality, flags, &cfg) != ASTCENC_SUCCESS) return 0;
