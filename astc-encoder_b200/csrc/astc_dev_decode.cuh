@@ -389,3 +389,89 @@ ASTC_COOP void decompress_block(int lane, uint32_t slice, const uint8_t* pcb, un
 	}
 	wsync();
 }
+
+// ---------------------------------------------------------------------------------------------
+// astcenc_get_block_info (astcenc_entry.cpp:1401-1517): the decoded view of one block. Filled by one warp.
+// ---------------------------------------------------------------------------------------------
+struct DevBlockInfo {
+	int is_error_block, is_constant_block, is_hdr_block, is_dual_plane_block;
+	unsigned int partition_count, partition_index, dual_plane_component;
+	unsigned int color_endpoint_modes[4];
+	unsigned int color_level_count, weight_level_count, weight_x, weight_y;
+	float color_endpoints[4][2][4];
+	float weight_values_plane1[ASTC_MAX_TEXELS];
+	float weight_values_plane2[ASTC_MAX_TEXELS];
+	uint8_t partition_assignment[ASTC_MAX_TEXELS];
+};
+
+ASTC_COOP void block_info(int lane, uint32_t slice, uint64_t lo, uint64_t hi, DevBlockInfo* out) {
+	int T = BSD.texel_count;
+	DecodeHdr& h = *reinterpret_cast<DecodeHdr*>(astc_smem + slice + D_HDR);
+	if (lane == 0) {
+		physical_to_symbolic(slice, lo, hi);
+	}
+	wsync();
+	int block_type = h.block_type;
+	if (lane == 0) {
+		out->is_error_block = block_type == SYM_BTYPE_ERROR;
+		out->is_constant_block = block_type == SYM_BTYPE_CONST_F16 || block_type == SYM_BTYPE_CONST_U16;
+	}
+	if (block_type != SYM_BTYPE_NONCONST) {
+		return;
+	}
+	int pc = h.partition_count;
+	int decode_mode = CFG.profile;
+	const DevBlockMode* bm = BSD.block_modes + h.block_mode_packed;
+	unsigned int d = ASTC_LDG(&bm->decimation_mode);
+	bool dual = ASTC_LDG(&bm->is_dual_plane) != 0;
+	SPtr<uint8_t> colors = sptr<uint8_t>(slice + D_COLORS);
+	if (lane == 0) {
+		out->weight_x = ASTC_LDG(&BSD.dec_modes[d].weight_x);
+		out->weight_y = ASTC_LDG(&BSD.dec_modes[d].weight_y);
+		out->is_dual_plane_block = dual ? 1 : 0;
+		out->partition_count = (unsigned int)pc;
+		out->partition_index = (unsigned int)h.partition_index;
+		out->dual_plane_component = (unsigned int)h.plane2_component;
+		out->color_level_count = quant_level_count(h.quant_mode);
+		out->weight_level_count = quant_level_count(ASTC_LDG(&bm->quant_mode));
+		int is_hdr = 0;
+		for (int p = 0; p < 4; p++) {
+			if (p >= pc) {
+				break;
+			}
+			uint8_t in[8];
+			for (int k = 0; k < 8; k++) {
+				in[k] = colors[p * 8 + k];
+			}
+			bool rgb_hdr, a_hdr;
+			i4 e[2];
+			unpack_color_endpoints(decode_mode, h.color_formats[p], in, rgb_hdr, a_hdr, e[0], e[1]);
+			out->color_endpoint_modes[p] = (unsigned int)h.color_formats[p];
+			is_hdr = is_hdr || rgb_hdr || a_hdr;
+			for (int j = 0; j < 2; j++) {
+				out->color_endpoints[p][j][0] = decode_component(e[j].x, rgb_hdr);
+				out->color_endpoints[p][j][1] = decode_component(e[j].y, rgb_hdr);
+				out->color_endpoints[p][j][2] = decode_component(e[j].z, rgb_hdr);
+				out->color_endpoints[p][j][3] = decode_component(e[j].w, a_hdr);
+			}
+		}
+		out->is_hdr_block = is_hdr;
+	}
+	DecView di = dec_view(d);
+	PartView pi = part_view_packed((unsigned int)pc, part_packed_index((unsigned int)pc, (unsigned int)h.partition_index));
+	SPtr<uint8_t> uq = sptr<uint8_t>(slice + D_WEIGHTS);
+	ASTC_NOUNROLL
+	for (int t = lane; t < T; t += ASTC_WARP) {
+		uint32_t ix = ASTC_LDG(&di.twi[t]);
+		uint32_t cx = ASTC_LDG(&di.tci[t]);
+		int i0 = (int)(ix & 0xFF), i1 = (int)((ix >> 8) & 0xFF), i2 = (int)((ix >> 16) & 0xFF), i3 = (int)(ix >> 24);
+		int c0 = (int)(cx & 0xFF), c1 = (int)((cx >> 8) & 0xFF), c2 = (int)((cx >> 16) & 0xFF), c3 = (int)(cx >> 24);
+		int w1 = (8 + uq[i0] * c0 + uq[i1] * c1 + uq[i2] * c2 + uq[i3] * c3) >> 4;
+		out->weight_values_plane1[t] = static_cast<float>(w1) * (1.0f / 16.0f);
+		if (dual) {
+			int w2 = (8 + uq[32 + i0] * c0 + uq[32 + i1] * c1 + uq[32 + i2] * c2 + uq[32 + i3] * c3) >> 4;
+			out->weight_values_plane2[t] = static_cast<float>(w2) * (1.0f / 16.0f);
+		}
+		out->partition_assignment[t] = ASTC_LDG(&pi.partition_of_texel[t]);
+	}
+}

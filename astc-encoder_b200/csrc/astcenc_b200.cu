@@ -127,6 +127,13 @@ astc_decompress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant
 	}
 }
 
+__global__ void __launch_bounds__(32, 1)
+astc_block_info_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img,
+                       unsigned long long lo, unsigned long long hi, DevBlockInfo* out) {
+	stage_launch_constants(bsd, cfg, img);
+	block_info(threadIdx.x & 31, ASTC_SMEM_HDR, lo, hi, out);
+}
+
 // ---- the single-kernel drivers (kept for A/B measurements: ASTCENC_B200_DRIVER=lockstep|warp) ----
 __global__ void __launch_bounds__(ASTC_CTA_THREADS_MAX, 1)
 astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img,
@@ -864,9 +871,64 @@ astcenc_error astcenc_decompress_reset(astcenc_context* ctx) {
 	return ASTCENC_SUCCESS;
 }
 
+// astcenc_get_block_info (astcenc_entry.cpp:1401-1517). A query for tools: one 32-thread launch per call.
 astcenc_error astcenc_get_block_info(astcenc_context* ctx, const uint8_t data[16], astcenc_block_info* info) {
-	(void)ctx; (void)data; (void)info;
-	return ASTCENC_ERR_NOT_IMPLEMENTED;
+	memset(info, 0, sizeof(*info));
+	info->profile = ctx->config.profile;
+	info->block_x = ctx->config.block_x;
+	info->block_y = ctx->config.block_y;
+	info->block_z = ctx->config.block_z;
+	info->texel_count = ctx->tables->bsd.texel_count;
+	CUDA_TRY(cudaSetDevice(ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
+	DevBlockInfo* d_info = nullptr;
+	CUDA_TRY(cudaMalloc(&d_info, sizeof(DevBlockInfo)), return ASTCENC_ERR_OUT_OF_MEM);
+	cudaMemsetAsync(d_info, 0, sizeof(DevBlockInfo), ctx->stream);
+	unsigned long long lo, hi;
+	memcpy(&lo, data, 8);
+	memcpy(&hi, data + 8, 8);
+	DevImage img;
+	memset(&img, 0, sizeof(img));
+	astc_block_info_kernel<<<1, 32, ASTC_SMEM_HDR + D_SLICE, ctx->stream>>>(ctx->tables->bsd, ctx->dcfg, img, lo, hi, d_info);
+	ctx->launches++;
+	DevBlockInfo h;
+	cudaError_t e = cudaMemcpyAsync(&h, d_info, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) {
+		e = cudaStreamSynchronize(ctx->stream);
+	}
+	cudaFree(d_info);
+	if (e != cudaSuccess) {
+		return ASTCENC_ERR_BAD_CONTEXT;
+	}
+	info->is_error_block = h.is_error_block != 0;
+	if (info->is_error_block) {
+		return ASTCENC_SUCCESS;
+	}
+	info->is_constant_block = h.is_constant_block != 0;
+	if (info->is_constant_block) {
+		return ASTCENC_SUCCESS;
+	}
+	info->is_hdr_block = h.is_hdr_block != 0;
+	info->is_dual_plane_block = h.is_dual_plane_block != 0;
+	info->partition_count = h.partition_count;
+	info->partition_index = h.partition_index;
+	info->dual_plane_component = h.dual_plane_component;
+	info->color_level_count = h.color_level_count;
+	info->weight_level_count = h.weight_level_count;
+	info->weight_x = h.weight_x;
+	info->weight_y = h.weight_y;
+	info->weight_z = 1;
+	for (unsigned int p = 0; p < h.partition_count && p < 4; p++) {
+		info->color_endpoint_modes[p] = h.color_endpoint_modes[p];
+		memcpy(info->color_endpoints[p], h.color_endpoints[p], sizeof(h.color_endpoints[p]));
+	}
+	for (unsigned int i = 0; i < info->texel_count; i++) {
+		info->weight_values_plane1[i] = h.weight_values_plane1[i];
+		if (info->is_dual_plane_block) {
+			info->weight_values_plane2[i] = h.weight_values_plane2[i];
+		}
+		info->partition_assignment[i] = h.partition_assignment[i];
+	}
+	return ASTCENC_SUCCESS;
 }
 
 const char* astcenc_get_error_string(astcenc_error status) {

@@ -42,6 +42,18 @@ class Swizzle(C.Structure):
     _fields_ = [("r", C.c_int), ("g", C.c_int), ("b", C.c_int), ("a", C.c_int)]
 
 
+class BlockInfo(C.Structure):
+    _fields_ = [
+        ("profile", C.c_int), ("block_x", C.c_uint), ("block_y", C.c_uint), ("block_z", C.c_uint), ("texel_count", C.c_uint),
+        ("is_error_block", C.c_bool), ("is_constant_block", C.c_bool), ("is_hdr_block", C.c_bool), ("is_dual_plane_block", C.c_bool),
+        ("partition_count", C.c_uint), ("partition_index", C.c_uint), ("dual_plane_component", C.c_uint),
+        ("color_endpoint_modes", C.c_uint * 4), ("color_level_count", C.c_uint), ("weight_level_count", C.c_uint),
+        ("weight_x", C.c_uint), ("weight_y", C.c_uint), ("weight_z", C.c_uint),
+        ("color_endpoints", C.c_float * 32), ("weight_values_plane1", C.c_float * 216), ("weight_values_plane2", C.c_float * 216),
+        ("partition_assignment", C.c_uint8 * 216),
+    ]
+
+
 def _bind(lib):
     lib.astcenc_config_init.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_float, C.c_uint, C.POINTER(Config)]
     lib.astcenc_config_init.restype = C.c_int
@@ -53,6 +65,8 @@ def _bind(lib):
     lib.astcenc_decompress_image.restype = C.c_int
     lib.astcenc_compress_reset.argtypes = [C.c_void_p]
     lib.astcenc_compress_reset.restype = C.c_int
+    lib.astcenc_get_block_info.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BlockInfo)]
+    lib.astcenc_get_block_info.restype = C.c_int
     lib.astcenc_context_free.argtypes = [C.c_void_p]
     lib.astcenc_context_free.restype = None
     lib.astcenc_get_error_string.argtypes = [C.c_int]
@@ -117,6 +131,26 @@ class AstcencLib:
 
 
     NP_TYPES = {TYPE_U8: np.uint8, TYPE_F16: np.float16, TYPE_F32: np.float32}
+
+    def block_infos(self, blocks, profile, bx, by, flags=0, quality=PRE_MEDIUM):
+        """astcenc_get_block_info of every 16-byte block; returns a list of raw struct bytes (for exact comparison)."""
+        cfg = self.config(profile, bx, by, quality, flags)
+        ctx = C.c_void_p()
+        err = self.lib.astcenc_context_alloc(C.byref(cfg), 1, C.byref(ctx), None)
+        if err:
+            raise RuntimeError("context_alloc failed: %d" % err)
+        try:
+            blocks = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, 16)
+            out = []
+            for b in blocks:
+                info = BlockInfo()
+                err = self.lib.astcenc_get_block_info(ctx, b.ctypes.data, C.byref(info))
+                if err:
+                    raise RuntimeError("get_block_info failed: %d" % err)
+                out.append(bytes(info))
+            return out
+        finally:
+            self.lib.astcenc_context_free(ctx)
 
     def decompress(self, blocks, w, h, profile, bx, by, out_type=TYPE_U8, flags=0, swz=(0, 1, 2, 3), quality=PRE_MEDIUM):
         """blocks: uint8 array of 16-byte blocks. Returns a numpy (h, w, 4) image of out_type; raises on API errors."""

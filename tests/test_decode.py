@@ -105,3 +105,17 @@ def test_decompress_error_order_and_slices(pkg, oracle):
             assert np.array_equal(vol[z], want)
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_get_block_info_matches_reference(pkg, reference, golden):
+    """astcenc_get_block_info: every field of the struct equals the reference build's, on real, random and void-extent blocks."""
+    prod = AstcencLib(os.path.join(ROOT, "astc-encoder_b200", "libastcenc_b200.so"))
+    rng = np.random.default_rng(31)
+    streams = [(golden["photo_6x6_medium"][:64 * 16], PRF_LDR, 6, 6), (golden["voronoi_8x8_thorough"][:48 * 16], PRF_LDR, 8, 8),
+               (golden["hdr_f16_6x6_medium"][:48 * 16], PRF_HDR, 6, 6), (rng.integers(0, 256, size=96 * 16, dtype=np.uint8), PRF_LDR, 5, 5),
+               (make_blocks("void", (24, 24), 6, 6, golden, 3), PRF_HDR, 6, 6)]
+    for blocks, prof, bx, by in streams:
+        want = reference.block_infos(blocks, prof, bx, by)
+        got = prod.block_infos(blocks, prof, bx, by)
+        assert got == want
