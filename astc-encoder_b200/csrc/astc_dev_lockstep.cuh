@@ -14,6 +14,8 @@
 // small state machine advanced between rounds. Results are bit-identical to the per-warp driver.
 #pragma once
 
+ASTC_FN bool block_has_alpha(const WCtx& w, const float* averages, float threshold, unsigned int pos_x, unsigned int pos_y);
+
 #if defined(ASTC_HOSTSIM) || defined(ASTC_DEBUG_SINGLE_LANE)
 ASTC_FN void cta_sync() {}
 ASTC_FN bool cta_any(bool p) { return p; }
@@ -641,6 +643,16 @@ ASTC_COOP void compress_blocks_lockstep(WCtx w, BlockFeed feed) {
 				}
 				unsigned int by = b / feed.blocks_x;
 				unsigned int bx = b - by * feed.blocks_x;
+				if (IMG.alpha_avg != nullptr && !block_has_alpha(w, IMG.alpha_avg, IMG.alpha_threshold, bx * BSD.dim_x, (by + IMG.block_row0) * BSD.dim_y)) {
+					if (w.lane == 0) {
+						BlkInfo& bi = bi_of(w);
+						bi.origin_texel = bi.data_min = bi.data_mean = bi.data_max = splat4(0.0f);
+						bi.grayscale = 1;
+					}
+					wsync();
+					emit_if_constant(w, b);
+					continue;
+				}
 				load_block(w, bx * BSD.dim_x, (by + IMG.block_row0) * BSD.dim_y);
 				if (emit_if_constant(w, b)) {
 					continue;

@@ -1779,5 +1779,6 @@ ASTC_NOINLINE void symbolic_to_physical(WCtx w, const ScbHdr& scb, uint8_t* out)
 #include "astc_dev_partition.cuh"
 #include "astc_dev_driver.cuh"
 #include "astc_dev_lockstep.cuh"
+#include "astc_dev_alpha.cuh"
 #include "astc_dev_wave.cuh"
 #include "astc_dev_decode.cuh"

@@ -133,4 +133,6 @@ struct DevImage {
 	unsigned int block_rows;   // number of block rows in this launch
 	int swz[4];
 	uint8_t* out;              // 16 bytes per block, slab-relative
+	const float* alpha_avg;    // per-texel alpha averages of the alpha-scale pre-pass, or NULL
+	float alpha_threshold;     // blocks with no average above this are emitted as constant zero
 };

@@ -143,6 +143,17 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 			while (feed_next(w, feed, b)) {
 				unsigned int by = b / a.blocks_x;
 				unsigned int bx = b - by * a.blocks_x;
+				if (IMG.alpha_avg != nullptr && !block_has_alpha(w, IMG.alpha_avg, IMG.alpha_threshold, bx * BSD.dim_x, (by + IMG.block_row0) * BSD.dim_y)) {
+					// alpha-scale RDO (astcenc_entry.cpp:1021-1030): the block is treated as all-zero
+					if (w.lane == 0) {
+						BlkInfo& bi = bi_of(w);
+						bi.origin_texel = bi.data_min = bi.data_mean = bi.data_max = splat4(0.0f);
+						bi.grayscale = 1;
+					}
+					wsync();
+					emit_if_constant(w, b);
+					continue;
+				}
 				load_block(w, bx * BSD.dim_x, (by + IMG.block_row0) * BSD.dim_y);
 				if (emit_if_constant(w, b)) {
 					continue;

@@ -111,6 +111,15 @@ astc_wave_emit_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant_
 	wave_emit(threadIdx.x & 31, ASTC_SMEM_HDR + (uint32_t)(threadIdx.x >> 5) * (32 * EMIT_SLICE), a);
 }
 
+// ---- alpha-scale pre-pass: one CTA per 32 x 32 tile ----
+#define ASTC_ALPHA_THREADS 128
+__global__ void __launch_bounds__(ASTC_ALPHA_THREADS, 1)
+astc_alpha_average_kernel(const __grid_constant__ DevImage img, unsigned int radius, unsigned int tiles_x, float* __restrict__ averages) {
+	unsigned int ty = blockIdx.x / tiles_x;
+	unsigned int tx = blockIdx.x - ty * tiles_x;
+	alpha_average_tile(img, radius, tx * ALPHA_TILE, ty * ALPHA_TILE, 0, averages, (int)threadIdx.x, (int)blockDim.x);
+}
+
 // ---- decompression: one warp per block, grid-stride ----
 #define ASTC_DECODE_THREADS 256
 __global__ void __launch_bounds__(ASTC_DECODE_THREADS, 2)
@@ -230,6 +239,9 @@ struct astcenc_context {
 	uint32_t* d_queues;          // 4 x capacity
 	size_t queue_capacity;
 	uint32_t* d_counters;        // count[4][MAX_WAVES] head[4][MAX_WAVES]
+	float* d_alpha;              // alpha-scale pre-pass: one average per texel
+	size_t d_alpha_bytes;
+	float alpha_threshold;
 	// optional per-stage timing (astcenc_b200_stage_timing): an event after every launch of the next call
 	int stage_timing;
 	std::vector<cudaEvent_t> stage_events;
@@ -322,6 +334,9 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	ctx->d_queues = nullptr;
 	ctx->queue_capacity = 0;
 	ctx->d_counters = nullptr;
+	ctx->d_alpha = nullptr;
+	ctx->d_alpha_bytes = 0;
+	ctx->alpha_threshold = 0.0f;
 	ctx->stage_timing = 0;
 	ctx->d_image = nullptr;
 	ctx->d_out = nullptr;
@@ -458,6 +473,7 @@ void astcenc_context_free(astcenc_context* ctx) {
 	cudaFree(ctx->d_records);
 	cudaFree(ctx->d_queues);
 	cudaFree(ctx->d_counters);
+	cudaFree(ctx->d_alpha);
 	for (cudaEvent_t e : ctx->stage_events) {
 		cudaEventDestroy(e);
 	}
@@ -510,6 +526,45 @@ static astcenc_error launch_slab(astcenc_context* ctx, const void* d_pixels, int
 	}
 	size_t rows_per_batch = batch_blocks / (blocks_x ? blocks_x : 1);
 	if (rows_per_batch < 1) rows_per_batch = 1;
+	const unsigned int radius = ctx->config.a_scale_radius;
+	if (radius != 0) {
+		// alpha-scale pre-pass over the whole image (every slab needs the averages of its own texels only, but the
+		// box filter reaches across slab borders, so the pass always reads the full image)
+		size_t need = (size_t)dim_x * dim_y * sizeof(float);
+		if (need > ctx->d_alpha_bytes) {
+			cudaFree(ctx->d_alpha);
+			ctx->d_alpha = nullptr;
+			ctx->d_alpha_bytes = 0;
+			CUDA_TRY(cudaMalloc(&ctx->d_alpha, need), return ASTCENC_ERR_OUT_OF_MEM);
+			ctx->d_alpha_bytes = need;
+		}
+		size_t pad = (size_t)ALPHA_TILE + 2 * (size_t)radius + 1;
+		size_t smem = pad * pad * sizeof(float);
+		if (smem > 200 * 1024) {
+			return ASTCENC_ERR_NOT_IMPLEMENTED;      // radius > ~94: the padded tile no longer fits shared memory
+		}
+		if (smem > 48 * 1024) {
+			CUDA_TRY(cudaFuncSetAttribute(astc_alpha_average_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), return ASTCENC_ERR_BAD_CONTEXT);
+		}
+		DevImage aimg;
+		memset(&aimg, 0, sizeof(aimg));
+		aimg.data = d_pixels;
+		aimg.data_type = data_type;
+		aimg.dim_x = dim_x;
+		aimg.dim_y = dim_y;
+		for (int i = 0; i < 4; i++) {
+			aimg.swz[i] = swz[i];
+		}
+		unsigned int tiles_x = (dim_x + ALPHA_TILE - 1) / ALPHA_TILE, tiles_y = (dim_y + ALPHA_TILE - 1) / ALPHA_TILE;
+		astc_alpha_average_kernel<<<tiles_x * tiles_y, ASTC_ALPHA_THREADS, smem, stream>>>(aimg, radius, tiles_x, ctx->d_alpha);
+		CUDA_TRY(cudaGetLastError(), return ASTCENC_ERR_BAD_CONTEXT);
+		ctx->launches++;
+		// astcenc_entry.cpp:983-988
+		size_t x_footprint = bsd.dim_x + 2 * ((size_t)radius - 1);
+		size_t y_footprint = bsd.dim_y + 2 * ((size_t)radius - 1);
+		float footprint = static_cast<float>(x_footprint * y_footprint);
+		ctx->alpha_threshold = 0.9f / (255.0f * footprint);
+	}
 	unsigned int done = 0;
 	while (done < block_rows) {
 		unsigned int rows = block_rows - done;
@@ -538,6 +593,8 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 		img.swz[i] = swz[i];
 	}
 	img.out = d_out;
+	img.alpha_avg = ctx->config.a_scale_radius != 0 ? ctx->d_alpha : nullptr;
+	img.alpha_threshold = ctx->alpha_threshold;
 	size_t total = (size_t)img.blocks_x * block_rows;
 	if (ctx->driver == 0) {
 		// ---- wave pipeline ----
@@ -709,8 +766,8 @@ astcenc_error astcenc_compress_image(astcenc_context* ctx, astcenc_image* imagep
 	if (data_len < block_count * 16) {
 		return ASTCENC_ERR_OUT_OF_MEM;
 	}
-	if (ctx->config.a_scale_radius != 0) {
-		// alpha-scale RDO pre-pass (compute_variance.cpp) is outside the hot path built here
+	if (ctx->config.a_scale_radius != 0 && image.dim_z != 1) {
+		// the alpha-scale pre-pass is built for 2D images; volumes would average across slices (compute_variance.cpp have_z)
 		return ASTCENC_ERR_NOT_IMPLEMENTED;
 	}
 	if (ctx->thread_count == 1) {
@@ -796,6 +853,8 @@ static astcenc_error decompress_image_gpu(astcenc_context* ctx, const uint8_t* d
 	img.swz[2] = (int)swizzle.b;
 	img.swz[3] = (int)swizzle.a;
 	img.out = nullptr;
+	img.alpha_avg = nullptr;
+	img.alpha_threshold = 0.0f;
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
 	unsigned int nblocks = (unsigned int)(blocks_x * blocks_y);

@@ -1,6 +1,9 @@
 // ORACLE (test infrastructure, not product code): CPU restatement of the reference's per-block
 // compressor. See astc_codec.h. Scalar C++, IEEE fp32, no FMA contraction (-ffp-contract=off).
 #include "astc_codec.h"
+#include <vector>
+#include <algorithm>
+#include <cstddef>
 
 #include <cstdlib>
 #include <cstring>

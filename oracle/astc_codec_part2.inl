@@ -1967,18 +1967,156 @@ void compress_block(const Context& ctx, const ImageBlock& blk, uint8_t pcb[16]) 
 	symbolic_to_physical(bsd, scb, pcb);
 }
 
+// brent_kung_prefix_sum (astcenc_compute_variance.cpp:52-100) on one float lane: in-place inclusive prefix sum whose
+// association order is the reference's reduction tree followed by its expansion tree.
+static void brent_kung_prefix_sum(float* d, size_t items, size_t stride) {
+	if (items < 2) {
+		return;
+	}
+	size_t lc_stride = 2;
+	size_t log2_stride = 1;
+	do {
+		size_t step = lc_stride >> 1;
+		size_t start = lc_stride - 1;
+		size_t iters = items >> log2_stride;
+		float* da = d + (start * stride);
+		ptrdiff_t ofs = -static_cast<ptrdiff_t>(step * stride);
+		size_t ofs_stride = stride << log2_stride;
+		while (iters) {
+			*da = *da + da[ofs];
+			da += ofs_stride;
+			iters--;
+		}
+		log2_stride += 1;
+		lc_stride <<= 1;
+	} while (lc_stride <= items);
+	do {
+		log2_stride -= 1;
+		lc_stride >>= 1;
+		size_t step = lc_stride >> 1;
+		size_t start = step + lc_stride - 1;
+		size_t iters = (items - step) >> log2_stride;
+		float* da = d + (start * stride);
+		ptrdiff_t ofs = -static_cast<ptrdiff_t>(step * stride);
+		size_t ofs_stride = stride << log2_stride;
+		while (iters) {
+			*da = *da + da[ofs];
+			da += ofs_stride;
+			iters--;
+		}
+	} while (lc_stride > 2);
+}
+
+// The alpha channel of the swizzled input texel as the averaging pass sees it (compute_variance.cpp:158-360)
+static inline float alpha_for_average(const void* data, int data_type, unsigned int dim_x, unsigned int x, unsigned int y, int swz_a) {
+	size_t o = (4 * (size_t)dim_x * y) + 4 * (size_t)x;
+	if (data_type == 0) {
+		const uint8_t* p = static_cast<const uint8_t*>(data) + o;
+		int v = swz_a < 4 ? p[swz_a] : (swz_a == 4 ? 0 : 255);
+		return static_cast<float>(v) * (1.0f / 255.0f);
+	}
+	if (data_type == 1) {
+		const uint16_t* p = static_cast<const uint16_t*>(data) + o;
+		int v = swz_a < 4 ? p[swz_a] : (swz_a == 4 ? 0 : 0x3C00);
+		// float16_to_float(vint4) of the F16C builds saturates the packed value (astcenc_vecmathlib_sse_4.h:1001)
+		return sf16_to_float((uint16_t)(v > 0x7FFF ? 0x7FFF : v));
+	}
+	const float* p = static_cast<const float*>(data) + o;
+	return swz_a < 4 ? p[swz_a] : (swz_a == 4 ? 0.0f : 1.0f);
+}
+
+// compute_averages + compute_pixel_region_variance for a 2D image (astcenc_entry.cpp:1056-1108,
+// astcenc_compute_variance.cpp:103-500): per 32x32 tile a summed-area table of the alpha channel, box average of radius r.
+static void compute_alpha_averages(const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4], unsigned int radius, float* averages) {
+	const size_t step = 32;
+	size_t kerneldim = 2 * (size_t)radius + 1;
+	std::vector<float> buf((step + kerneldim) * (step + kerneldim));
+	float alpha_kdim = static_cast<float>(2 * radius + 1);
+	float alpha_rsamples = 1.0f / (alpha_kdim * alpha_kdim);
+	for (size_t oy = 0; oy < dim_y; oy += step) {
+		size_t size_y = std::min(step, (size_t)dim_y - oy);
+		for (size_t ox = 0; ox < dim_x; ox += step) {
+			size_t size_x = std::min(step, (size_t)dim_x - ox);
+			size_t padsize_x = size_x + kerneldim, padsize_y = size_y + kerneldim;
+			size_t yst = padsize_x;
+			for (size_t y = 1; y < padsize_y; y++) {
+				size_t y_src = (y - 1) + oy;
+				y_src = y_src <= radius ? 0 : y_src - radius;
+				y_src = std::min(y_src, (size_t)dim_y - 1);
+				for (size_t x = 1; x < padsize_x; x++) {
+					size_t x_src = (x - 1) + ox;
+					x_src = x_src <= radius ? 0 : x_src - radius;
+					x_src = std::min(x_src, (size_t)dim_x - 1);
+					buf[y * yst + x] = alpha_for_average(data, data_type, dim_x, (unsigned int)x_src, (unsigned int)y_src, swz[3]);
+				}
+			}
+			for (size_t y = 0; y < padsize_y; y++) buf[y * yst] = 0.0f;
+			for (size_t x = 0; x < padsize_x; x++) buf[x] = 0.0f;
+			for (size_t y = 1; y < padsize_y; y++) {
+				brent_kung_prefix_sum(&buf[y * yst + 1], padsize_x - 1, 1);
+			}
+			for (size_t x = 1; x < padsize_x; x++) {
+				brent_kung_prefix_sum(&buf[1 * yst + x], padsize_y - 1, yst);
+			}
+			for (size_t y = 0; y < size_y; y++) {
+				size_t y_src = y + radius;
+				size_t y_low = y_src - radius, y_high = y_src + radius + 1;
+				for (size_t x = 0; x < size_x; x++) {
+					size_t x_src = x + radius;
+					size_t x_low = x_src - radius, x_high = x_src + radius + 1;
+					float vasum = buf[y_low * yst + x_low] - buf[y_low * yst + x_high] - buf[y_high * yst + x_low] + buf[y_high * yst + x_high];
+					averages[(y + oy) * dim_x + (x + ox)] = vasum * alpha_rsamples;
+				}
+			}
+		}
+	}
+}
+
 void compress_image(const Context& ctx, const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4], uint8_t* out) {
 	unsigned int bx = ctx.bsd->dim_x, by = ctx.bsd->dim_y;
 	unsigned int blocks_x = (dim_x + bx - 1) / bx;
 	unsigned int blocks_y = (dim_y + by - 1) / by;
 	ImageBlock blk;
+	std::vector<float> alpha_averages;
+	unsigned int radius = ctx.config.a_scale_radius;
+	if (radius != 0) {
+		alpha_averages.resize((size_t)dim_x * dim_y);
+		compute_alpha_averages(data, data_type, dim_x, dim_y, swz, radius, alpha_averages.data());
+	}
 	for (unsigned int y = 0; y < blocks_y; y++) {
 		for (unsigned int x = 0; x < blocks_x; x++) {
-			load_block(ctx, data, data_type, dim_x, dim_y, x * bx, y * by, swz, blk);
-			if (ctx.config.flags & FLG_USE_ALPHA_WEIGHT) {
-				float alpha_scale = blk.data_max.w * (1.0f / 65535.0f);
-				blk.channel_weight = mk4(ctx.config.cw_r_weight * alpha_scale, ctx.config.cw_g_weight * alpha_scale,
-				                         ctx.config.cw_b_weight * alpha_scale, ctx.config.cw_a_weight);
+			// alpha-scale RDO (astcenc_entry.cpp:973-1003): blocks whose footprint has (almost) no alpha become constant zero
+			bool use_full_block = true;
+			if (radius != 0) {
+				size_t start_x = (size_t)x * bx, end_x = std::min((size_t)dim_x, start_x + bx);
+				size_t start_y = (size_t)y * by, end_y = std::min((size_t)dim_y, start_y + by);
+				size_t x_footprint = bx + 2 * ((size_t)radius - 1);
+				size_t y_footprint = by + 2 * ((size_t)radius - 1);
+				float footprint = static_cast<float>(x_footprint * y_footprint);
+				float threshold = 0.9f / (255.0f * footprint);
+				use_full_block = false;
+				for (size_t ay = start_y; ay < end_y && !use_full_block; ay++) {
+					for (size_t ax = start_x; ax < end_x; ax++) {
+						if (alpha_averages[ay * dim_x + ax] > threshold) {
+							use_full_block = true;
+							break;
+						}
+					}
+				}
+			}
+			if (use_full_block) {
+				load_block(ctx, data, data_type, dim_x, dim_y, x * bx, y * by, swz, blk);
+				if (ctx.config.flags & FLG_USE_ALPHA_WEIGHT) {
+					float alpha_scale = blk.data_max.w * (1.0f / 65535.0f);
+					blk.channel_weight = mk4(ctx.config.cw_r_weight * alpha_scale, ctx.config.cw_g_weight * alpha_scale,
+					                         ctx.config.cw_b_weight * alpha_scale, ctx.config.cw_a_weight);
+				}
+			} else {
+				blk.origin_texel = splat4(0.0f);
+				blk.data_min = splat4(0.0f);
+				blk.data_mean = splat4(0.0f);
+				blk.data_max = splat4(0.0f);
+				blk.grayscale = true;
 			}
 			compress_block(ctx, blk, out + ((size_t)y * blocks_x + x) * 16);
 		}

@@ -7,7 +7,7 @@ using namespace ao;
 extern "C" {
 
 // Returns an opaque context or nullptr. `tune_overrides` may be null; otherwise 3 entries:
-// {tune_partition_count_limit (0 = keep), tune_2plane_early_out_limit_correlation (<0 = keep), reserved}.
+// {tune_partition_count_limit (0 = keep), tune_2plane_early_out_limit_correlation (<0 = keep), a_scale_radius (0 = off)}.
 void* oracle_context_create(int profile, unsigned int block_x, unsigned int block_y, float quality, unsigned int flags, const float* tune_overrides) {
 	Config cfg;
 	if (config_init(profile, block_x, block_y, quality, flags, cfg) != 0) {
@@ -16,6 +16,7 @@ void* oracle_context_create(int profile, unsigned int block_x, unsigned int bloc
 	if (tune_overrides) {
 		if (tune_overrides[0] > 0.0f) cfg.tune_partition_count_limit = (unsigned int)tune_overrides[0];
 		if (tune_overrides[1] >= 0.0f) cfg.tune_2plane_early_out_limit_correlation = tune_overrides[1];
+		if (tune_overrides[2] > 0.0f) cfg.a_scale_radius = (unsigned int)tune_overrides[2];
 	}
 	if (config_finalize(cfg) != 0) {
 		return nullptr;

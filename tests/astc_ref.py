@@ -223,11 +223,11 @@ class Oracle:
         finally:
             self.lib.oracle_context_destroy(ctx)
 
-    def compress(self, img, profile, bx, by, quality, flags=0, swz=None, partition_count_limit=0, plane2_correlation=-1.0):
+    def compress(self, img, profile, bx, by, quality, flags=0, swz=None, partition_count_limit=0, plane2_correlation=-1.0, a_scale_radius=0):
         img = np.ascontiguousarray(img)
         h, w = img.shape[:2]
         dt = {np.dtype(np.uint8): TYPE_U8, np.dtype(np.float16): TYPE_F16, np.dtype(np.float32): TYPE_F32}[img.dtype]
-        ov = (C.c_float * 3)(float(partition_count_limit), float(plane2_correlation), 0.0)
+        ov = (C.c_float * 3)(float(partition_count_limit), float(plane2_correlation), float(a_scale_radius))
         ctx = self.lib.oracle_context_create(profile, bx, by, quality, flags, ov)
         if not ctx:
             raise RuntimeError("oracle context failed")

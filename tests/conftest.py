@@ -72,5 +72,6 @@ def hostsim():
     lib.hostsim_compress_image.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float, C.c_uint, C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.POINTER(C.c_int), C.c_void_p]
     lib.hostsim_arena_bytes.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_float, C.c_uint]
     lib.hostsim_arena_bytes.restype = C.c_uint
+    lib.hostsim_set_a_scale_radius.argtypes = [C.c_uint]
     lib.hostsim_decompress_image.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.POINTER(C.c_int)]
     return lib

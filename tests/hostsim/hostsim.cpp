@@ -11,10 +11,14 @@
 #include <cstring>
 #include <cstdlib>
 
+static unsigned int g_hostsim_a_scale_radius = 0;
+extern "C" void hostsim_set_a_scale_radius(unsigned int r) { g_hostsim_a_scale_radius = r; }
+
 extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int by, float quality, unsigned int flags,
                                       const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, const int* swz, uint8_t* out) {
 	astcenc_config cfg;
 	if (astc_host::config_init((astcenc_profile)profile, bx, by, 1, quality, flags, &cfg) != ASTCENC_SUCCESS) return 1;
+	cfg.a_scale_radius = g_hostsim_a_scale_radius;
 	if (astc_host::validate_config(cfg) != ASTCENC_SUCCESS) return 2;
 	astc_host::BlockSizeTables* t = astc_host::build_block_size_tables(bx, by, (flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0, cfg.tune_partition_count_limit,
 	                                                                   static_cast<float>(cfg.tune_block_mode_limit) / 100.0f);
@@ -39,6 +43,27 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	img.block_rows = (dim_y + by - 1) / by;
 	for (int i = 0; i < 4; i++) img.swz[i] = swz ? swz[i] : i;
 	img.out = out;
+	img.alpha_avg = nullptr;
+	img.alpha_threshold = 0.0f;
+	std::vector<float> alpha_avg;
+	if (cfg.a_scale_radius != 0) {
+		// the pre-pass, tile by tile, through the device source (one simulated thread)
+		unsigned int r = cfg.a_scale_radius;
+		alpha_avg.resize((size_t)dim_x * dim_y);
+		size_t pad = ALPHA_TILE + 2 * (size_t)r + 1;
+		std::vector<uint8_t> tile_mem(pad * pad * 4 + 64);
+		uint8_t* saved = astc_smem;
+		astc_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tile_mem.data()) + 15) & ~(uintptr_t)15);
+		for (unsigned int oy = 0; oy < dim_y; oy += ALPHA_TILE) {
+			for (unsigned int ox = 0; ox < dim_x; ox += ALPHA_TILE) {
+				alpha_average_tile(img, r, ox, oy, 0, alpha_avg.data(), 0, 1);
+			}
+		}
+		astc_smem = saved;
+		img.alpha_avg = alpha_avg.data();
+		size_t x_footprint = bx + 2 * ((size_t)r - 1), y_footprint = by + 2 * ((size_t)r - 1);
+		img.alpha_threshold = 0.9f / (255.0f * static_cast<float>(x_footprint * y_footprint));
+	}
 	SmemHdr* hdr = reinterpret_cast<SmemHdr*>(astc_smem);
 	hdr->bsd = pk.bsd;
 	hdr->cfg = dcfg;
@@ -126,6 +151,8 @@ extern "C" int hostsim_decompress_image(int profile, unsigned int bx, unsigned i
 	img.block_rows = (dim_y + by - 1) / by;
 	for (int i = 0; i < 4; i++) img.swz[i] = swz ? swz[i] : i;
 	img.out = nullptr;
+	img.alpha_avg = nullptr;
+	img.alpha_threshold = 0.0f;
 	SmemHdr* hdr = reinterpret_cast<SmemHdr*>(astc_smem);
 	hdr->bsd = pk.bsd;
 	hdr->cfg = dcfg;
