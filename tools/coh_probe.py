@@ -1,6 +1,6 @@
 """Dev tool: time the kernel on a 1024^2 photo (29k blocks), normal vs coherence probe (set by env)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from astc_ref import *
 import astc_images as I
 prod = AstcencLib(os.path.join(ROOT, "astc-encoder_b200", "libastcenc_b200.so"))

@@ -1,6 +1,6 @@
 """Quick on-GPU sanity run (dev tool): product library vs the reference build / oracle on a few images."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from astc_ref import *
 import astc_images as I

@@ -1,6 +1,6 @@
 """Dev tool: compress ONE block with the tracing build and print the intermediate values."""
 import sys, os, ctypes as C
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from astc_ref import *
 import astc_images as I

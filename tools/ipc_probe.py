@@ -1,7 +1,7 @@
 """Dev tool: run the product library on one image with search-limiting config overrides (to vary the hot code
 footprint) - meant to be run under `ncu --metrics ...` to compare issue rates and instruction-cache hit rates."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from astc_ref import *
 import astc_images as I
