@@ -180,6 +180,7 @@ ASTC_COOP float refine_candidates(WCtx w, unsigned int pc, unsigned int packed, 
 				work.block_type = SYM_BTYPE_NONCONST;
 			}
 
+			unpack_work_endpoints(w, partition_count, formats, ends_off_of(w));
 			bool stop_all = false;
 			if (l == 0) {
 				float errorval = compute_symbolic_block_difference(w, partition_count, formats, plane2_component, pi, (unsigned int)dmode, dual);

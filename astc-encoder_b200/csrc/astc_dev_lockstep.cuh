@@ -532,6 +532,8 @@ ASTC_COOP void refine_pack(WCtx w, const Trial& t, Refine& r) {
 	work.block_mode = r.mode_index;
 	work.block_type = SYM_BTYPE_NONCONST;
 	r.formats = formats;
+	// integer endpoints of the packed candidate, once per step: both scores and the realignment read them
+	unpack_work_endpoints(w, t.dual ? 1u : t.partition_count, formats, ends_off_of(w));
 }
 
 ASTC_FN float refine_score(WCtx w, const Trial& t, const Refine& r) {

@@ -792,73 +792,84 @@ ASTC_COOP void recompute_ideal_colors_1plane(WCtx w, const PartView& pi, unsigne
 		}
 	}
 	wsync();
-	// phase C: the solves, one lane per partition
-	SPtr<f4> ep = ep_of(w);
+	// phase C: the solves, one lane per (partition, channel): every channel of the reference's vfloat4 algebra is
+	// independent, the per-partition scalars are recomputed by the four lanes of a partition
+	SPtr<float> epf = sptr<float>(ep_of(w).off);          // endpoint slots as floats: slot * 4 + channel
 	ASTC_NOUNROLL
-	for (unsigned int i = (unsigned int)w.lane; i < pc; i += ASTC_WARP) {
+	for (unsigned int k = (unsigned int)w.lane; k < pc * 4; k += ASTC_WARP) {
+		unsigned int i = k >> 2;
+		int c = (int)(k & 3);
 		SPtr<float> a = tmpf + (int)i * 14;
-		float left_sum_s = a[0], middle_sum_s = a[1], right_sum_s = a[2], weight_weight_sum_s = a[3];
-		f4 color_vec_x = mk4(a[4], a[5], a[6], a[7]);
-		f4 color_vec_y = mk4(a[8], a[9], a[10], a[11]);
-		f4 scale_vec = mk4(a[12], a[13], 0.0f, 0.0f);
-		SPtr<float> sdp = sdv + (int)i * 4;
-		f4 sdir = mk4(sdp[0], sdp[1], sdp[2], sdp[3]);
-		f4 rws = max4(color_weight * static_cast<float>(pv_count(pi, i)), splat4(1e-17f));
+		float left_sum_s = a[0], middle_sum_s = a[1], right_sum_s = a[2];
+		float cw_c = lane(color_weight, c);
+		float color_vec_x = a[4 + c] * cw_c;
+		float color_vec_y = a[8 + c] * cw_c;
+		float scale_vec_x = a[12], scale_vec_y = a[13];
+		float sdir_c = sdv[(int)i * 4 + c];
+		float rws_c = maxf(cw_c * static_cast<float>(pv_count(pi, i)), 1e-17f);
 		float wmn = mm[(int)i * 4], wmx = mm[(int)i * 4 + 1], smn = mm[(int)i * 4 + 2], smx = mm[(int)i * 4 + 3];
-		f4 left_sum = splat4(left_sum_s) * color_weight;
-		f4 middle_sum = splat4(middle_sum_s) * color_weight;
-		f4 right_sum = splat4(right_sum_s) * color_weight;
-		f4 lmrs_sum = mk4(left_sum_s, middle_sum_s, right_sum_s, 0.0f) * ls_weight;
-		color_vec_x = color_vec_x * color_weight;
-		color_vec_y = color_vec_y * color_weight;
+		float left_sum = left_sum_s * cw_c;
+		float middle_sum = middle_sum_s * cw_c;
+		float right_sum = right_sum_s * cw_c;
+		float lmrs_x = left_sum_s * ls_weight, lmrs_y = middle_sum_s * ls_weight, lmrs_z = right_sum_s * ls_weight;
 		float scalediv = smn / maxf(smx, 1e-10f);
 		scalediv = clamp1f(scalediv);
-		f4 sds = sdir * smx;
-		f4 rgbs = mk4(sds.x, sds.y, sds.z, scalediv);
-		f4 e0 = ep[EP_WORK_0 + (int)i], e1 = ep[EP_WORK_1 + (int)i];
+		float rgbs_c = c < 3 ? sdir_c * smx : scalediv;
+		float e0 = epf[(EP_WORK_0 + (int)i) * 4 + c], e1 = epf[(EP_WORK_1 + (int)i) * 4 + c];
 		if (wmn >= wmx * 0.999f) {
-			f4 avg = (color_vec_x + color_vec_y) / rws;
-			e0 = sel4(e0, avg, avg.x == avg.x, avg.y == avg.y, avg.z == avg.z, avg.w == avg.w);
-			e1 = sel4(e1, avg, avg.x == avg.x, avg.y == avg.y, avg.z == avg.z, avg.w == avg.w);
-			rgbs = mk4(sds.x, sds.y, sds.z, 1.0f);
+			float avg = (color_vec_x + color_vec_y) / rws_c;
+			if (avg == avg) {
+				e0 = avg;
+				e1 = avg;
+			}
+			if (c == 3) {
+				rgbs_c = 1.0f;
+			}
 		} else {
-			f4 color_det1 = (left_sum * right_sum) - (middle_sum * middle_sum);
-			f4 color_rdet1 = splat4(1.0f) / color_det1;
-			float ls_det1 = (lmrs_sum.x * lmrs_sum.z) - (lmrs_sum.y * lmrs_sum.y);
+			float color_det1 = (left_sum * right_sum) - (middle_sum * middle_sum);
+			float color_rdet1 = 1.0f / color_det1;
+			float ls_det1 = (lmrs_x * lmrs_z) - (lmrs_y * lmrs_y);
 			float ls_rdet1 = 1.0f / ls_det1;
-			f4 color_mss1 = (left_sum * left_sum) + (splat4(2.0f) * middle_sum * middle_sum) + (right_sum * right_sum);
-			float ls_mss1 = (lmrs_sum.x * lmrs_sum.x) + (2.0f * lmrs_sum.y * lmrs_sum.y) + (lmrs_sum.z * lmrs_sum.z);
-			f4 ep0 = (right_sum * color_vec_x - middle_sum * color_vec_y) * color_rdet1;
-			f4 ep1 = (left_sum * color_vec_y - middle_sum * color_vec_x) * color_rdet1;
-			f4 thr = color_mss1 * 1e-4f;
-			bool m0 = absf(color_det1.x) > thr.x && ep0.x == ep0.x && ep1.x == ep1.x;
-			bool m1 = absf(color_det1.y) > thr.y && ep0.y == ep0.y && ep1.y == ep1.y;
-			bool m2 = absf(color_det1.z) > thr.z && ep0.z == ep0.z && ep1.z == ep1.z;
-			bool m3 = absf(color_det1.w) > thr.w && ep0.w == ep0.w && ep1.w == ep1.w;
-			e0 = sel4(e0, ep0, m0, m1, m2, m3);
-			e1 = sel4(e1, ep1, m0, m1, m2, m3);
-			float scale_ep0 = (lmrs_sum.z * scale_vec.x - lmrs_sum.y * scale_vec.y) * ls_rdet1;
-			float scale_ep1 = (lmrs_sum.x * scale_vec.y - lmrs_sum.y * scale_vec.x) * ls_rdet1;
+			float color_mss1 = (left_sum * left_sum) + (2.0f * middle_sum * middle_sum) + (right_sum * right_sum);
+			float ls_mss1 = (lmrs_x * lmrs_x) + (2.0f * lmrs_y * lmrs_y) + (lmrs_z * lmrs_z);
+			float ep0 = (right_sum * color_vec_x - middle_sum * color_vec_y) * color_rdet1;
+			float ep1 = (left_sum * color_vec_y - middle_sum * color_vec_x) * color_rdet1;
+			float thr = color_mss1 * 1e-4f;
+			if (absf(color_det1) > thr && ep0 == ep0 && ep1 == ep1) {
+				e0 = ep0;
+				e1 = ep1;
+			}
+			float scale_ep0 = (lmrs_z * scale_vec_x - lmrs_y * scale_vec_y) * ls_rdet1;
+			float scale_ep1 = (lmrs_x * scale_vec_y - lmrs_y * scale_vec_x) * ls_rdet1;
 			if (fabsf(ls_det1) > (ls_mss1 * 1e-4f) && scale_ep0 == scale_ep0 && scale_ep1 == scale_ep1 && scale_ep0 < scale_ep1) {
-				float scalediv2 = scale_ep0 / scale_ep1;
-				f4 sdsm = sdir * scale_ep1;
-				rgbs = mk4(sdsm.x, sdsm.y, sdsm.z, scalediv2);
+				rgbs_c = c < 3 ? sdir_c * scale_ep1 : scale_ep0 / scale_ep1;
 			}
 		}
-		ep[EP_WORK_0 + (int)i] = e0;
-		ep[EP_WORK_1 + (int)i] = e1;
-		ep[EP_RGBS + (int)i] = rgbs;
-		if (bi.rgb_lns0 || bi.alpha_lns0) {
+		epf[(EP_WORK_0 + (int)i) * 4 + c] = e0;
+		epf[(EP_WORK_1 + (int)i) * 4 + c] = e1;
+		epf[(EP_RGBS + (int)i) * 4 + c] = rgbs_c;
+	}
+	wsync();
+	if (bi.rgb_lns0 || bi.alpha_lns0) {
+		// HDR: the RGBO fit mixes the channels - one lane per partition
+		SPtr<f4> ep = ep_of(w);
+		ASTC_NOUNROLL
+		for (unsigned int i = (unsigned int)w.lane; i < pc; i += ASTC_WARP) {
+			SPtr<float> a = tmpf + (int)i * 14;
+			float right_sum_s = a[2], weight_weight_sum_s = a[3];
+			f4 color_vec_x = mk4(a[4], a[5], a[6], a[7]) * color_weight;
+			f4 color_vec_y = mk4(a[8], a[9], a[10], a[11]) * color_weight;
+			f4 rws = max4(color_weight * static_cast<float>(pv_count(pi, i)), splat4(1e-17f));
 			f4 weight_weight_sum = splat4(weight_weight_sum_s) * color_weight;
 			float psum = right_sum_s * hadd_rgb_s(color_weight);
 			f4 rgbq_sum = color_vec_x + color_vec_y;
 			rgbq_sum.w = hadd_rgb_s(color_vec_y);
 			f4 rgbovec = compute_rgbo_vector(rws, weight_weight_sum, rgbq_sum, psum);
-			rgbo_fallback(rgbovec, e0, e1);
+			rgbo_fallback(rgbovec, ep[EP_WORK_0 + (int)i], ep[EP_WORK_1 + (int)i]);
 			ep[EP_RGBO + (int)i] = rgbovec;
 		}
+		wsync();
 	}
-	wsync();
 }
 
 // recompute_ideal_colors_2planes :1369-1650. Per-texel terms (texel order):
@@ -940,93 +951,82 @@ ASTC_COOP void recompute_ideal_colors_2planes(WCtx w, unsigned int d, int plane2
 	float wmin1 = wmin_f(a), wmax1 = wmax_f(b), wmin2 = wmin_f(a2), wmax2 = wmax_f(b2);
 	float scale_min = wmin_f(c), scale_max = wmax_f(dd);
 	wsync();
-	if (w.lane == 0) {
+	// the solves: one lane per channel (the plane-2 component uses the plane-2 sums, the others the plane-1 sums)
+	{
+		SPtr<float> t = tmpf;
+		SPtr<float> epf = sptr<float>(ep_of(w).off);
+		ASTC_NOUNROLL
+		for (int c = w.lane; c < 4; c += ASTC_WARP) {
+			bool p2 = c == plane2_component;
+			float cw_c = lane(color_weight, c);
+			float color_vec_x = t[6 + c] * cw_c;
+			float color_vec_y = t[10 + c] * cw_c;
+			float rws_c = lane(rgba_weight_sum, c);
+			float left_s = p2 ? t[3] : t[0], middle_s = p2 ? t[4] : t[1], right_s = p2 ? t[5] : t[2];
+			float wmn = p2 ? wmin2 : wmin1, wmx = p2 ? wmax2 : wmax1;
+			float left_sum = left_s * cw_c, middle_sum = middle_s * cw_c, right_sum = right_s * cw_c;
+			float e0 = epf[EP_WORK_0 * 4 + c], e1 = epf[EP_WORK_1 * 4 + c];
+			if (wmn >= wmx * 0.999f) {
+				float avg = (color_vec_x + color_vec_y) / rws_c;
+				if (avg == avg) {
+					e0 = avg;
+					e1 = avg;
+				}
+			} else {
+				float color_det = (left_sum * right_sum) - (middle_sum * middle_sum);
+				float color_rdet = 1.0f / color_det;
+				float color_mss = (left_sum * left_sum) + (2.0f * middle_sum * middle_sum) + (right_sum * right_sum);
+				float ep0 = (right_sum * color_vec_x - middle_sum * color_vec_y) * color_rdet;
+				float ep1 = (left_sum * color_vec_y - middle_sum * color_vec_x) * color_rdet;
+				if (absf(color_det) > color_mss * 1e-4f && ep0 == ep0 && ep1 == ep1) {
+					e0 = ep0;
+					e1 = ep1;
+				}
+			}
+			// the RGBS vector always comes from plane 1
+			float lmrs_x = t[0] * ls_weight, lmrs_y = t[1] * ls_weight, lmrs_z = t[2] * ls_weight;
+			float scalediv = scale_min / maxf(scale_max, 1e-10f);
+			scalediv = clamp1f(scalediv);
+			float sdir_c = lane(scale_dir, c);
+			float rgbs_c = c < 3 ? sdir_c * scale_max : scalediv;
+			if (wmin1 >= wmax1 * 0.999f) {
+				if (c == 3) {
+					rgbs_c = 1.0f;
+				}
+			} else {
+				float ls_det1 = (lmrs_x * lmrs_z) - (lmrs_y * lmrs_y);
+				float ls_rdet1 = 1.0f / ls_det1;
+				float ls_mss1 = (lmrs_x * lmrs_x) + (2.0f * lmrs_y * lmrs_y) + (lmrs_z * lmrs_z);
+				float scale_ep0 = (lmrs_z * t[14] - lmrs_y * t[15]) * ls_rdet1;
+				float scale_ep1 = (lmrs_x * t[15] - lmrs_y * t[14]) * ls_rdet1;
+				if (fabsf(ls_det1) > (ls_mss1 * 1e-4f) && scale_ep0 == scale_ep0 && scale_ep1 == scale_ep1 && scale_ep0 < scale_ep1) {
+					rgbs_c = c < 3 ? sdir_c * scale_ep1 : scale_ep0 / scale_ep1;
+				}
+			}
+			epf[EP_WORK_0 * 4 + c] = e0;
+			epf[EP_WORK_1 * 4 + c] = e1;
+			epf[EP_RGBS * 4 + c] = rgbs_c;
+		}
+	}
+	wsync();
+	if ((bi.rgb_lns0 || bi.alpha_lns0) && w.lane == 0) {
+		// HDR: the RGBO fit mixes the channels
 		SPtr<float> t = tmpf;
 		SPtr<f4> ep = ep_of(w);
 		bool p20 = plane2_component == 0, p21 = plane2_component == 1, p22 = plane2_component == 2, p23 = plane2_component == 3;
-		float left1_sum_s = t[0], middle1_sum_s = t[1], right1_sum_s = t[2];
-		float left2_sum_s = t[3], middle2_sum_s = t[4], right2_sum_s = t[5];
-		f4 color_vec_x = mk4(t[6], t[7], t[8], t[9]);
-		f4 color_vec_y = mk4(t[10], t[11], t[12], t[13]);
-		f4 scale_vec = mk4(t[14], t[15], 0.0f, 0.0f);
-		f4 weight_weight_sum = mk4(t[16], t[17], t[18], t[19]);
-		f4 left1_sum = splat4(left1_sum_s) * color_weight;
-		f4 middle1_sum = splat4(middle1_sum_s) * color_weight;
-		f4 right1_sum = splat4(right1_sum_s) * color_weight;
-		f4 lmrs_sum = mk4(left1_sum_s, middle1_sum_s, right1_sum_s, 0.0f) * ls_weight;
-		f4 left2_sum = splat4(left2_sum_s) * color_weight;
-		f4 middle2_sum = splat4(middle2_sum_s) * color_weight;
-		f4 right2_sum = splat4(right2_sum_s) * color_weight;
-		color_vec_x = color_vec_x * color_weight;
-		color_vec_y = color_vec_y * color_weight;
-		float scalediv = scale_min / maxf(scale_max, 1e-10f);
-		scalediv = clamp1f(scalediv);
-		f4 sds = scale_dir * scale_max;
-		f4 rgbs_vector = mk4(sds.x, sds.y, sds.z, scalediv);
-		f4 e0 = ep[EP_WORK_0], e1 = ep[EP_WORK_1];
-		if (wmin1 >= wmax1 * 0.999f) {
-			f4 avg = (color_vec_x + color_vec_y) / rgba_weight_sum;
-			bool m0 = !p20 && avg.x == avg.x, m1 = !p21 && avg.y == avg.y, m2 = !p22 && avg.z == avg.z, m3 = !p23 && avg.w == avg.w;
-			e0 = sel4(e0, avg, m0, m1, m2, m3);
-			e1 = sel4(e1, avg, m0, m1, m2, m3);
-			rgbs_vector = mk4(sds.x, sds.y, sds.z, 1.0f);
-		} else {
-			f4 color_det1 = (left1_sum * right1_sum) - (middle1_sum * middle1_sum);
-			f4 color_rdet1 = splat4(1.0f) / color_det1;
-			float ls_det1 = (lmrs_sum.x * lmrs_sum.z) - (lmrs_sum.y * lmrs_sum.y);
-			float ls_rdet1 = 1.0f / ls_det1;
-			f4 color_mss1 = (left1_sum * left1_sum) + (splat4(2.0f) * middle1_sum * middle1_sum) + (right1_sum * right1_sum);
-			float ls_mss1 = (lmrs_sum.x * lmrs_sum.x) + (2.0f * lmrs_sum.y * lmrs_sum.y) + (lmrs_sum.z * lmrs_sum.z);
-			f4 ep0 = (right1_sum * color_vec_x - middle1_sum * color_vec_y) * color_rdet1;
-			f4 ep1 = (left1_sum * color_vec_y - middle1_sum * color_vec_x) * color_rdet1;
-			float scale_ep0 = (lmrs_sum.z * scale_vec.x - lmrs_sum.y * scale_vec.y) * ls_rdet1;
-			float scale_ep1 = (lmrs_sum.x * scale_vec.y - lmrs_sum.y * scale_vec.x) * ls_rdet1;
-			f4 thr = color_mss1 * 1e-4f;
-			bool m0 = !p20 && absf(color_det1.x) > thr.x && ep0.x == ep0.x && ep1.x == ep1.x;
-			bool m1 = !p21 && absf(color_det1.y) > thr.y && ep0.y == ep0.y && ep1.y == ep1.y;
-			bool m2 = !p22 && absf(color_det1.z) > thr.z && ep0.z == ep0.z && ep1.z == ep1.z;
-			bool m3 = !p23 && absf(color_det1.w) > thr.w && ep0.w == ep0.w && ep1.w == ep1.w;
-			e0 = sel4(e0, ep0, m0, m1, m2, m3);
-			e1 = sel4(e1, ep1, m0, m1, m2, m3);
-			if (fabsf(ls_det1) > (ls_mss1 * 1e-4f) && scale_ep0 == scale_ep0 && scale_ep1 == scale_ep1 && scale_ep0 < scale_ep1) {
-				float scalediv2 = scale_ep0 / scale_ep1;
-				f4 sdsm = scale_dir * scale_ep1;
-				rgbs_vector = mk4(sdsm.x, sdsm.y, sdsm.z, scalediv2);
-			}
-		}
-		if (wmin2 >= wmax2 * 0.999f) {
-			f4 avg = (color_vec_x + color_vec_y) / rgba_weight_sum;
-			bool m0 = p20 && avg.x == avg.x, m1 = p21 && avg.y == avg.y, m2 = p22 && avg.z == avg.z, m3 = p23 && avg.w == avg.w;
-			e0 = sel4(e0, avg, m0, m1, m2, m3);
-			e1 = sel4(e1, avg, m0, m1, m2, m3);
-		} else {
-			f4 color_det2 = (left2_sum * right2_sum) - (middle2_sum * middle2_sum);
-			f4 color_rdet2 = splat4(1.0f) / color_det2;
-			f4 color_mss2 = (left2_sum * left2_sum) + (splat4(2.0f) * middle2_sum * middle2_sum) + (right2_sum * right2_sum);
-			f4 ep0 = (right2_sum * color_vec_x - middle2_sum * color_vec_y) * color_rdet2;
-			f4 ep1 = (left2_sum * color_vec_y - middle2_sum * color_vec_x) * color_rdet2;
-			f4 thr = color_mss2 * 1e-4f;
-			bool m0 = p20 && absf(color_det2.x) > thr.x && ep0.x == ep0.x && ep1.x == ep1.x;
-			bool m1 = p21 && absf(color_det2.y) > thr.y && ep0.y == ep0.y && ep1.y == ep1.y;
-			bool m2 = p22 && absf(color_det2.z) > thr.z && ep0.z == ep0.z && ep1.z == ep1.z;
-			bool m3 = p23 && absf(color_det2.w) > thr.w && ep0.w == ep0.w && ep1.w == ep1.w;
-			e0 = sel4(e0, ep0, m0, m1, m2, m3);
-			e1 = sel4(e1, ep1, m0, m1, m2, m3);
-		}
-		ep[EP_WORK_0] = e0;
-		ep[EP_WORK_1] = e1;
-		ep[EP_RGBS] = rgbs_vector;
-		if (bi.rgb_lns0 || bi.alpha_lns0) {
-			weight_weight_sum = weight_weight_sum * color_weight;
-			f4 rsel = mk4(p20 ? right2_sum.x : right1_sum.x, p21 ? right2_sum.y : right1_sum.y, p22 ? right2_sum.z : right1_sum.z,
-			              p23 ? right2_sum.w : right1_sum.w);
-			float psum = dot3_s(rsel, color_weight);
-			f4 rgbq_sum = color_vec_x + color_vec_y;
-			rgbq_sum.w = hadd_rgb_s(color_vec_y);
-			f4 rgbo_vector = compute_rgbo_vector(rgba_weight_sum, weight_weight_sum, rgbq_sum, psum);
-			rgbo_fallback(rgbo_vector, e0, e1);
-			ep[EP_RGBO] = rgbo_vector;
-		}
+		f4 color_vec_x = mk4(t[6], t[7], t[8], t[9]) * color_weight;
+		f4 color_vec_y = mk4(t[10], t[11], t[12], t[13]) * color_weight;
+		f4 weight_weight_sum = mk4(t[16], t[17], t[18], t[19]) * color_weight;
+		f4 right1_sum = splat4(t[2]) * color_weight;
+		f4 right2_sum = splat4(t[5]) * color_weight;
+		f4 rsel = mk4(p20 ? right2_sum.x : right1_sum.x, p21 ? right2_sum.y : right1_sum.y, p22 ? right2_sum.z : right1_sum.z,
+		              p23 ? right2_sum.w : right1_sum.w);
+		float psum = dot3_s(rsel, color_weight);
+		f4 rgbq_sum = color_vec_x + color_vec_y;
+		rgbq_sum.w = hadd_rgb_s(color_vec_y);
+		f4 rgbo_vector = compute_rgbo_vector(rgba_weight_sum, weight_weight_sum, rgbq_sum, psum);
+		rgbo_fallback(rgbo_vector, ep[EP_WORK_0], ep[EP_WORK_1]);
+		ep[EP_RGBO] = rgbo_vector;
 	}
 	wsync();
 }
@@ -1068,7 +1068,8 @@ ASTC_COOP void unpack_work_endpoints(WCtx w, unsigned int pc, uint32_t formats, 
 ASTC_FN uint32_t pack_formats(const ScbHdr& h) {
 	return (uint32_t)h.color_formats[0] | ((uint32_t)h.color_formats[1] << 8) | ((uint32_t)h.color_formats[2] << 16) | ((uint32_t)h.color_formats[3] << 24);
 }
-// the unpacked endpoints live in tmpf[96..128) (32 ints) during scoring / realignment
+// the unpacked endpoints live in tmpf[96..128) (32 ints) from the end of the packing stage of a refinement step until its
+// last score: packing is the only thing that changes them, scoring and realignment only read them
 ASTC_FN uint32_t ends_off_of(const WCtx& w) { return w.base + A_TMPF + 96 * 4; }
 
 // compute_symbolic_block_difference_{2plane,1plane,1plane_1partition} (:313-618) on the work candidate.
@@ -1082,7 +1083,7 @@ ASTC_COOP float compute_symbolic_block_difference(WCtx w, unsigned int pc, uint3
 	float rgbm_scale = CFG.rgbm_m_scale;
 	bool fast = !dual && pc == 1 && !rgbm;
 	bool u8 = u8_mask(w);
-	unpack_work_endpoints(w, pc, formats, ends_off_of(w));
+	(void)formats;      // the caller unpacked the work candidate's endpoints (unpack_work_endpoints) after packing them
 	SPtr<int> ends = sptr<int>(ends_off_of(w));
 	SPtr<uint8_t> uq = work_weights_of(w);
 	SPtr<float> texel_err = sptr<float>(rs.texel_err);
@@ -1199,7 +1200,7 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 	int T = w.T;
 	bool decimated = weight_count != T;
 	unsigned int max_plane = is_dual ? 1u : 0u;
-	unpack_work_endpoints(w, pc, formats, ends_off_of(w));
+	(void)formats;      // endpoints already unpacked by the caller (once per refinement step)
 	SPtr<int> ends = sptr<int>(ends_off_of(w));
 	f4 ew = bi_of(w).channel_weight;
 	SPtr<float> uqf = sptr<float>(rs.uqf);
