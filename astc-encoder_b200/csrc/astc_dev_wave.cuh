@@ -266,6 +266,16 @@ ASTC_COOP void wave_finish_trial(WCtx w, const WaveArgs& a, unsigned int b, Bloc
 	route_block(w, a, b, next);
 }
 
+#if defined(ASTC_STEP_STATS)
+// dev instrumentation (make libastcenc_b200_stats.so, tools/step_stats.py): cycles per refinement-step part by kind
+// of step, [class][part]; class = realign path (0 undecimated, 1 dense wavefront, 2 per-weight) + 3 for the first step
+// of a candidate; parts: recompute, pack, score1, realign, score2, block change, wait at the vote, number of steps
+__device__ unsigned long long g_step_stats[6][8];
+#define STAT_T(v) long long v = clock64()
+#else
+#define STAT_T(v)
+#endif
+
 ASTC_COOP void wave_refine(WCtx w, WaveArgs a) {
 	BlockSearch s;
 	Trial t;
@@ -279,6 +289,10 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a) {
 	t.packed = 0;
 	unsigned int round = 0;
 	const unsigned int vote_mask = (1u << ((a.sync_mask >> 8) & 7)) - 1u;
+#if defined(ASTC_STEP_STATS)
+	int st_prev_class = -1;
+	long long st_prev_end = 0;
+#endif
 	while (true) {
 		while (!has_item && !drained) {
 			if (!q_pop(w, a, Q_REFINE, a.wave, b)) {
@@ -300,27 +314,58 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a) {
 			}
 			has_item = true;
 		}
+		STAT_T(tv);
 		// (vote_period: tuning knob - vote only every 2^n-th round)
 		if ((round++ & vote_mask) == 0) {
 			if (!cta_any(has_item)) {
 				break;
 			}
 		}
+		STAT_T(t0);
+#if defined(ASTC_STEP_STATS)
+		bool st_on = has_item;
+		int st_first = r.l == 0 ? 3 : 0;
+		if (st_on && w.lane == 0 && st_prev_class >= 0) {
+			atomicAdd(&g_step_stats[st_prev_class][5], (unsigned long long)(tv - st_prev_end));
+			atomicAdd(&g_step_stats[st_prev_class][6], (unsigned long long)(t0 - tv));
+		}
+#endif
 		if (has_item) {
 			r.in_step = true;
 			refine_recompute(w, t, r);
 		}
+		STAT_T(t1);
 		if (a.sync_mask & 16) cta_sync();
 		if (has_item) refine_pack(w, t, r);
+		STAT_T(t2);
 		if (a.sync_mask & 32) cta_sync();
 		if (has_item && r.l == 0) refine_first_score(w, t, r, s);
+		STAT_T(t3);
 		if (a.sync_mask & 64) cta_sync();
 		if (has_item && r.running && r.in_step) {
 			PartView pi = part_view_packed(t.partition_count, t.packed);
 			r.adjustments = realign_weights(w, t.partition_count, r.formats, t.plane2_component, pi, r.qmode, t.dual != 0, (unsigned int)r.dmode);
 		}
+		STAT_T(t4);
 		if (a.sync_mask & 128) cta_sync();
 		if (has_item && r.running && r.in_step) refine_second_score(w, t, r, s);
+		STAT_T(t5);
+#if defined(ASTC_STEP_STATS)
+		if (st_on) {
+			const DevDecMode* dmp = BSD.dec_modes + r.dmode;
+			int cls = (dec_view((unsigned int)r.dmode).W == w.T ? 0 : (ASTC_LDG(&dmp->max_weight_texels) <= 6 ? 1 : 2)) + st_first;
+			if (w.lane == 0) {
+				atomicAdd(&g_step_stats[cls][0], (unsigned long long)(t1 - t0));
+				atomicAdd(&g_step_stats[cls][1], (unsigned long long)(t2 - t1));
+				atomicAdd(&g_step_stats[cls][2], (unsigned long long)(t3 - t2));
+				atomicAdd(&g_step_stats[cls][3], (unsigned long long)(t4 - t3));
+				atomicAdd(&g_step_stats[cls][4], (unsigned long long)(t5 - t4));
+				atomicAdd(&g_step_stats[cls][7], 1ull);
+			}
+			st_prev_class = cls;
+			st_prev_end = t5;
+		}
+#endif
 		if (has_item && !r.running) {
 			wave_finish_trial(w, a, b, s, t, r.best_errorval_in_mode);
 			has_item = false;
@@ -359,6 +404,17 @@ ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
 // ---------------------------------------------------------------------------------------------
 #define EMIT_SLICE 96
 ASTC_COOP void wave_emit(int lane, uint32_t slices_base, WaveArgs a) {
+#if defined(ASTC_STEP_STATS)
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		for (int c = 0; c < 6; c++) {
+			unsigned long long n = g_step_stats[c][7];
+			printf("steps class %d n %llu: recompute %llu pack %llu score1 %llu realign %llu score2 %llu change %llu wait %llu (cycles per step)\n", c, n,
+			       g_step_stats[c][0] / (n ? n : 1), g_step_stats[c][1] / (n ? n : 1), g_step_stats[c][2] / (n ? n : 1), g_step_stats[c][3] / (n ? n : 1),
+			       g_step_stats[c][4] / (n ? n : 1), g_step_stats[c][5] / (n ? n : 1), g_step_stats[c][6] / (n ? n : 1));
+			for (int k = 0; k < 8; k++) g_step_stats[c][k] = 0;
+		}
+	}
+#endif
 	uint32_t n = q_load(a.count + Q_EMIT * ASTC_MAX_WAVES);
 	while (true) {
 		uint32_t i0 = 0;

@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
 """Aggregate an ncu source page by device function (dev tool).
-   python tools/ncu_by_function.py report.ncu-rep lib.so [blocks] [kernel-substring]"""
+   python tools/ncu_by_function.py report.ncu-rep lib.so [blocks] [kernel-substring] [nth-matching-launch]"""
 import csv, subprocess, sys, re
 rep, lib = sys.argv[1], sys.argv[2]
 blocks = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
 kern = sys.argv[4] if len(sys.argv) > 4 else ""
+nth = int(sys.argv[5]) if len(sys.argv) > 5 else 0      # which matching launch of the report
 elf = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
 syms = []
 insym = False
@@ -32,7 +33,7 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(out.splitlines()))
 # several kernels may be in the report: take the first whose name matches
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
-sel = next(i for i in starts if kern in rows[i][1])
+sel = [i for i in starts if kern in rows[i][1]][nth]
 end = next((i for i in starts if i > sel), len(rows))
 rows = rows[sel:end]
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")

@@ -1,11 +1,13 @@
 #!/usr/bin/env python3
 """Aggregate an ncu SASS page by source line using nvdisasm -g line info (dev tool).
-   python tools/ncu_by_line.py report.ncu-rep lib.so kernel-substring [blocks] [top] [file-filter]"""
+   python tools/ncu_by_line.py report.ncu-rep lib.so kernel-substring [blocks] [top] [file-filter] [nth-matching-launch]"""
 import csv, subprocess, sys, re, os, tempfile, glob
 rep, lib, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 blocks = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
 ffilter = sys.argv[6] if len(sys.argv) > 6 else ""
+nth = int(sys.argv[7]) if len(sys.argv) > 7 else 0          # which matching launch of the report
+by = 2 if os.environ.get("BY_SAMPLES") else 0              # BY_SAMPLES=1: sort by stall samples instead of instructions
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
 cubin = max(glob.glob(os.path.join(tmp, "*.cubin")), key=os.path.getsize)
@@ -30,7 +32,7 @@ for l in dis.splitlines():
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
-sel = next(i for i in starts if kern in rows[i][1])
+sel = [i for i in starts if kern in rows[i][1]][nth]
 end = next((i for i in starts if i > sel), len(rows))
 rows = rows[sel:end]
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
@@ -55,7 +57,7 @@ def srcline(f, n):
     s = srcs[f]
     return s[n - 1].strip()[:90] if 0 < n <= len(s) else ""
 print(f"{'file:line':34s} {'instr/blk':>9s} {'%instr':>6s} {'lanes':>5s} {'%smp':>6s}  source")
-for (f, n), a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+for (f, n), a in sorted(agg.items(), key=lambda kv: -kv[1][by]):
     if ffilter and ffilter not in f:
         continue
     if top <= 0:
