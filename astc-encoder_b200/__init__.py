@@ -27,7 +27,7 @@ ERROR_NAMES = ["ASTCENC_SUCCESS", "ASTCENC_ERR_OUT_OF_MEM", "ASTCENC_ERR_BAD_CPU
                "ASTCENC_ERR_NOT_IMPLEMENTED", "ASTCENC_ERR_BAD_DECODE_MODE"]
 
 
-ERR_OUT_OF_MEM, ERR_BAD_PARAM, ERR_BAD_SWIZZLE, ERR_BAD_CONTEXT, ERR_NOT_IMPLEMENTED = 1, 3, 7, 9, 10
+ERR_OUT_OF_MEM, ERR_BAD_PARAM, ERR_BAD_BLOCK_SIZE, ERR_BAD_SWIZZLE, ERR_BAD_CONTEXT, ERR_NOT_IMPLEMENTED = 1, 3, 4, 7, 9, 10
 
 
 class AstcencError(RuntimeError):
@@ -60,6 +60,17 @@ class Image(C.Structure):
 
 class Swizzle(C.Structure):
     _fields_ = [("r", C.c_int), ("g", C.c_int), ("b", C.c_int), ("a", C.c_int)]
+
+
+class ErrorMetrics(C.Structure):
+    """struct astcenc_b200_error_metrics (include/astcenc.h)."""
+    _fields_ = [(n, C.c_double) for n in ("psnr", "alpha_psnr", "rgb_psnr", "rgb_peak", "peak_psnr", "mpsnr", "log_rmse",
+                                          "mean_angular_error", "worst_angular_error")] + [("sum_squared_error", C.c_double * 4)]
+
+
+class CImageHeader(C.Structure):
+    """struct astcenc_b200_cimage_header (include/astcenc.h): the fields of the 16-byte .astc header."""
+    _fields_ = [(n, C.c_uint) for n in ("block_x", "block_y", "block_z", "dim_x", "dim_y", "dim_z")]
 
 
 def build(verbose=False):
@@ -106,6 +117,13 @@ def lib():
         l.astcenc_b200_last_timing.restype = C.c_int
         l.astcenc_b200_stage_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint)]
         l.astcenc_b200_stage_timing.restype = C.c_int
+        l.astcenc_b200_compute_error_metrics.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image), C.c_int, C.c_int,
+                                                         C.POINTER(ErrorMetrics)]
+        l.astcenc_b200_compute_error_metrics.restype = C.c_int
+        l.astcenc_b200_store_cimage.argtypes = [C.c_char_p, C.POINTER(CImageHeader), C.c_void_p, C.c_size_t]
+        l.astcenc_b200_store_cimage.restype = C.c_int
+        l.astcenc_b200_load_cimage.argtypes = [C.c_char_p, C.POINTER(CImageHeader), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        l.astcenc_b200_load_cimage.restype = C.c_int
         _lib = l
     return _lib
 
@@ -200,10 +218,51 @@ class Context:
         lib().astcenc_b200_stage_timing(self.handle, 1 if enable else 0, None, None)
         return None
 
+    def compute_error_metrics(self, img1, img2, hdr=False, normal=False, input_components=4, fstop_lo=-10, fstop_hi=10):
+        """astcenc_b200_compute_error_metrics: the CLI's compute_error_metrics (astcenccli_error_metrics.cpp:109-413) on the
+        device. img1 = original, img2 = decoded, numpy (H, W, 4) uint8 / float16 / float32. Returns a dict."""
+        imgs = []
+        for im in (img1, img2):
+            im = np.ascontiguousarray(im)
+            slices = (C.c_void_p * 1)(im.ctypes.data)
+            imgs.append((im, slices, Image(im.shape[1], im.shape[0], 1, _DTYPES[im.dtype], slices)))
+        out = ErrorMetrics()
+        err = lib().astcenc_b200_compute_error_metrics(self.handle, int(hdr), int(normal), input_components, C.byref(imgs[0][2]), C.byref(imgs[1][2]),
+                                                       fstop_lo, fstop_hi, C.byref(out))
+        if err:
+            raise AstcencError(err, "astcenc_b200_compute_error_metrics")
+        d = {n: getattr(out, n) for n, _ in ErrorMetrics._fields_[:9]}
+        d["sum_squared_error"] = list(out.sum_squared_error)
+        return d
+
     def last_timing(self):
         ms = C.c_float(); a = C.c_size_t(); b = C.c_size_t()
         lib().astcenc_b200_last_timing(self.handle, C.byref(ms), C.byref(a), C.byref(b))
         return ms.value, a.value, b.value
+
+
+def store_cimage(filename, blocks, dim_x, dim_y, block_x, block_y, dim_z=1, block_z=1):
+    """Write a .astc file (store_cimage, astcenccli_image_load_store.cpp:2691-2730): 16-byte header + the blocks."""
+    data = np.ascontiguousarray(np.frombuffer(bytes(blocks), dtype=np.uint8) if not isinstance(blocks, np.ndarray) else blocks.view(np.uint8).reshape(-1))
+    hdr = CImageHeader(block_x, block_y, block_z, dim_x, dim_y, dim_z)
+    err = lib().astcenc_b200_store_cimage(os.fsencode(filename), C.byref(hdr), data.ctypes.data, data.nbytes)
+    if err:
+        raise AstcencError(err, "astcenc_b200_store_cimage")
+
+
+def load_cimage(filename):
+    """Read a .astc file (load_cimage, astcenccli_image_load_store.cpp:2599-2688). Returns (blocks uint8 array, header dict);
+    corrupt files raise AstcencError like the reference tool refuses them."""
+    hdr = CImageHeader()
+    n = C.c_size_t()
+    err = lib().astcenc_b200_load_cimage(os.fsencode(filename), C.byref(hdr), None, 0, C.byref(n))
+    if err:
+        raise AstcencError(err, "astcenc_b200_load_cimage")
+    data = np.empty(n.value, dtype=np.uint8)
+    err = lib().astcenc_b200_load_cimage(os.fsencode(filename), C.byref(hdr), data.ctypes.data, data.nbytes, C.byref(n))
+    if err:
+        raise AstcencError(err, "astcenc_b200_load_cimage")
+    return data, {k: getattr(hdr, k) for k, _ in CImageHeader._fields_}
 
 
 def slab_rows(blocks_y, rank, world):

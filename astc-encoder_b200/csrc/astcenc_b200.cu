@@ -19,6 +19,7 @@
 #include <new>
 
 #include "astc_dev_search.cuh"
+#include "astc_dev_metrics.cuh"
 #include "astc_host_pack.h"
 #include "astc_host_config.h"
 
@@ -988,6 +989,127 @@ astcenc_error astcenc_get_block_info(astcenc_context* ctx, const uint8_t data[16
 			info->weight_values_plane2[i] = h.weight_values_plane2[i];
 		}
 		info->partition_assignment[i] = h.partition_assignment[i];
+	}
+	return ASTCENC_SUCCESS;
+}
+
+// astcenc_b200_compute_error_metrics: the CLI's compute_error_metrics (astcenccli_error_metrics.cpp:109-413) with the
+// per-texel work and the reductions on the device; the final dB figures are computed here exactly as the CLI prints them.
+astcenc_error astcenc_b200_compute_error_metrics(astcenc_context* ctx, int compute_hdr_metrics, int compute_normal_metrics, int input_components,
+                                                 const astcenc_image* img1, const astcenc_image* img2, int fstop_lo, int fstop_hi,
+                                                 astcenc_b200_error_metrics* out) {
+	if (!ctx || !img1 || !img2 || !out || input_components < 1 || input_components > 4 || !img1->data || !img2->data) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	if (fstop_lo < -125 || fstop_hi > 125) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	memset(out, 0, sizeof(*out));
+	unsigned int dim_x = img1->dim_x < img2->dim_x ? img1->dim_x : img2->dim_x;
+	unsigned int dim_y = img1->dim_y < img2->dim_y ? img1->dim_y : img2->dim_y;
+	unsigned int dim_z = img1->dim_z < img2->dim_z ? img1->dim_z : img2->dim_z;
+	if (dim_x == 0 || dim_y == 0 || dim_z == 0) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	CUDA_TRY(cudaSetDevice(ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
+	static const size_t comp_bytes[3] = {1, 2, 4};
+	size_t slice1 = (size_t)img1->dim_x * img1->dim_y * 4 * comp_bytes[img1->data_type];
+	size_t slice2 = (size_t)img2->dim_x * img2->dim_y * 4 * comp_bytes[img2->data_type];
+	int ctas = 148 * 4;
+	size_t texels = (size_t)dim_x * dim_y;
+	if ((size_t)ctas * 256 > texels) {
+		ctas = (int)((texels + 255) / 256);
+	}
+	uint8_t* d1 = nullptr;
+	uint8_t* d2 = nullptr;
+	double* d_part = nullptr;
+	astcenc_error status = ASTCENC_SUCCESS;
+	double sums[ASTC_METRIC_SUMS];
+	do {
+		if (cudaMalloc(&d1, slice1) != cudaSuccess || cudaMalloc(&d2, slice2) != cudaSuccess ||
+		    cudaMalloc(&d_part, ((size_t)ctas * dim_z + 1) * ASTC_METRIC_SUMS * sizeof(double)) != cudaSuccess) {
+			status = ASTCENC_ERR_OUT_OF_MEM;
+			break;
+		}
+		MetricArgs a;
+		a.img1.type = (int)img1->data_type;
+		a.img1.dim_x = img1->dim_x;
+		a.img2.type = (int)img2->data_type;
+		a.img2.dim_x = img2->dim_x;
+		a.dim_x = dim_x;
+		a.dim_y = dim_y;
+		a.hdr = compute_hdr_metrics != 0;
+		a.normal = compute_normal_metrics != 0;
+		a.fstop_lo = fstop_lo;
+		a.fstop_hi = fstop_hi;
+		a.inv_pixels = 1.0 / (double)(dim_x * dim_y * dim_z);      // (unsigned product, like the reference's :281)
+		cudaError_t e = cudaSuccess;
+		for (unsigned int z = 0; z < dim_z && e == cudaSuccess; z++) {
+			// (stream-ordered: the next slice's copy waits for this slice's kernel)
+			e = cudaMemcpyAsync(d1, img1->data[z], slice1, cudaMemcpyHostToDevice, ctx->stream);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(d2, img2->data[z], slice2, cudaMemcpyHostToDevice, ctx->stream);
+			a.img1.data = d1;
+			a.img2.data = d2;
+			a.partials = d_part + (size_t)z * ctas * ASTC_METRIC_SUMS;
+			astc_error_metrics_kernel<<<ctas, 256, 0, ctx->stream>>>(a);
+			ctx->launches++;
+		}
+		double* d_out = d_part + (size_t)ctas * dim_z * ASTC_METRIC_SUMS;
+		astc_error_metrics_finish_kernel<<<1, 32, 0, ctx->stream>>>(d_part, ctas * (int)dim_z, d_out);
+		ctx->launches++;
+		if (e == cudaSuccess) e = cudaMemcpyAsync(sums, d_out, sizeof(sums), cudaMemcpyDeviceToHost, ctx->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+		if (e == cudaSuccess) e = cudaGetLastError();
+		if (e != cudaSuccess) {
+			status = ASTCENC_ERR_BAD_CONTEXT;
+		}
+	} while (false);
+	cudaFree(d1);
+	cudaFree(d2);
+	cudaFree(d_part);
+	if (status != ASTCENC_SUCCESS) {
+		return status;
+	}
+	// the closing arithmetic of compute_error_metrics (:285-411)
+	static const int componentmasks[5] = {0x00, 0x07, 0x0C, 0x07, 0x0F};
+	int mask = componentmasks[input_components];
+	double pixels = (double)(dim_x * dim_y * dim_z);
+	double samples = 0.0, num = 0.0, alpha_num = 0.0, log_num = 0.0, mpsnr_num = 0.0;
+	for (int c = 0; c < 4; c++) {
+		if (mask & (1 << c)) {
+			num += sums[MS_ERR + c];
+			alpha_num += sums[MS_AERR + c];
+			if (c < 3) {
+				log_num += sums[MS_LOG + c];
+				mpsnr_num += sums[MS_MPSNR + c];
+			}
+			samples += pixels;
+		}
+	}
+	double stopcount = (double)(fstop_hi - fstop_lo + 1);
+	double mpsnr_denom = pixels * 3.0 * stopcount * 255.0 * 255.0;
+	double psnr = num == 0.0 ? 999.0 : 10.0 * log10(samples / num);
+	double rgb_psnr = psnr;
+	out->psnr = psnr;
+	out->alpha_psnr = psnr;
+	if (mask & 8) {
+		out->alpha_psnr = alpha_num == 0.0 ? 999.0 : 10.0 * log10(samples / alpha_num);
+		double rgb_num = sums[MS_ERR + 0] + sums[MS_ERR + 1] + sums[MS_ERR + 2];
+		rgb_psnr = rgb_num == 0.0 ? 999.0 : 10.0 * log10(pixels * 3.0 / rgb_num);
+	}
+	out->rgb_psnr = rgb_psnr;
+	out->rgb_peak = sums[MS_PEAK];
+	if (compute_hdr_metrics) {
+		out->peak_psnr = rgb_psnr + 20.0 * log10(sums[MS_PEAK]);
+		out->mpsnr = mpsnr_num == 0.0 ? 999.0 : 10.0 * log10(mpsnr_denom / mpsnr_num);
+		out->log_rmse = sqrt(log_num / pixels);
+	}
+	if (compute_normal_metrics) {
+		out->mean_angular_error = sums[MS_ANG_MEAN];
+		out->worst_angular_error = sums[MS_ANG_WORST];
+	}
+	for (int c = 0; c < 4; c++) {
+		out->sum_squared_error[c] = sums[MS_ERR + c];
 	}
 	return ASTCENC_SUCCESS;
 }

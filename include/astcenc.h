@@ -204,4 +204,45 @@ ASTCENC_PUBLIC enum astcenc_error astcenc_b200_stage_timing(struct astcenc_conte
  * recent astcenc_compress_image() call on this context, and its H2D / D2H byte counts. */
 ASTCENC_PUBLIC enum astcenc_error astcenc_b200_last_timing(struct astcenc_context* context, float* kernel_ms, size_t* h2d_bytes, size_t* d2h_bytes);
 
+/**
+ * Image error metrics on the device: what the reference's command line tool computes on the host after a -t* round trip
+ * (Source/astcenccli_error_metrics.cpp:109-413, compute_error_metrics(); it prints, this returns). img1 is the
+ * original, img2 the decoded image (host pointers, any mix of U8 / F16 / F32; only the intersection is compared).
+ * input_components (1-4) selects the channels that count, as in the reference (1: RGB, 2: BA, 3: RGB, 4: RGBA).
+ * Fields not requested (HDR / normal-map metrics) are zero. PSNR values are 999.0 for identical images.
+ */
+struct astcenc_b200_error_metrics {
+	double psnr;                  /* "PSNR (LDR-RGBA)" when alpha counts, else "PSNR (LDR-RGB)" */
+	double alpha_psnr;            /* "Alpha-weighted PSNR" (= psnr when alpha does not count) */
+	double rgb_psnr;              /* "PSNR (LDR-RGB)" */
+	double rgb_peak;              /* largest R/G/B value of img1 */
+	double peak_psnr;             /* HDR: "PSNR (RGB norm to peak)" */
+	double mpsnr;                 /* HDR: "mPSNR (RGB)" over fstop_lo..fstop_hi */
+	double log_rmse;              /* HDR: "LogRMSE (RGB)" */
+	double mean_angular_error;    /* normal maps: degrees */
+	double worst_angular_error;   /* normal maps: degrees */
+	double sum_squared_error[4];  /* per channel, values scaled to 0..1 (LDR) */
+};
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_compute_error_metrics(struct astcenc_context* context, int compute_hdr_metrics, int compute_normal_metrics,
+                                                                     int input_components, const struct astcenc_image* img1, const struct astcenc_image* img2,
+                                                                     int fstop_lo, int fstop_hi, struct astcenc_b200_error_metrics* metrics);
+
+/**
+ * The .astc container (Docs/FileFormat.md; Source/astcenccli_image_load_store.cpp:2573-2760, load_cimage / store_cimage):
+ * a 16-byte header - magic 13 AB A1 5C, block dimensions (one byte each), image dimensions (24 bits each, little endian)
+ * - followed by the blocks as astcenc_compress_image() wrote them.
+ * store: data_len must be the size of the block grid the header describes.
+ * load: call with data == NULL to get the header and the payload size in *data_len, then again with a buffer;
+ * corrupt files (bad magic, zero dimensions, size overflow, fewer payload bytes than the header promises) give
+ * ASTCENC_ERR_BAD_PARAM, a buffer smaller than the payload ASTCENC_ERR_OUT_OF_MEM.
+ */
+struct astcenc_b200_cimage_header {
+	unsigned int block_x, block_y, block_z;
+	unsigned int dim_x, dim_y, dim_z;
+};
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_store_cimage(const char* filename, const struct astcenc_b200_cimage_header* header,
+                                                            const uint8_t* data, size_t data_len);
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_load_cimage(const char* filename, struct astcenc_b200_cimage_header* header,
+                                                           uint8_t* data, size_t data_capacity, size_t* data_len);
+
 #endif

@@ -48,3 +48,5 @@ void oracle_get_config(void* ctx, Config* out) {
 }
 
 }
+
+#include "astc_error_metrics.inl"

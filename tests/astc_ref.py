@@ -132,6 +132,27 @@ class AstcencLib:
 
     NP_TYPES = {TYPE_U8: np.uint8, TYPE_F16: np.float16, TYPE_F32: np.float32}
 
+    def error_metrics(self, img1, img2, hdr=False, normal=False, components=4, fstop_lo=-10, fstop_hi=10):
+        """astcenc_b200_compute_error_metrics (product library only)."""
+        fn = self.lib.astcenc_b200_compute_error_metrics
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image), C.c_int, C.c_int, C.POINTER(ErrorMetrics)]
+        fn.restype = C.c_int
+        cfg = self.config(PRF_LDR, 6, 6, PRE_FAST, FLG_DECOMPRESS_ONLY)
+        ctx = C.c_void_p()
+        err = self.lib.astcenc_context_alloc(C.byref(cfg), 1, C.byref(ctx), None)
+        if err:
+            raise RuntimeError("context_alloc failed: %d" % err)
+        try:
+            a1, s1, i1 = _image_of(img1)
+            a2, s2, i2 = _image_of(img2)
+            out = ErrorMetrics()
+            err = fn(ctx, int(hdr), int(normal), components, C.byref(i1), C.byref(i2), fstop_lo, fstop_hi, C.byref(out))
+            if err:
+                raise RuntimeError("compute_error_metrics failed: %d" % err)
+            return out.as_dict()
+        finally:
+            self.lib.astcenc_context_free(ctx)
+
     def block_infos(self, blocks, profile, bx, by, flags=0, quality=PRE_MEDIUM):
         """astcenc_get_block_info of every 16-byte block; returns a list of raw struct bytes (for exact comparison)."""
         cfg = self.config(profile, bx, by, quality, flags)
@@ -177,6 +198,67 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+# ---- image error metrics (astcenccli_error_metrics.cpp) -------------------------------------------------------
+REF_METRICS_SO = os.path.join(ROOT, "oracle", "_ref", "libastcenc_ref_metrics.so")
+_NP2TYPE = {np.dtype(np.uint8): TYPE_U8, np.dtype(np.float16): TYPE_F16, np.dtype(np.float32): TYPE_F32}
+METRIC_FIELDS = ("psnr", "alpha_psnr", "rgb_psnr", "rgb_peak", "peak_psnr", "mpsnr", "log_rmse", "mean_angular_error", "worst_angular_error")
+
+
+class ErrorMetrics(C.Structure):
+    """struct astcenc_b200_error_metrics (include/astcenc.h) == OracleErrorMetrics (oracle/astc_error_metrics.inl)."""
+    _fields_ = [(n, C.c_double) for n in METRIC_FIELDS] + [("sum_squared_error", C.c_double * 4)]
+
+    def as_dict(self):
+        d = {n: getattr(self, n) for n in METRIC_FIELDS}
+        d["sum_squared_error"] = list(self.sum_squared_error)
+        return d
+
+
+def _image_of(arr):
+    arr = np.ascontiguousarray(arr)
+    h, w = arr.shape[:2]
+    slices = (C.c_void_p * 1)(arr.ctypes.data)
+    return arr, slices, Image(w, h, 1, _NP2TYPE[arr.dtype], slices)
+
+
+def have_ref_metrics():
+    return os.path.exists(REF_METRICS_SO)
+
+
+def ref_error_metrics(img1, img2, hdr=False, normal=False, components=4, fstop_lo=-10, fstop_hi=10):
+    """Runs the UNMODIFIED reference compute_error_metrics() and parses what it prints (4 decimals)."""
+    import re, sys, tempfile
+    lib = C.CDLL(REF_METRICS_SO, mode=os.RTLD_LOCAL)
+    lib.ref_compute_error_metrics.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(Image), C.POINTER(Image), C.c_int, C.c_int]
+    lib.ref_compute_error_metrics.restype = None
+    a1, s1, i1 = _image_of(img1)
+    a2, s2, i2 = _image_of(img2)
+    sys.stdout.flush()
+    with tempfile.TemporaryFile(mode="w+b") as tf:
+        saved = os.dup(1)
+        try:
+            os.dup2(tf.fileno(), 1)
+            lib.ref_compute_error_metrics(int(hdr), int(normal), components, C.byref(i1), C.byref(i2), fstop_lo, fstop_hi)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        tf.seek(0)
+        text = tf.read().decode()
+    keys = {"PSNR (LDR-RGBA)": "psnr", "Alpha-weighted PSNR": "alpha_psnr", "PSNR (LDR-RGB)": "rgb_psnr", "PSNR (RGB norm to peak)": "peak_psnr",
+            "mPSNR (RGB)": "mpsnr", "LogRMSE (RGB)": "log_rmse", "Mean Angular Error": "mean_angular_error", "Worst Angular Error": "worst_angular_error"}
+    out = {}
+    for line in text.splitlines():
+        m = re.match(r"\s*([^:]+):\s+(-?[0-9.]+|inf|-inf|nan)", line)
+        if m and m.group(1).strip() in keys:
+            out[keys[m.group(1).strip()]] = float(m.group(2))
+        m = re.search(r"\(peak ([0-9.eE+-]+)\)", line)
+        if m:
+            out["rgb_peak"] = float(m.group(1))
+    if "psnr" not in out:
+        out["psnr"] = out["rgb_psnr"]      # without alpha the CLI prints the one figure as "PSNR (LDR-RGB)"
+    return out
+
+
 def ref_lib():
     return AstcencLib(REF_SO)
 
@@ -209,6 +291,19 @@ class Oracle:
         lib.oracle_decompress_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.POINTER(C.c_int)]
         lib.oracle_decompress_image.restype = C.c_int
         self.lib = lib
+
+    def error_metrics(self, img1, img2, hdr=False, normal=False, components=4, fstop_lo=-10, fstop_hi=10):
+        a1 = np.ascontiguousarray(img1)
+        a2 = np.ascontiguousarray(img2)
+        out = ErrorMetrics()
+        self.lib.oracle_error_metrics.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint, C.c_uint,
+                                                  C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.POINTER(ErrorMetrics)]
+        self.lib.oracle_error_metrics.restype = C.c_int
+        err = self.lib.oracle_error_metrics(int(hdr), int(normal), components, a1.ctypes.data, _NP2TYPE[a1.dtype], a1.shape[1], a1.shape[0],
+                                            a2.ctypes.data, _NP2TYPE[a2.dtype], a2.shape[1], a2.shape[0], fstop_lo, fstop_hi, C.byref(out))
+        if err:
+            raise RuntimeError("oracle_error_metrics failed: %d" % err)
+        return out.as_dict()
 
     def decompress(self, blocks, w, h, profile, bx, by, out_type=TYPE_U8, flags=0, swz=None, quality=PRE_MEDIUM):
         ctx = self.lib.oracle_context_create(profile, bx, by, quality, flags, None)
