@@ -21,13 +21,18 @@
 #pragma once
 
 #define ASTC_MAX_WAVES 64
-enum { Q_SETUP = 0, Q_REFINE = 1, Q_PREPARE = 2, Q_EMIT = 3 };
+// Set-up and refinement items are queued by the kind of trial they belong to (class 0: one partition, one or two
+// planes; class p-1: p partitions): a late wave holds a mix of 2-plane and n-partition trials whose steps differ ~2x in
+// length, and warps of a CTA wait for each other every round. Each warp drains class 0, then 1, ... so that the warps
+// voting together are (almost always) doing the same kind of step.
+#define ASTC_Q_CLASSES 4
+enum { Q_SETUP = 0, Q_REFINE = ASTC_Q_CLASSES, Q_PREPARE = 2 * ASTC_Q_CLASSES, Q_EMIT = 2 * ASTC_Q_CLASSES + 1, ASTC_Q_KINDS = 2 * ASTC_Q_CLASSES + 2 };
 
 struct WaveArgs {
 	uint8_t* records;            // [blocks] x record_bytes
-	uint32_t* queue[4];          // item lists (block indices), capacity = blocks each
-	uint32_t* count;             // [4][ASTC_MAX_WAVES] items pushed (Q_EMIT uses wave slot 0)
-	uint32_t* head;              // [4][ASTC_MAX_WAVES] items popped
+	uint32_t* queue[ASTC_Q_KINDS];   // item lists (block indices), capacity = blocks each
+	uint32_t* count;             // [ASTC_Q_KINDS][ASTC_MAX_WAVES] items pushed (Q_EMIT uses wave slot 0)
+	uint32_t* head;              // [ASTC_Q_KINDS][ASTC_MAX_WAVES] items popped
 	unsigned int total;          // blocks in this launch
 	unsigned int blocks_x;
 	int wave;
@@ -63,6 +68,17 @@ ASTC_FN bool q_pop(const WCtx& w, const WaveArgs& a, int kind, int wave, unsigne
 	}
 	b = q_load(a.queue[kind] + i);
 	return true;
+}
+
+// pop from the classes of a kind in order; cls is the warp's cursor
+ASTC_FN bool q_pop_classes(const WCtx& w, const WaveArgs& a, int kind, int wave, int& cls, unsigned int& b) {
+	while (cls < ASTC_Q_CLASSES) {
+		if (q_pop(w, a, kind + cls, wave, b)) {
+			return true;
+		}
+		cls++;
+	}
+	return false;
 }
 
 ASTC_FN void q_push(const WCtx& w, const WaveArgs& a, int kind, int wave, unsigned int b) {
@@ -115,10 +131,15 @@ ASTC_FN void record_restore(const WCtx& w, const WaveArgs& a, unsigned int b, Bl
 	t = trial_of(w);
 }
 
-// where a block goes after its state machine advanced
-ASTC_FN void route_block(const WCtx& w, const WaveArgs& a, unsigned int b, int next) {
+ASTC_FN int trial_class(const Trial& t) {
+	int c = t.dual ? 0 : (int)t.partition_count - 1;
+	return c < 0 ? 0 : (c >= ASTC_Q_CLASSES ? ASTC_Q_CLASSES - 1 : c);
+}
+
+// where a block goes after its state machine advanced (t: the trial it will run next, if any)
+ASTC_FN void route_block(const WCtx& w, const WaveArgs& a, unsigned int b, int next, const Trial& t) {
 	if (next == NEXT_TRIAL) {
-		q_push(w, a, Q_SETUP, a.wave + 1, b);
+		q_push(w, a, Q_SETUP + trial_class(t), a.wave + 1, b);
 	} else if (next == NEXT_PREPARE) {
 		q_push(w, a, Q_PREPARE, a.wave, b);
 	} else {
@@ -136,6 +157,7 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 	feed.ticket = a.head + Q_SETUP * ASTC_MAX_WAVES;      // wave 0 has no queue: its head counter is the image ticket
 	feed.total = a.total;
 	feed.blocks_x = a.blocks_x;
+	int cls = 0;
 	while (true) {
 		bool active = false;
 		unsigned int b = 0;
@@ -164,7 +186,7 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 				active = true;
 				break;
 			}
-		} else if (q_pop(w, a, Q_SETUP, a.wave, b)) {
+		} else if (q_pop_classes(w, a, Q_SETUP, a.wave, cls, b)) {
 			record_restore(w, a, b, s, t);
 			active = true;
 		}
@@ -235,7 +257,7 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 				}
 			}
 			record_save(w, a, b, s, t, a.wave == 0);
-			q_push(w, a, Q_REFINE, a.wave, b);
+			q_push(w, a, Q_REFINE + trial_class(t), a.wave, b);
 		}
 	}
 }
@@ -259,11 +281,11 @@ ASTC_COOP void wave_finish_trial(WCtx w, const WaveArgs& a, unsigned int b, Bloc
 		wsync();
 		t.candidate_count = ready;
 		record_save(w, a, b, s, t);
-		q_push(w, a, Q_REFINE, a.wave + 1, b);
+		q_push(w, a, Q_REFINE + trial_class(t), a.wave + 1, b);
 		return;
 	}
 	record_save(w, a, b, s, t);
-	route_block(w, a, b, next);
+	route_block(w, a, b, next, t);
 }
 
 #if defined(ASTC_STEP_STATS)
@@ -288,6 +310,7 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a) {
 	t.partition_count = 1;
 	t.packed = 0;
 	unsigned int round = 0;
+	int cls = 0;
 	const unsigned int vote_mask = (1u << ((a.sync_mask >> 8) & 7)) - 1u;
 #if defined(ASTC_STEP_STATS)
 	int st_prev_class = -1;
@@ -295,7 +318,7 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a) {
 #endif
 	while (true) {
 		while (!has_item && !drained) {
-			if (!q_pop(w, a, Q_REFINE, a.wave, b)) {
+			if (!q_pop_classes(w, a, Q_REFINE, a.wave, cls, b)) {
 				drained = true;
 				break;
 			}
@@ -393,7 +416,7 @@ ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
 				next = block_search_advance(w, s, t);
 			} while (next == NEXT_PREPARE);
 			record_save(w, a, b, s, t);
-			route_block(w, a, b, next);
+			route_block(w, a, b, next, t);
 		}
 	}
 }

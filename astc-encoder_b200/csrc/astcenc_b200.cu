@@ -62,13 +62,22 @@ static __device__ __forceinline__ void stage_sincos_tables() {
 }
 
 // ---- the stage kernels of the wave pipeline (astc_dev_wave.cuh) ----
+// nothing queued in any class of this kind for the launch's wave?
+static __device__ __forceinline__ bool wave_queue_empty(const WaveArgs& a, int kind) {
+	uint32_t n = 0;
+	for (int c = 0; c < ASTC_Q_CLASSES; c++) {
+		n += __ldcg(a.count + (kind + c) * ASTC_MAX_WAVES + a.wave);
+	}
+	return n == 0;
+}
+
 #define ASTC_SETUP_THREADS_MAX 512
 #define ASTC_REFINE_THREADS_MAX 768
 #define ASTC_EMIT_THREADS 256
 
 __global__ void __launch_bounds__(ASTC_SETUP_THREADS_MAX, 1)
 astc_wave_setup_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img, const __grid_constant__ WaveArgs a) {
-	if (a.wave != 0 && __ldcg(a.count + Q_SETUP * ASTC_MAX_WAVES + a.wave) == 0) {
+	if (a.wave != 0 && wave_queue_empty(a, Q_SETUP)) {
 		return;
 	}
 	stage_launch_constants(bsd, cfg, img);
@@ -82,7 +91,7 @@ astc_wave_setup_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant
 
 __global__ void __launch_bounds__(ASTC_REFINE_THREADS_MAX, 1)
 astc_wave_refine_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img, const __grid_constant__ WaveArgs a) {
-	if (__ldcg(a.count + Q_REFINE * ASTC_MAX_WAVES + a.wave) == 0) {
+	if (wave_queue_empty(a, Q_REFINE)) {
 		return;
 	}
 	stage_launch_constants(bsd, cfg, img);
@@ -453,7 +462,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			}
 			if (waves > ASTC_MAX_WAVES - 1) waves = ASTC_MAX_WAVES - 1;
 			ctx->max_waves = waves;
-			CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(uint32_t) * 2 * 4 * ASTC_MAX_WAVES), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
+			CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(uint32_t) * 2 * ASTC_Q_KINDS * ASTC_MAX_WAVES), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
 		}
 		CUDA_TRY(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
 	}
@@ -603,7 +612,7 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 			cudaFree(ctx->d_queues);
 			ctx->d_queues = nullptr;
 			ctx->queue_capacity = 0;
-			CUDA_TRY(cudaMalloc(&ctx->d_queues, sizeof(uint32_t) * 4 * total), return ASTCENC_ERR_OUT_OF_MEM);
+			CUDA_TRY(cudaMalloc(&ctx->d_queues, sizeof(uint32_t) * ASTC_Q_KINDS * total), return ASTCENC_ERR_OUT_OF_MEM);
 			ctx->queue_capacity = total;
 		}
 		size_t rec_bytes = total * (size_t)bsd.record_bytes;
@@ -614,14 +623,14 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 			CUDA_TRY(cudaMalloc(&ctx->d_records, rec_bytes), return ASTCENC_ERR_OUT_OF_MEM);
 			ctx->d_records_bytes = rec_bytes;
 		}
-		CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, sizeof(uint32_t) * 2 * 4 * ASTC_MAX_WAVES, stream), return ASTCENC_ERR_BAD_CONTEXT);
+		CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, sizeof(uint32_t) * 2 * ASTC_Q_KINDS * ASTC_MAX_WAVES, stream), return ASTCENC_ERR_BAD_CONTEXT);
 		WaveArgs a;
 		a.records = ctx->d_records;
-		for (int k = 0; k < 4; k++) {
+		for (int k = 0; k < ASTC_Q_KINDS; k++) {
 			a.queue[k] = ctx->d_queues + (size_t)k * ctx->queue_capacity;
 		}
 		a.count = ctx->d_counters;
-		a.head = ctx->d_counters + 4 * ASTC_MAX_WAVES;
+		a.head = ctx->d_counters + ASTC_Q_KINDS * ASTC_MAX_WAVES;
 		a.total = (unsigned int)total;
 		a.blocks_x = img.blocks_x;
 		a.sync_mask = 0;      // measured: once every kernel runs one kind of work, the stage barriers no longer pay (110.7 -> 106.5 ms)

@@ -100,13 +100,13 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 		// the wave pipeline, driven like the CUDA host code does (one simulated warp per "kernel")
 		unsigned int total = img.blocks_x * img.block_rows;
 		std::vector<uint8_t> records((size_t)total * pk.bsd.record_bytes + 16);
-		std::vector<uint32_t> queues((size_t)4 * total);
-		std::vector<uint32_t> counters(2 * 4 * ASTC_MAX_WAVES, 0);
+		std::vector<uint32_t> queues((size_t)ASTC_Q_KINDS * total);
+		std::vector<uint32_t> counters(2 * ASTC_Q_KINDS * ASTC_MAX_WAVES, 0);
 		WaveArgs a;
 		a.records = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(records.data()) + 15) & ~(uintptr_t)15);
-		for (int k = 0; k < 4; k++) a.queue[k] = queues.data() + (size_t)k * total;
+		for (int k = 0; k < ASTC_Q_KINDS; k++) a.queue[k] = queues.data() + (size_t)k * total;
 		a.count = counters.data();
-		a.head = counters.data() + 4 * ASTC_MAX_WAVES;
+		a.head = counters.data() + ASTC_Q_KINDS * ASTC_MAX_WAVES;
 		a.total = total;
 		a.blocks_x = img.blocks_x;
 		a.sync_mask = 0xFF;
@@ -176,5 +176,10 @@ extern "C" unsigned int hostsim_arena_bytes(int profile, unsigned int bx, unsign
 	unsigned int lim[3] = {cfg.tune_2partition_index_limit, cfg.tune_3partition_index_limit, cfg.tune_4partition_index_limit};
 	astc_host::pack_device_tables(*t, lim, pk);
 	astc_host::free_block_size_tables(t);
+	if (getenv("HOSTSIM_ARENA_PRINT")) {
+		fprintf(stderr, "arena %u small %u | fixed %u scratch@%u (%u B) ei@%u dwi@%u lowhigh@%u mode_err@%u record %u | dec modes %u block modes %u\n",
+		        pk.bsd.arena_bytes, pk.bsd.arena_bytes_small, (unsigned)ASTC_ARENA_FIXED, pk.bsd.off_scratch, pk.bsd.scratch_bytes, pk.bsd.off_ei, pk.bsd.off_dwi,
+		        pk.bsd.off_lowhigh, pk.bsd.off_mode_err, pk.bsd.record_bytes, pk.bsd.decimation_mode_count_selected, pk.bsd.block_mode_count_1plane_2plane_selected);
+	}
 	return pk.bsd.arena_bytes;
 }
