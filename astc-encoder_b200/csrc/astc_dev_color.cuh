@@ -464,7 +464,8 @@ ASTC_FN void quantize_luminance_alpha(f4 c0, f4 c1, uint8_t out[4], const QuantC
 // pack_color_endpoints (astcenc_color_quantize.cpp:1909-2147)
 ASTC_NOINLINE uint8_t pack_color_endpoints(f4 color0, f4 color1, f4 rgbs_color, f4 rgbo_color, int format, uint8_t* output, int quant_level) {
 	QuantCtx q;
-	q.tab = ASTC_CT->color_unquant_to_uquant[quant_level - QUANT_6];
+	q.tab = STAGED.cq_smem_off != 0 ? astc_smem + STAGED.cq_smem_off + 512 * (quant_level - QUANT_6)
+	                                : ASTC_CT->color_unquant_to_uquant[quant_level - QUANT_6];
 	q.quant_level = quant_level;
 
 	color0 = vclamp4(0.0f, 65535.0f, color0);

@@ -41,6 +41,7 @@
 	#define ASTC_LDG(p) (*(p))
 	static const DevConstTables* g_astc_ct;
 	#define ASTC_CT g_astc_ct
+	static const int g_astc_dense_limit = 6;
 	static uint8_t* astc_smem;           // stands in for the CTA's shared window
 #else
 	#define ASTC_FN static __device__ __forceinline__
@@ -61,11 +62,13 @@
 	#define ASTC_LDG(p) __ldg(p)
 	__constant__ const DevConstTables* g_astc_ct;
 	#define ASTC_CT g_astc_ct
+	// realign_weights: grids whose weights touch at most this many texels take the anti-diagonal wavefront path
+	// (tuning knob ASTCENC_B200_DENSE_LIMIT)
+	__constant__ int g_astc_dense_limit = 6;
 	extern __shared__ __align__(16) uint8_t astc_smem[];
 #endif
 
 #include "astc_dev_math.cuh"
-#include "astc_dev_color.cuh"
 
 // Optional tracing of intermediate values (debug builds only: -DASTC_TRACE), printed by lane 0.
 #if defined(ASTC_TRACE)
@@ -100,6 +103,10 @@ struct SmemHdr {
 	DevBsd bsd;
 	DevConfig cfg;
 	DevImage img;
+	// tables a kernel staged behind the header (offsets into the shared window, 0 = read them from global memory):
+	// the packed decimation tables [0, bsd.dec_stage_bytes) and color_unquant_to_uquant
+	uint32_t dec_smem_off;
+	uint32_t cq_smem_off;
 };
 #define ASTC_SMEM_HDR 512
 static_assert(sizeof(SmemHdr) <= ASTC_SMEM_HDR, "launch constants must fit the shared header");
@@ -108,6 +115,11 @@ static_assert(sizeof(SmemHdr) <= ASTC_SMEM_HDR, "launch constants must fit the s
 #define BSD (reinterpret_cast<const SmemHdr*>(astc_smem)->bsd)
 #define CFG (reinterpret_cast<const SmemHdr*>(astc_smem)->cfg)
 #define IMG (reinterpret_cast<const SmemHdr*>(astc_smem)->img)
+#define STAGED (*reinterpret_cast<const SmemHdr*>(astc_smem))
+// loads of decimation-table entries: generic, the tables may live in shared memory (staged) or in global memory
+#define ASTC_LDD(p) (*(p))
+
+#include "astc_dev_color.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Warp primitives
@@ -280,7 +292,7 @@ struct DecView {
 ASTC_FN DecView dec_view(unsigned int d) {
 	DecView v;
 	const DevDecMode* dm = BSD.dec_modes + d;
-	const uint8_t* blob = BSD.dec_blob + ASTC_LDG(&dm->blob_offset);
+	const uint8_t* blob = (STAGED.dec_smem_off != 0 ? astc_smem + STAGED.dec_smem_off : BSD.dec_blob) + ASTC_LDG(&dm->blob_offset);
 	v.T = BSD.texel_count;
 	v.W = ASTC_LDG(&dm->weight_count);
 	v.max_twc = ASTC_LDG(&dm->max_texel_weight_count);
@@ -299,7 +311,7 @@ ASTC_FN f4 dec_contribs(const DecView& di, int t) {
 	const float* p = di.tcf + 4 * t;
 	return mk4(p[0], p[1], p[2], p[3]);
 #else
-	float4 v = __ldg(reinterpret_cast<const float4*>(di.tcf) + t);
+	float4 v = *(reinterpret_cast<const float4*>(di.tcf) + t);
 	return mk4(v.x, v.y, v.z, v.w);
 #endif
 }
@@ -932,7 +944,7 @@ ASTC_COOP void compute_ideal_colors_and_weights_2planes(WCtx w, unsigned int pla
 // Grids whose texels touch at most two weights skip the second pair in the reference; adding its (+0.0 + +0.0)
 // here leaves the non-negative sum unchanged bit for bit, so one form serves every grid.
 ASTC_FN float bilinear_infill(const DecView& di, SPtr<float> weights, int t) {
-	uint32_t ix = ASTC_LDG(&di.twi[t]);
+	uint32_t ix = ASTC_LDD(&di.twi[t]);
 	f4 c = dec_contribs(di, t);
 	return (weights[(int)(ix & 0xFF)] * c.x + weights[(int)((ix >> 8) & 0xFF)] * c.y) +
 	       (weights[(int)((ix >> 16) & 0xFF)] * c.z + weights[(int)(ix >> 24)] * c.w);
@@ -970,11 +982,11 @@ ASTC_COOP void compute_ideal_weights_for_decimation(WCtx w, unsigned int d, int 
 		float wes0 = eis[0];
 		float weight_weight = 1e-10f;
 		float initial_weight = 0.0f;
-		int off = ASTC_LDG(&di.wto[i]);
-		int end = ASTC_LDG(&di.wto[i + 1]);
+		int off = ASTC_LDD(&di.wto[i]);
+		int end = ASTC_LDD(&di.wto[i + 1]);
 		ASTC_NOUNROLL
 		for (int j = off; j < end; j++) {
-			uint32_t e = ASTC_LDG(&di.wtc[j]);
+			uint32_t e = ASTC_LDD(&di.wtc[j]);
 			int texel = (int)(e & 0xFF);
 			float weight = static_cast<float>(e >> 8);
 			float wes = constant_wes ? wes0 : eis[texel];
@@ -1006,11 +1018,11 @@ ASTC_COOP void compute_ideal_weights_for_decimation(WCtx w, unsigned int d, int 
 		float weight_val = out[id];
 		float error_change0 = 1e-10f;
 		float error_change1 = 0.0f;
-		int off = ASTC_LDG(&di.wto[i]);
-		int end = ASTC_LDG(&di.wto[i + 1]);
+		int off = ASTC_LDD(&di.wto[i]);
+		int end = ASTC_LDD(&di.wto[i + 1]);
 		ASTC_NOUNROLL
 		for (int j = off; j < end; j++) {
-			uint32_t e = ASTC_LDG(&di.wtc[j]);
+			uint32_t e = ASTC_LDD(&di.wtc[j]);
 			int texel = (int)(e & 0xFF);
 			float contrib_weight = static_cast<float>(e >> 8);
 			float wes = constant_wes ? wes0 : eis[texel];

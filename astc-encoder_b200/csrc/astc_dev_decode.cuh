@@ -366,8 +366,8 @@ ASTC_COOP void decompress_block(int lane, uint32_t slice, const uint8_t* pcb, un
 	SPtr<uint8_t> uq = sptr<uint8_t>(slice + D_WEIGHTS);
 	ASTC_NOUNROLL
 	for (int t = lane; t < T; t += ASTC_WARP) {
-		uint32_t ix = ASTC_LDG(&di.twi[t]);
-		uint32_t cx = ASTC_LDG(&di.tci[t]);
+		uint32_t ix = ASTC_LDD(&di.twi[t]);
+		uint32_t cx = ASTC_LDD(&di.tci[t]);
 		int i0 = (int)(ix & 0xFF), i1 = (int)((ix >> 8) & 0xFF), i2 = (int)((ix >> 16) & 0xFF), i3 = (int)(ix >> 24);
 		int c0 = (int)(cx & 0xFF), c1 = (int)((cx >> 8) & 0xFF), c2 = (int)((cx >> 16) & 0xFF), c3 = (int)(cx >> 24);
 		int w1 = (8 + uq[i0] * c0 + uq[i1] * c1 + uq[i2] * c2 + uq[i3] * c3) >> 4;
@@ -462,8 +462,8 @@ ASTC_COOP void block_info(int lane, uint32_t slice, uint64_t lo, uint64_t hi, De
 	SPtr<uint8_t> uq = sptr<uint8_t>(slice + D_WEIGHTS);
 	ASTC_NOUNROLL
 	for (int t = lane; t < T; t += ASTC_WARP) {
-		uint32_t ix = ASTC_LDG(&di.twi[t]);
-		uint32_t cx = ASTC_LDG(&di.tci[t]);
+		uint32_t ix = ASTC_LDD(&di.twi[t]);
+		uint32_t cx = ASTC_LDD(&di.tci[t]);
 		int i0 = (int)(ix & 0xFF), i1 = (int)((ix >> 8) & 0xFF), i2 = (int)((ix >> 16) & 0xFF), i3 = (int)(ix >> 24);
 		int c0 = (int)(cx & 0xFF), c1 = (int)((cx >> 8) & 0xFF), c2 = (int)((cx >> 16) & 0xFF), c3 = (int)(cx >> 24);
 		int w1 = (8 + uq[i0] * c0 + uq[i1] * c1 + uq[i2] * c2 + uq[i3] * c3) >> 4;

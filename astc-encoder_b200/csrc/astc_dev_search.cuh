@@ -69,7 +69,7 @@ ASTC_COOP void quantize_and_score_modes(WCtx w, unsigned int start_mode, unsigne
 		float rscale1 = z1.rscale, lowb1 = z1.low_bound;
 		ASTC_NOUNROLL
 		for (int t = 0; t < T; t++) {
-			uint32_t ix = ASTC_LDG(&di.twi[t]);
+			uint32_t ix = ASTC_LDD(&di.twi[t]);
 			f4 cf = dec_contribs(di, t);
 			int i0 = (int)(ix & 0xFF), i1 = (int)((ix >> 8) & 0xFF), i2 = (int)((ix >> 16) & 0xFF), i3 = (int)(ix >> 24);
 			float c0 = cf.x, c1 = cf.y, c2 = cf.z, c3 = cf.w;
@@ -663,7 +663,7 @@ ASTC_COOP void undecimate_weights(WCtx w, unsigned int d, int planes) {
 		if (di.max_twc == 1) {
 			v = static_cast<float>(uq[t]) * (1.0f / 64.0f);
 		} else {
-			uint32_t ix = ASTC_LDG(&di.twi[t]);
+			uint32_t ix = ASTC_LDD(&di.twi[t]);
 			f4 c = dec_contribs(di, t);
 			v = ((static_cast<float>(uq[(int)(ix & 0xFF)]) * (1.0f / 64.0f)) * c.x + (static_cast<float>(uq[(int)((ix >> 8) & 0xFF)]) * (1.0f / 64.0f)) * c.y) +
 			    ((static_cast<float>(uq[(int)((ix >> 16) & 0xFF)]) * (1.0f / 64.0f)) * c.z + (static_cast<float>(uq[(int)(ix >> 24)]) * (1.0f / 64.0f)) * c.w);
@@ -1094,8 +1094,8 @@ ASTC_COOP float compute_symbolic_block_difference(WCtx w, unsigned int pc, uint3
 	bool reject = false;
 	ASTC_NOUNROLL
 	for (int t = w.lane; t < T; t += ASTC_WARP) {
-		uint32_t ix = ASTC_LDG(&di.twi[t]);
-		uint32_t cx = ASTC_LDG(&di.tci[t]);
+		uint32_t ix = ASTC_LDD(&di.twi[t]);
+		uint32_t cx = ASTC_LDD(&di.tci[t]);
 		int i0 = (int)(ix & 0xFF), i1 = (int)((ix >> 8) & 0xFF), i2 = (int)((ix >> 16) & 0xFF), i3 = (int)(ix >> 24);
 		int c0 = (int)(cx & 0xFF), c1 = (int)((cx >> 8) & 0xFF), c2 = (int)((cx >> 16) & 0xFF), c3 = (int)(cx >> 24);
 		int w1 = (8 + uq[i0] * c0 + uq[i1] * c1 + uq[i2] * c2 + uq[i3] * c3) >> 4;
@@ -1272,7 +1272,7 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 		SPtr<uint16_t> s_wtc = sptr<uint16_t>(rs.tile + 128 + 136 + 144);    // [E] (<= 4 T)
 		ASTC_NOUNROLL
 		for (int we = w.lane; we <= weight_count; we += ASTC_WARP) {
-			s_wto[we] = ASTC_LDG(&di.wto[we]);
+			s_wto[we] = ASTC_LDD(&di.wto[we]);
 			if (we < weight_count) {
 				int uq = dec_weights_uquant[we];
 				uqf[we] = static_cast<float>(uq);
@@ -1287,7 +1287,7 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 		int E = s_wto[weight_count];
 		ASTC_NOUNROLL
 		for (int e = w.lane; e < E; e += ASTC_WARP) {
-			s_wtc[e] = ASTC_LDG(&di.wtc[e]);
+			s_wtc[e] = ASTC_LDD(&di.wtc[e]);
 		}
 		ASTC_NOUNROLL
 		for (int t = w.lane; t < T; t += ASTC_WARP) {
@@ -1302,7 +1302,7 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 		// walking its weight's texels in order. Same decisions, about half the sequential steps.
 		const DevDecMode* dmp = BSD.dec_modes + d;
 		int gw = ASTC_LDG(&dmp->weight_x), gh = ASTC_LDG(&dmp->weight_y);
-		if (ASTC_LDG(&dmp->max_weight_texels) <= 6) {
+		if ((int)ASTC_LDG(&dmp->max_weight_texels) <= g_astc_dense_limit) {
 #if ASTC_WARP == 1
 			const int groups = 1;
 #else

@@ -90,6 +90,7 @@ struct DevBsd {
 	const uint16_t* block_mode_packed_index;    // [2048]
 	const DevDecMode* dec_modes;
 	const uint8_t* dec_blob;
+	uint32_t dec_stage_bytes;                   // prefix of dec_blob that holds every grid the search can select
 	const uint8_t* partitions[5];               // [1]: single entry, [2..4]: packed partitionings
 	const uint16_t* partitioning_packed_index[3];
 	const uint64_t* coverage_bitmaps[5];        // [pc][packed * pc + p]

@@ -37,6 +37,8 @@ struct WaveArgs {
 	unsigned int blocks_x;
 	int wave;
 	unsigned int sync_mask;      // tuning: which stage barriers are active (bit i = i-th barrier of the kernel loop)
+	uint32_t stage_bytes_setup;  // set-up kernel: the same (decimation tables only)
+	uint32_t stage_bytes;        // refine kernel: bytes of tables staged between the header and the arenas (0 = none)
 };
 
 #if defined(ASTC_HOSTSIM)

@@ -159,6 +159,7 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 		// arena slot for the decimated ideal weights (only grids the search can reference)
 		dm.dwi_offset = (uint16_t)dwi_total;
 		if (d < t.decimation_mode_count_selected) {
+			b.dec_stage_bytes = (uint32_t)((dblob.size() + 15) / 16 * 16);
 			dwi_total += W * (dm.maxprec_2planes >= 0 ? 2u : 1u);
 			dwi_total = (dwi_total + 3u) & ~3u;
 		}

@@ -45,6 +45,42 @@ static __device__ __forceinline__ void stage_launch_constants(const DevBsd& bsd,
 	for (unsigned int i = threadIdx.x; i < sizeof(DevImage) / 4; i += blockDim.x) {
 		dst[offsetof(SmemHdr, img) / 4 + i] = s2[i];
 	}
+	if (threadIdx.x == 0) {
+		dst[offsetof(SmemHdr, dec_smem_off) / 4] = 0;
+		dst[offsetof(SmemHdr, cq_smem_off) / 4] = 0;
+	}
+	__syncthreads();
+}
+
+// Refinement reads the packed decimation tables (infill in every score / refit / realignment) and, from single lanes in
+// long dependent chains, the colour quantisation tables; its arenas leave ~50 KB of the shared window free at 6x6, so
+// both are copied behind the header once per CTA and read from there (when they fit without costing a warp).
+#define ASTC_CQ_BYTES (17 * 512)
+static __device__ __forceinline__ void stage_tables(uint32_t stage_bytes, uint32_t at, bool with_colour) {
+	if (stage_bytes == 0) {
+		return;
+	}
+	const DevBsd& bsd = BSD;
+	uint32_t dec_bytes = (bsd.dec_stage_bytes + 15u) & ~15u;
+	uint4* dst = reinterpret_cast<uint4*>(astc_smem + at);
+	const uint4* src = reinterpret_cast<const uint4*>(bsd.dec_blob);
+	for (unsigned int i = threadIdx.x; i < dec_bytes / 16; i += blockDim.x) {
+		dst[i] = __ldg(src + i);
+	}
+	if (with_colour) {
+		uint4* dst2 = reinterpret_cast<uint4*>(astc_smem + at + dec_bytes);
+		const uint4* src2 = reinterpret_cast<const uint4*>(&ASTC_CT->color_unquant_to_uquant[0][0]);
+		for (unsigned int i = threadIdx.x; i < ASTC_CQ_BYTES / 16; i += blockDim.x) {
+			dst2[i] = __ldg(src2 + i);
+		}
+	}
+	if (threadIdx.x == 0) {
+		uint32_t* hdr = reinterpret_cast<uint32_t*>(astc_smem);
+		hdr[offsetof(SmemHdr, dec_smem_off) / 4] = at;
+		if (with_colour) {
+			hdr[offsetof(SmemHdr, cq_smem_off) / 4] = at + dec_bytes;
+		}
+	}
 	__syncthreads();
 }
 
@@ -82,9 +118,10 @@ astc_wave_setup_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant
 	}
 	stage_launch_constants(bsd, cfg, img);
 	stage_sincos_tables();
+	stage_tables(a.stage_bytes_setup, ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES, false);
 	WCtx w;
 	w.lane = threadIdx.x & 31;
-	w.base = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + (uint32_t)(threadIdx.x >> 5) * bsd.arena_bytes;
+	w.base = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + a.stage_bytes_setup + (uint32_t)(threadIdx.x >> 5) * bsd.arena_bytes;
 	w.T = bsd.texel_count;
 	wave_setup(w, a);
 }
@@ -95,9 +132,10 @@ astc_wave_refine_kernel(const __grid_constant__ DevBsd bsd, const __grid_constan
 		return;
 	}
 	stage_launch_constants(bsd, cfg, img);
+	stage_tables(a.stage_bytes, ASTC_SMEM_HDR, true);
 	WCtx w;
 	w.lane = threadIdx.x & 31;
-	w.base = ASTC_SMEM_HDR + (uint32_t)(threadIdx.x >> 5) * bsd.arena_bytes_small;
+	w.base = ASTC_SMEM_HDR + a.stage_bytes + (uint32_t)(threadIdx.x >> 5) * bsd.arena_bytes_small;
 	w.T = bsd.texel_count;
 	wave_refine(w, a);
 }
@@ -241,7 +279,9 @@ struct astcenc_context {
 	int lockstep;                // single-kernel drivers: phase-aligned CTA (1) or independent warps (0)
 	int driver;                  // 0 = wave pipeline (default), 1 = single kernel
 	int warps_setup, warps_small;   // warps per CTA of the setup / refine+prepare kernels
-	size_t smem_setup, smem_small;
+	size_t smem_setup, smem_small, smem_refine;
+	uint32_t setup_stage_bytes;
+	uint32_t refine_stage_bytes;   // tables staged behind the header of the refine kernel's shared window (0 = none)
 	int max_waves;
 	// wave pipeline buffers, grown on demand
 	uint8_t* d_records;
@@ -420,6 +460,10 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			int v = atoi(e);
 			if (v >= 1 && v <= 8) ctx->grid = prop.multiProcessorCount * v;
 		}
+		if (const char* e = getenv("ASTCENC_B200_DENSE_LIMIT")) {
+			int v = atoi(e);
+			cudaMemcpyToSymbol(g_astc_dense_limit, &v, sizeof(v));
+		}
 		ctx->lockstep = 1;
 		ctx->driver = 0;
 		if (const char* e = getenv("ASTCENC_B200_DRIVER")) {
@@ -436,6 +480,12 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			if (ws > ASTC_SETUP_THREADS_MAX / 32) ws = ASTC_SETUP_THREADS_MAX / 32;
 			int wr = (int)((smem_limit - ASTC_SMEM_HDR) / arena_small);
 			if (wr > ASTC_REFINE_THREADS_MAX / 32) wr = ASTC_REFINE_THREADS_MAX / 32;
+			// stage the decimation + colour quantisation tables in the refine kernel's shared window if that costs no warp
+			size_t stage = (((size_t)ctx->tables->bsd.dec_stage_bytes + 15) & ~(size_t)15) + ASTC_CQ_BYTES;
+			ctx->refine_stage_bytes = 0;
+			if (smem_limit > ASTC_SMEM_HDR + stage && (int)((smem_limit - ASTC_SMEM_HDR - stage) / arena_small) >= wr && !getenv("ASTCENC_B200_NO_STAGE")) {
+				ctx->refine_stage_bytes = (uint32_t)stage;
+			}
 			if (const char* e = getenv("ASTCENC_B200_WARPS_SETUP")) {
 				int v = atoi(e);
 				if (v >= 1 && v <= ws) ws = v;
@@ -446,8 +496,20 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			}
 			ctx->warps_setup = ws;
 			ctx->warps_small = wr;
-			ctx->smem_setup = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + arena * ws;
+			// (experiment: stage the decimation tables in the set-up kernel too, paid for with warps)
+			ctx->setup_stage_bytes = 0;
+			if (getenv("ASTCENC_B200_STAGE_SETUP")) {
+				size_t st = ((size_t)ctx->tables->bsd.dec_stage_bytes + 15) & ~(size_t)15;
+				int ws2 = smem_limit > ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + st ? (int)((smem_limit - ASTC_SMEM_HDR - ASTC_SMEM_SINCOS_BYTES - st) / arena) : 0;
+				if (ws2 >= 1) {
+					if (ws2 < ws) ws = ws2;
+					ctx->warps_setup = ws;
+					ctx->setup_stage_bytes = (uint32_t)st;
+				}
+			}
+			ctx->smem_setup = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + ctx->setup_stage_bytes + arena * ws;
 			ctx->smem_small = ASTC_SMEM_HDR + arena_small * wr;
+			ctx->smem_refine = ASTC_SMEM_HDR + ctx->refine_stage_bytes + arena_small * wr;
 			CUDA_TRY(cudaFuncSetAttribute(astc_wave_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
 			         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
 			CUDA_TRY(cudaFuncSetAttribute(astc_wave_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
@@ -633,6 +695,8 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 		a.head = ctx->d_counters + ASTC_Q_KINDS * ASTC_MAX_WAVES;
 		a.total = (unsigned int)total;
 		a.blocks_x = img.blocks_x;
+		a.stage_bytes = ctx->refine_stage_bytes;
+		a.stage_bytes_setup = ctx->setup_stage_bytes;
 		a.sync_mask = 0;      // measured: once every kernel runs one kind of work, the stage barriers no longer pay (110.7 -> 106.5 ms)
 		if (const char* e = getenv("ASTCENC_B200_SYNC_MASK")) {
 			a.sync_mask = (unsigned int)strtoul(e, nullptr, 0);
@@ -663,7 +727,7 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 			a.wave = wave;
 			astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
 			mark(0);
-			astc_wave_refine_kernel<<<grid, ctx->warps_small * 32, ctx->smem_small, stream>>>(bsd, ctx->dcfg, img, a);
+			astc_wave_refine_kernel<<<grid, ctx->warps_small * 32, ctx->smem_refine, stream>>>(bsd, ctx->dcfg, img, a);
 			mark(1);
 			// (statistics / partition search gain nothing from phase alignment: two half-size CTAs per SM wait less; measured 5.1 -> 4.4 ms)
 			int wp = ctx->warps_small >= 2 ? ctx->warps_small / 2 : 1;

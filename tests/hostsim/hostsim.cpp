@@ -68,6 +68,8 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	hdr->bsd = pk.bsd;
 	hdr->cfg = dcfg;
 	hdr->img = img;
+	hdr->dec_smem_off = 0;
+	hdr->cq_smem_off = 0;
 	WCtx w;
 	w.lane = 0;
 	w.base = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES;
@@ -110,6 +112,8 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 		a.total = total;
 		a.blocks_x = img.blocks_x;
 		a.sync_mask = 0xFF;
+		a.stage_bytes = 0;
+		a.stage_bytes_setup = 0;
 		for (int wave = 0; wave < ASTC_MAX_WAVES - 1; wave++) {
 			a.wave = wave;
 			wave_setup(w, a);
@@ -157,6 +161,8 @@ extern "C" int hostsim_decompress_image(int profile, unsigned int bx, unsigned i
 	hdr->bsd = pk.bsd;
 	hdr->cfg = dcfg;
 	hdr->img = img;
+	hdr->dec_smem_off = 0;
+	hdr->cq_smem_off = 0;
 	for (unsigned int y = 0; y < img.block_rows; y++) {
 		for (unsigned int x = 0; x < img.blocks_x; x++) {
 			decompress_block(0, ASTC_SMEM_HDR, blocks + ((size_t)y * img.blocks_x + x) * 16, x, y);
@@ -177,9 +183,9 @@ extern "C" unsigned int hostsim_arena_bytes(int profile, unsigned int bx, unsign
 	astc_host::pack_device_tables(*t, lim, pk);
 	astc_host::free_block_size_tables(t);
 	if (getenv("HOSTSIM_ARENA_PRINT")) {
-		fprintf(stderr, "arena %u small %u | fixed %u scratch@%u (%u B) ei@%u dwi@%u lowhigh@%u mode_err@%u record %u | dec modes %u block modes %u\n",
+		fprintf(stderr, "arena %u small %u | fixed %u scratch@%u (%u B) ei@%u dwi@%u lowhigh@%u mode_err@%u record %u | dec modes %u block modes %u | dec tables %u B\n",
 		        pk.bsd.arena_bytes, pk.bsd.arena_bytes_small, (unsigned)ASTC_ARENA_FIXED, pk.bsd.off_scratch, pk.bsd.scratch_bytes, pk.bsd.off_ei, pk.bsd.off_dwi,
-		        pk.bsd.off_lowhigh, pk.bsd.off_mode_err, pk.bsd.record_bytes, pk.bsd.decimation_mode_count_selected, pk.bsd.block_mode_count_1plane_2plane_selected);
+		        pk.bsd.off_lowhigh, pk.bsd.off_mode_err, pk.bsd.record_bytes, pk.bsd.decimation_mode_count_selected, pk.bsd.block_mode_count_1plane_2plane_selected, pk.bsd.dec_stage_bytes);
 	}
 	return pk.bsd.arena_bytes;
 }
