@@ -460,8 +460,12 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			int v = atoi(e);
 			if (v >= 1 && v <= 8) ctx->grid = prop.multiProcessorCount * v;
 		}
-		if (const char* e = getenv("ASTCENC_B200_DENSE_LIMIT")) {
-			int v = atoi(e);
+		{
+			// (a device-wide constant: written by every context so that a tuning override does not outlive its context)
+			int v = 6;
+			if (const char* e = getenv("ASTCENC_B200_DENSE_LIMIT")) {
+				v = atoi(e);
+			}
 			cudaMemcpyToSymbol(g_astc_dense_limit, &v, sizeof(v));
 		}
 		ctx->lockstep = 1;
@@ -480,10 +484,11 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			if (ws > ASTC_SETUP_THREADS_MAX / 32) ws = ASTC_SETUP_THREADS_MAX / 32;
 			int wr = (int)((smem_limit - ASTC_SMEM_HDR) / arena_small);
 			if (wr > ASTC_REFINE_THREADS_MAX / 32) wr = ASTC_REFINE_THREADS_MAX / 32;
-			// stage the decimation + colour quantisation tables in the refine kernel's shared window if that costs no warp
+			// Staging the decimation (+ colour quantisation) tables in the refine kernel's spare shared memory is possible
+			// without losing a warp at 6x6, but measured no gain (refine 42.4 vs 41.8 ms: L1 already serves these loads): opt-in.
 			size_t stage = (((size_t)ctx->tables->bsd.dec_stage_bytes + 15) & ~(size_t)15) + ASTC_CQ_BYTES;
 			ctx->refine_stage_bytes = 0;
-			if (smem_limit > ASTC_SMEM_HDR + stage && (int)((smem_limit - ASTC_SMEM_HDR - stage) / arena_small) >= wr && !getenv("ASTCENC_B200_NO_STAGE")) {
+			if (getenv("ASTCENC_B200_STAGE_REFINE") && smem_limit > ASTC_SMEM_HDR + stage && (int)((smem_limit - ASTC_SMEM_HDR - stage) / arena_small) >= wr) {
 				ctx->refine_stage_bytes = (uint32_t)stage;
 			}
 			if (const char* e = getenv("ASTCENC_B200_WARPS_SETUP")) {
@@ -496,12 +501,18 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			}
 			ctx->warps_setup = ws;
 			ctx->warps_small = wr;
-			// (experiment: stage the decimation tables in the set-up kernel too, paid for with warps)
+			// The set-up kernel walks the decimation tables of every grid for every block (decimated ideal weights, per-mode
+			// scoring): with them in shared memory it is faster even with one warp less (6x6 medium: 21 KB of tables, 15
+			// instead of 16 warps, 39.4 -> 37.9 ms). Done when it costs at most one warp (ASTCENC_B200_STAGE_SETUP=0/1 forces).
 			ctx->setup_stage_bytes = 0;
-			if (getenv("ASTCENC_B200_STAGE_SETUP")) {
+			{
 				size_t st = ((size_t)ctx->tables->bsd.dec_stage_bytes + 15) & ~(size_t)15;
 				int ws2 = smem_limit > ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + st ? (int)((smem_limit - ASTC_SMEM_HDR - ASTC_SMEM_SINCOS_BYTES - st) / arena) : 0;
-				if (ws2 >= 1) {
+				bool want = ws2 >= 1 && ws2 >= ws - 1;
+				if (const char* e = getenv("ASTCENC_B200_STAGE_SETUP")) {
+					want = atoi(e) != 0 && ws2 >= 1;
+				}
+				if (want) {
 					if (ws2 < ws) ws = ws2;
 					ctx->warps_setup = ws;
 					ctx->setup_stage_bytes = (uint32_t)st;
