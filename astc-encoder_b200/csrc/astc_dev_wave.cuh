@@ -38,6 +38,7 @@ struct WaveArgs {
 	int wave;
 	unsigned int sync_mask;      // tuning: which stage barriers are active (bit i = i-th barrier of the kernel loop)
 	uint32_t stage_bytes_setup;  // set-up kernel: the same (decimation tables only)
+	uint32_t refine_state_off;   // refine kernel: offset of the per-warp Refine slots (ASTC_REFINE_STATE_BYTES each) in the shared window
 	uint32_t stage_bytes;        // refine kernel: bytes of tables staged between the header and the arenas (0 = none)
 };
 
@@ -120,7 +121,8 @@ static_assert(sizeof(BlockSearch) <= 128 && sizeof(Trial) <= 64, "search state m
 
 // park the search state in the arena and write the record
 ASTC_FN void record_save(const WCtx& w, const WaveArgs& a, unsigned int b, const BlockSearch& s, const Trial& t, bool with_texels = false) {
-	if (w.lane == 0) {
+	// (the refine kernel keeps s and t in their arena slots already)
+	if (w.lane == 0 && &s != &search_of(w)) {
 		search_of(w) = s;
 		trial_of(w) = t;
 	}
@@ -129,8 +131,10 @@ ASTC_FN void record_save(const WCtx& w, const WaveArgs& a, unsigned int b, const
 }
 ASTC_FN void record_restore(const WCtx& w, const WaveArgs& a, unsigned int b, BlockSearch& s, Trial& t) {
 	record_copy(w, a, b, false);
-	s = search_of(w);
-	t = trial_of(w);
+	if (&s != &search_of(w)) {
+		s = search_of(w);
+		t = trial_of(w);
+	}
 }
 
 ASTC_FN int trial_class(const Trial& t) {
@@ -300,10 +304,18 @@ __device__ unsigned long long g_step_stats[6][8];
 #define STAT_T(v)
 #endif
 
-ASTC_COOP void wave_refine(WCtx w, WaveArgs a) {
-	BlockSearch s;
-	Trial t;
-	Refine r;
+// The search state (BlockSearch, Trial, Refine) is identical in every lane of the warp and every step function takes it by
+// reference - as automatic variables the three structs live in local memory, 32 copies per warp (~10 KB), far more than the
+// L1 left beside the arenas holds (ncu: L1 hit rate 39 %, long-scoreboard stalls on local loads). The refine kernel therefore
+// works on ONE copy per warp in shared memory: BlockSearch and Trial in their arena slots (where the record keeps them
+// anyway), Refine in a slot behind the arenas. Every lane stores the same values, so the concurrent stores are benign.
+#define ASTC_REFINE_STATE_BYTES 128
+static_assert(sizeof(Refine) <= ASTC_REFINE_STATE_BYTES, "Refine must fit its shared-memory slot");
+
+ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
+	BlockSearch& s = search_of(w);
+	Trial& t = trial_of(w);
+	Refine& r = *reinterpret_cast<Refine*>(astc_smem + a.refine_state_off + warp_index * ASTC_REFINE_STATE_BYTES);
 	bool has_item = false;
 	bool drained = false;
 	unsigned int b = 0;

@@ -137,7 +137,7 @@ astc_wave_refine_kernel(const __grid_constant__ DevBsd bsd, const __grid_constan
 	w.lane = threadIdx.x & 31;
 	w.base = ASTC_SMEM_HDR + a.stage_bytes + (uint32_t)(threadIdx.x >> 5) * bsd.arena_bytes_small;
 	w.T = bsd.texel_count;
-	wave_refine(w, a);
+	wave_refine(w, a, threadIdx.x >> 5);
 }
 
 __global__ void __launch_bounds__(ASTC_REFINE_THREADS_MAX, 1)
@@ -482,13 +482,13 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			size_t arena_small = ctx->tables->bsd.arena_bytes_small;
 			int ws = (int)((smem_limit - ASTC_SMEM_HDR - ASTC_SMEM_SINCOS_BYTES) / arena);
 			if (ws > ASTC_SETUP_THREADS_MAX / 32) ws = ASTC_SETUP_THREADS_MAX / 32;
-			int wr = (int)((smem_limit - ASTC_SMEM_HDR) / arena_small);
+			int wr = (int)((smem_limit - ASTC_SMEM_HDR) / (arena_small + ASTC_REFINE_STATE_BYTES));
 			if (wr > ASTC_REFINE_THREADS_MAX / 32) wr = ASTC_REFINE_THREADS_MAX / 32;
 			// Staging the decimation (+ colour quantisation) tables in the refine kernel's spare shared memory is possible
 			// without losing a warp at 6x6, but measured no gain (refine 42.4 vs 41.8 ms: L1 already serves these loads): opt-in.
 			size_t stage = (((size_t)ctx->tables->bsd.dec_stage_bytes + 15) & ~(size_t)15) + ASTC_CQ_BYTES;
 			ctx->refine_stage_bytes = 0;
-			if (getenv("ASTCENC_B200_STAGE_REFINE") && smem_limit > ASTC_SMEM_HDR + stage && (int)((smem_limit - ASTC_SMEM_HDR - stage) / arena_small) >= wr) {
+			if (getenv("ASTCENC_B200_STAGE_REFINE") && smem_limit > ASTC_SMEM_HDR + stage && (int)((smem_limit - ASTC_SMEM_HDR - stage) / (arena_small + ASTC_REFINE_STATE_BYTES)) >= wr) {
 				ctx->refine_stage_bytes = (uint32_t)stage;
 			}
 			if (const char* e = getenv("ASTCENC_B200_WARPS_SETUP")) {
@@ -520,7 +520,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			}
 			ctx->smem_setup = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + ctx->setup_stage_bytes + arena * ws;
 			ctx->smem_small = ASTC_SMEM_HDR + arena_small * wr;
-			ctx->smem_refine = ASTC_SMEM_HDR + ctx->refine_stage_bytes + arena_small * wr;
+			ctx->smem_refine = ASTC_SMEM_HDR + ctx->refine_stage_bytes + arena_small * wr + (size_t)ASTC_REFINE_STATE_BYTES * wr;
 			CUDA_TRY(cudaFuncSetAttribute(astc_wave_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
 			         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
 			CUDA_TRY(cudaFuncSetAttribute(astc_wave_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
@@ -707,6 +707,7 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 		a.total = (unsigned int)total;
 		a.blocks_x = img.blocks_x;
 		a.stage_bytes = ctx->refine_stage_bytes;
+		a.refine_state_off = (uint32_t)(ASTC_SMEM_HDR + ctx->refine_stage_bytes + (size_t)bsd.arena_bytes_small * ctx->warps_small);
 		a.stage_bytes_setup = ctx->setup_stage_bytes;
 		a.sync_mask = 0;      // measured: once every kernel runs one kind of work, the stage barriers no longer pay (110.7 -> 106.5 ms)
 		if (const char* e = getenv("ASTCENC_B200_SYNC_MASK")) {

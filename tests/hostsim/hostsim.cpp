@@ -31,7 +31,7 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	DevConfig dcfg;
 	astc_host::make_device_config(cfg, dcfg);
 	// the simulated shared window: launch constants, then one arena (16-byte aligned like the device's)
-	std::vector<uint8_t> window(ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + pk.bsd.arena_bytes + 64 + 32 * EMIT_SLICE, 0xCD);
+	std::vector<uint8_t> window(ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + pk.bsd.arena_bytes + 64 + 32 * EMIT_SLICE + ASTC_REFINE_STATE_BYTES, 0xCD);
 	astc_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(window.data()) + 15) & ~(uintptr_t)15);
 	DevImage img;
 	img.data = data;
@@ -113,11 +113,12 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 		a.blocks_x = img.blocks_x;
 		a.sync_mask = 0xFF;
 		a.stage_bytes = 0;
+		a.refine_state_off = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + pk.bsd.arena_bytes + 32 * EMIT_SLICE + 16;
 		a.stage_bytes_setup = 0;
 		for (int wave = 0; wave < ASTC_MAX_WAVES - 1; wave++) {
 			a.wave = wave;
 			wave_setup(w, a);
-			wave_refine(w, a);
+			wave_refine(w, a, 0);
 			wave_prepare(w, a);
 		}
 		a.wave = 0;
