@@ -157,8 +157,11 @@ ASTC_FN void route_block(const WCtx& w, const WaveArgs& a, unsigned int b, int n
 // S: trial setup. Wave 0 reads the image (load_block, constant-colour blocks are emitted on the spot).
 // ---------------------------------------------------------------------------------------------
 ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
-	BlockSearch s;
-	Trial t;
+	// one copy of the search state per warp, in the arena slots the record keeps it in (see wave_refine); the widened
+	// copy of the trial used by the shared set-up sits in the work / mod colour slots, which only refinement uses
+	BlockSearch& s = search_of(w);
+	Trial& t = trial_of(w);
+	Trial& tf = *reinterpret_cast<Trial*>(astc_smem + w.base + A_SCB + 160);
 	BlockFeed feed;
 	feed.ticket = a.head + Q_SETUP * ASTC_MAX_WAVES;      // wave 0 has no queue: its head counter is the image ticket
 	feed.total = a.total;
@@ -206,9 +209,11 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 		// errors of the shared modes are identical (compress_symbolic.cpp:1243-1270 runs the same code twice).
 		// One set-up over the full range therefore serves both; the second candidate list waits in A_CAND2.
 		bool shared = active && !t.dual && t.only_always && t.partition_count == 1;
-		Trial tf = t;
-		if (shared) {
-			tf.only_always = 0;
+		if (active) {
+			tf = t;
+			if (shared) {
+				tf.only_always = 0;
+			}
 		}
 		if (active) stage_ideal(w, tf);
 		if (a.sync_mask & 1) cta_sync();
@@ -414,8 +419,8 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 // P: block statistics / partition search.
 // ---------------------------------------------------------------------------------------------
 ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
-	BlockSearch s;
-	Trial t;
+	BlockSearch& s = search_of(w);
+	Trial& t = trial_of(w);
 	while (true) {
 		unsigned int b = 0;
 		bool active = q_pop(w, a, Q_PREPARE, a.wave, b);
