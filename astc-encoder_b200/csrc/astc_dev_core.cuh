@@ -1210,58 +1210,82 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 			rec[it] = r;
 		}
 		wsync();
-		// phase 2: :298-355
-		if (in_round && steps != 0) {
-			float best_err[ASTC_ANGULAR_STEPS + 4], best_idx[ASTC_ANGULAR_STEPS + 4], best_cut[ASTC_ANGULAR_STEPS + 4];
+		// phase 2 (:298-355): the reference walks a pair's steps once and keeps, per span bucket, the best
+		// (error, step, cut) in three arrays; only the buckets of the quant levels 0..max_precision are ever read. Here one
+		// lane owns one (pair, quant level): it scans the pair's step records for ITS bucket in the same order with the
+		// same strict comparisons, so it ends with exactly the entry the arrays would hold - in registers, all lanes busy.
+		{
+			int nitems2 = npair * 8;
 			ASTC_NOUNROLL
-			for (int i = 0; i < steps + 4; i++) {
-				best_err[i] = ERROR_CALC_DEFAULT;
-				best_idx[i] = -1.0f;
-				best_cut[i] = 0.0f;
-			}
-			SPtr<AngStep> rp = rec + first;
-			ASTC_NOUNROLL
-			for (int sp = 0; sp < steps; sp++) {
-				AngStep r = rp[sp];
-				int span = r.span;
-				float i_flt = static_cast<float>(sp);
-				float error = r.error;
-				float error_cut_low = error + r.cut_low_err;
-				float error_cut_high = error + r.cut_high_err;
-				float error_cut_low_high = error + r.cut_low_err + r.cut_high_err;
-				if (best_err[span] > error) {
-					best_err[span] = error;
-					best_idx[span] = i_flt;
-					best_cut[span] = 0.0f;
+			for (int it0 = 0; it0 < nitems2; it0 += ASTC_WARP) {
+#if defined(ASTC_HOSTSIM) || defined(ASTC_DEBUG_SINGLE_LANE)
+				ASTC_NOUNROLL
+				for (int it = it0; it < nitems2; it++) {
+				int qi = it & 7;
+				int p_steps = steps, p_first = first, p_d = d, p_pl = pl;
+				unsigned int p_mp = max_precision;
+				bool act = true;
+#else
+				{
+				int it = it0 + w.lane;
+				int qi = it & 7;
+				bool act = it < nitems2;
+				int src = act ? (it >> 3) : 0;
+				int p_steps = __shfl_sync(0xffffffffu, steps, src);
+				int p_first = __shfl_sync(0xffffffffu, first, src);
+				int p_d = __shfl_sync(0xffffffffu, d, src);
+				int p_pl = __shfl_sync(0xffffffffu, pl, src);
+				unsigned int p_mp = __shfl_sync(0xffffffffu, max_precision, src);
+#endif
+				if (act && p_steps != 0 && (unsigned int)qi <= p_mp) {
+					int q = steps_for_quant_level((unsigned int)qi);
+					float best = ERROR_CALC_DEFAULT;
+					int bidx = -1;
+					float bcut = 0.0f;
+					SPtr<AngStep> rp = rec + p_first;
+					ASTC_NOUNROLL
+					for (int sp = 0; sp < p_steps; sp++) {
+						AngStep r = rp[sp];
+						int span = r.span;
+						float error = r.error;
+						if (span == q) {
+							if (best > error) {
+								best = error;
+								bidx = sp;
+								bcut = 0.0f;
+							}
+						} else if (span - 1 == q) {
+							float error_cut_low = error + r.cut_low_err;
+							float error_cut_high = error + r.cut_high_err;
+							if (best > error_cut_low) {
+								best = error_cut_low;
+								bidx = sp;
+								bcut = 1.0f;
+							}
+							if (best > error_cut_high) {
+								best = error_cut_high;
+								bidx = sp;
+								bcut = 0.0f;
+							}
+						} else if (span - 2 == q) {
+							float error_cut_low_high = error + r.cut_low_err + r.cut_high_err;
+							if (best > error_cut_low_high) {
+								best = error_cut_low_high;
+								bidx = sp;
+								bcut = 1.0f;
+							}
+						}
+					}
+					int bsi = maxi(0, bidx);
+					AngStep r = rp[bsi];
+					float lwi = r.minidx + bcut;
+					float hwi = lwi + static_cast<float>(q) - 1.0f;
+					float stepsize = 1.0f / (1.0f + static_cast<float>(bsi));
+					SPtr<float> lh = lowhigh + (p_d * 2 + p_pl) * 16;
+					lh[2 * qi] = (r.offset + lwi) * stepsize;
+					lh[2 * qi + 1] = (r.offset + hwi) * stepsize;
 				}
-				if (best_err[span - 1] > error_cut_low) {
-					best_err[span - 1] = error_cut_low;
-					best_idx[span - 1] = i_flt;
-					best_cut[span - 1] = 1.0f;
 				}
-				if (best_err[span - 1] > error_cut_high) {
-					best_err[span - 1] = error_cut_high;
-					best_idx[span - 1] = i_flt;
-					best_cut[span - 1] = 0.0f;
-				}
-				if (best_err[span - 2] > error_cut_low_high) {
-					best_err[span - 2] = error_cut_low_high;
-					best_idx[span - 2] = i_flt;
-					best_cut[span - 2] = 1.0f;
-				}
-			}
-			SPtr<float> lh = lowhigh + (d * 2 + pl) * 16;
-			ASTC_NOUNROLL
-			for (unsigned int i = 0; i <= max_precision; i++) {
-				int q = steps_for_quant_level(i);
-				int bsi = (int)best_idx[q];
-				bsi = maxi(0, bsi);
-				AngStep r = rp[bsi];
-				float lwi = r.minidx + best_cut[q];
-				float hwi = lwi + static_cast<float>(q) - 1.0f;
-				float stepsize = 1.0f / (1.0f + static_cast<float>(bsi));
-				lh[2 * (int)i] = (r.offset + lwi) * stepsize;
-				lh[2 * (int)i + 1] = (r.offset + hwi) * stepsize;
 			}
 		}
 		wsync();
