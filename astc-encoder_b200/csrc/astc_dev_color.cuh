@@ -34,7 +34,7 @@ ASTC_FN void bit_transfer_signed4(i4& a, i4& b) {
 	bit_transfer_signed1(a.w, b.w);
 }
 
-ASTC_NOINLINE void rgba_delta_unpack(i4 in0, i4 in1, i4& out0, i4& out1) {   // :61-102
+ASTC_FN void rgba_delta_unpack(i4 in0, i4 in1, i4& out0, i4& out1) {   // :61-102
 	bit_transfer_signed4(in1, in0);
 	int rgb_sum = in1.x + in1.y + in1.z;
 	in1 = mki4(in1.x + in0.x, in1.y + in0.y, in1.z + in0.z, in1.w + in0.w);
@@ -60,7 +60,9 @@ ASTC_FN void rgba_unpack(i4 in0, i4 in1, i4& out0, i4& out1) {   // :105-135
 #include "astc_dev_color_hdr_unpack.cuh"
 
 // unpack_color_endpoints (astcenc_color_unquantize.cpp:844-1022)
-ASTC_NOINLINE void unpack_color_endpoints(int decode_mode, int format, const uint8_t* in, bool& rgb_hdr, bool& alpha_hdr, i4& o0, i4& o1) {
+// (the _inl form lets a caller keep the results in registers: reference parameters of an out-of-line function force the
+// caller's variables into local memory)
+ASTC_FN void unpack_color_endpoints_inl(int decode_mode, int format, const uint8_t* in, bool& rgb_hdr, bool& alpha_hdr, i4& o0, i4& o1) {
 	rgb_hdr = false;
 	alpha_hdr = false;
 	bool alpha_hdr_default = false;
@@ -204,6 +206,10 @@ ASTC_NOINLINE void unpack_color_endpoints(int decode_mode, int format, const uin
 	}
 }
 
+ASTC_NOINLINE void unpack_color_endpoints(int decode_mode, int format, const uint8_t* in, bool& rgb_hdr, bool& alpha_hdr, i4& o0, i4& o1) {
+	unpack_color_endpoints_inl(decode_mode, format, in, rgb_hdr, alpha_hdr, o0, o1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Pack (astcenc_color_quantize.cpp)
 // ---------------------------------------------------------------------------------------------
@@ -212,10 +218,10 @@ struct QuantCtx {
 	int quant_level;
 };
 
-ASTC_FN int quant_color(const QuantCtx& q, int value) {   // :72-79 (round to nearest, ties up)
+ASTC_FN int quant_color(QuantCtx q, int value) {   // :72-79 (round to nearest, ties up)
 	return q.tab[value * 2 + 1];
 }
-ASTC_FN int quant_color_f(const QuantCtx& q, int value, float valuef) {   // :109-126
+ASTC_FN int quant_color_f(QuantCtx q, int value, float valuef) {   // :109-126
 	int index = value * 2;
 	float residual = valuef - static_cast<float>(value);
 	if (residual >= -0.1f) {
@@ -223,10 +229,10 @@ ASTC_FN int quant_color_f(const QuantCtx& q, int value, float valuef) {   // :10
 	}
 	return q.tab[index];
 }
-ASTC_FN i4 quant_color3(const QuantCtx& q, i4 v) {
+ASTC_FN i4 quant_color3(QuantCtx q, i4 v) {
 	return mki4(quant_color(q, v.x), quant_color(q, v.y), quant_color(q, v.z), 0);
 }
-ASTC_FN i4 quant_color3_f(const QuantCtx& q, i4 v, f4 vf) {
+ASTC_FN i4 quant_color3_f(QuantCtx q, i4 v, f4 vf) {
 	return mki4(quant_color_f(q, v.x, vf.x), quant_color_f(q, v.y, vf.y), quant_color_f(q, v.z, vf.z), 0);
 }
 ASTC_FN i4 f4_to_i4_rtn(f4 a) { return mki4(f2i_rtn(a.x), f2i_rtn(a.y), f2i_rtn(a.z), f2i_rtn(a.w)); }
@@ -237,7 +243,14 @@ ASTC_FN float get_rgba_encoding_error(f4 uq0, f4 uq1, i4 q0, i4 q1) {   // :50-6
 	return hadd_s(e0 * e0 + e1 * e1);
 }
 
-ASTC_NOINLINE void quantize_rgb(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {   // :169-193
+// Results of the out-of-line quantisers come back BY VALUE (registers); the inline wrappers below keep the reference
+// style of the reference code without forcing the caller's endpoints into local memory.
+struct QEnds {
+	i4 a, b;
+	bool ok;
+};
+
+ASTC_NOINLINE QEnds quantize_rgb_v(f4 c0, f4 c1, QuantCtx q) {   // :169-193
 	i4 c0i, c1i;
 	do {
 		i4 a = f4_to_i4_rtn(c0);
@@ -249,11 +262,19 @@ ASTC_NOINLINE void quantize_rgb(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q)
 		c1i = quant_color3_f(q, c1q, c1);
 		c1 = c1 + splat4(0.2f);
 	} while ((c0i.x + c0i.y + c0i.z) > (c1i.x + c1i.y + c1i.z));
-	o0 = c0i;
-	o1 = c1i;
+	QEnds r;
+	r.a = c0i;
+	r.b = c1i;
+	r.ok = true;
+	return r;
+}
+ASTC_FN void quantize_rgb(f4 c0, f4 c1, i4& o0, i4& o1, QuantCtx q) {
+	QEnds r = quantize_rgb_v(c0, c1, q);
+	o0 = r.a;
+	o1 = r.b;
 }
 
-ASTC_FN void quantize_rgba(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {   // :207-220
+ASTC_FN void quantize_rgba(f4 c0, f4 c1, i4& o0, i4& o1, QuantCtx q) {   // :207-220
 	quantize_rgb(c0, c1, o0, o1, q);
 	o0.w = quant_color_f(q, f2i_rtn(c0.w), c0.w);
 	o1.w = quant_color_f(q, f2i_rtn(c1.w), c1.w);
@@ -269,23 +290,36 @@ ASTC_FN f4 blue_contract_fwd(f4 c) {   // c += c - c.bbba
 	return mk4(c.x + (c.x - c.z), c.y + (c.y - c.z), c.z + (c.z - c.z), c.w + (c.w - c.w));
 }
 
-ASTC_NOINLINE bool try_quantize_rgb_blue_contract(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {   // :237-267
+ASTC_NOINLINE QEnds try_quantize_rgb_blue_contract_v(f4 c0, f4 c1, QuantCtx q) {   // :237-267
+	QEnds r;
+	r.a = r.b = mki4(0, 0, 0, 0);
+	r.ok = false;
 	c0 = blue_contract_fwd(c0);
 	c1 = blue_contract_fwd(c1);
 	if (!in_0_255(c0) || !in_0_255(c1)) {
-		return false;
+		return r;
 	}
 	i4 c0i = quant_color3_f(q, f4_to_i4_rtn(c0), c0);
 	i4 c1i = quant_color3_f(q, f4_to_i4_rtn(c1), c1);
 	if ((c1i.x + c1i.y + c1i.z) <= (c0i.x + c0i.y + c0i.z)) {
-		return false;
+		return r;
 	}
-	o0 = c1i;
-	o1 = c0i;
-	return true;
+	r.a = c1i;
+	r.b = c0i;
+	r.ok = true;
+	return r;
+}
+// (a failed attempt leaves o0 / o1 untouched, like the reference)
+ASTC_FN bool try_quantize_rgb_blue_contract(f4 c0, f4 c1, i4& o0, i4& o1, QuantCtx q) {
+	QEnds r = try_quantize_rgb_blue_contract_v(c0, c1, q);
+	if (r.ok) {
+		o0 = r.a;
+		o1 = r.b;
+	}
+	return r.ok;
 }
 
-ASTC_FN bool try_quantize_rgba_blue_contract(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {   // :283-303
+ASTC_FN bool try_quantize_rgba_blue_contract(f4 c0, f4 c1, i4& o0, i4& o1, QuantCtx q) {   // :283-303
 	if (try_quantize_rgb_blue_contract(c0, c1, o0, o1, q)) {
 		o0.w = quant_color_f(q, f2i_rtn(c1.w), c1.w);
 		o1.w = quant_color_f(q, f2i_rtn(c0.w), c0.w);
@@ -295,7 +329,10 @@ ASTC_FN bool try_quantize_rgba_blue_contract(f4 c0, f4 c1, i4& o0, i4& o1, const
 }
 
 // common body of try_quantize_rgb_delta (:321-400) and ..._delta_blue_contract (:403-488)
-ASTC_NOINLINE bool rgb_delta_core(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q, bool want_negative_sum) {
+ASTC_NOINLINE QEnds rgb_delta_core_v(f4 c0, f4 c1, QuantCtx q, bool want_negative_sum) {
+	QEnds res;
+	res.a = res.b = mki4(0, 0, 0, 0);
+	res.ok = false;
 	i4 c0a = f4_to_i4_rtn(c0);
 	c0a = mki4(c0a.x << 1, c0a.y << 1, c0a.z << 1, c0a.w << 1);
 	i4 c0b = mki4(c0a.x & 0xFF, c0a.y & 0xFF, c0a.z & 0xFF, c0a.w & 0xFF);
@@ -304,35 +341,44 @@ ASTC_NOINLINE bool rgb_delta_core(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& 
 	i4 c1d = f4_to_i4_rtn(c1);
 	c1d = mki4((c1d.x << 1) - c0b.x, (c1d.y << 1) - c0b.y, (c1d.z << 1) - c0b.z, 0);
 	if (c1d.x > 63 || c1d.x < -64 || c1d.y > 63 || c1d.y < -64 || c1d.z > 63 || c1d.z < -64) {
-		return false;
+		return res;
 	}
 	c1d = mki4((c1d.x & 0x7F) | ((c0b.x & 0x100) >> 1), (c1d.y & 0x7F) | ((c0b.y & 0x100) >> 1),
 	           (c1d.z & 0x7F) | ((c0b.z & 0x100) >> 1), (c1d.w & 0x7F) | ((c0b.w & 0x100) >> 1));
 	i4 c1de = quant_color3(q, c1d);
 	if ((((c1d.x ^ c1de.x) | (c1d.y ^ c1de.y) | (c1d.z ^ c1de.z)) & 0xC0) != 0) {
-		return false;
+		return res;
 	}
 	i4 ep0 = c0be;
 	i4 ep1 = c1de;
 	bit_transfer_signed4(ep1, ep0);
 	int sum = ep1.x + ep1.y + ep1.z;
 	if (want_negative_sum ? (sum >= 0) : (sum < 0)) {
-		return false;
+		return res;
 	}
 	ep0 = mki4(ep0.x + ep1.x, ep0.y + ep1.y, ep0.z + ep1.z, ep0.w + ep1.w);
 	if (ep0.x < 0 || ep0.x > 0xFF || ep0.y < 0 || ep0.y > 0xFF || ep0.z < 0 || ep0.z > 0xFF || ep0.w < 0 || ep0.w > 0xFF) {
-		return false;
+		return res;
 	}
-	o0 = c0be;
-	o1 = c1de;
-	return true;
+	res.a = c0be;
+	res.b = c1de;
+	res.ok = true;
+	return res;
+}
+ASTC_FN bool rgb_delta_core(f4 c0, f4 c1, i4& o0, i4& o1, QuantCtx q, bool want_negative_sum) {
+	QEnds r = rgb_delta_core_v(c0, c1, q, want_negative_sum);
+	if (r.ok) {
+		o0 = r.a;
+		o1 = r.b;
+	}
+	return r.ok;
 }
 
-ASTC_FN bool try_quantize_rgb_delta(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {
+ASTC_FN bool try_quantize_rgb_delta(f4 c0, f4 c1, i4& o0, i4& o1, QuantCtx q) {
 	return rgb_delta_core(c0, c1, o0, o1, q, false);
 }
 
-ASTC_FN bool try_quantize_rgb_delta_blue_contract(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {
+ASTC_FN bool try_quantize_rgb_delta_blue_contract(f4 c0, f4 c1, i4& o0, i4& o1, QuantCtx q) {
 	f4 t = c0; c0 = c1; c1 = t;
 	c0 = blue_contract_fwd(c0);
 	c1 = blue_contract_fwd(c1);
@@ -342,7 +388,14 @@ ASTC_FN bool try_quantize_rgb_delta_blue_contract(f4 c0, f4 c1, i4& o0, i4& o1, 
 	return rgb_delta_core(c0, c1, o0, o1, q, true);
 }
 
-ASTC_NOINLINE bool try_quantize_alpha_delta(f4 c0, f4 c1, i4& o0, i4& o1, const QuantCtx& q) {   // :504-570
+struct QAlpha {
+	int a0, a1;
+	bool ok;
+};
+ASTC_NOINLINE QAlpha try_quantize_alpha_delta_v(f4 c0, f4 c1, QuantCtx q) {   // :504-570
+	QAlpha res;
+	res.a0 = res.a1 = 0;
+	res.ok = false;
 	float a0 = c0.w, a1 = c1.w;
 	int a0a = f2i_rtn(a0);
 	a0a <<= 1;
@@ -354,14 +407,14 @@ ASTC_NOINLINE bool try_quantize_alpha_delta(f4 c0, f4 c1, i4& o0, i4& o1, const 
 	a1d <<= 1;
 	a1d -= a0b;
 	if (a1d > 63 || a1d < -64) {
-		return false;
+		return res;
 	}
 	a1d &= 0x7F;
 	a1d |= (a0b & 0x100) >> 1;
 	int a1de = quant_color(q, a1d);
 	int a1du = a1de;
 	if ((a1d ^ a1du) & 0xC0) {
-		return false;
+		return res;
 	}
 	a1du &= 0x7F;
 	if (a1du & 0x40) {
@@ -369,14 +422,23 @@ ASTC_NOINLINE bool try_quantize_alpha_delta(f4 c0, f4 c1, i4& o0, i4& o1, const 
 	}
 	a1du += a0b;
 	if (a1du < 0 || a1du > 0x1FF) {
-		return false;
+		return res;
 	}
-	o0.w = a0be;
-	o1.w = a1de;
-	return true;
+	res.a0 = a0be;
+	res.a1 = a1de;
+	res.ok = true;
+	return res;
+}
+ASTC_FN bool try_quantize_alpha_delta(f4 c0, f4 c1, i4& o0, i4& o1, QuantCtx q) {
+	QAlpha r = try_quantize_alpha_delta_v(c0, c1, q);
+	if (r.ok) {
+		o0.w = r.a0;
+		o1.w = r.a1;
+	}
+	return r.ok;
 }
 
-ASTC_NOINLINE bool try_quantize_luminance_alpha_delta(f4 c0, f4 c1, uint8_t out[4], const QuantCtx& q) {   // :573-694
+ASTC_NOINLINE bool try_quantize_luminance_alpha_delta(f4 c0, f4 c1, uint8_t out[4], QuantCtx q) {   // :573-694
 	float l0 = hadd_rgb_s(c0) * (1.0f / 3.0f);
 	float l1 = hadd_rgb_s(c1) * (1.0f / 3.0f);
 	float a0 = c0.w, a1 = c1.w;
@@ -419,7 +481,7 @@ ASTC_NOINLINE bool try_quantize_luminance_alpha_delta(f4 c0, f4 c1, uint8_t out[
 	return true;
 }
 
-ASTC_NOINLINE void quantize_rgbs(f4 color, uint8_t out[4], const QuantCtx& q) {   // :734-763
+ASTC_NOINLINE void quantize_rgbs(f4 color, uint8_t out[4], QuantCtx q) {   // :734-763
 	float scale = 1.0f / 257.0f;
 	float r = clampf(color.x * scale, 0.0f, 255.0f);
 	float g = clampf(color.y * scale, 0.0f, 255.0f);
@@ -438,7 +500,7 @@ ASTC_NOINLINE void quantize_rgbs(f4 color, uint8_t out[4], const QuantCtx& q) { 
 	out[3] = (uint8_t)quant_color(q, scale_idx);
 }
 
-ASTC_FN void quantize_luminance(f4 c0, f4 c1, uint8_t out[2], const QuantCtx& q) {   // :795-815
+ASTC_FN void quantize_luminance(f4 c0, f4 c1, uint8_t out[2], QuantCtx q) {   // :795-815
 	float lum0 = hadd_rgb_s(c0) * (1.0f / 3.0f);
 	float lum1 = hadd_rgb_s(c1) * (1.0f / 3.0f);
 	if (lum0 > lum1) {
@@ -450,7 +512,7 @@ ASTC_FN void quantize_luminance(f4 c0, f4 c1, uint8_t out[2], const QuantCtx& q)
 	out[1] = (uint8_t)quant_color_f(q, f2i_rtn(lum1), lum1);
 }
 
-ASTC_FN void quantize_luminance_alpha(f4 c0, f4 c1, uint8_t out[4], const QuantCtx& q) {   // :828-846
+ASTC_FN void quantize_luminance_alpha(f4 c0, f4 c1, uint8_t out[4], QuantCtx q) {   // :828-846
 	float lum0 = hadd_rgb_s(c0) * (1.0f / 3.0f);
 	float lum1 = hadd_rgb_s(c1) * (1.0f / 3.0f);
 	out[0] = (uint8_t)quant_color_f(q, f2i_rtn(lum0), lum0);

@@ -1,6 +1,6 @@
 // HDR endpoint quantisers (astcenc_color_quantize.cpp:856-1906). Included by astc_dev_color.cuh.
 
-ASTC_NOINLINE uint8_t quant_retain_top_bits(const QuantCtx& q, uint8_t value, int topmask) {   // :856-919
+ASTC_NOINLINE uint8_t quant_retain_top_bits(QuantCtx q, uint8_t value, int topmask) {   // :856-919
 	int perform_loop;
 	uint8_t quantval;
 	do {
@@ -15,7 +15,7 @@ ASTC_NOINLINE uint8_t quant_retain_top_bits(const QuantCtx& q, uint8_t value, in
 	return quantval;
 }
 
-ASTC_NOINLINE void quantize_hdr_rgbo(f4 color, uint8_t output[4], const QuantCtx& q) {   // :925-1250
+ASTC_NOINLINE void quantize_hdr_rgbo(f4 color, uint8_t output[4], QuantCtx q) {   // :925-1250
 	color.x = color.x + color.w;
 	color.y = color.y + color.w;
 	color.z = color.z + color.w;
@@ -154,7 +154,7 @@ ASTC_NOINLINE void quantize_hdr_rgbo(f4 color, uint8_t output[4], const QuantCtx
 	}
 }
 
-ASTC_NOINLINE void quantize_hdr_rgb(f4 color0, f4 color1, uint8_t output[6], const QuantCtx& q) {   // :1253-1788
+ASTC_NOINLINE void quantize_hdr_rgb(f4 color0, f4 color1, uint8_t output[6], QuantCtx q) {   // :1253-1788
 	color0 = vclamp4(0.0f, 65535.0f, color0);
 	color1 = vclamp4(0.0f, 65535.0f, color1);
 	f4 color0_bak = color0;
@@ -317,7 +317,7 @@ ASTC_NOINLINE void quantize_hdr_rgb(f4 color0, f4 color1, uint8_t output[6], con
 	}
 }
 
-ASTC_FN void quantize_hdr_rgb_ldr_alpha(f4 color0, f4 color1, uint8_t output[8], const QuantCtx& q) {   // :1791-1817
+ASTC_FN void quantize_hdr_rgb_ldr_alpha(f4 color0, f4 color1, uint8_t output[8], QuantCtx q) {   // :1791-1817
 	float scale = 1.0f / 257.0f;
 	float a0 = clampf(color0.w * scale, 0.0f, 255.0f);
 	float a1 = clampf(color1.w * scale, 0.0f, 255.0f);
@@ -326,7 +326,7 @@ ASTC_FN void quantize_hdr_rgb_ldr_alpha(f4 color0, f4 color1, uint8_t output[8],
 	quantize_hdr_rgb(color0, color1, output, q);
 }
 
-ASTC_NOINLINE void quantize_hdr_luminance_large_range(f4 color0, f4 color1, uint8_t output[2], const QuantCtx& q) {   // :1659-1720
+ASTC_NOINLINE void quantize_hdr_luminance_large_range(f4 color0, f4 color1, uint8_t output[2], QuantCtx q) {   // :1659-1720
 	float lum0 = hadd_rgb_s(color0) * (1.0f / 3.0f);
 	float lum1 = hadd_rgb_s(color1) * (1.0f / 3.0f);
 	if (lum1 < lum0) {
@@ -366,7 +366,7 @@ ASTC_NOINLINE void quantize_hdr_luminance_large_range(f4 color0, f4 color1, uint
 	output[1] = (uint8_t)quant_color(q, v1);
 }
 
-ASTC_NOINLINE bool try_quantize_hdr_luminance_small_range(f4 color0, f4 color1, uint8_t output[2], const QuantCtx& q) {   // :1723-1817
+ASTC_NOINLINE bool try_quantize_hdr_luminance_small_range(f4 color0, f4 color1, uint8_t output[2], QuantCtx q) {   // :1723-1817
 	float lum0 = hadd_rgb_s(color0) * (1.0f / 3.0f);
 	float lum1 = hadd_rgb_s(color1) * (1.0f / 3.0f);
 	if (lum1 < lum0) {
@@ -428,7 +428,7 @@ ASTC_NOINLINE bool try_quantize_hdr_luminance_small_range(f4 color0, f4 color1, 
 	return true;
 }
 
-ASTC_NOINLINE void quantize_hdr_alpha(float alpha0, float alpha1, uint8_t output[2], const QuantCtx& q) {   // :1820-1890
+ASTC_NOINLINE void quantize_hdr_alpha(float alpha0, float alpha1, uint8_t output[2], QuantCtx q) {   // :1820-1890
 	alpha0 = clampf(alpha0, 0.0f, 65280.0f);
 	alpha1 = clampf(alpha1, 0.0f, 65280.0f);
 	int ialpha0 = f2i_rtn(alpha0);
@@ -470,7 +470,7 @@ ASTC_NOINLINE void quantize_hdr_alpha(float alpha0, float alpha1, uint8_t output
 	output[1] = (uint8_t)quant_color(q, v7);
 }
 
-ASTC_FN void quantize_hdr_rgb_alpha(f4 color0, f4 color1, uint8_t output[8], const QuantCtx& q) {   // :1893-1906
+ASTC_FN void quantize_hdr_rgb_alpha(f4 color0, f4 color1, uint8_t output[8], QuantCtx q) {   // :1893-1906
 	quantize_hdr_rgb(color0, color1, output, q);
 	quantize_hdr_alpha(color0.w, color1.w, output + 6, q);
 }

@@ -46,12 +46,13 @@ ASTC_COOP uint32_t pack_work_endpoints(WCtx w, unsigned int pc, uint32_t formats
 	SPtr<uint32_t> xch = sptr<uint32_t>(w.base + A_TMPF);
 	ASTC_NOUNROLL
 	for (unsigned int j = (unsigned int)w.lane; j < pc; j += ASTC_WARP) {
-		uint8_t out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		// (packed straight into the shared arena: a local byte array behind a pointer would live in local memory)
+		uint8_t* out = &colors[(int)j * 8];
+		for (int k = 0; k < 8; k++) {
+			out[k] = 0;
+		}
 		uint8_t fmt = pack_color_endpoints(ep[EP_WORK_0 + (int)j], ep[EP_WORK_1 + (int)j], ep[EP_RGBS + (int)j], ep[EP_RGBO + (int)j],
 		                                   (int)((formats_in >> (8 * j)) & 0xFF), out, quant_level);
-		for (int k = 0; k < 8; k++) {
-			colors[(int)j * 8 + k] = out[k];
-		}
 		xch[(int)j] = fmt;
 	}
 	wsync();

@@ -1052,13 +1052,10 @@ ASTC_COOP void unpack_work_endpoints(WCtx w, unsigned int pc, uint32_t formats, 
 	SPtr<uint8_t> wc = work_colors_of(w);
 	ASTC_NOUNROLL
 	for (unsigned int p = (unsigned int)w.lane; p < pc; p += ASTC_WARP) {
-		uint8_t in[8];
-		for (int k = 0; k < 8; k++) {
-			in[k] = wc[(int)p * 8 + k];
-		}
+		const uint8_t* in = &wc[(int)p * 8];      // (straight from the shared arena: no local copy)
 		bool rgb_lns, a_lns;
 		i4 e0, e1;
-		unpack_color_endpoints(CFG.profile, (int)((formats >> (8 * p)) & 0xFF), in, rgb_lns, a_lns, e0, e1);
+		unpack_color_endpoints_inl(CFG.profile, (int)((formats >> (8 * p)) & 0xFF), in, rgb_lns, a_lns, e0, e1);
 		SPtr<int> o = ends + (int)p * 8;
 		o[0] = e0.x; o[1] = e0.y; o[2] = e0.z; o[3] = e0.w;
 		o[4] = e1.x; o[5] = e1.y; o[6] = e1.z; o[7] = e1.w;
