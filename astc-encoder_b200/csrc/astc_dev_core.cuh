@@ -41,7 +41,6 @@
 	#define ASTC_LDG(p) (*(p))
 	static const DevConstTables* g_astc_ct;
 	#define ASTC_CT g_astc_ct
-	static const int g_astc_dense_limit = 6;
 	static uint8_t* astc_smem;           // stands in for the CTA's shared window
 #else
 	#define ASTC_FN static __device__ __forceinline__
@@ -62,9 +61,6 @@
 	#define ASTC_LDG(p) __ldg(p)
 	__constant__ const DevConstTables* g_astc_ct;
 	#define ASTC_CT g_astc_ct
-	// realign_weights: grids whose weights touch at most this many texels take the anti-diagonal wavefront path
-	// (tuning knob ASTCENC_B200_DENSE_LIMIT)
-	__constant__ int g_astc_dense_limit = 6;
 	extern __shared__ __align__(16) uint8_t astc_smem[];
 #endif
 

@@ -288,9 +288,9 @@ struct astcenc_context {
 	// wave pipeline buffers, grown on demand
 	uint8_t* d_records;
 	size_t d_records_bytes;
-	uint32_t* d_queues;          // 4 x capacity
+	uint32_t* d_queues;          // ASTC_Q_KINDS x capacity
 	size_t queue_capacity;
-	uint32_t* d_counters;        // count[4][MAX_WAVES] head[4][MAX_WAVES]
+	uint32_t* d_counters;        // count[ASTC_Q_KINDS][MAX_WAVES] head[ASTC_Q_KINDS][MAX_WAVES]
 	float* d_alpha;              // alpha-scale pre-pass: one average per texel
 	size_t d_alpha_bytes;
 	float alpha_threshold;
@@ -461,14 +461,6 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 		if (const char* e = getenv("ASTCENC_B200_CTAS_PER_SM")) {
 			int v = atoi(e);
 			if (v >= 1 && v <= 8) ctx->grid = prop.multiProcessorCount * v;
-		}
-		{
-			// (a device-wide constant: written by every context so that a tuning override does not outlive its context)
-			int v = 6;
-			if (const char* e = getenv("ASTCENC_B200_DENSE_LIMIT")) {
-				v = atoi(e);
-			}
-			cudaMemcpyToSymbol(g_astc_dense_limit, &v, sizeof(v));
 		}
 		ctx->lockstep = 1;
 		ctx->driver = 0;
@@ -1089,6 +1081,9 @@ astcenc_error astcenc_b200_compute_error_metrics(astcenc_context* ctx, int compu
 		return ASTCENC_ERR_BAD_PARAM;
 	}
 	if (fstop_lo < -125 || fstop_hi > 125) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	if ((int)img1->data_type < 0 || (int)img1->data_type > 2 || (int)img2->data_type < 0 || (int)img2->data_type > 2) {
 		return ASTCENC_ERR_BAD_PARAM;
 	}
 	memset(out, 0, sizeof(*out));

@@ -266,11 +266,9 @@ def test_batched_slabs_and_stage_barriers(gpu, oracle, monkeypatch):
     assert np.array_equal(gpu_compress(gpu, img, PRF_LDR, 6, 6, PRE_MEDIUM, S), want)
 
 
-@pytest.mark.parametrize("env", [{"ASTCENC_B200_STAGE_REFINE": "1"}, {"ASTCENC_B200_STAGE_SETUP": "0"}, {"ASTCENC_B200_STAGE_SETUP": "1"}, {"ASTCENC_B200_DENSE_LIMIT": "16"},
-                                 {"ASTCENC_B200_DENSE_LIMIT": "0"}])
-def test_table_staging_and_wavefront_limit_change_nothing(gpu, oracle, monkeypatch, env):
-    """Decimation / colour tables read from shared memory or from global memory, and either realignment path
-    (anti-diagonal wavefront vs one weight at a time) for every decimated grid: same bytes."""
+@pytest.mark.parametrize("env", [{"ASTCENC_B200_STAGE_REFINE": "1"}, {"ASTCENC_B200_STAGE_SETUP": "0"}, {"ASTCENC_B200_STAGE_SETUP": "1"}])
+def test_table_staging_changes_nothing(gpu, oracle, monkeypatch, env):
+    """Decimation / colour tables read from shared memory or from global memory: same bytes."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     for img, prof, bx, by, q in ((I.photo_like(120, 96, seed=21), PRF_LDR, 6, 6, PRE_MEDIUM), (I.voronoi_flat(64, 64, seed=3), PRF_LDR, 8, 8, PRE_MEDIUM),
