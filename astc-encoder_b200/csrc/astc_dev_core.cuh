@@ -29,7 +29,12 @@
 	#define ASTC_MFN inline
 	#define ASTC_NOINLINE static
 	#define ASTC_COOP static
-	#define ASTC_WARP 1
+	#if defined(ASTC_HOSTSIM_LANES32)
+		#define ASTC_WARP 32      /* tests/hostsim/simt_emul.h: 32 host threads stand in for the lanes */
+	#else
+		#define ASTC_WARP 1
+		#define ASTC_ONE_LANE 1
+	#endif
 	#define ASTC_NOUNROLL
 	#define ASTC_RINT(a) nearbyintf(a)
 	static inline uint32_t astc_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
@@ -49,6 +54,7 @@
 	#define ASTC_COOP static __device__ __noinline__
 	#if defined(ASTC_DEBUG_SINGLE_LANE)
 		#define ASTC_WARP 1       /* debug build: lane 0 of each warp does all the work serially */
+		#define ASTC_ONE_LANE 1
 	#else
 		#define ASTC_WARP 32
 	#endif
@@ -120,7 +126,7 @@ static_assert(sizeof(SmemHdr) <= ASTC_SMEM_HDR, "launch constants must fit the s
 // ---------------------------------------------------------------------------------------------
 // Warp primitives
 // ---------------------------------------------------------------------------------------------
-#if defined(ASTC_HOSTSIM) || defined(ASTC_DEBUG_SINGLE_LANE)
+#if defined(ASTC_ONE_LANE)
 ASTC_FN void wsync() {}
 ASTC_FN float wmin_f(float v) { return v; }
 ASTC_FN float wmax_f(float v) { return v; }
@@ -1118,7 +1124,7 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 		bool in_round = id < pairs && incl <= cap;
 		int npair = wcount(id < pairs && incl <= cap);      // a prefix of the lanes (incl is monotone)
 		int nitems = 0;
-#if defined(ASTC_HOSTSIM) || defined(ASTC_DEBUG_SINGLE_LANE)
+#if defined(ASTC_ONE_LANE)
 		nitems = incl;
 #else
 		nitems = __shfl_sync(0xffffffffu, incl, npair - 1);
@@ -1214,7 +1220,7 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 			int nitems2 = npair * 8;
 			ASTC_NOUNROLL
 			for (int it0 = 0; it0 < nitems2; it0 += ASTC_WARP) {
-#if defined(ASTC_HOSTSIM) || defined(ASTC_DEBUG_SINGLE_LANE)
+#if defined(ASTC_ONE_LANE)
 				ASTC_NOUNROLL
 				for (int it = it0; it < nitems2; it++) {
 				int qi = it & 7;

@@ -16,7 +16,7 @@
 
 ASTC_FN bool block_has_alpha(const WCtx& w, const float* averages, float threshold, unsigned int pos_x, unsigned int pos_y);
 
-#if defined(ASTC_HOSTSIM) || defined(ASTC_DEBUG_SINGLE_LANE)
+#if defined(ASTC_ONE_LANE)
 ASTC_FN void cta_sync() {}
 ASTC_FN bool cta_any(bool p) { return p; }
 #else
@@ -32,7 +32,7 @@ struct BlockFeed {
 };
 
 ASTC_FN bool feed_next(const WCtx& w, const BlockFeed& f, unsigned int& b) {
-#if defined(ASTC_HOSTSIM)
+#if defined(ASTC_HOSTSIM) && defined(ASTC_ONE_LANE)
 	b = (*f.ticket)++;
 #elif defined(ASTC_DEBUG_SINGLE_LANE)
 	b = atomicAdd(f.ticket, 1u);

@@ -51,7 +51,7 @@ ASTC_FN uint32_t q_load(const uint32_t* p) { return __ldcg(p); }
 #endif
 
 ASTC_FN uint32_t wbroadcast0(const WCtx& w, uint32_t v) {
-#if defined(ASTC_HOSTSIM) || defined(ASTC_DEBUG_SINGLE_LANE)
+#if defined(ASTC_ONE_LANE)
 	(void)w;
 	return v;
 #else
@@ -159,9 +159,18 @@ ASTC_FN void route_block(const WCtx& w, const WaveArgs& a, unsigned int b, int n
 ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 	// one copy of the search state per warp, in the arena slots the record keeps it in (see wave_refine); the widened
 	// copy of the trial used by the shared set-up sits in the work / mod colour slots, which only refinement uses
+#if defined(ASTC_HOSTSIM_LANES32)
+	// (the thread-per-lane simulation has no lockstep execution between collectives: private copies, see wave_refine)
+	BlockSearch s_private;
+	Trial t_private, tf_private;
+	BlockSearch& s = s_private;
+	Trial& t = t_private;
+	Trial& tf = tf_private;
+#else
 	BlockSearch& s = search_of(w);
 	Trial& t = trial_of(w);
 	Trial& tf = *reinterpret_cast<Trial*>(astc_smem + w.base + A_SCB + 160);
+#endif
 	BlockFeed feed;
 	feed.ticket = a.head + Q_SETUP * ASTC_MAX_WAVES;      // wave 0 has no queue: its head counter is the image ticket
 	feed.total = a.total;
@@ -313,14 +322,26 @@ __device__ unsigned long long g_step_stats[6][8];
 // reference - as automatic variables the three structs live in local memory, 32 copies per warp (~10 KB), far more than the
 // L1 left beside the arenas holds (ncu: L1 hit rate 39 %, long-scoreboard stalls on local loads). The refine kernel therefore
 // works on ONE copy per warp in shared memory: BlockSearch and Trial in their arena slots (where the record keeps them
-// anyway), Refine in a slot behind the arenas. Every lane stores the same values, so the concurrent stores are benign.
+// anyway), Refine in a slot behind the arenas. Every lane stores the same values at the same (converged) instruction, so
+// the concurrent stores are benign; this leans on the warp executing the scalar bookkeeping between two __syncwarp()s in
+// lockstep, which the thread-per-lane host simulation does not provide - that build keeps private copies.
 #define ASTC_REFINE_STATE_BYTES 128
 static_assert(sizeof(Refine) <= ASTC_REFINE_STATE_BYTES, "Refine must fit its shared-memory slot");
 
 ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
+#if defined(ASTC_HOSTSIM_LANES32)
+	BlockSearch s_private;
+	Trial t_private;
+	Refine r_private;
+	BlockSearch& s = s_private;
+	Trial& t = t_private;
+	Refine& r = r_private;
+	(void)warp_index;
+#else
 	BlockSearch& s = search_of(w);
 	Trial& t = trial_of(w);
 	Refine& r = *reinterpret_cast<Refine*>(astc_smem + a.refine_state_off + warp_index * ASTC_REFINE_STATE_BYTES);
+#endif
 	bool has_item = false;
 	bool drained = false;
 	unsigned int b = 0;
@@ -419,8 +440,15 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 // P: block statistics / partition search.
 // ---------------------------------------------------------------------------------------------
 ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
+#if defined(ASTC_HOSTSIM_LANES32)
+	BlockSearch s_private;
+	Trial t_private;
+	BlockSearch& s = s_private;
+	Trial& t = t_private;
+#else
 	BlockSearch& s = search_of(w);
 	Trial& t = trial_of(w);
+#endif
 	while (true) {
 		unsigned int b = 0;
 		bool active = q_pop(w, a, Q_PREPARE, a.wave, b);

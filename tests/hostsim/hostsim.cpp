@@ -1,8 +1,14 @@
-// TEST TOOL (not a product path): compiles the warp-cooperative device source for the host with a
-// single simulated lane (ASTC_HOSTSIM), so the lane-independent logic of the kernels can be checked
-// against the oracle / reference without a GPU. Races and shuffle bugs are NOT visible here; those are
-// covered by the -m gpu tests. The product library never links this.
+// TEST TOOL (not a product path): compiles the warp-cooperative device source for the host (ASTC_HOSTSIM), so the
+// kernels' logic can be checked against the oracle / reference without a GPU. Two builds:
+//   default               one simulated lane: state machines, arithmetic order, table layouts (fast)
+//   -DASTC_HOSTSIM_LANES32 32 host threads emulate the lanes of one warp, the CUDA warp primitives are collectives over
+//                         them (simt_emul.h): shuffle partners, ordered sums across lanes, results that must be uniform
+//                         across the warp, missing __syncwarp between producer and consumer lanes (slow: small images)
+// The product library never links this.
 #define ASTC_HOSTSIM 1
+#if defined(ASTC_HOSTSIM_LANES32)
+#include "simt_emul.h"
+#endif
 #include "../../astc-encoder_b200/csrc/astc_dev_search.cuh"
 #include "../../astc-encoder_b200/csrc/astc_host_pack.h"
 #include "../../astc-encoder_b200/csrc/astc_host_config.h"
@@ -10,6 +16,16 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+
+// run fn(lane) for every simulated lane
+template <typename F> static void run_lanes(F fn) {
+#if defined(ASTC_HOSTSIM_LANES32)
+	simt::run_warp(fn);
+#else
+	fn(0);
+#endif
+}
+extern "C" int hostsim_lanes() { return ASTC_WARP; }
 
 static unsigned int g_hostsim_a_scale_radius = 0;
 extern "C" void hostsim_set_a_scale_radius(unsigned int r) { g_hostsim_a_scale_radius = r; }
@@ -47,18 +63,21 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	img.alpha_threshold = 0.0f;
 	std::vector<float> alpha_avg;
 	if (cfg.a_scale_radius != 0) {
-		// the pre-pass, tile by tile, through the device source (one simulated thread)
+		// the pre-pass, tile by tile, through the device source (the simulated lanes stand in for the CTA's threads)
 		unsigned int r = cfg.a_scale_radius;
 		alpha_avg.resize((size_t)dim_x * dim_y);
 		size_t pad = ALPHA_TILE + 2 * (size_t)r + 1;
 		std::vector<uint8_t> tile_mem(pad * pad * 4 + 64);
 		uint8_t* saved = astc_smem;
 		astc_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tile_mem.data()) + 15) & ~(uintptr_t)15);
-		for (unsigned int oy = 0; oy < dim_y; oy += ALPHA_TILE) {
-			for (unsigned int ox = 0; ox < dim_x; ox += ALPHA_TILE) {
-				alpha_average_tile(img, r, ox, oy, 0, alpha_avg.data(), 0, 1);
+		run_lanes([&](int lane) {
+			for (unsigned int oy = 0; oy < dim_y; oy += ALPHA_TILE) {
+				for (unsigned int ox = 0; ox < dim_x; ox += ALPHA_TILE) {
+					alpha_average_tile(img, r, ox, oy, 0, alpha_avg.data(), lane, ASTC_WARP);
+					cta_sync();      // (on the device every tile is its own CTA; here the same lanes reuse the tile buffer)
+				}
 			}
-		}
+		});
 		astc_smem = saved;
 		img.alpha_avg = alpha_avg.data();
 		size_t x_footprint = bx + 2 * ((size_t)r - 1), y_footprint = by + 2 * ((size_t)r - 1);
@@ -70,9 +89,7 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	hdr->img = img;
 	hdr->dec_smem_off = 0;
 	hdr->cq_smem_off = 0;
-	WCtx w;
-	w.lane = 0;
-	w.base = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES;
+	const uint32_t arena_base = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES;
 	{
 		float* sc = reinterpret_cast<float*>(astc_smem + ASTC_SMEM_HDR);
 		for (int j = 0; j < 64; j++) {
@@ -82,48 +99,53 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 			}
 		}
 	}
-	w.T = pk.bsd.texel_count;
 	const char* driver = getenv("HOSTSIM_DRIVER");
-	if (driver && !strcmp(driver, "warp")) {
-		for (unsigned int y = 0; y < img.block_rows; y++) {
-			for (unsigned int x = 0; x < img.blocks_x; x++) {
-				load_block(w, x * bx, y * by);
-				compress_block(w, out + ((size_t)y * img.blocks_x + x) * 16);
+	unsigned int counter = 0;
+	unsigned int total = img.blocks_x * img.block_rows;
+	std::vector<uint8_t> records((size_t)total * pk.bsd.record_bytes + 16);
+	std::vector<uint32_t> queues((size_t)ASTC_Q_KINDS * total);
+	std::vector<uint32_t> counters(2 * ASTC_Q_KINDS * ASTC_MAX_WAVES, 0);
+	run_lanes([&](int lane) {
+		WCtx w;
+		w.lane = lane;
+		w.base = arena_base;
+		w.T = pk.bsd.texel_count;
+		if (driver && !strcmp(driver, "warp")) {
+			for (unsigned int y = 0; y < img.block_rows; y++) {
+				for (unsigned int x = 0; x < img.blocks_x; x++) {
+					load_block(w, x * bx, y * by);
+					compress_block(w, out + ((size_t)y * img.blocks_x + x) * 16);
+				}
 			}
+		} else if (driver && !strcmp(driver, "lockstep")) {
+			BlockFeed feed;
+			feed.ticket = &counter;
+			feed.total = img.blocks_x * img.block_rows;
+			feed.blocks_x = img.blocks_x;
+			compress_blocks_lockstep(w, feed);
+		} else {
+			// the wave pipeline, driven like the CUDA host code does (one simulated warp per "kernel")
+			WaveArgs a;
+			a.records = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(records.data()) + 15) & ~(uintptr_t)15);
+			for (int k = 0; k < ASTC_Q_KINDS; k++) a.queue[k] = queues.data() + (size_t)k * total;
+			a.count = counters.data();
+			a.head = counters.data() + ASTC_Q_KINDS * ASTC_MAX_WAVES;
+			a.total = total;
+			a.blocks_x = img.blocks_x;
+			a.sync_mask = 0xFF;
+			a.stage_bytes = 0;
+			a.refine_state_off = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + pk.bsd.arena_bytes + 32 * EMIT_SLICE + 16;
+			a.stage_bytes_setup = 0;
+			for (int wave = 0; wave < ASTC_MAX_WAVES - 1; wave++) {
+				a.wave = wave;
+				wave_setup(w, a);
+				wave_refine(w, a, 0);
+				wave_prepare(w, a);
+			}
+			a.wave = 0;
+			wave_emit(lane, ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + pk.bsd.arena_bytes, a);
 		}
-	} else if (driver && !strcmp(driver, "lockstep")) {
-		unsigned int counter = 0;
-		BlockFeed feed;
-		feed.ticket = &counter;
-		feed.total = img.blocks_x * img.block_rows;
-		feed.blocks_x = img.blocks_x;
-		compress_blocks_lockstep(w, feed);
-	} else {
-		// the wave pipeline, driven like the CUDA host code does (one simulated warp per "kernel")
-		unsigned int total = img.blocks_x * img.block_rows;
-		std::vector<uint8_t> records((size_t)total * pk.bsd.record_bytes + 16);
-		std::vector<uint32_t> queues((size_t)ASTC_Q_KINDS * total);
-		std::vector<uint32_t> counters(2 * ASTC_Q_KINDS * ASTC_MAX_WAVES, 0);
-		WaveArgs a;
-		a.records = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(records.data()) + 15) & ~(uintptr_t)15);
-		for (int k = 0; k < ASTC_Q_KINDS; k++) a.queue[k] = queues.data() + (size_t)k * total;
-		a.count = counters.data();
-		a.head = counters.data() + ASTC_Q_KINDS * ASTC_MAX_WAVES;
-		a.total = total;
-		a.blocks_x = img.blocks_x;
-		a.sync_mask = 0xFF;
-		a.stage_bytes = 0;
-		a.refine_state_off = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + pk.bsd.arena_bytes + 32 * EMIT_SLICE + 16;
-		a.stage_bytes_setup = 0;
-		for (int wave = 0; wave < ASTC_MAX_WAVES - 1; wave++) {
-			a.wave = wave;
-			wave_setup(w, a);
-			wave_refine(w, a, 0);
-			wave_prepare(w, a);
-		}
-		a.wave = 0;
-		wave_emit(0, ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + pk.bsd.arena_bytes, a);
-	}
+	});
 	astc_host::free_block_size_tables(t);
 	return 0;
 }
@@ -164,11 +186,13 @@ extern "C" int hostsim_decompress_image(int profile, unsigned int bx, unsigned i
 	hdr->img = img;
 	hdr->dec_smem_off = 0;
 	hdr->cq_smem_off = 0;
-	for (unsigned int y = 0; y < img.block_rows; y++) {
-		for (unsigned int x = 0; x < img.blocks_x; x++) {
-			decompress_block(0, ASTC_SMEM_HDR, blocks + ((size_t)y * img.blocks_x + x) * 16, x, y);
+	run_lanes([&](int lane) {
+		for (unsigned int y = 0; y < img.block_rows; y++) {
+			for (unsigned int x = 0; x < img.blocks_x; x++) {
+				decompress_block(lane, ASTC_SMEM_HDR, blocks + ((size_t)y * img.blocks_x + x) * 16, x, y);
+			}
 		}
-	}
+	});
 	astc_host::free_block_size_tables(t);
 	return 0;
 }
