@@ -16,7 +16,7 @@
 //
 // One "wave" = S, R, P over the blocks still searching; the host enqueues as many waves as a block can have trials
 // (kernels whose queue is empty return at once) and one E at the end. A block's record is the persistent head of
-// its arena plus its texels (DevBsd::record_bytes, ~1.8 KB at 6x6): 466 k blocks x ~7 KB moved per trial is
+// its arena plus its texels (DevBsd::record_bytes, 2.4 KB at 6x6): 466 k blocks x ~7 KB moved per trial is
 // noise next to 6.5 TB/s of HBM. Results are bit-identical to the single-kernel drivers.
 #pragma once
 
