@@ -117,7 +117,7 @@ ASTC_FN void block_search_begin(const WCtx& w, BlockSearch& s) {
 //   NEXT_FINISHED : the search is over
 enum { NEXT_TRIAL = 0, NEXT_PREPARE = 1, NEXT_FINISHED = 2 };
 
-ASTC_FN int block_search_advance(const WCtx& w, BlockSearch& s, Trial& t) {
+ASTC_FN int block_search_advance_on(const WCtx& w, BlockSearch& s, Trial& t) {
 	const BlkInfo& bi = bi_of(w);
 	while (true) {
 		if (s.phase == 0) {
@@ -206,6 +206,21 @@ ASTC_FN int block_search_advance(const WCtx& w, BlockSearch& s, Trial& t) {
 	}
 }
 
+// The stage kernels keep ONE BlockSearch / Trial per warp in shared memory and every lane runs this bookkeeping. The
+// counters are read-modify-write (idx++, pc++): each lane therefore works on a private copy taken before, and stored
+// after, a __syncwarp() - all lanes read the old state, all lanes write the same new state, no lane can see a
+// half-updated one whatever the lanes' relative timing.
+ASTC_FN int block_search_advance(const WCtx& w, BlockSearch& s_io, Trial& t_io) {
+	BlockSearch s = s_io;
+	Trial t = t_io;
+	wsync();
+	int next = block_search_advance_on(w, s, t);
+	s_io = s;
+	t_io = t;
+	wsync();
+	return next;
+}
+
 // The work a phase needs before its first trial: block statistics (2 planes, :1283-1289) or the partition search
 // of the current partition count (:1341-1360).
 ASTC_COOP void block_search_prepare(WCtx w, BlockSearch& s) {
@@ -246,7 +261,7 @@ ASTC_COOP bool block_search_next(WCtx w, BlockSearch& s, Trial& t) {
 }
 
 // Book-keeping after a trial returned errorval (= best_errorval_in_mode of the trial).
-ASTC_FN void block_search_after_trial(const WCtx& w, BlockSearch& s, const Trial& t, float errorval) {
+ASTC_FN void block_search_after_trial_on(const WCtx& w, BlockSearch& s, const Trial& t, float errorval) {
 	if (s.phase == 0) {
 		if (s.scb.block_type != SYM_BTYPE_ERROR) {
 			s.quant_limit = ASTC_LDG(&BSD.block_modes[ASTC_LDG(&BSD.block_mode_packed_index[s.scb.block_mode])].quant_mode);
@@ -279,6 +294,13 @@ ASTC_FN void block_search_after_trial(const WCtx& w, BlockSearch& s, const Trial
 			s.idx++;
 		}
 	}
+}
+ASTC_FN void block_search_after_trial(const WCtx& w, BlockSearch& s_io, const Trial& t, float errorval) {
+	BlockSearch s = s_io;      // (private copy between two __syncwarp()s, see block_search_advance)
+	wsync();
+	block_search_after_trial_on(w, s, t, errorval);
+	s_io = s;
+	wsync();
 }
 
 ASTC_FN void emit_block(const WCtx& w, BlockSearch& s) {
@@ -543,12 +565,16 @@ ASTC_FN float refine_score(WCtx w, const Trial& t, const Refine& r) {
 
 // advance to the next candidate / finish the trial
 ASTC_FN void refine_next_candidate(const Trial& t, Refine& r, bool stop_all) {
+	unsigned int i = r.i;      // (read - __syncwarp - write: r is shared by the lanes of the warp, see block_search_advance)
+	wsync();
+	i = stop_all ? t.candidate_count : i + 1;
 	r.in_step = false;
 	r.l = 0;
-	r.i = stop_all ? t.candidate_count : r.i + 1;
-	if (r.i >= t.candidate_count) {
+	r.i = i;
+	if (i >= t.candidate_count) {
 		r.running = false;
 	}
+	wsync();
 }
 
 // step part 3 (first iteration of a candidate only): score before realignment (:606-640)
@@ -608,9 +634,13 @@ ASTC_FN void refine_second_score(WCtx w, const Trial& t, Refine& r, BlockSearch&
 		refine_next_candidate(t, r, false);
 		return;
 	}
-	r.l++;
+	unsigned int l = r.l;
+	wsync();
+	l++;
+	r.l = l;
 	r.in_step = false;
-	if (r.l >= refinement_limit) {
+	wsync();
+	if (l >= refinement_limit) {
 		refine_next_candidate(t, r, false);
 	}
 }
