@@ -159,7 +159,7 @@ ASTC_FN void route_block(const WCtx& w, const WaveArgs& a, unsigned int b, int n
 ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 	// one copy of the search state per warp, in the arena slots the record keeps it in (see wave_refine); the widened
 	// copy of the trial used by the shared set-up sits in the work / mod colour slots, which only refinement uses
-#if defined(ASTC_HOSTSIM_LANES32)
+#if defined(ASTC_HOSTSIM_LANES32) && !defined(ASTC_HOSTSIM_SHARED_STATE)
 	// (the thread-per-lane simulation has no lockstep execution between collectives: private copies, see wave_refine)
 	BlockSearch s_private;
 	Trial t_private, tf_private;
@@ -324,12 +324,15 @@ __device__ unsigned long long g_step_stats[6][8];
 // works on ONE copy per warp in shared memory: BlockSearch and Trial in their arena slots (where the record keeps them
 // anyway), Refine in a slot behind the arenas. Every lane stores the same values at the same (converged) instruction, so
 // the concurrent stores are benign; this leans on the warp executing the scalar bookkeeping between two __syncwarp()s in
-// lockstep, which the thread-per-lane host simulation does not provide - that build keeps private copies.
+// lockstep, which the thread-per-lane host simulation does not provide - that build keeps private copies (building it with
+// -DASTC_HOSTSIM_SHARED_STATE shows the dependence: with arbitrary lane timing a lagging lane reads the next step's flags).
+// The read-modify-write counters do not lean on it (block_search_advance); compute-sanitizer's racecheck lists the
+// remaining accesses as warnings (profiles/r01_summary.md).
 #define ASTC_REFINE_STATE_BYTES 128
 static_assert(sizeof(Refine) <= ASTC_REFINE_STATE_BYTES, "Refine must fit its shared-memory slot");
 
 ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
-#if defined(ASTC_HOSTSIM_LANES32)
+#if defined(ASTC_HOSTSIM_LANES32) && !defined(ASTC_HOSTSIM_SHARED_STATE)
 	BlockSearch s_private;
 	Trial t_private;
 	Refine r_private;
@@ -440,7 +443,7 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 // P: block statistics / partition search.
 // ---------------------------------------------------------------------------------------------
 ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
-#if defined(ASTC_HOSTSIM_LANES32)
+#if defined(ASTC_HOSTSIM_LANES32) && !defined(ASTC_HOSTSIM_SHARED_STATE)
 	BlockSearch s_private;
 	Trial t_private;
 	BlockSearch& s = s_private;
