@@ -3,7 +3,8 @@
 //   g++ -std=c++14 -O1 -g -fsanitize=thread -pthread -ffp-contract=off -DASTC_HOSTSIM_LANES32=1 -x c++ \
 //       tests/hostsim/lanes32_main.cpp tests/hostsim/hostsim.cpp astc-encoder_b200/csrc/astc_host_tables.cpp \
 //       astc-encoder_b200/csrc/astc_host_config.cpp -o /tmp/lanes32_tsan
-//   /tmp/lanes32_tsan <profile 0-3> <block_x> <block_y> <quality> <width> <height> <seed> [kind: 0 noise, 1 two-colour cells, 2 hdr]
+//   /tmp/lanes32_tsan <profile 0-3> <block_x> <block_y> <quality> <width> <height> <seed> [kind: 0 noise, 1 two-colour stripes, 2 hdr,
+//                     3 = stripes + decode of the result, 4 = alpha-scale pre-pass (radius 2) on stripes with transparent rows]
 // ThreadSanitizer sees every shared-memory access of every lane; the warp collectives are its only synchronisation, so a
 // report is a missing __syncwarp() between a producer lane and a consumer lane. Prints an FNV hash of the output blocks.
 #include <cstdint>
@@ -14,6 +15,9 @@
 
 extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int by, float quality, unsigned int flags,
                                       const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, const int* swz, uint8_t* out);
+extern "C" int hostsim_decompress_image(int profile, unsigned int bx, unsigned int by, unsigned int flags, const uint8_t* blocks, void* out, int data_type,
+                                        unsigned int dim_x, unsigned int dim_y, const int* swz);
+extern "C" void hostsim_set_a_scale_radius(unsigned int r);
 
 int main(int argc, char** argv) {
 	if (argc < 8) {
@@ -35,7 +39,7 @@ int main(int argc, char** argv) {
 		for (unsigned int x = 0; x < w; x++) {
 			for (int k = 0; k < 4; k++) {
 				size_t i = ((size_t)y * w + x) * 4 + k;
-				if (kind == 1) {
+				if (kind == 1 || kind == 3 || kind == 4) {
 					img8[i] = (uint8_t)(cell[((x * 3 + y * 5) / 7) & 1][k] + (rnd() & 7));      // two colours in diagonal stripes + a little noise
 				} else {
 					img8[i] = (uint8_t)rnd();
@@ -45,12 +49,28 @@ int main(int argc, char** argv) {
 			}
 		}
 	}
+	unsigned int flags = 32;      // ASTCENC_FLG_SELF_DECOMPRESS_ONLY
+	if (kind == 4) {
+		for (unsigned int y = 0; y < h; y += 3) {
+			for (unsigned int x = 0; x < w; x++) img8[((size_t)y * w + x) * 4 + 3] = 0;      // transparent rows
+		}
+		flags |= 4;               // ASTCENC_FLG_USE_ALPHA_WEIGHT
+		hostsim_set_a_scale_radius(2);
+	}
+	if (kind == 3) {
+		flags = 0;                // full tables: the result is decoded below
+	}
 	unsigned int nb = ((w + bx - 1) / bx) * ((h + by - 1) / by);
 	std::vector<uint8_t> out((size_t)nb * 16);
-	int rc = hostsim_compress_image(profile, bx, by, quality, 32 /* SELF_DECOMPRESS_ONLY */, kind == 2 ? (const void*)img16.data() : (const void*)img8.data(),
+	int rc = hostsim_compress_image(profile, bx, by, quality, flags, kind == 2 ? (const void*)img16.data() : (const void*)img8.data(),
 	                                kind == 2 ? 1 : 0, w, h, nullptr, out.data());
 	uint64_t hash = 1469598103934665603ull;
 	for (uint8_t b : out) { hash = (hash ^ b) * 1099511628211ull; }
+	if (kind == 3 && rc == 0) {
+		std::vector<uint8_t> dec((size_t)w * h * 4);
+		rc = hostsim_decompress_image(profile, bx, by, 0, out.data(), dec.data(), 0, w, h, nullptr);
+		for (uint8_t b : dec) { hash = (hash ^ b) * 1099511628211ull; }
+	}
 	printf("rc %d blocks %u hash %016llx\n", rc, nb, (unsigned long long)hash);
 	return rc;
 }

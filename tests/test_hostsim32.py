@@ -75,7 +75,8 @@ def test_decode_on_32_lanes(hostsim32):
         assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
 
 
-@pytest.mark.parametrize("args", ["1 6 6 60 18 12 1 0", "1 6 6 60 24 18 2 1", "3 6 6 60 12 12 3 2", "1 4 4 98 12 12 4 1", "1 8 8 60 16 16 5 1"])
+@pytest.mark.parametrize("args", ["1 6 6 60 18 12 1 0", "1 6 6 60 24 18 2 1", "3 6 6 60 12 12 3 2", "1 4 4 98 12 12 4 1", "1 8 8 60 16 16 5 1",
+                                  "1 6 6 10 18 18 6 3", "1 6 6 60 18 18 7 4"])      # last two: + decode of the result, alpha-scale pre-pass
 def test_no_data_race_between_lanes(lanes32_tsan, args):
     """ThreadSanitizer over the whole wave pipeline: any report is a missing __syncwarp() between lanes (removing one is
     detected at once - tried by hand on pack_work_endpoints)."""
