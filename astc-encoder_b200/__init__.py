@@ -124,6 +124,10 @@ def lib():
         l.astcenc_b200_store_cimage.restype = C.c_int
         l.astcenc_b200_load_cimage.argtypes = [C.c_char_p, C.POINTER(CImageHeader), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         l.astcenc_b200_load_cimage.restype = C.c_int
+        l.astcenc_b200_store_ktx_cimage.argtypes = [C.c_char_p, C.POINTER(CImageHeader), C.c_int, C.c_void_p, C.c_size_t]
+        l.astcenc_b200_store_ktx_cimage.restype = C.c_int
+        l.astcenc_b200_load_ktx_cimage.argtypes = [C.c_char_p, C.POINTER(CImageHeader), C.POINTER(C.c_int), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        l.astcenc_b200_load_ktx_cimage.restype = C.c_int
         _lib = l
     return _lib
 
@@ -263,6 +267,30 @@ def load_cimage(filename):
     if err:
         raise AstcencError(err, "astcenc_b200_load_cimage")
     return data, {k: getattr(hdr, k) for k, _ in CImageHeader._fields_}
+
+
+def store_ktx_cimage(filename, blocks, dim_x, dim_y, block_x, block_y, is_srgb=False, dim_z=1, block_z=1):
+    """Write the blocks as a KTX 1 file (store_ktx_compressed_image, astcenccli_image_load_store.cpp:1396-1440)."""
+    data = np.ascontiguousarray(np.frombuffer(bytes(blocks), dtype=np.uint8) if not isinstance(blocks, np.ndarray) else blocks.view(np.uint8).reshape(-1))
+    hdr = CImageHeader(block_x, block_y, block_z, dim_x, dim_y, dim_z)
+    err = lib().astcenc_b200_store_ktx_cimage(os.fsencode(filename), C.byref(hdr), int(is_srgb), data.ctypes.data, data.nbytes)
+    if err:
+        raise AstcencError(err, "astcenc_b200_store_ktx_cimage")
+
+
+def load_ktx_cimage(filename):
+    """Read an ASTC payload from a KTX 1 file (load_ktx_compressed_image, :1294-1385). Returns (blocks, header dict, is_srgb)."""
+    hdr = CImageHeader()
+    n = C.c_size_t()
+    srgb = C.c_int()
+    err = lib().astcenc_b200_load_ktx_cimage(os.fsencode(filename), C.byref(hdr), C.byref(srgb), None, 0, C.byref(n))
+    if err:
+        raise AstcencError(err, "astcenc_b200_load_ktx_cimage")
+    data = np.empty(n.value, dtype=np.uint8)
+    err = lib().astcenc_b200_load_ktx_cimage(os.fsencode(filename), C.byref(hdr), C.byref(srgb), data.ctypes.data, data.nbytes, C.byref(n))
+    if err:
+        raise AstcencError(err, "astcenc_b200_load_ktx_cimage")
+    return data, {k: getattr(hdr, k) for k, _ in CImageHeader._fields_}, bool(srgb.value)
 
 
 def slab_rows(blocks_y, rank, world):

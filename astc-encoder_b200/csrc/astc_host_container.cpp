@@ -58,6 +58,61 @@ astcenc_error parse_header(const RawHeader& raw, astcenc_b200_cimage_header* hdr
 	return ASTCENC_SUCCESS;
 }
 
+// ---- KTX 1 (astcenccli_image_load_store.cpp:870-905 header, :1294-1440 load / store of compressed images) ----
+const unsigned char k_ktx_magic[12] = {0xAB, 0x4B, 0x54, 0x58, 0x20, 0x31, 0x31, 0xBB, 0x0D, 0x0A, 0x1A, 0x0A};
+const uint32_t k_gl_rgba = 0x1908;
+
+struct KtxHeader {
+	unsigned char magic[12];
+	uint32_t endianness, gl_type, gl_type_size, gl_format, gl_internal_format, gl_base_internal_format;
+	uint32_t pixel_width, pixel_height, pixel_depth, number_of_array_elements, number_of_faces, number_of_mipmap_levels, bytes_of_key_value_data;
+};
+static_assert(sizeof(KtxHeader) == 64, "the KTX 1 header is 64 bytes");
+
+// GL_COMPRESSED_RGBA_ASTC_<x>x<y>_KHR = 0x93B0 + i, ..._<x>x<y>x<z>_OES = 0x93C0 + j, the sRGB8_ALPHA8 variants + 0x20
+// (the table at :760-835)
+const unsigned char k_fp2d[14][2] = {{4, 4}, {5, 4}, {5, 5}, {6, 5}, {6, 6}, {8, 5}, {8, 6}, {8, 8}, {10, 5}, {10, 6}, {10, 8}, {10, 10}, {12, 10}, {12, 12}};
+const unsigned char k_fp3d[10][3] = {{3, 3, 3}, {4, 3, 3}, {4, 4, 3}, {4, 4, 4}, {5, 4, 4}, {5, 5, 4}, {5, 5, 5}, {6, 5, 5}, {6, 6, 5}, {6, 6, 6}};
+
+uint32_t gl_format_of(unsigned int x, unsigned int y, unsigned int z, bool srgb) {
+	for (unsigned int i = 0; i < 14; i++) {
+		if (z == 1 && k_fp2d[i][0] == x && k_fp2d[i][1] == y) {
+			return 0x93B0u + i + (srgb ? 0x20u : 0u);
+		}
+	}
+	for (unsigned int i = 0; i < 10; i++) {
+		if (k_fp3d[i][0] == x && k_fp3d[i][1] == y && k_fp3d[i][2] == z) {
+			return 0x93C0u + i + (srgb ? 0x20u : 0u);
+		}
+	}
+	return 0;
+}
+
+bool footprint_of(uint32_t fmt, astcenc_b200_cimage_header* hdr, int* srgb) {
+	*srgb = 0;
+	if (fmt >= 0x93D0u && fmt <= 0x93E9u) {
+		*srgb = 1;
+		fmt -= 0x20u;
+	}
+	if (fmt >= 0x93B0u && fmt <= 0x93BDu) {
+		hdr->block_x = k_fp2d[fmt - 0x93B0u][0];
+		hdr->block_y = k_fp2d[fmt - 0x93B0u][1];
+		hdr->block_z = 1;
+		return true;
+	}
+	if (fmt >= 0x93C0u && fmt <= 0x93C9u) {
+		hdr->block_x = k_fp3d[fmt - 0x93C0u][0];
+		hdr->block_y = k_fp3d[fmt - 0x93C0u][1];
+		hdr->block_z = k_fp3d[fmt - 0x93C0u][2];
+		return true;
+	}
+	return false;
+}
+
+inline uint32_t bswap32(uint32_t v) {
+	return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24);
+}
+
 }      // namespace
 
 extern "C" {
@@ -131,6 +186,105 @@ astcenc_error astcenc_b200_load_cimage(const char* filename, astcenc_b200_cimage
 			if (data_capacity < payload) {
 				status = ASTCENC_ERR_OUT_OF_MEM;
 			} else if (payload && fread(data, 1, payload, f) != payload) {
+				status = ASTCENC_ERR_BAD_PARAM;
+			}
+		}
+	}
+	fclose(f);
+	return status;
+}
+
+astcenc_error astcenc_b200_store_ktx_cimage(const char* filename, const astcenc_b200_cimage_header* hdr, int is_srgb, const uint8_t* data, size_t data_len) {
+	if (!filename || !hdr || (!data && data_len) || data_len > 0xFFFFFFFFull || hdr->dim_x == 0 || hdr->dim_y == 0 || hdr->dim_z == 0) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	uint32_t fmt = gl_format_of(hdr->block_x, hdr->block_y, hdr->block_z, is_srgb != 0);
+	if (fmt == 0) {
+		return ASTCENC_ERR_BAD_BLOCK_SIZE;
+	}
+	KtxHeader k;
+	memcpy(k.magic, k_ktx_magic, 12);
+	k.endianness = 0x04030201u;
+	k.gl_type = 0;
+	k.gl_type_size = 1;
+	k.gl_format = 0;
+	k.gl_internal_format = fmt;
+	k.gl_base_internal_format = k_gl_rgba;
+	k.pixel_width = hdr->dim_x;
+	k.pixel_height = hdr->dim_y;
+	k.pixel_depth = hdr->dim_z == 1 ? 0 : hdr->dim_z;
+	k.number_of_array_elements = 0;
+	k.number_of_faces = 1;
+	k.number_of_mipmap_levels = 1;
+	k.bytes_of_key_value_data = 0;
+	FILE* f = fopen(filename, "wb");
+	if (!f) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	uint32_t len32 = (uint32_t)data_len;
+	bool ok = fwrite(&k, sizeof(k), 1, f) == 1 && fwrite(&len32, 4, 1, f) == 1 && (data_len == 0 || fwrite(data, 1, data_len, f) == data_len);
+	ok = (fclose(f) == 0) && ok;
+	return ok ? ASTCENC_SUCCESS : ASTCENC_ERR_BAD_PARAM;
+}
+
+astcenc_error astcenc_b200_load_ktx_cimage(const char* filename, astcenc_b200_cimage_header* hdr, int* is_srgb, uint8_t* data, size_t data_capacity,
+                                           size_t* data_len) {
+	if (!filename || !hdr || !is_srgb || !data_len) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	*data_len = 0;
+	FILE* f = fopen(filename, "rb");
+	if (!f) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	astcenc_error status = ASTCENC_SUCCESS;
+	KtxHeader k;
+	bool swapped = false;
+	if (fread(&k, sizeof(k), 1, f) != 1 || memcmp(k.magic, k_ktx_magic, 12) != 0 || (k.endianness != 0x04030201u && k.endianness != 0x01020304u)) {
+		status = ASTCENC_ERR_BAD_PARAM;
+	} else {
+		if (k.endianness == 0x01020304u) {
+			// written on a machine of the other byte order: every 32-bit field is reversed (:1321-1326)
+			swapped = true;
+			uint32_t* fields = &k.endianness;
+			for (int i = 0; i < 13; i++) {
+				fields[i] = bswap32(fields[i]);
+			}
+		}
+		if (k.gl_type != 0 || k.gl_format != 0 || k.gl_type_size != 1 || k.gl_base_internal_format != k_gl_rgba ||
+		    !footprint_of(k.gl_internal_format, hdr, is_srgb) || k.pixel_width == 0 || k.pixel_height == 0) {
+			status = ASTCENC_ERR_BAD_PARAM;      // not an ASTC payload this library understands
+		}
+	}
+	uint32_t len32 = 0;
+	if (status == ASTCENC_SUCCESS) {
+		hdr->dim_x = k.pixel_width;
+		hdr->dim_y = k.pixel_height;
+		hdr->dim_z = k.pixel_depth == 0 ? 1 : k.pixel_depth;
+		if (fseek(f, (long)k.bytes_of_key_value_data, SEEK_CUR) != 0 || fread(&len32, 4, 1, f) != 1) {
+			status = ASTCENC_ERR_BAD_PARAM;
+		} else if (swapped) {
+			len32 = bswap32(len32);
+		}
+	}
+	if (status == ASTCENC_SUCCESS) {
+		long at = ftell(f);
+		if (at < 0 || fseek(f, 0, SEEK_END) != 0) {
+			status = ASTCENC_ERR_BAD_PARAM;
+		} else {
+			long end = ftell(f);
+			if (end < at || (size_t)(end - at) < (size_t)len32) {
+				status = ASTCENC_ERR_BAD_PARAM;      // truncated payload
+			}
+			fseek(f, at, SEEK_SET);
+		}
+	}
+	if (status == ASTCENC_SUCCESS) {
+		*data_len = len32;
+		if (data) {
+			if (data_capacity < (size_t)len32) {
+				status = ASTCENC_ERR_OUT_OF_MEM;
+			} else if (len32 && fread(data, 1, len32, f) != len32) {
 				status = ASTCENC_ERR_BAD_PARAM;
 			}
 		}

@@ -245,4 +245,17 @@ ASTCENC_PUBLIC enum astcenc_error astcenc_b200_store_cimage(const char* filename
 ASTCENC_PUBLIC enum astcenc_error astcenc_b200_load_cimage(const char* filename, struct astcenc_b200_cimage_header* header,
                                                            uint8_t* data, size_t data_capacity, size_t* data_len);
 
+/**
+ * The same payload in a KTX 1 container (Source/astcenccli_image_load_store.cpp:870-905 header, :1294-1440
+ * load_ktx_compressed_image / store_ktx_compressed_image): 64-byte header with glInternalFormat =
+ * GL_COMPRESSED_RGBA_ASTC_<footprint> (or the SRGB8_ALPHA8 variant when is_srgb), one mip level, no key/value data, then
+ * the 32-bit payload size and the blocks. load accepts files of either byte order, skips key/value data and reads the first
+ * mip level; the two-call protocol (data == NULL first) and the error codes are those of astcenc_b200_load_cimage, a footprint
+ * without a GL enum gives ASTCENC_ERR_BAD_BLOCK_SIZE on store.
+ */
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_store_ktx_cimage(const char* filename, const struct astcenc_b200_cimage_header* header, int is_srgb,
+                                                                const uint8_t* data, size_t data_len);
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_load_ktx_cimage(const char* filename, struct astcenc_b200_cimage_header* header, int* is_srgb,
+                                                               uint8_t* data, size_t data_capacity, size_t* data_len);
+
 #endif

@@ -81,3 +81,61 @@ def test_fixture_blocks_decode_like_the_oracle(pkg, tmp_path):
         ctx.close()
     want = Oracle().decompress(data, hdr["dim_x"], hdr["dim_y"], PRF_LDR, hdr["block_x"], hdr["block_y"])
     assert np.array_equal(np.asarray(img).reshape(-1), np.asarray(want).reshape(-1))
+
+
+# ---- KTX 1 (astcenccli_image_load_store.cpp:870-905 header, :1294-1440 load / store of compressed images) ----
+KTX_MAGIC = bytes([0xAB, 0x4B, 0x54, 0x58, 0x20, 0x31, 0x31, 0xBB, 0x0D, 0x0A, 0x1A, 0x0A])
+
+
+def _u32(raw, i):
+    return int.from_bytes(raw[i:i + 4], "little")
+
+
+@pytest.mark.parametrize("bx,by,srgb,glfmt", [(4, 4, False, 0x93B0), (6, 6, False, 0x93B4), (12, 12, False, 0x93BD), (6, 5, True, 0x93D3), (10, 8, True, 0x93DA)])
+def test_ktx_round_trip_and_header_fields(pkg, tmp_path, bx, by, srgb, glfmt):
+    """Header fields as store_ktx_compressed_image writes them (:1404-1418) and the GL enums of the footprint table (:725-753)."""
+    rng = np.random.default_rng(bx * 16 + by)
+    w, h = 37, 29
+    n = ((w + bx - 1) // bx) * ((h + by - 1) // by)
+    blocks = rng.integers(0, 256, n * 16, dtype=np.uint8)
+    p = str(tmp_path / "t.ktx")
+    pkg.store_ktx_cimage(p, blocks, w, h, bx, by, is_srgb=srgb)
+    raw = open(p, "rb").read()
+    assert raw[:12] == KTX_MAGIC and len(raw) == 64 + 4 + n * 16
+    fields = [_u32(raw, 12 + 4 * i) for i in range(13)]
+    # endianness, glType, glTypeSize, glFormat, glInternalFormat, glBaseInternalFormat (GL_RGBA), width, height, depth, array elements, faces, mip levels, kv bytes
+    assert fields == [0x04030201, 0, 1, 0, glfmt, 0x1908, w, h, 0, 0, 1, 1, 0]
+    assert _u32(raw, 64) == n * 16 and raw[68:] == blocks.tobytes()
+    data, hdr, is_srgb = pkg.load_ktx_cimage(p)
+    assert np.array_equal(data, blocks) and is_srgb == srgb
+    assert (hdr["block_x"], hdr["block_y"], hdr["block_z"], hdr["dim_x"], hdr["dim_y"], hdr["dim_z"]) == (bx, by, 1, w, h, 1)
+
+
+def test_ktx_other_byte_order_and_key_value_data(pkg, tmp_path):
+    """A file written on a big-endian machine (every 32-bit field reversed, :1321-1326) with key/value data to skip (:1343)."""
+    blocks = np.arange(32, dtype=np.uint8)
+    fields = [0x04030201, 0, 1, 0, 0x93B4, 0x1908, 7, 6, 0, 0, 1, 1, 8]
+    raw = KTX_MAGIC + b"".join(v.to_bytes(4, "big") for v in fields) + b"KEYVALUE" + (32).to_bytes(4, "big") + blocks.tobytes()
+    p = tmp_path / "be.ktx"
+    p.write_bytes(raw)
+    data, hdr, is_srgb = pkg.load_ktx_cimage(str(p))
+    assert np.array_equal(data, blocks) and not is_srgb
+    assert (hdr["block_x"], hdr["block_y"], hdr["dim_x"], hdr["dim_y"]) == (6, 6, 7, 6)
+
+
+def test_ktx_refusals(pkg, tmp_path):
+    good = [0x04030201, 0, 1, 0, 0x93B4, 0x1908, 6, 6, 0, 0, 1, 1, 0]
+
+    def write(name, fields=good, magic=KTX_MAGIC, payload=bytes(16), length=16):
+        p = tmp_path / name
+        p.write_bytes(magic + b"".join(v.to_bytes(4, "little") for v in fields) + length.to_bytes(4, "little") + payload)
+        return str(p)
+    pkg.load_ktx_cimage(write("ok.ktx"))
+    for name, kw in (("magic.ktx", dict(magic=b"\x00" + KTX_MAGIC[1:])), ("endian.ktx", dict(fields=[0x11223344] + good[1:])),
+                     ("uncompressed.ktx", dict(fields=good[:1] + [0x1401] + good[2:])), ("format.ktx", dict(fields=good[:4] + [0x8058] + good[5:])),
+                     ("base.ktx", dict(fields=good[:5] + [0x1907] + good[6:])), ("short.ktx", dict(payload=bytes(8)))):
+        with pytest.raises(pkg.AstcencError):
+            pkg.load_ktx_cimage(write(name, **kw))
+    with pytest.raises(pkg.AstcencError) as e:
+        pkg.store_ktx_cimage(str(tmp_path / "x.ktx"), bytes(16), 7, 7, 7, 7)      # no GL enum for a 7x7 footprint
+    assert e.value.code == pkg.ERR_BAD_BLOCK_SIZE
