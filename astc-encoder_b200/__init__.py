@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libastcenc_b200.so")
+LIB_PATH = os.environ.get("ASTCENC_B200_LIB") or os.path.join(_HERE, "libastcenc_b200.so")      # (the override is for A/B builds in tools/)
 
 PRF_LDR_SRGB, PRF_LDR, PRF_HDR_RGB_LDR_A, PRF_HDR = 0, 1, 2, 3
 PRE_FASTEST, PRE_FAST, PRE_MEDIUM, PRE_THOROUGH, PRE_VERYTHOROUGH, PRE_EXHAUSTIVE = 0.0, 10.0, 60.0, 98.0, 99.0, 100.0
@@ -128,8 +128,34 @@ def lib():
         l.astcenc_b200_store_ktx_cimage.restype = C.c_int
         l.astcenc_b200_load_ktx_cimage.argtypes = [C.c_char_p, C.POINTER(CImageHeader), C.POINTER(C.c_int), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         l.astcenc_b200_load_ktx_cimage.restype = C.c_int
+        l.astcenc_b200_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+        l.astcenc_b200_comm_unique_id.restype = C.c_int
+        l.astcenc_b200_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        l.astcenc_b200_comm_init.restype = C.c_int
+        l.astcenc_b200_comm_free.argtypes = [C.c_void_p]
+        l.astcenc_b200_comm_free.restype = C.c_int
+        l.astcenc_b200_slab_rows.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+        l.astcenc_b200_slab_rows.restype = C.c_int
+        l.astcenc_b200_compress_image_sharded.argtypes = [C.c_void_p, C.POINTER(Image), C.POINTER(Swizzle), C.c_void_p, C.c_size_t, C.c_int]
+        l.astcenc_b200_compress_image_sharded.restype = C.c_int
+        l.astcenc_b200_compress_batch.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Image)), C.c_uint, C.POINTER(Swizzle), C.POINTER(C.c_void_p), C.c_size_t, C.c_int]
+        l.astcenc_b200_compress_batch.restype = C.c_int
+        l.astcenc_b200_comm_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        l.astcenc_b200_comm_last_timing.restype = C.c_int
         _lib = l
     return _lib
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """astcenc_b200_comm_unique_id: the 128-byte NCCL rendezvous id (made on one rank, shipped to the others by the caller)."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    err = lib().astcenc_b200_comm_unique_id(buf, COMM_ID_BYTES)
+    if err:
+        raise AstcencError(err, "astcenc_b200_comm_unique_id")
+    return bytes(buf)
 
 
 def config_init(profile, block_x, block_y, quality, flags=0, block_z=1, **overrides):
@@ -211,6 +237,71 @@ class Context:
 
     def launch_count(self):
         return int(lib().astcenc_b200_launch_count(self.handle))
+
+    # ---- multi-GPU (one process per GPU; include/astcenc.h "Multi-GPU sharding") ----
+    def comm_init(self, rank, world, unique_id=None):
+        self.rank, self.world = rank, world
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id) if unique_id is not None else None
+        err = lib().astcenc_b200_comm_init(self.handle, rank, world, buf, COMM_ID_BYTES if buf is not None else 0)
+        if err:
+            raise AstcencError(err, "astcenc_b200_comm_init")
+
+    def comm_free(self):
+        if self.handle:
+            lib().astcenc_b200_comm_free(self.handle)
+
+    def slab_rows(self, dim_y, rank, world):
+        a = C.c_uint(); n = C.c_uint()
+        err = lib().astcenc_b200_slab_rows(self.handle, dim_y, rank, world, C.byref(a), C.byref(n))
+        if err:
+            raise AstcencError(err, "astcenc_b200_slab_rows")
+        return a.value, n.value
+
+    def compress_image_sharded(self, img, out=None, root=0, swizzle=(0, 1, 2, 3)):
+        """Slab mode (collective): every rank passes the same (H, W, 4) image; the root gets the whole payload in `out`."""
+        img = np.ascontiguousarray(img)
+        h, w = img.shape[:2]
+        slices = (C.c_void_p * 1)(img.ctypes.data)
+        image = Image(w, h, 1, _DTYPES[img.dtype], slices)
+        sw = Swizzle(*swizzle)
+        nbx, nby = self.blocks(w, h)
+        is_root = getattr(self, "rank", 0) == root
+        if out is None and is_root:
+            out = np.empty(nbx * nby * 16, dtype=np.uint8)
+        err = lib().astcenc_b200_compress_image_sharded(self.handle, C.byref(image), C.byref(sw), out.ctypes.data if out is not None else None,
+                                                        out.nbytes if out is not None else 0, root)
+        if err:
+            raise AstcencError(err, "astcenc_b200_compress_image_sharded")
+        return out
+
+    def compress_batch(self, images, outs=None, root=0, swizzle=(0, 1, 2, 3)):
+        """Batch mode (collective): images[i] (None for images of other ranks) -> outs[i] on the root."""
+        n = len(images)
+        keep = []
+        ptrs = (C.POINTER(Image) * n)()
+        for i, im in enumerate(images):
+            if im is None:
+                continue
+            im = np.ascontiguousarray(im)
+            slices = (C.c_void_p * 1)(im.ctypes.data)
+            st = Image(im.shape[1], im.shape[0], 1, _DTYPES[im.dtype], slices)
+            keep.append((im, slices, st))
+            ptrs[i] = C.pointer(st)
+        sw = Swizzle(*swizzle)
+        optr = None
+        each = 0
+        if outs is not None:
+            optr = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+            each = outs[0].nbytes
+        err = lib().astcenc_b200_compress_batch(self.handle, ptrs, n, C.byref(sw), optr, each, root)
+        if err:
+            raise AstcencError(err, "astcenc_b200_compress_batch")
+        return outs
+
+    def comm_last_timing(self):
+        a = C.c_float(); b = C.c_float()
+        lib().astcenc_b200_comm_last_timing(self.handle, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def stage_timing(self, enable, fetch=False):
         """Enable / disable per-launch events; with fetch=True also return ({kernel: ms}, {kernel: launches}) of the last call."""

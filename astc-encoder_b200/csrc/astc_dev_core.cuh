@@ -58,7 +58,11 @@
 	#else
 		#define ASTC_WARP 32
 	#endif
-	#define ASTC_NOUNROLL _Pragma("unroll 1")
+	#if defined(ASTC_UNROLL_DEFAULT)
+		#define ASTC_NOUNROLL                     /* experiment: leave loop unrolling to the compiler */
+	#else
+		#define ASTC_NOUNROLL _Pragma("unroll 1")
+	#endif
 	#define ASTC_RINT(a) rintf(a)
 	#define ASTC_F2U(f) __float_as_uint(f)
 	#define ASTC_U2F(u) __uint_as_float(u)

@@ -33,8 +33,12 @@ struct WaveArgs {
 	uint32_t* queue[ASTC_Q_KINDS];   // item lists (block indices), capacity = blocks each
 	uint32_t* count;             // [ASTC_Q_KINDS][ASTC_MAX_WAVES] items pushed (Q_EMIT uses wave slot 0)
 	uint32_t* head;              // [ASTC_Q_KINDS][ASTC_MAX_WAVES] items popped
-	unsigned int total;          // blocks in this launch
+	unsigned int total;          // blocks of the slab (capacity of every queue)
 	unsigned int blocks_x;
+	// wave 0 reads the image; the host may cut it into bands of block rows (upload of band k+1 under the set-up of band k):
+	// a wave-0 launch takes blocks [first_block, first_block + band_blocks) from its own ticket counter
+	uint32_t* ticket;
+	unsigned int first_block, band_blocks;
 	int wave;
 	unsigned int sync_mask;      // tuning: which stage barriers are active (bit i = i-th barrier of the kernel loop)
 	uint32_t stage_bytes_setup;  // set-up kernel: the same (decimation tables only)
@@ -172,8 +176,8 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 	Trial& tf = *reinterpret_cast<Trial*>(astc_smem + w.base + A_SCB + 160);
 #endif
 	BlockFeed feed;
-	feed.ticket = a.head + Q_SETUP * ASTC_MAX_WAVES;      // wave 0 has no queue: its head counter is the image ticket
-	feed.total = a.total;
+	feed.ticket = a.ticket;      // wave 0 has no queue: a ticket counter hands out the band's blocks
+	feed.total = a.band_blocks;
 	feed.blocks_x = a.blocks_x;
 	int cls = 0;
 	while (true) {
@@ -181,6 +185,7 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 		unsigned int b = 0;
 		if (a.wave == 0) {
 			while (feed_next(w, feed, b)) {
+				b += a.first_block;
 				unsigned int by = b / a.blocks_x;
 				unsigned int bx = b - by * a.blocks_x;
 				if (IMG.alpha_avg != nullptr && !block_has_alpha(w, IMG.alpha_avg, IMG.alpha_threshold, bx * BSD.dim_x, (by + IMG.block_row0) * BSD.dim_y)) {

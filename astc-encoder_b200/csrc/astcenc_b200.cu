@@ -256,8 +256,38 @@ astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 // Context
 // ---------------------------------------------------------------------------------------------
+static const bool g_debug_cuda = getenv("ASTCENC_B200_DEBUG") != nullptr;
 #define CUDA_TRY(expr, onfail) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
-	if (getenv("ASTCENC_B200_DEBUG")) fprintf(stderr, "astcenc_b200: %s failed: %s\n", #expr, cudaGetErrorString(e_)); onfail; } } while (0)
+	if (g_debug_cuda) fprintf(stderr, "astcenc_b200: %s failed: %s\n", #expr, cudaGetErrorString(e_)); onfail; } } while (0)
+
+// Every entry point runs on the context's device and leaves the caller's current device as it found it
+// (single-process multi-GPU callers such as PyTorch keep their own notion of the current device).
+struct DeviceGuard {
+	int prev, target;
+	bool ok;
+	explicit DeviceGuard(int device) : prev(device), target(device), ok(true) {
+		ok = cudaGetDevice(&prev) == cudaSuccess;
+		if (ok && prev != target) {
+			ok = cudaSetDevice(target) == cudaSuccess;
+		}
+	}
+	~DeviceGuard() {
+		if (ok && prev != target) {
+			cudaSetDevice(prev);
+		}
+	}
+};
+
+// Tuning / experiment knobs, read ONCE when the context is created (INTEGRATION.md lists them).
+struct Knobs {
+	size_t batch_blocks;         // ASTCENC_B200_BATCH_BLOCKS: blocks per batch of a slab (records are reused batch after batch)
+	unsigned int sync_mask;      // ASTCENC_B200_SYNC_MASK: stage barriers of the wave kernels
+	int coherence_probe;         // ASTCENC_B200_COHERENCE_PROBE (single-kernel driver experiment)
+	int upload_bands;            // ASTCENC_B200_UPLOAD_BANDS: bands the host-pointer path cuts an image into (1 = one copy)
+	int stage_print;             // ASTCENC_B200_STAGE_PRINT
+};
+#define ASTC_MAX_BANDS 8
+#define ASTC_COUNTER_WORDS (2 * ASTC_Q_KINDS * ASTC_MAX_WAVES + ASTC_MAX_BANDS)
 
 struct DeviceTables {            // shared between a parent context and its children
 	std::atomic<int> refcount;
@@ -303,6 +333,23 @@ struct astcenc_context {
 	size_t d_image_bytes;
 	uint8_t* d_out;
 	size_t d_out_bytes;
+	Knobs knobs;
+	// The per-context scratch (records, queues, counters, alpha averages) serves ONE pipeline pass at a time: launch_mtx
+	// serialises the host side, scratch_done orders a pass on one stream behind the previous pass on another.
+	std::mutex launch_mtx;
+	cudaEvent_t scratch_done;
+	bool scratch_used;
+	// host-pointer path: uploads run on copy_stream, band by band, under the set-up of the previous band
+	cudaStream_t copy_stream;
+	cudaEvent_t band_ready[ASTC_MAX_BANDS];
+	cudaEvent_t out_ready;
+	uint8_t* d_image2;           // second image buffer of the batch API (double-buffered uploads)
+	size_t d_image2_bytes;
+	// multi-GPU (astc_host_multi.inl): one process per GPU, NCCL for the payload gather
+	void* nccl_comm;
+	int rank, world;
+	cudaEvent_t ev_g0, ev_g1;
+	float last_gather_ms, last_compress_ms;
 	// caller protocol
 	std::mutex mtx;
 	std::condition_variable cv;
@@ -355,6 +402,8 @@ astcenc_error astcenc_config_init(astcenc_profile profile, unsigned int block_x,
 	return astc_host::config_init(profile, block_x, block_y, block_z, quality, flags, config);
 }
 
+void astcenc_context_free(astcenc_context* ctx);
+
 astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int thread_count, astcenc_context** context, const astcenc_context* parent) {
 	astcenc_error status = astc_host::validate_cpu_float();
 	if (status != ASTCENC_SUCCESS) {
@@ -375,11 +424,20 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	if (!ctx) {
 		return ASTCENC_ERR_OUT_OF_MEM;
 	}
+	// every resource starts out null, so that astcenc_context_free() can release a partially built context
 	ctx->config = *configp;
 	ctx->thread_count = thread_count;
+	ctx->device = -1;
 	ctx->tables = nullptr;
 	ctx->stream = nullptr;
+	ctx->copy_stream = nullptr;
 	ctx->ev0 = ctx->ev1 = nullptr;
+	ctx->scratch_done = nullptr;
+	ctx->scratch_used = false;
+	ctx->out_ready = nullptr;
+	for (int i = 0; i < ASTC_MAX_BANDS; i++) {
+		ctx->band_ready[i] = nullptr;
+	}
 	ctx->d_ticket = nullptr;
 	ctx->d_records = nullptr;
 	ctx->d_records_bytes = 0;
@@ -391,8 +449,14 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	ctx->alpha_threshold = 0.0f;
 	ctx->stage_timing = 0;
 	ctx->d_image = nullptr;
+	ctx->d_image2 = nullptr;
 	ctx->d_out = nullptr;
-	ctx->d_image_bytes = ctx->d_out_bytes = 0;
+	ctx->d_image_bytes = ctx->d_image2_bytes = ctx->d_out_bytes = 0;
+	ctx->nccl_comm = nullptr;
+	ctx->rank = 0;
+	ctx->world = 1;
+	ctx->ev_g0 = ctx->ev_g1 = nullptr;
+	ctx->last_gather_ms = ctx->last_compress_ms = 0.0f;
 	ctx->state = 0;
 	ctx->result = ASTCENC_SUCCESS;
 	ctx->dstate = 0;
@@ -401,19 +465,38 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	ctx->launches = 0;
 	ctx->last_kernel_ms = 0.0f;
 	ctx->last_h2d = ctx->last_d2h = 0;
+	ctx->warps_per_cta = ctx->grid = 0;
+	ctx->max_waves = 0;
+	// environment knobs: read here, once
+	ctx->knobs.batch_blocks = (size_t)1 << 20;
+	if (const char* e = getenv("ASTCENC_B200_BATCH_BLOCKS")) {
+		long v = atol(e);
+		if (v > 0) ctx->knobs.batch_blocks = (size_t)v;
+	}
+	ctx->knobs.sync_mask = 0;      // measured: once every kernel runs one kind of work, the stage barriers no longer pay (110.7 -> 106.5 ms)
+	if (const char* e = getenv("ASTCENC_B200_SYNC_MASK")) {
+		ctx->knobs.sync_mask = (unsigned int)strtoul(e, nullptr, 0);
+	}
+	ctx->knobs.coherence_probe = getenv("ASTCENC_B200_COHERENCE_PROBE") ? 1 : 0;
+	ctx->knobs.stage_print = getenv("ASTCENC_B200_STAGE_PRINT") ? 1 : 0;
+	ctx->knobs.upload_bands = 4;
+	if (const char* e = getenv("ASTCENC_B200_UPLOAD_BANDS")) {
+		int v = atoi(e);
+		if (v >= 1 && v <= ASTC_MAX_BANDS) ctx->knobs.upload_bands = v;
+	}
+	// one exit for every failure: whatever was built so far is released by astcenc_context_free()
+	#define ALLOC_FAIL(code) do { astcenc_context_free(ctx); return (code); } while (0)
 	status = astc_host::validate_config(ctx->config);
 	if (status != ASTCENC_SUCCESS) {
-		delete ctx;
-		return status;
+		ALLOC_FAIL(status);
 	}
 	// The GPU is mandatory: no device, no context.
 	int device = 0;
-	CUDA_TRY(cudaGetDevice(&device), { delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+	CUDA_TRY(cudaGetDevice(&device), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
 	ctx->device = device;
 	status = ensure_const_tables(device);
 	if (status != ASTCENC_SUCCESS) {
-		delete ctx;
-		return status;
+		ALLOC_FAIL(status);
 	}
 	const astcenc_config& cfg = ctx->config;
 	if (has_parent) {
@@ -423,23 +506,24 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 		DeviceTables* t = new DeviceTables;
 		t->refcount = 1;
 		t->d_blob = nullptr;
+		t->host_tables = nullptr;
+		ctx->tables = t;
 		bool can_omit = (cfg.flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0;
 		t->host_tables = astc_host::build_block_size_tables(cfg.block_x, cfg.block_y, can_omit, cfg.tune_partition_count_limit,
 		                                                    static_cast<float>(cfg.tune_block_mode_limit) / 100.0f);
 		astc_host::PackedTables pk;
 		unsigned int lim[3] = {cfg.tune_2partition_index_limit, cfg.tune_3partition_index_limit, cfg.tune_4partition_index_limit};
 		astc_host::pack_device_tables(*t->host_tables, lim, pk);
-		CUDA_TRY(cudaMalloc(&t->d_blob, pk.blob.size()), { release_tables(t); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
-		CUDA_TRY(cudaMemcpy(t->d_blob, pk.blob.data(), pk.blob.size(), cudaMemcpyHostToDevice), { release_tables(t); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+		CUDA_TRY(cudaMalloc(&t->d_blob, pk.blob.size()), ALLOC_FAIL(ASTCENC_ERR_OUT_OF_MEM));
+		CUDA_TRY(cudaMemcpy(t->d_blob, pk.blob.data(), pk.blob.size(), cudaMemcpyHostToDevice), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
 		t->bsd = pk.bsd;
 		astc_host::relocate_bsd(t->bsd, t->d_blob);
-		ctx->tables = t;
 	}
 	astc_host::make_device_config(cfg, ctx->dcfg);
 
 	if (!(cfg.flags & ASTCENC_FLG_DECOMPRESS_ONLY)) {
 		cudaDeviceProp prop;
-		CUDA_TRY(cudaGetDeviceProperties(&prop, device), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+		CUDA_TRY(cudaGetDeviceProperties(&prop, device), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
 		// The per-warp arena lives in shared memory only: one CTA per SM with as many warps as fit (at most 16).
 		size_t smem_limit = prop.sharedMemPerBlockOptin;
 		size_t arena = ctx->tables->bsd.arena_bytes;
@@ -447,9 +531,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 		if (warps > ASTC_CTA_THREADS_MAX / 32) warps = ASTC_CTA_THREADS_MAX / 32;
 		if (warps < 1) {
 			// block sizes / presets whose working set exceeds one SM's shared memory are not supported by this build
-			release_tables(ctx->tables);
-			delete ctx;
-			return ASTCENC_ERR_NOT_IMPLEMENTED;
+			ALLOC_FAIL(ASTCENC_ERR_NOT_IMPLEMENTED);
 		}
 		ctx->warps_per_cta = warps;
 		ctx->grid = prop.multiProcessorCount;
@@ -469,8 +551,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			else if (!strcmp(e, "warp")) { ctx->driver = 1; ctx->lockstep = 0; }
 		}
 		ctx->smem_bytes = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + arena * ctx->warps_per_cta;
-		CUDA_TRY(cudaFuncSetAttribute(astc_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
-		         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+		CUDA_TRY(cudaFuncSetAttribute(astc_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
 		// wave pipeline: the setup kernel needs the full arena, refinement / preparation only up to the union scratch
 		{
 			size_t arena_small = ctx->tables->bsd.arena_bytes_small;
@@ -515,12 +596,9 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			ctx->smem_setup = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + ctx->setup_stage_bytes + arena * ws;
 			ctx->smem_small = ASTC_SMEM_HDR + arena_small * wr;
 			ctx->smem_refine = ASTC_SMEM_HDR + ctx->refine_stage_bytes + arena_small * wr + (size_t)ASTC_REFINE_STATE_BYTES * wr;
-			CUDA_TRY(cudaFuncSetAttribute(astc_wave_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
-			         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
-			CUDA_TRY(cudaFuncSetAttribute(astc_wave_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
-			         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
-			CUDA_TRY(cudaFuncSetAttribute(astc_wave_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit),
-			         { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+			CUDA_TRY(cudaFuncSetAttribute(astc_wave_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+			CUDA_TRY(cudaFuncSetAttribute(astc_wave_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+			CUDA_TRY(cudaFuncSetAttribute(astc_wave_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
 			// a block runs at most this many trials (compress_block: mode-0 + full 1-plane, 4 two-plane, then the partition candidates)
 			int waves = 2 + 4;
 			const unsigned int cl[3] = {cfg.tune_2partitioning_candidate_limit, cfg.tune_3partitioning_candidate_limit, cfg.tune_4partitioning_candidate_limit};
@@ -529,23 +607,42 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			}
 			if (waves > ASTC_MAX_WAVES - 1) waves = ASTC_MAX_WAVES - 1;
 			ctx->max_waves = waves;
-			CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(uint32_t) * 2 * ASTC_Q_KINDS * ASTC_MAX_WAVES), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
+			// count[kinds][waves], head[kinds][waves], then one image ticket per upload band
+			CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(uint32_t) * ASTC_COUNTER_WORDS), ALLOC_FAIL(ASTCENC_ERR_OUT_OF_MEM));
 		}
-		CUDA_TRY(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_OUT_OF_MEM; });
+		CUDA_TRY(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)), ALLOC_FAIL(ASTCENC_ERR_OUT_OF_MEM));
 	}
-	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
-	CUDA_TRY(cudaEventCreate(&ctx->ev0), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
-	CUDA_TRY(cudaEventCreate(&ctx->ev1), { release_tables(ctx->tables); delete ctx; return ASTCENC_ERR_BAD_CONTEXT; });
+	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+	CUDA_TRY(cudaEventCreate(&ctx->ev0), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+	CUDA_TRY(cudaEventCreate(&ctx->ev1), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+	CUDA_TRY(cudaEventCreate(&ctx->ev_g0), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+	CUDA_TRY(cudaEventCreate(&ctx->ev_g1), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+	CUDA_TRY(cudaEventCreateWithFlags(&ctx->scratch_done, cudaEventDisableTiming), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+	CUDA_TRY(cudaEventCreateWithFlags(&ctx->out_ready, cudaEventDisableTiming), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+	for (int i = 0; i < ASTC_MAX_BANDS; i++) {
+		CUDA_TRY(cudaEventCreateWithFlags(&ctx->band_ready[i], cudaEventDisableTiming), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+	}
+	#undef ALLOC_FAIL
 	*context = ctx;
 	return ASTCENC_SUCCESS;
 }
+
+static void comm_destroy(astcenc_context* ctx);
 
 void astcenc_context_free(astcenc_context* ctx) {
 	if (!ctx) {
 		return;
 	}
-	cudaSetDevice(ctx->device);
+	if (ctx->device < 0) {
+		// nothing on the device yet (astcenc_context_alloc failed before it picked one)
+		delete ctx;
+		return;
+	}
+	DeviceGuard guard(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+	comm_destroy(ctx);
 	cudaFree(ctx->d_ticket);
 	cudaFree(ctx->d_records);
 	cudaFree(ctx->d_queues);
@@ -555,10 +652,19 @@ void astcenc_context_free(astcenc_context* ctx) {
 		cudaEventDestroy(e);
 	}
 	cudaFree(ctx->d_image);
+	cudaFree(ctx->d_image2);
 	cudaFree(ctx->d_out);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	if (ctx->ev_g0) cudaEventDestroy(ctx->ev_g0);
+	if (ctx->ev_g1) cudaEventDestroy(ctx->ev_g1);
+	if (ctx->scratch_done) cudaEventDestroy(ctx->scratch_done);
+	if (ctx->out_ready) cudaEventDestroy(ctx->out_ready);
+	for (int i = 0; i < ASTC_MAX_BANDS; i++) {
+		if (ctx->band_ready[i]) cudaEventDestroy(ctx->band_ready[i]);
+	}
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	release_tables(ctx->tables);
 	delete ctx;
 }
@@ -587,23 +693,66 @@ static size_t block_count_axis(size_t dim, size_t blk) {
 	return n;
 }
 
+// Upload plan of the host-pointer path: the image (one 2D slice) is copied to the device in bands of block rows on the
+// context's copy stream; wave 0 of the pipeline - the only reader of the image - is launched band by band, each launch
+// waiting for its band only, so the copy of band k+1 runs under the set-up of band k.
+struct UploadPlan {
+	const uint8_t* host;         // first byte of the slice in host memory (pageable or pinned)
+	uint8_t* device;             // where the slice goes
+	size_t row_bytes;            // bytes per image row
+	int bands;                   // 1 .. ASTC_MAX_BANDS
+};
+
 static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
-                                  unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream);
+                                  unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream, const UploadPlan* up);
 
 // A slab of block rows is processed in batches of at most ~1 M blocks: the per-block search records (a few KB each)
 // are the only buffer that grows with the image, and the batches reuse them in stream order.
+// The context's scratch buffers serve one pass at a time. Calls may come from several host threads and on different
+// streams: launch_mtx serialises the enqueueing, and every pass starts by making its stream wait for the event that
+// closes the previous pass (a no-op when both ran on the same stream).
+static astcenc_error launch_slab_locked(astcenc_context* ctx, const void* d_pixels, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
+                                        unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream, const UploadPlan* up);
+
 static astcenc_error launch_slab(astcenc_context* ctx, const void* d_pixels, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
-                                 unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream) {
+                                 unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream, const UploadPlan* up = nullptr) {
+	std::lock_guard<std::mutex> lk(ctx->launch_mtx);
+	if (ctx->scratch_used) {
+		CUDA_TRY(cudaStreamWaitEvent(stream, ctx->scratch_done, 0), return ASTCENC_ERR_BAD_CONTEXT);
+	}
+	astcenc_error st = launch_slab_locked(ctx, d_pixels, data_type, dim_x, dim_y, swz, block_row0, block_rows, d_out, stream, up);
+	CUDA_TRY(cudaEventRecord(ctx->scratch_done, stream), return ASTCENC_ERR_BAD_CONTEXT);
+	ctx->scratch_used = true;
+	return st;
+}
+
+static astcenc_error upload_whole(astcenc_context* ctx, const UploadPlan& up, unsigned int dim_y, cudaStream_t stream) {
+	CUDA_TRY(cudaMemcpyAsync(up.device, up.host, up.row_bytes * dim_y, cudaMemcpyHostToDevice, ctx->copy_stream), return ASTCENC_ERR_BAD_CONTEXT);
+	CUDA_TRY(cudaEventRecord(ctx->band_ready[0], ctx->copy_stream), return ASTCENC_ERR_BAD_CONTEXT);
+	CUDA_TRY(cudaStreamWaitEvent(stream, ctx->band_ready[0], 0), return ASTCENC_ERR_BAD_CONTEXT);
+	return ASTCENC_SUCCESS;
+}
+
+static astcenc_error launch_slab_locked(astcenc_context* ctx, const void* d_pixels, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
+                                        unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream, const UploadPlan* up) {
 	const DevBsd& bsd = ctx->tables->bsd;
 	size_t blocks_x = (dim_x + bsd.dim_x - 1) / bsd.dim_x;
-	size_t batch_blocks = (size_t)1 << 20;
-	if (const char* e = getenv("ASTCENC_B200_BATCH_BLOCKS")) {
-		long v = atol(e);
-		if (v > 0) batch_blocks = (size_t)v;
-	}
-	size_t rows_per_batch = batch_blocks / (blocks_x ? blocks_x : 1);
+	size_t rows_per_batch = ctx->knobs.batch_blocks / (blocks_x ? blocks_x : 1);
 	if (rows_per_batch < 1) rows_per_batch = 1;
 	const unsigned int radius = ctx->config.a_scale_radius;
+	// banded uploads need the whole slab in one batch on the wave pipeline, and no pre-pass that reads the whole image first
+	bool banded = up != nullptr && up->bands > 1 && radius == 0 && ctx->driver == 0 && (size_t)block_rows <= rows_per_batch && block_rows >= (unsigned int)up->bands * 4;
+	if (up != nullptr && !banded) {
+		// the upload streams on the copy stream; it must not overtake a pass that still reads the image buffer
+		if (ctx->scratch_used) {
+			CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->scratch_done, 0), return ASTCENC_ERR_BAD_CONTEXT);
+		}
+		astcenc_error st = upload_whole(ctx, *up, dim_y, stream);
+		if (st != ASTCENC_SUCCESS) {
+			return st;
+		}
+		up = nullptr;
+	}
 	if (radius != 0) {
 		// alpha-scale pre-pass over the whole image (every slab needs the averages of its own texels only, but the
 		// box filter reaches across slab borders, so the pass always reads the full image)
@@ -646,7 +795,7 @@ static astcenc_error launch_slab(astcenc_context* ctx, const void* d_pixels, int
 	while (done < block_rows) {
 		unsigned int rows = block_rows - done;
 		if ((size_t)rows > rows_per_batch) rows = (unsigned int)rows_per_batch;
-		astcenc_error st = launch_batch(ctx, d_pixels, data_type, dim_x, dim_y, swz, block_row0 + done, rows, d_out + (size_t)done * blocks_x * 16, stream);
+		astcenc_error st = launch_batch(ctx, d_pixels, data_type, dim_x, dim_y, swz, block_row0 + done, rows, d_out + (size_t)done * blocks_x * 16, stream, banded ? up : nullptr);
 		if (st != ASTCENC_SUCCESS) {
 			return st;
 		}
@@ -656,7 +805,7 @@ static astcenc_error launch_slab(astcenc_context* ctx, const void* d_pixels, int
 }
 
 static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
-                                  unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream) {
+                                  unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream, const UploadPlan* up) {
 	const DevBsd& bsd = ctx->tables->bsd;
 	DevImage img;
 	img.data = d_pixels;
@@ -690,7 +839,7 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 			CUDA_TRY(cudaMalloc(&ctx->d_records, rec_bytes), return ASTCENC_ERR_OUT_OF_MEM);
 			ctx->d_records_bytes = rec_bytes;
 		}
-		CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, sizeof(uint32_t) * 2 * ASTC_Q_KINDS * ASTC_MAX_WAVES, stream), return ASTCENC_ERR_BAD_CONTEXT);
+		CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, sizeof(uint32_t) * ASTC_COUNTER_WORDS, stream), return ASTCENC_ERR_BAD_CONTEXT);
 		WaveArgs a;
 		a.records = ctx->d_records;
 		for (int k = 0; k < ASTC_Q_KINDS; k++) {
@@ -700,13 +849,13 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 		a.head = ctx->d_counters + ASTC_Q_KINDS * ASTC_MAX_WAVES;
 		a.total = (unsigned int)total;
 		a.blocks_x = img.blocks_x;
+		a.ticket = ctx->d_counters + 2 * ASTC_Q_KINDS * ASTC_MAX_WAVES;
+		a.first_block = 0;
+		a.band_blocks = (unsigned int)total;
 		a.stage_bytes = ctx->refine_stage_bytes;
 		a.refine_state_off = (uint32_t)(ASTC_SMEM_HDR + ctx->refine_stage_bytes + (size_t)bsd.arena_bytes_small * ctx->warps_small);
 		a.stage_bytes_setup = ctx->setup_stage_bytes;
-		a.sync_mask = 0;      // measured: once every kernel runs one kind of work, the stage barriers no longer pay (110.7 -> 106.5 ms)
-		if (const char* e = getenv("ASTCENC_B200_SYNC_MASK")) {
-			a.sync_mask = (unsigned int)strtoul(e, nullptr, 0);
-		}
+		a.sync_mask = ctx->knobs.sync_mask;
 		int grid = ctx->grid;
 		size_t ev_used = 0;
 		auto mark = [&](int kind) {
@@ -731,8 +880,44 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 		mark(-1);
 		for (int wave = 0; wave < ctx->max_waves; wave++) {
 			a.wave = wave;
-			astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
-			mark(0);
+			if (wave == 0 && up != nullptr) {
+				// bands of block rows, growing (1 : 3 : 4 : 8 ...) so that the first copy - the only one nothing hides - is short
+				static const unsigned int shares[ASTC_MAX_BANDS] = {1, 3, 4, 8, 8, 8, 8, 8};
+				unsigned int sum = 0;
+				for (int k = 0; k < up->bands; k++) sum += shares[k];
+				if (ctx->scratch_used) {
+					CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->scratch_done, 0), return ASTCENC_ERR_BAD_CONTEXT);
+				}
+				unsigned int row = 0, acc = 0;
+				for (int k = 0; k < up->bands; k++) {
+					acc += shares[k];
+					unsigned int row_end = k == up->bands - 1 ? block_rows : (unsigned int)((size_t)block_rows * acc / sum);
+					if (row_end <= row) {
+						continue;
+					}
+					// image rows of block rows [row, row_end) of this slab
+					size_t y0 = (size_t)(block_row0 + row) * bsd.dim_y;
+					size_t y1 = (size_t)(block_row0 + row_end) * bsd.dim_y;
+					if (y1 > dim_y) y1 = dim_y;
+					if (y1 > y0) {
+						CUDA_TRY(cudaMemcpyAsync(up->device + y0 * up->row_bytes, up->host + y0 * up->row_bytes, (y1 - y0) * up->row_bytes, cudaMemcpyHostToDevice, ctx->copy_stream),
+						         return ASTCENC_ERR_BAD_CONTEXT);
+					}
+					CUDA_TRY(cudaEventRecord(ctx->band_ready[k], ctx->copy_stream), return ASTCENC_ERR_BAD_CONTEXT);
+					CUDA_TRY(cudaStreamWaitEvent(stream, ctx->band_ready[k], 0), return ASTCENC_ERR_BAD_CONTEXT);
+					a.ticket = ctx->d_counters + 2 * ASTC_Q_KINDS * ASTC_MAX_WAVES + k;
+					a.first_block = row * img.blocks_x;
+					a.band_blocks = (row_end - row) * img.blocks_x;
+					astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
+					ctx->launches++;
+					row = row_end;
+				}
+				mark(0);
+				ctx->launches--;      // (the loop below counts one set-up launch per wave)
+			} else {
+				astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
+				mark(0);
+			}
 			astc_wave_refine_kernel<<<grid, ctx->warps_small * 32, ctx->smem_refine, stream>>>(bsd, ctx->dcfg, img, a);
 			mark(1);
 			// (statistics / partition search gain nothing from phase alignment: two half-size CTAs per SM wait less; measured 5.1 -> 4.4 ms)
@@ -757,33 +942,45 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 	if ((size_t)grid > needed) {
 		grid = (int)(needed ? needed : 1);
 	}
-	astc_compress_kernel<<<grid, ctx->warps_per_cta * 32, ctx->smem_bytes, stream>>>(bsd, ctx->dcfg, img, ctx->d_ticket, getenv("ASTCENC_B200_COHERENCE_PROBE") ? 1 : 0, ctx->lockstep);
+	astc_compress_kernel<<<grid, ctx->warps_per_cta * 32, ctx->smem_bytes, stream>>>(bsd, ctx->dcfg, img, ctx->d_ticket, ctx->knobs.coherence_probe, ctx->lockstep);
 	CUDA_TRY(cudaGetLastError(), return ASTCENC_ERR_BAD_CONTEXT);
 	ctx->launches++;
 	return ASTCENC_SUCCESS;
 }
 
+static astcenc_error ensure_buffer(uint8_t*& buf, size_t& have, size_t need) {
+	if (have < need) {
+		cudaFree(buf);
+		buf = nullptr;
+		have = 0;
+		CUDA_TRY(cudaMalloc(&buf, need), return ASTCENC_ERR_OUT_OF_MEM);
+		have = need;
+	}
+	return ASTCENC_SUCCESS;
+}
+
+// The host-pointer path (what the reference's callers use: astcenccli_toplevel.cpp:2195-2215 passes plain heap memory).
+// The image goes up in bands on the copy stream while wave 0 already works on the bands that arrived; the payload comes
+// back with one copy when the emit kernel is done. Works with pageable and with pinned host memory alike (with pageable
+// memory the driver stages each band through its own pinned buffers and the call blocks for the band's duration -
+// the kernels of the earlier bands are running meanwhile).
 static astcenc_error compress_image_gpu(astcenc_context* ctx, const astcenc_image& image, const astcenc_swizzle& swizzle, uint8_t* data_out) {
 	const DevBsd& bsd = ctx->tables->bsd;
-	CUDA_TRY(cudaSetDevice(ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
+	DeviceGuard guard(ctx->device);
+	if (!guard.ok) {
+		return ASTCENC_ERR_BAD_CONTEXT;
+	}
 	size_t bpt = image.data_type == ASTCENC_TYPE_U8 ? 4 : image.data_type == ASTCENC_TYPE_F16 ? 8 : 16;
 	size_t slice_bytes = (size_t)image.dim_x * image.dim_y * bpt;
 	size_t blocks_x = block_count_axis(image.dim_x, bsd.dim_x);
 	size_t blocks_y = block_count_axis(image.dim_y, bsd.dim_y);
 	size_t out_bytes = blocks_x * blocks_y * 16;
-	if (ctx->d_image_bytes < slice_bytes) {
-		cudaFree(ctx->d_image);
-		ctx->d_image = nullptr;
-		ctx->d_image_bytes = 0;
-		CUDA_TRY(cudaMalloc(&ctx->d_image, slice_bytes), return ASTCENC_ERR_OUT_OF_MEM);
-		ctx->d_image_bytes = slice_bytes;
+	astcenc_error st = ensure_buffer(ctx->d_image, ctx->d_image_bytes, slice_bytes);
+	if (st == ASTCENC_SUCCESS) {
+		st = ensure_buffer(ctx->d_out, ctx->d_out_bytes, out_bytes);
 	}
-	if (ctx->d_out_bytes < out_bytes) {
-		cudaFree(ctx->d_out);
-		ctx->d_out = nullptr;
-		ctx->d_out_bytes = 0;
-		CUDA_TRY(cudaMalloc(&ctx->d_out, out_bytes), return ASTCENC_ERR_OUT_OF_MEM);
-		ctx->d_out_bytes = out_bytes;
+	if (st != ASTCENC_SUCCESS) {
+		return st;
 	}
 	int swz[4] = {(int)swizzle.r, (int)swizzle.g, (int)swizzle.b, (int)swizzle.a};
 	ctx->last_h2d = ctx->last_d2h = 0;
@@ -794,9 +991,13 @@ static astcenc_error compress_image_gpu(astcenc_context* ctx, const astcenc_imag
 		if (ctx->cancel.load()) {
 			break;
 		}
-		CUDA_TRY(cudaMemcpyAsync(ctx->d_image, image.data[z], slice_bytes, cudaMemcpyHostToDevice, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		UploadPlan up;
+		up.host = static_cast<const uint8_t*>(image.data[z]);
+		up.device = ctx->d_image;
+		up.row_bytes = (size_t)image.dim_x * bpt;
+		up.bands = ctx->knobs.upload_bands;
 		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
-		astcenc_error st = launch_slab(ctx, ctx->d_image, (int)image.data_type, image.dim_x, image.dim_y, swz, 0, (unsigned int)blocks_y, ctx->d_out, ctx->stream);
+		st = launch_slab(ctx, ctx->d_image, (int)image.data_type, image.dim_x, image.dim_y, swz, 0, (unsigned int)blocks_y, ctx->d_out, ctx->stream, &up);
 		if (st != ASTCENC_SUCCESS) {
 			return st;
 		}
@@ -902,7 +1103,14 @@ static astcenc_error validate_decompression_swizzle(const astcenc_swizzle& s) { 
 
 static astcenc_error decompress_image_gpu(astcenc_context* ctx, const uint8_t* data, astcenc_image& image, const astcenc_swizzle& swizzle) {
 	const DevBsd& bsd = ctx->tables->bsd;
-	CUDA_TRY(cudaSetDevice(ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
+	DeviceGuard guard(ctx->device);
+	if (!guard.ok) {
+		return ASTCENC_ERR_BAD_CONTEXT;
+	}
+	std::lock_guard<std::mutex> launch_lock(ctx->launch_mtx);      // (shares d_image / d_out with the compression path)
+	if (ctx->scratch_used) {
+		CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->scratch_done, 0), return ASTCENC_ERR_BAD_CONTEXT);
+	}
 	size_t bpt = image.data_type == ASTCENC_TYPE_U8 ? 4 : image.data_type == ASTCENC_TYPE_F16 ? 8 : 16;
 	size_t slice_bytes = (size_t)image.dim_x * image.dim_y * bpt;
 	size_t blocks_x = block_count_axis(image.dim_x, bsd.dim_x);
@@ -1020,7 +1228,10 @@ astcenc_error astcenc_get_block_info(astcenc_context* ctx, const uint8_t data[16
 	info->block_y = ctx->config.block_y;
 	info->block_z = ctx->config.block_z;
 	info->texel_count = ctx->tables->bsd.texel_count;
-	CUDA_TRY(cudaSetDevice(ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
+	DeviceGuard guard(ctx->device);
+	if (!guard.ok) {
+		return ASTCENC_ERR_BAD_CONTEXT;
+	}
 	DevBlockInfo* d_info = nullptr;
 	CUDA_TRY(cudaMalloc(&d_info, sizeof(DevBlockInfo)), return ASTCENC_ERR_OUT_OF_MEM);
 	cudaMemsetAsync(d_info, 0, sizeof(DevBlockInfo), ctx->stream);
@@ -1093,7 +1304,10 @@ astcenc_error astcenc_b200_compute_error_metrics(astcenc_context* ctx, int compu
 	if (dim_x == 0 || dim_y == 0 || dim_z == 0) {
 		return ASTCENC_ERR_BAD_PARAM;
 	}
-	CUDA_TRY(cudaSetDevice(ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
+	DeviceGuard guard(ctx->device);
+	if (!guard.ok) {
+		return ASTCENC_ERR_BAD_CONTEXT;
+	}
 	static const size_t comp_bytes[3] = {1, 2, 4};
 	size_t slice1 = (size_t)img1->dim_x * img1->dim_y * 4 * comp_bytes[img1->data_type];
 	size_t slice2 = (size_t)img2->dim_x * img2->dim_y * 4 * comp_bytes[img2->data_type];
@@ -1234,7 +1448,10 @@ astcenc_error astcenc_b200_compress_device(astcenc_context* ctx, const void* d_p
 	if (block_rows == 0) {
 		return ASTCENC_SUCCESS;
 	}
-	CUDA_TRY(cudaSetDevice(ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
+	DeviceGuard guard(ctx->device);
+	if (!guard.ok) {
+		return ASTCENC_ERR_BAD_CONTEXT;
+	}
 	int swz[4] = {(int)swizzle->r, (int)swizzle->g, (int)swizzle->b, (int)swizzle->a};
 	cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
 	return launch_slab(ctx, d_pixels, (int)data_type, dim_x, dim_y, swz, block_row0, block_rows, d_out, s);
@@ -1244,7 +1461,8 @@ astcenc_error astcenc_b200_stage_timing(astcenc_context* ctx, int enable, float 
 	if (!ctx) {
 		return ASTCENC_ERR_BAD_PARAM;
 	}
-	cudaSetDevice(ctx->device);
+	DeviceGuard guard(ctx->device);
+	std::lock_guard<std::mutex> launch_lock(ctx->launch_mtx);
 	if (stage_ms && stage_launches && ctx->stage_timing && ctx->stage_kinds.size() > 1) {
 		// durations of the launches of the last astcenc_b200_compress_device() call, summed per kernel
 		cudaEventSynchronize(ctx->stage_events[ctx->stage_kinds.size() - 1]);
@@ -1256,7 +1474,7 @@ astcenc_error astcenc_b200_stage_timing(astcenc_context* ctx, int enable, float 
 			float ms = 0.0f;
 			cudaEventElapsedTime(&ms, ctx->stage_events[i - 1], ctx->stage_events[i]);
 			int k = ctx->stage_kinds[i];
-			if (getenv("ASTCENC_B200_STAGE_PRINT")) {
+			if (ctx->knobs.stage_print) {
 				fprintf(stderr, "launch %zu kind %d %.3f ms\n", i - 1, k, ms);
 			}
 			if (k >= 0 && k < 4) {
@@ -1268,6 +1486,12 @@ astcenc_error astcenc_b200_stage_timing(astcenc_context* ctx, int enable, float 
 	ctx->stage_timing = enable ? 1 : 0;
 	return ASTCENC_SUCCESS;
 }
+
+}  // extern "C"
+
+#include "astc_host_multi.inl"
+
+extern "C" {
 
 unsigned long long astcenc_b200_launch_count(astcenc_context* ctx) {
 	return ctx->launches;

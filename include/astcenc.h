@@ -181,13 +181,55 @@ ASTCENC_PUBLIC const char* astcenc_get_error_string(enum astcenc_error status);
 
 /* ---- B200 extensions ------------------------------------------------------------------------ */
 
+/* Behaviour notes for the ten reference entry points above, where the GPU implementation differs in timing (never in
+ * results) from the reference's thread pool:
+ *  - progress_callback is called once per 2D slice (at 100 % for a 2D image); the reference calls it per 16-block ticket
+ *    (astcenc_entry.cpp:937). astcenc_compress_cancel() takes effect between slices: a pipeline pass that is already
+ *    enqueued runs to its end (the reference stops handing out tickets, astcenc_internal_entry.h:219).
+ *  - Every entry point runs on the CUDA device that was current in astcenc_context_alloc() and restores the caller's
+ *    current device before it returns.
+ *  - A context owns ONE set of search scratch buffers: passes of the same context are serialised - on the host by a mutex,
+ *    on the device by an event chain - whatever streams they are enqueued on. Use one context per concurrent stream.
+ */
+
 /* Compress block rows [block_row0, block_row0 + block_rows) of an image that is ALREADY RESIDENT in device
  * memory (d_pixels: the whole dim_x * dim_y image), writing block_rows * blocks_x * 16 bytes to the device
  * buffer d_out. Enqueued on `cuda_stream` (a cudaStream_t passed as void*, 0 = the context's own stream);
- * returns without synchronising. Used for slab sharding across GPUs and by bench.py's device-resident timing. */
+ * returns without synchronising. Used for slab sharding across GPUs and by bench.py's device-resident timing.
+ * Calls on different streams of the same context are ordered one after the other (see above). */
 ASTCENC_PUBLIC enum astcenc_error astcenc_b200_compress_device(struct astcenc_context* context, const void* d_pixels, enum astcenc_type data_type,
                                                                unsigned int dim_x, unsigned int dim_y, const struct astcenc_swizzle* swizzle,
                                                                unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, void* cuda_stream);
+
+/**
+ * Multi-GPU sharding: one process per GPU, each with its own context; the only exchange is the gather of the compressed
+ * payload over NCCL (loaded at run time: "libnccl.so.2"; ASTCENC_ERR_NOT_IMPLEMENTED when it cannot be loaded).
+ * The reference has no counterpart - its unit of distribution is the block ticket of one process
+ * (astcenc_internal_entry.h:97-324); the payload layout the ranks agree on is astcenc_entry.cpp:1036.
+ *
+ * astcenc_b200_comm_unique_id   rank 0 makes the 128-byte rendezvous id; the caller ships it to the other ranks
+ * astcenc_b200_comm_init        collective: joins `world` ranks (world == 1: no communicator, the calls below run locally)
+ * astcenc_b200_slab_rows        the block rows [first, first + rows) rank `rank` of `world` owns for an image of height dim_y
+ * astcenc_b200_compress_image_sharded
+ *     collective, SLAB MODE: every rank passes the same 2D image (host pointer, only the rows of its own slab are read and
+ *     uploaded), compresses its slab, and the slabs are gathered into the root's device buffer (grouped ncclSend/ncclRecv)
+ *     and copied to data_out on the root (data_out is ignored elsewhere). Bytes are identical to astcenc_compress_image().
+ * astcenc_b200_compress_batch
+ *     collective, BATCH MODE: image i of `images` belongs to rank i % world (other entries are not touched on this rank and
+ *     may be NULL); all images share size and type. Each rank searches its images one after the other with the upload of
+ *     the next image overlapped (two device image buffers); payload i arrives in data_out[i] on the root.
+ * astcenc_b200_comm_last_timing device milliseconds of the last sharded call on this rank: search, and the gather alone
+ */
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_comm_unique_id(void* id_out, size_t id_bytes);
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_comm_init(struct astcenc_context* context, int rank, int world, const void* id, size_t id_bytes);
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_comm_free(struct astcenc_context* context);
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_slab_rows(struct astcenc_context* context, unsigned int dim_y, int rank, int world,
+                                                         unsigned int* first_block_row, unsigned int* block_rows);
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_compress_image_sharded(struct astcenc_context* context, struct astcenc_image* image,
+                                                                      const struct astcenc_swizzle* swizzle, uint8_t* data_out, size_t data_len, int root);
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_compress_batch(struct astcenc_context* context, struct astcenc_image* const* images, unsigned int image_count,
+                                                              const struct astcenc_swizzle* swizzle, uint8_t* const* data_out, size_t data_len_each, int root);
+ASTCENC_PUBLIC enum astcenc_error astcenc_b200_comm_last_timing(struct astcenc_context* context, float* compress_ms, float* gather_ms);
 
 /* Number of kernel launches issued by this context so far (bench.py reports it as gpu_launches). */
 ASTCENC_PUBLIC unsigned long long astcenc_b200_launch_count(struct astcenc_context* context);

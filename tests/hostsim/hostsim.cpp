@@ -132,6 +132,9 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 			a.head = counters.data() + ASTC_Q_KINDS * ASTC_MAX_WAVES;
 			a.total = total;
 			a.blocks_x = img.blocks_x;
+			a.ticket = &counter;
+			a.first_block = 0;
+			a.band_blocks = total;
 			a.sync_mask = 0xFF;
 			a.stage_bytes = 0;
 			a.refine_state_off = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + pk.bsd.arena_bytes + 32 * EMIT_SLICE + 16;
