@@ -193,6 +193,16 @@ ASTC_FN int wcount(bool p) { return __popc(__ballot_sync(0xffffffffu, p)); }
 // ---------------------------------------------------------------------------------------------
 // Per-warp context and arena
 // ---------------------------------------------------------------------------------------------
+struct WCtx;
+ASTC_FN uint32_t wbroadcast0(const WCtx& w, uint32_t v) {     // lane 0's value for everybody
+	(void)w;
+#if defined(ASTC_ONE_LANE)
+	return v;
+#else
+	return __shfl_sync(0xffffffffu, v, 0);
+#endif
+}
+
 struct BlkInfo {
 	f4 origin_texel, data_min, data_mean, data_max, channel_weight;
 	uint8_t grayscale, decode_unorm8, rgb_lns0, alpha_lns0;

@@ -80,35 +80,46 @@ struct Trial {
 
 ASTC_FN SPtr<uint16_t> partition_list_of(const WCtx& w) { return sptr<uint16_t>(w.base + A_STATE + (uint32_t)offsetof(BlkInfo, partition_list)); }
 
-ASTC_FN void block_search_begin(const WCtx& w, BlockSearch& s) {
-	const BlkInfo& bi = bi_of(w);
-	s.scb.block_type = SYM_BTYPE_ERROR;
-	s.scb.partition_count = 0;
-	s.scb.color_formats_matched = 0;
-	s.scb.plane2_component = -1;
-	s.scb.block_mode = 0;
-	s.scb.partition_index = 0;
-	s.scb.color_formats[0] = s.scb.color_formats[1] = s.scb.color_formats[2] = s.scb.color_formats[3] = 0;
-	s.scb.quant_mode = 0;
-	s.scb.errorval = ERROR_CALC_DEFAULT;
-	s.scb.constant_color[0] = s.scb.constant_color[1] = s.scb.constant_color[2] = s.scb.constant_color[3] = 0;
-	bool block_is_l = is_luminance(w);
-	float block_is_l_scale = block_is_l ? 1.0f / 1.5f : 1.0f;
-	bool block_is_la = is_luminancealpha(w);
-	float block_is_la_scale = block_is_la ? 1.0f / 1.05f : 1.0f;
-	float error_weight_sum = hadd_s(bi.channel_weight) * BSD.texel_count;
-	s.error_threshold = CFG.tune_db_limit * error_weight_sum * block_is_l_scale * block_is_la_scale;
-	s.errorval_overshoot = 1.0f / CFG.tune_mse_overshoot;
-	s.best_pc1 = ERROR_CALC_DEFAULT;
-	s.best_error_in_prev = ERROR_CALC_DEFAULT;
-	s.best_error_cur = ERROR_CALC_DEFAULT;
-	s.quant_limit = QUANT_32;
-	s.phase = 0;
-	s.idx = CFG.tune_search_mode0_enable >= 0.85f ? 0 : 1;
-	s.pc = 2;
-	s.actual_trials = 0;
-	s.phase_entered = false;
-	s.skip_two_plane = false;
+// THE SEARCH STATE (BlockSearch, Trial, Refine) EXISTS ONCE PER WARP, IN SHARED MEMORY (as per-lane automatic variables the
+// three structs were 32 copies per warp in local memory). The discipline that makes this independent of how the lanes of a
+// warp are scheduled: lanes READ the state into registers; a __syncwarp() separates the last read from the next write;
+// LANE 0 ALONE WRITES; a __syncwarp() publishes the write before anybody reads again. Scalar bookkeeping that only the
+// state itself needs (the decision tree) runs on lane 0 in place and its verdict is broadcast with a shuffle.
+#define ST_WRITE_BEGIN(w) wsync(); if ((w).lane == 0) {
+#define ST_WRITE_END(w) } wsync();
+
+ASTC_FN void block_search_begin(const WCtx& w, BlockSearch& s, unsigned int out_index) {
+	ST_WRITE_BEGIN(w)
+		const BlkInfo& bi = bi_of(w);
+		s.scb.block_type = SYM_BTYPE_ERROR;
+		s.scb.partition_count = 0;
+		s.scb.color_formats_matched = 0;
+		s.scb.plane2_component = -1;
+		s.scb.block_mode = 0;
+		s.scb.partition_index = 0;
+		s.scb.color_formats[0] = s.scb.color_formats[1] = s.scb.color_formats[2] = s.scb.color_formats[3] = 0;
+		s.scb.quant_mode = 0;
+		s.scb.errorval = ERROR_CALC_DEFAULT;
+		s.scb.constant_color[0] = s.scb.constant_color[1] = s.scb.constant_color[2] = s.scb.constant_color[3] = 0;
+		bool block_is_l = is_luminance(w);
+		float block_is_l_scale = block_is_l ? 1.0f / 1.5f : 1.0f;
+		bool block_is_la = is_luminancealpha(w);
+		float block_is_la_scale = block_is_la ? 1.0f / 1.05f : 1.0f;
+		float error_weight_sum = hadd_s(bi.channel_weight) * BSD.texel_count;
+		s.error_threshold = CFG.tune_db_limit * error_weight_sum * block_is_l_scale * block_is_la_scale;
+		s.errorval_overshoot = 1.0f / CFG.tune_mse_overshoot;
+		s.best_pc1 = ERROR_CALC_DEFAULT;
+		s.best_error_in_prev = ERROR_CALC_DEFAULT;
+		s.best_error_cur = ERROR_CALC_DEFAULT;
+		s.quant_limit = QUANT_32;
+		s.phase = 0;
+		s.idx = CFG.tune_search_mode0_enable >= 0.85f ? 0 : 1;
+		s.pc = 2;
+		s.actual_trials = 0;
+		s.phase_entered = false;
+		s.skip_two_plane = false;
+		s.out_index = out_index;
+	ST_WRITE_END(w)
 }
 
 // Pick the next trial of the block (compress_block :1236-1443 unrolled into a state machine).
@@ -206,17 +217,14 @@ ASTC_FN int block_search_advance_on(const WCtx& w, BlockSearch& s, Trial& t) {
 	}
 }
 
-// The stage kernels keep ONE BlockSearch / Trial per warp in shared memory and every lane runs this bookkeeping. The
-// counters are read-modify-write (idx++, pc++): each lane therefore works on a private copy taken before, and stored
-// after, a __syncwarp() - all lanes read the old state, all lanes write the same new state, no lane can see a
-// half-updated one whatever the lanes' relative timing.
-ASTC_FN int block_search_advance(const WCtx& w, BlockSearch& s_io, Trial& t_io) {
-	BlockSearch s = s_io;
-	Trial t = t_io;
+// The decision tree runs on lane 0, in place on the shared state; every lane gets the verdict.
+ASTC_FN int block_search_advance(const WCtx& w, BlockSearch& s, Trial& t) {
+	int next = 0;
 	wsync();
-	int next = block_search_advance_on(w, s, t);
-	s_io = s;
-	t_io = t;
+	if (w.lane == 0) {
+		next = block_search_advance_on(w, s, t);
+	}
+	next = (int)wbroadcast0(w, (uint32_t)next);
 	wsync();
 	return next;
 }
@@ -224,29 +232,33 @@ ASTC_FN int block_search_advance(const WCtx& w, BlockSearch& s_io, Trial& t_io) 
 // The work a phase needs before its first trial: block statistics (2 planes, :1283-1289) or the partition search
 // of the current partition count (:1341-1360).
 ASTC_COOP void block_search_prepare(WCtx w, BlockSearch& s) {
-	if (s.phase == 1) {
+	int phase = s.phase;
+	int pc = s.pc;
+	if (phase == 1) {
 		float lowest_correl = prepare_block_statistics(w);
-		s.skip_two_plane = lowest_correl > CFG.tune_2plane_early_out_limit_correlation;
-		s.phase_entered = true;
+		ST_WRITE_BEGIN(w)
+			s.skip_two_plane = lowest_correl > CFG.tune_2plane_early_out_limit_correlation;
+			s.phase_entered = true;
+		ST_WRITE_END(w)
 		return;
 	}
 	unsigned int partition_indices[8];
-	unsigned int requested_indices = CFG.tune_partition_index_limit[s.pc - 2];
-	unsigned int requested_trials = CFG.tune_partitioning_candidate_limit[s.pc - 2];
+	unsigned int requested_indices = CFG.tune_partition_index_limit[pc - 2];
+	unsigned int requested_trials = CFG.tune_partitioning_candidate_limit[pc - 2];
 	requested_trials = requested_trials < requested_indices ? requested_trials : requested_indices;
-	s.actual_trials = find_best_partition_candidates(w, (unsigned int)s.pc, requested_indices, partition_indices, requested_trials);
+	unsigned int actual_trials = find_best_partition_candidates(w, (unsigned int)pc, requested_indices, partition_indices, requested_trials);
 	SPtr<uint16_t> pl = partition_list_of(w);
-	if (w.lane == 0) {
+	ST_WRITE_BEGIN(w)
 		for (unsigned int k = 0; k < 8; k++) {
-			if (k < s.actual_trials) {
+			if (k < actual_trials) {
 				pl[(int)k] = (uint16_t)partition_indices[k];
 			}
 		}
-	}
-	wsync();
-	s.best_error_cur = ERROR_CALC_DEFAULT;
-	s.idx = 0;
-	s.phase_entered = true;
+		s.actual_trials = actual_trials;
+		s.best_error_cur = ERROR_CALC_DEFAULT;
+		s.idx = 0;
+		s.phase_entered = true;
+	ST_WRITE_END(w)
 }
 
 ASTC_COOP bool block_search_next(WCtx w, BlockSearch& s, Trial& t) {
@@ -295,22 +307,19 @@ ASTC_FN void block_search_after_trial_on(const WCtx& w, BlockSearch& s, const Tr
 		}
 	}
 }
-ASTC_FN void block_search_after_trial(const WCtx& w, BlockSearch& s_io, const Trial& t, float errorval) {
-	BlockSearch s = s_io;      // (private copy between two __syncwarp()s, see block_search_advance)
-	wsync();
-	block_search_after_trial_on(w, s, t, errorval);
-	s_io = s;
-	wsync();
+ASTC_FN void block_search_after_trial(const WCtx& w, BlockSearch& s, const Trial& t, float errorval) {
+	ST_WRITE_BEGIN(w)
+		block_search_after_trial_on(w, s, t, errorval);
+	ST_WRITE_END(w)
 }
 
 ASTC_FN void emit_block(const WCtx& w, BlockSearch& s) {
-	if (s.scb.block_type == SYM_BTYPE_ERROR) {
-		constant_color_u16(w, s.scb);
-	}
-	if (w.lane == 0) {
+	ST_WRITE_BEGIN(w)
+		if (s.scb.block_type == SYM_BTYPE_ERROR) {
+			constant_color_u16(w, s.scb);
+		}
 		symbolic_to_physical(w, s.scb, IMG.out + (size_t)s.out_index * 16);
-	}
-	wsync();
+	ST_WRITE_END(w)
 }
 
 // Constant-colour blocks never enter the search (compress_block :1176-1222). Returns true when the block was emitted.
@@ -373,10 +382,14 @@ ASTC_COOP void stage_decimate(WCtx w, const Trial& t) {
 // weight cut-offs (:430-432 / :791-798) and the block-mode range of the trial
 ASTC_FN void trial_cutoffs(const WCtx& w, Trial& t) {
 	SPtr<f4> ep = ep_of(w);
-	if (!t.dual) {
+	int dual = t.dual, only_always = t.only_always, plane2_component = t.plane2_component;
+	unsigned int partition_count = t.partition_count;
+	float cutoff1, cutoff2;
+	unsigned int start_mode, end_mode;
+	if (!dual) {
 		f4 min_ep = splat4(10.0f);
 		ASTC_NOUNROLL
-		for (unsigned int i = 0; i < t.partition_count; i++) {
+		for (unsigned int i = 0; i < partition_count; i++) {
 			f4 e0 = ep[EP_EI1_0 + (int)i];
 			f4 e1 = ep[EP_EI1_1 + (int)i];
 			min_ep.x = min_ep_cutoff(e0.x, e1.x, min_ep.x);
@@ -384,50 +397,61 @@ ASTC_FN void trial_cutoffs(const WCtx& w, Trial& t) {
 			min_ep.z = min_ep_cutoff(e0.z, e1.z, min_ep.z);
 			min_ep.w = min_ep_cutoff(e0.w, e1.w, min_ep.w);
 		}
-		t.cutoff1 = hmin_s(min_ep);
-		t.cutoff2 = t.cutoff1;
-		t.start_mode = 0;
-		t.end_mode = t.only_always ? BSD.block_mode_count_1plane_always : BSD.block_mode_count_1plane_selected;
+		cutoff1 = hmin_s(min_ep);
+		cutoff2 = cutoff1;
+		start_mode = 0;
+		end_mode = only_always ? BSD.block_mode_count_1plane_always : BSD.block_mode_count_1plane_selected;
 	} else {
 		f4 a0 = ep[EP_EI1_0], a1 = ep[EP_EI1_1], b0 = ep[EP_EI2_0], b1 = ep[EP_EI2_1];
 		f4 min_ep1 = mk4(min_ep_cutoff(a0.x, a1.x, 10.0f), min_ep_cutoff(a0.y, a1.y, 10.0f), min_ep_cutoff(a0.z, a1.z, 10.0f), min_ep_cutoff(a0.w, a1.w, 10.0f));
 		f4 min_ep2 = mk4(min_ep_cutoff(b0.x, b1.x, 10.0f), min_ep_cutoff(b0.y, b1.y, 10.0f), min_ep_cutoff(b0.z, b1.z, 10.0f), min_ep_cutoff(b0.w, b1.w, 10.0f));
 		f4 m1 = min_ep1;
-		set_lane(m1, t.plane2_component, ERROR_CALC_DEFAULT);
-		t.cutoff1 = hmin_s(m1);
+		set_lane(m1, plane2_component, ERROR_CALC_DEFAULT);
+		cutoff1 = hmin_s(m1);
 		f4 m2 = splat4(ERROR_CALC_DEFAULT);
-		set_lane(m2, t.plane2_component, lane(min_ep2, t.plane2_component));
-		t.cutoff2 = hmin_s(m2);
-		t.start_mode = BSD.block_mode_count_1plane_selected;
-		t.end_mode = BSD.block_mode_count_1plane_2plane_selected;
+		set_lane(m2, plane2_component, lane(min_ep2, plane2_component));
+		cutoff2 = hmin_s(m2);
+		start_mode = BSD.block_mode_count_1plane_selected;
+		end_mode = BSD.block_mode_count_1plane_2plane_selected;
 	}
+	ST_WRITE_BEGIN(w)
+		t.cutoff1 = cutoff1;
+		t.cutoff2 = cutoff2;
+		t.start_mode = start_mode;
+		t.end_mode = end_mode;
+	ST_WRITE_END(w)
 }
 
 ASTC_COOP void stage_formats(WCtx w, Trial& t) {
 	SPtr<f4> ep = ep_of(w);
+	unsigned int count;
 	if (!t.dual) {
 		PartView pi = part_view_packed(t.partition_count, t.packed);
-		t.candidate_count = compute_ideal_endpoint_formats(w, pi, EP_EI1_0, EP_EI1_1, 1, t.start_mode, t.end_mode);
+		count = compute_ideal_endpoint_formats(w, pi, EP_EI1_0, EP_EI1_1, 1, t.start_mode, t.end_mode);
 		ASTC_NOUNROLL
 		for (int k = w.lane; k < 4; k += ASTC_WARP) {
 			ep[EP_BASE_0 + k] = ep[EP_EI1_0 + k];
 			ep[EP_BASE_1 + k] = ep[EP_EI1_1 + k];
 		}
-		wsync();
 	} else {
 		// merge_endpoints :37-66
+		int plane2_component = t.plane2_component;
 		f4 a0 = ep[EP_EI1_0], a1 = ep[EP_EI1_1], b0 = ep[EP_EI2_0], b1 = ep[EP_EI2_1];
 		f4 epm0 = a0, epm1 = a1;
-		set_lane(epm0, t.plane2_component, lane(b0, t.plane2_component));
-		set_lane(epm1, t.plane2_component, lane(b1, t.plane2_component));
+		set_lane(epm0, plane2_component, lane(b0, plane2_component));
+		set_lane(epm1, plane2_component, lane(b1, plane2_component));
+		wsync();
 		if (w.lane == 0) {
 			ep[EP_BASE_0] = epm0;
 			ep[EP_BASE_1] = epm1;
 		}
 		wsync();
 		PartView pi = part_view_packed(1, 0);
-		t.candidate_count = compute_ideal_endpoint_formats(w, pi, EP_BASE_0, EP_BASE_1, 2, t.start_mode, t.end_mode);
+		count = compute_ideal_endpoint_formats(w, pi, EP_BASE_0, EP_BASE_1, 2, t.start_mode, t.end_mode);
 	}
+	ST_WRITE_BEGIN(w)
+		t.candidate_count = count;
+	ST_WRITE_END(w)
 }
 
 // Refinement state of the candidate a warp is working on (the loop nest of :504-699 / :886-1044 flattened into steps).
@@ -444,26 +468,40 @@ struct Refine {
 	bool from_candw;                // candidate weights were quantised by the setup kernel (A_CANDW) instead of being derived here
 };
 
+// a trial begins: no candidate refined yet
+ASTC_FN void refine_begin_trial(const WCtx& w, const Trial& t, Refine& r, const BlockSearch& s, bool from_candw) {
+	unsigned int candidate_count = t.candidate_count;
+	float scb_errorval = s.scb.errorval;
+	ST_WRITE_BEGIN(w)
+		r.i = 0;
+		r.l = 0;
+		r.running = candidate_count > 0;
+		r.in_step = false;
+		r.best_errorval_in_mode = ERROR_CALC_DEFAULT;
+		r.best_errorval_in_scb = scb_errorval;
+		r.adjustments = false;
+		r.from_candw = from_candw;
+	ST_WRITE_END(w)
+}
+
 // start candidate r.i (quantise its weights, reset the work endpoints): the part of the candidate loop before `for l`
 ASTC_COOP void refine_begin_candidate(WCtx w, const Trial& t, Refine& r) {
-	Candidate cd = cand_of(w)[(int)r.i];
+	unsigned int ci = r.i;
+	bool from_candw = r.from_candw;
+	Candidate cd = cand_of(w)[(int)ci];
 	const DevBlockMode* qw_bm = BSD.block_modes + cd.block_mode;
-	r.dmode = ASTC_LDG(&qw_bm->decimation_mode);
-	r.qmode = ASTC_LDG(&qw_bm->quant_mode);
-	r.mode_index = ASTC_LDG(&qw_bm->mode_index);
-	r.quant_level = cd.quant_level;
-	r.quant_level_mod = cd.quant_level_mod;
-	r.cd_formats = (uint32_t)cd.formats[0] | ((uint32_t)cd.formats[1] << 8) | ((uint32_t)cd.formats[2] << 16) | ((uint32_t)cd.formats[3] << 24);
-	if (r.from_candw) {
+	int dmode = ASTC_LDG(&qw_bm->decimation_mode);
+	int qmode = ASTC_LDG(&qw_bm->quant_mode);
+	uint16_t mode_index = ASTC_LDG(&qw_bm->mode_index);
+	if (from_candw) {
 		SPtr<uint32_t> ww = sptr<uint32_t>(work_weights_of(w).off);
-		SPtr<uint32_t> cw = sptr<uint32_t>(w.base + A_CANDW + r.i * 64u);
+		SPtr<uint32_t> cw = sptr<uint32_t>(w.base + A_CANDW + ci * 64u);
 		ASTC_NOUNROLL
 		for (int k = w.lane; k < 16; k += ASTC_WARP) {
 			ww[k] = cw[k];
 		}
-		wsync();
 	} else {
-		quantize_candidate_weights(w, r.dmode, r.qmode, t.dual ? 2 : 1, t.cutoff1, t.cutoff2);
+		quantize_candidate_weights(w, dmode, qmode, t.dual ? 2 : 1, t.cutoff1, t.cutoff2);
 	}
 	SPtr<f4> ep = ep_of(w);
 	ASTC_NOUNROLL
@@ -478,15 +516,26 @@ ASTC_COOP void refine_begin_candidate(WCtx w, const Trial& t, Refine& r) {
 	for (int k = w.lane; k < 8; k += ASTC_WARP) {
 		wc32[k] = 0;
 	}
-	wsync();
-	r.work.errorval = 0.0f;
-	r.work.color_formats[0] = r.work.color_formats[1] = r.work.color_formats[2] = r.work.color_formats[3] = 0;
-	r.work.constant_color[0] = r.work.constant_color[1] = r.work.constant_color[2] = r.work.constant_color[3] = 0;
+	ST_WRITE_BEGIN(w)
+		r.dmode = dmode;
+		r.qmode = qmode;
+		r.mode_index = mode_index;
+		r.quant_level = cd.quant_level;
+		r.quant_level_mod = cd.quant_level_mod;
+		r.cd_formats = (uint32_t)cd.formats[0] | ((uint32_t)cd.formats[1] << 8) | ((uint32_t)cd.formats[2] << 16) | ((uint32_t)cd.formats[3] << 24);
+		r.work.errorval = 0.0f;
+		r.work.color_formats[0] = r.work.color_formats[1] = r.work.color_formats[2] = r.work.color_formats[3] = 0;
+		r.work.constant_color[0] = r.work.constant_color[1] = r.work.constant_color[2] = r.work.constant_color[3] = 0;
+	ST_WRITE_END(w)
 }
 
 // step part 1: refit the endpoint colours
 ASTC_COOP void refine_recompute(WCtx w, const Trial& t, Refine& r) {
-	if (r.l == 0) {
+	bool first = r.l == 0;
+	ST_WRITE_BEGIN(w)
+		r.in_step = true;
+	ST_WRITE_END(w)
+	if (first) {
 		refine_begin_candidate(w, t, r);
 	}
 	if (t.dual) {
@@ -499,26 +548,26 @@ ASTC_COOP void refine_recompute(WCtx w, const Trial& t, Refine& r) {
 
 // step part 2: quantise the endpoints (with the matched-format retry of :560-601)
 ASTC_COOP void refine_pack(WCtx w, const Trial& t, Refine& r) {
-	ScbHdr& work = r.work;
+	uint32_t cd_formats = r.cd_formats;
+	int quant_level = r.quant_level, quant_level_mod = r.quant_level_mod;
+	uint16_t mode_index = r.mode_index;
+	int dual = t.dual;
+	unsigned int partition_count = dual ? 1u : t.partition_count;
+	unsigned int partition_index = dual ? 0u : t.partition_index;
+	int plane2_component = dual ? t.plane2_component : -1;
 	uint32_t formats;
-	if (t.dual) {
-		formats = pack_work_endpoints(w, 1, r.cd_formats, r.quant_level, work_colors_of(w).off);
+	int matched = 0;
+	if (dual) {
+		formats = pack_work_endpoints(w, 1, cd_formats, quant_level, work_colors_of(w).off);
 		formats &= 0xFF;
-		work.partition_count = 1;
-		work.partition_index = 0;
-		work.quant_mode = (uint8_t)r.quant_level;
-		work.color_formats_matched = 0;
-		work.plane2_component = static_cast<int8_t>(t.plane2_component);
 	} else {
-		unsigned int partition_count = t.partition_count;
-		formats = pack_work_endpoints(w, partition_count, r.cd_formats, r.quant_level, work_colors_of(w).off);
-		bool all_same = r.quant_level != r.quant_level_mod;
+		formats = pack_work_endpoints(w, partition_count, cd_formats, quant_level, work_colors_of(w).off);
+		bool all_same = quant_level != quant_level_mod;
 		for (unsigned int j = 1; j < 4; j++) {
 			if (j < partition_count) {
 				all_same = all_same && ((formats >> (8 * j)) & 0xFF) == (formats & 0xFF);
 			}
 		}
-		work.color_formats_matched = 0;
 		if (partition_count >= 2 && all_same) {
 			SPtr<uint32_t> wc32 = sptr<uint32_t>(work_colors_of(w).off);
 			SPtr<uint32_t> mc32 = sptr<uint32_t>(mod_colors_of(w).off);
@@ -528,7 +577,7 @@ ASTC_COOP void refine_pack(WCtx w, const Trial& t, Refine& r) {
 			}
 			wsync();
 			// (the reference stops packing at the first format mismatch; the later partitions' values are then unused)
-			uint32_t formats_mod = pack_work_endpoints(w, partition_count, r.cd_formats, r.quant_level_mod, mod_colors_of(w).off);
+			uint32_t formats_mod = pack_work_endpoints(w, partition_count, cd_formats, quant_level_mod, mod_colors_of(w).off);
 			bool all_same_mod = true;
 			for (unsigned int j = 1; j < 4; j++) {
 				if (j < partition_count) {
@@ -536,7 +585,7 @@ ASTC_COOP void refine_pack(WCtx w, const Trial& t, Refine& r) {
 				}
 			}
 			if (all_same_mod) {
-				work.color_formats_matched = 1;
+				matched = 1;
 				ASTC_NOUNROLL
 				for (int k = w.lane; k < 8; k += ASTC_WARP) {
 					wc32[k] = mc32[k];
@@ -545,17 +594,21 @@ ASTC_COOP void refine_pack(WCtx w, const Trial& t, Refine& r) {
 				wsync();
 			}
 		}
-		work.partition_count = static_cast<uint8_t>(partition_count);
-		work.partition_index = static_cast<uint16_t>(t.partition_index);
-		work.plane2_component = -1;
-		work.quant_mode = (uint8_t)(work.color_formats_matched ? r.quant_level_mod : r.quant_level);
 	}
-	set_formats(work, formats);
-	work.block_mode = r.mode_index;
-	work.block_type = SYM_BTYPE_NONCONST;
-	r.formats = formats;
+	ST_WRITE_BEGIN(w)
+		ScbHdr& work = r.work;
+		work.partition_count = static_cast<uint8_t>(partition_count);
+		work.partition_index = static_cast<uint16_t>(partition_index);
+		work.plane2_component = static_cast<int8_t>(plane2_component);
+		work.color_formats_matched = static_cast<uint8_t>(matched);
+		work.quant_mode = (uint8_t)(matched ? quant_level_mod : quant_level);
+		set_formats(work, formats);
+		work.block_mode = mode_index;
+		work.block_type = SYM_BTYPE_NONCONST;
+		r.formats = formats;
+	ST_WRITE_END(w)
 	// integer endpoints of the packed candidate, once per step: both scores and the realignment read them
-	unpack_work_endpoints(w, t.dual ? 1u : t.partition_count, formats, ends_off_of(w));
+	unpack_work_endpoints(w, partition_count, formats, ends_off_of(w));
 }
 
 ASTC_FN float refine_score(WCtx w, const Trial& t, const Refine& r) {
@@ -563,43 +616,66 @@ ASTC_FN float refine_score(WCtx w, const Trial& t, const Refine& r) {
 	return compute_symbolic_block_difference(w, t.partition_count, r.formats, t.plane2_component, pi, (unsigned int)r.dmode, t.dual != 0);
 }
 
-// advance to the next candidate / finish the trial
-ASTC_FN void refine_next_candidate(const Trial& t, Refine& r, bool stop_all) {
-	unsigned int i = r.i;      // (read - __syncwarp - write: r is shared by the lanes of the warp, see block_search_advance)
-	wsync();
-	i = stop_all ? t.candidate_count : i + 1;
-	r.in_step = false;
-	r.l = 0;
-	r.i = i;
-	if (i >= t.candidate_count) {
-		r.running = false;
+// What a score does to the candidate loop. The flags are computed by every lane from registers; the state changes
+// they imply are written by lane 0 in one go (refine_apply).
+enum { RF_KEEP = 0, RF_NEXT_CANDIDATE = 1, RF_STOP_ALL = 2, RF_NEXT_ITERATION = 3 };
+
+// advance to the next candidate / the next refinement iteration / finish the trial
+ASTC_FN void refine_apply(const WCtx& w, const Trial& t, Refine& r, BlockSearch& s, int action, bool error_block, float best_in_mode, bool new_best, float errorval) {
+	unsigned int i = r.i, l = r.l;
+	unsigned int candidate_count = t.candidate_count;
+	ST_WRITE_BEGIN(w)
+		if (error_block) {
+			r.work.block_type = SYM_BTYPE_ERROR;
+		}
+		r.best_errorval_in_mode = best_in_mode;
+		if (new_best) {
+			r.best_errorval_in_scb = errorval;
+			r.work.errorval = errorval;
+			s.scb = r.work;
+		}
+		if (action == RF_NEXT_CANDIDATE || action == RF_STOP_ALL) {
+			i = action == RF_STOP_ALL ? candidate_count : i + 1;
+			r.in_step = false;
+			r.l = 0;
+			r.i = i;
+			if (i >= candidate_count) {
+				r.running = false;
+			}
+		} else if (action == RF_NEXT_ITERATION) {
+			r.l = l + 1;
+			r.in_step = false;
+		}
+	ST_WRITE_END(w)
+	if (new_best) {
+		copy_work_to_best(w);
 	}
-	wsync();
 }
 
 // step part 3 (first iteration of a candidate only): score before realignment (:606-640)
 ASTC_FN void refine_first_score(WCtx w, const Trial& t, Refine& r, BlockSearch& s) {
 	float errorval = refine_score(w, t, r);
+	float best_in_mode = r.best_errorval_in_mode, best_in_scb = r.best_errorval_in_scb;
+	unsigned int l = r.l;
+	bool error_block = false;
 	if (errorval == -ERROR_CALC_DEFAULT) {
 		errorval = -errorval;
-		r.work.block_type = SYM_BTYPE_ERROR;
+		error_block = true;
 	}
-	r.best_errorval_in_mode = minf(errorval, r.best_errorval_in_mode);
-	unsigned int iters_remaining = CFG.tune_refinement_limit - r.l;
+	best_in_mode = minf(errorval, best_in_mode);
+	unsigned int iters_remaining = CFG.tune_refinement_limit - l;
 	float threshold = (0.045f * static_cast<float>(iters_remaining)) + 1.08f;
-	if (errorval > (threshold * r.best_errorval_in_scb)) {
-		refine_next_candidate(t, r, false);
-		return;
-	}
-	if (errorval < r.best_errorval_in_scb) {
-		r.best_errorval_in_scb = errorval;
-		r.work.errorval = errorval;
-		s.scb = r.work;
-		copy_work_to_best(w);
+	int action = RF_KEEP;
+	bool new_best = false;
+	if (errorval > (threshold * best_in_scb)) {
+		action = RF_NEXT_CANDIDATE;
+	} else if (errorval < best_in_scb) {
+		new_best = true;
 		if (errorval < t.tune_errorval_threshold) {
-			refine_next_candidate(t, r, true);
+			action = RF_STOP_ALL;
 		}
 	}
+	refine_apply(w, t, r, s, action, error_block, best_in_mode, new_best, errorval);
 }
 
 // step part 5: score after realignment and decide how to go on (:642-698)
@@ -608,41 +684,42 @@ ASTC_FN void refine_second_score(WCtx w, const Trial& t, Refine& r, BlockSearch&
 	if (r.work.block_type != SYM_BTYPE_ERROR) {
 		errorval = refine_score(w, t, r);
 	}
+	float best_in_mode = r.best_errorval_in_mode, best_in_scb = r.best_errorval_in_scb;
+	unsigned int l = r.l;
+	bool adjustments = r.adjustments;
+	bool error_block = false;
 	if (errorval == -ERROR_CALC_DEFAULT) {
 		errorval = -errorval;
-		r.work.block_type = SYM_BTYPE_ERROR;
+		error_block = true;
 	}
-	r.best_errorval_in_mode = minf(errorval, r.best_errorval_in_mode);
+	best_in_mode = minf(errorval, best_in_mode);
 	unsigned int refinement_limit = CFG.tune_refinement_limit;
-	unsigned int iters_remaining = refinement_limit - 1 - r.l;
+	unsigned int iters_remaining = refinement_limit - 1 - l;
 	float threshold = (0.045f * static_cast<float>(iters_remaining)) + 1.0f;
-	if (errorval > (threshold * r.best_errorval_in_scb)) {
-		refine_next_candidate(t, r, false);
-		return;
-	}
-	if (errorval < r.best_errorval_in_scb) {
-		r.best_errorval_in_scb = errorval;
-		r.work.errorval = errorval;
-		s.scb = r.work;
-		copy_work_to_best(w);
-		if (errorval < t.tune_errorval_threshold) {
-			refine_next_candidate(t, r, true);
-			return;
+	int action;
+	bool new_best = false;
+	if (errorval > (threshold * best_in_scb)) {
+		action = RF_NEXT_CANDIDATE;
+	} else {
+		new_best = errorval < best_in_scb;
+		if (new_best && errorval < t.tune_errorval_threshold) {
+			action = RF_STOP_ALL;
+		} else if (!adjustments || l + 1 >= refinement_limit) {
+			action = RF_NEXT_CANDIDATE;
+		} else {
+			action = RF_NEXT_ITERATION;
 		}
 	}
-	if (!r.adjustments) {
-		refine_next_candidate(t, r, false);
-		return;
-	}
-	unsigned int l = r.l;
-	wsync();
-	l++;
-	r.l = l;
-	r.in_step = false;
-	wsync();
-	if (l >= refinement_limit) {
-		refine_next_candidate(t, r, false);
-	}
+	refine_apply(w, t, r, s, action, error_block, best_in_mode, new_best, errorval);
+}
+
+// step part 4: realign the weights of the work candidate
+ASTC_FN void refine_realign(WCtx w, const Trial& t, Refine& r) {
+	PartView pi = part_view_packed(t.partition_count, t.packed);
+	bool adjustments = realign_weights(w, t.partition_count, r.formats, t.plane2_component, pi, r.qmode, t.dual != 0, (unsigned int)r.dmode);
+	ST_WRITE_BEGIN(w)
+		r.adjustments = adjustments;
+	ST_WRITE_END(w)
 }
 
 #if defined(ASTC_HOSTSIM) && defined(ASTC_TRIAL_STATS)
@@ -650,19 +727,22 @@ ASTC_FN void refine_second_score(WCtx w, const Trial& t, Refine& r, BlockSearch&
 static unsigned int g_trial_steps;
 #endif
 
-// The CTA main loop. Every warp of the CTA must call this (barriers inside).
-ASTC_COOP void compress_blocks_lockstep(WCtx w, BlockFeed feed) {
-	BlockSearch s;
-	Trial t;
-	Refine r;
+// The CTA main loop. Every warp of the CTA must call this (barriers inside). The search state lives in the warp's arena
+// slots (BlockSearch, Trial) and in the Refine slot the caller provides (shared memory, ASTC_REFINE_STATE_BYTES).
+ASTC_COOP void compress_blocks_lockstep(WCtx w, BlockFeed feed, uint32_t refine_state_off) {
+	BlockSearch& s = *reinterpret_cast<BlockSearch*>(astc_smem + w.base + A_SEARCH);
+	Trial& t = *reinterpret_cast<Trial*>(astc_smem + w.base + A_TRIAL);
+	Refine& r = *reinterpret_cast<Refine*>(astc_smem + refine_state_off);
 	bool has_block = false;
 	bool exhausted = false;
-	s.phase = 3;
-	t.candidate_count = 0;
-	t.dual = 0;
-	t.partition_count = 1;
-	t.packed = 0;
-	r.running = false;
+	ST_WRITE_BEGIN(w)
+		s.phase = 3;
+		t.candidate_count = 0;
+		t.dual = 0;
+		t.partition_count = 1;
+		t.packed = 0;
+		r.running = false;
+	ST_WRITE_END(w)
 	while (true) {
 		// ---- between rounds: finish / fetch blocks until this warp has a trial to run
 		bool active = false;
@@ -676,6 +756,7 @@ ASTC_COOP void compress_blocks_lockstep(WCtx w, BlockFeed feed) {
 				unsigned int by = b / feed.blocks_x;
 				unsigned int bx = b - by * feed.blocks_x;
 				if (IMG.alpha_avg != nullptr && !block_has_alpha(w, IMG.alpha_avg, IMG.alpha_threshold, bx * BSD.dim_x, (by + IMG.block_row0) * BSD.dim_y)) {
+					wsync();
 					if (w.lane == 0) {
 						BlkInfo& bi = bi_of(w);
 						bi.origin_texel = bi.data_min = bi.data_mean = bi.data_max = splat4(0.0f);
@@ -689,8 +770,7 @@ ASTC_COOP void compress_blocks_lockstep(WCtx w, BlockFeed feed) {
 				if (emit_if_constant(w, b)) {
 					continue;
 				}
-				block_search_begin(w, s);
-				s.out_index = b;
+				block_search_begin(w, s, b);
 				has_block = true;
 			}
 			if (block_search_next(w, s, t)) {
@@ -717,36 +797,29 @@ ASTC_COOP void compress_blocks_lockstep(WCtx w, BlockFeed feed) {
 		cta_sync();
 		if (active) stage_formats(w, t);
 		// ---- refinement steps
-		r.i = 0;
-		r.l = 0;
-		r.running = active && t.candidate_count > 0;
-		r.in_step = false;
-		r.best_errorval_in_mode = ERROR_CALC_DEFAULT;
-		r.best_errorval_in_scb = s.scb.errorval;
-		r.adjustments = false;
-		r.from_candw = false;
+		if (active) {
+			refine_begin_trial(w, t, r, s, false);
+		}
+		bool running = active && r.running;
 #if defined(ASTC_HOSTSIM) && defined(ASTC_TRIAL_STATS)
 		g_trial_steps = 0;
 #endif
-		while (cta_any(r.running)) {
-			if (r.running) {
-				r.in_step = true;
+		while (cta_any(running)) {
+			if (running) {
 #if defined(ASTC_HOSTSIM) && defined(ASTC_TRIAL_STATS)
 				g_trial_steps++;
 #endif
 				refine_recompute(w, t, r);
 			}
 			cta_sync();
-			if (r.running) refine_pack(w, t, r);
+			if (running) refine_pack(w, t, r);
 			cta_sync();
-			if (r.running && r.l == 0) refine_first_score(w, t, r, s);
+			if (running && r.l == 0) refine_first_score(w, t, r, s);
 			cta_sync();
-			if (r.running && r.in_step) {
-				PartView pi = part_view_packed(t.partition_count, t.packed);
-				r.adjustments = realign_weights(w, t.partition_count, r.formats, t.plane2_component, pi, r.qmode, t.dual != 0, (unsigned int)r.dmode);
-			}
+			if (running && r.running && r.in_step) refine_realign(w, t, r);
 			cta_sync();
-			if (r.running && r.in_step) refine_second_score(w, t, r, s);
+			if (running && r.running && r.in_step) refine_second_score(w, t, r, s);
+			running = running && r.running;
 		}
 #if defined(ASTC_HOSTSIM) && defined(ASTC_TRIAL_STATS)
 		if (active) {

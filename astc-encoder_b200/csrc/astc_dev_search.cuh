@@ -1291,160 +1291,8 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 			wb[t] = bilinear_infill(di, uqf, t);
 		}
 		wsync();
-		// Dense grids (every weight touches only a few texels) leave most lanes of the per-weight scheme idle and
-		// are dominated by its sequential overhead. Weights (x, y) and (x', y') only interact when they are grid
-		// neighbours, and the reference's index order lets (x, y) see exactly its neighbours (x-1, y), (x-1, y-1),
-		// (x, y-1), (x+1, y-1) updated - which is what the anti-diagonal order k = x + 2 y guarantees as well. So all
-		// weights of one k are processed at once, one per group of four lanes (one lane per channel), each group
-		// walking its weight's texels in order. Same decisions, about half the sequential steps.
-		const DevDecMode* dmp = BSD.dec_modes + d;
-		int gw = ASTC_LDG(&dmp->weight_x), gh = ASTC_LDG(&dmp->weight_y);
-		if (ASTC_LDG(&dmp->max_weight_texels) <= 6) {      // (limits of 9 / 12 / 16 measured the same: 86.1 ms each)
 #if ASTC_WARP == 1
-			const int groups = 1;
-#else
-			const int groups = 8;
-			int lc = w.lane & 3;
-			float ew_c = lane(ew, lc);
-#endif
-			ASTC_NOUNROLL
-			for (int k = 0; k <= (gw - 1) + 2 * (gh - 1); k++) {
-				int y0 = k > gw - 1 ? (k - (gw - 1) + 1) >> 1 : 0;
-				int y1 = (k >> 1) < gh - 1 ? (k >> 1) : gh - 1;
-				int n = y1 - y0 + 1;
-				ASTC_NOUNROLL
-				for (int j0 = 0; j0 < n; j0 += groups) {
-#if ASTC_WARP == 1
-					int j = j0;
-#else
-					int j = j0 + (w.lane >> 2);
-#endif
-					bool act = j < n;
-					int we = 0, off = 0, cnt = 0, uqw = 0;
-					float uqw_down = 0.0f, uqw_up = 0.0f, uqw_diff_down = 0.0f, uqw_diff_up = 0.0f;
-					if (act) {
-						int y = y0 + j;
-						we = y * gw + (k - 2 * y);
-						uint32_t pn = s_pn[we];
-						float uqw_base = uqf[we];
-						uqw = (int)uqw_base;
-						uqw_down = static_cast<float>(pn & 0xFF);
-						uqw_up = static_cast<float>((pn >> 8) & 0xFF);
-						uqw_diff_down = uqw_down - uqw_base;
-						uqw_diff_up = uqw_up - uqw_base;
-						off = s_wto[we];
-						cnt = s_wto[we + 1] - off;
-					}
-					float error_base, error_down, error_up;
-#if ASTC_WARP == 1
-					{
-						float acc[12];
-						for (int q = 0; q < 12; q++) acc[q] = 0.0f;
-						for (int te = 0; te < cnt; te++) {
-							uint32_t e = s_wtc[off + te];
-							int texel = (int)(e & 0xFF);
-							float tw_base = static_cast<float>(e >> 8) * (1.0f / 16.0f);
-							float weight_base = wb[texel];
-							float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
-							float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
-							int partition = s_pot[texel];
-							for (int c = 0; c < 4; c++) {
-								float color_offset = eo[partition * 4 + c];
-								float color = eb[partition * 4 + c] + color_offset * weight_base;
-								float orig = sptr<float>(b0.off + (uint32_t)c * cs)[texel];
-								float color_diff = color - orig;
-								float color_down_diff = color_diff + color_offset * weight_down;
-								float color_up_diff = color_diff + color_offset * weight_up;
-								acc[c] = acc[c] + color_diff * color_diff;
-								acc[4 + c] = acc[4 + c] + color_down_diff * color_down_diff;
-								acc[8 + c] = acc[8 + c] + color_up_diff * color_up_diff;
-							}
-						}
-						for (int q = 0; q < 12; q++) acc[q] = acc[q] * lane(ew, q & 3);
-						error_base = (acc[0] + acc[2]) + (acc[1] + acc[3]);
-						error_down = (acc[4] + acc[6]) + (acc[5] + acc[7]);
-						error_up = (acc[8] + acc[10]) + (acc[9] + acc[11]);
-					}
-#else
-					{
-						float sb = 0.0f, sd = 0.0f, su = 0.0f;
-						ASTC_NOUNROLL
-						for (int te = 0; te < cnt; te++) {
-							uint32_t e = s_wtc[off + te];
-							int texel = (int)(e & 0xFF);
-							float tw_base = static_cast<float>(e >> 8) * (1.0f / 16.0f);
-							float weight_base = wb[texel];
-							float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
-							float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
-							int pidx = s_pot[texel] * 4 + lc;
-							float color_offset = eo[pidx];
-							float color = eb[pidx] + color_offset * weight_base;
-							float orig = sptr<float>(b0.off + (uint32_t)lc * cs)[texel];
-							float color_diff = color - orig;
-							float color_down_diff = color_diff + color_offset * weight_down;
-							float color_up_diff = color_diff + color_offset * weight_up;
-							sb = sb + color_diff * color_diff;
-							sd = sd + color_down_diff * color_down_diff;
-							su = su + color_up_diff * color_up_diff;
-						}
-						float vb = sb * ew_c, vd = sd * ew_c, vu = su * ew_c;
-						vb = vb + __shfl_xor_sync(0xffffffffu, vb, 2);
-						vd = vd + __shfl_xor_sync(0xffffffffu, vd, 2);
-						vu = vu + __shfl_xor_sync(0xffffffffu, vu, 2);
-						error_base = vb + __shfl_xor_sync(0xffffffffu, vb, 1);
-						error_down = vd + __shfl_xor_sync(0xffffffffu, vd, 1);
-						error_up = vu + __shfl_xor_sync(0xffffffffu, vu, 1);
-					}
-#endif
-					float new_uqw = -1.0f;
-					if (act) {
-						if ((error_up < error_base) && (error_up < error_down) && (uqw < 64)) {
-							new_uqw = uqw_up;
-						} else if ((error_down < error_base) && (uqw > 0)) {
-							new_uqw = uqw_down;
-						}
-					}
-					bool changed = new_uqw >= 0.0f;
-#if ASTC_WARP == 1
-					if (changed) {
-						uqf[we] = new_uqw;
-						dec_weights_uquant[we] = static_cast<uint8_t>(new_uqw);
-						adjustments = true;
-						for (int te = 0; te < cnt; te++) {
-							int texel = (int)(s_wtc[off + te] & 0xFF);
-							wb[texel] = bilinear_infill(di, uqf, texel);
-						}
-					}
-#else
-					if (wany(changed)) {
-						adjustments = true;
-						if (changed && lc == 0) {
-							uqf[we] = new_uqw;
-							dec_weights_uquant[we] = static_cast<uint8_t>(new_uqw);
-						}
-						wsync();
-						if (changed) {
-							// the four lanes of the group share the texels whose infill moved
-							ASTC_NOUNROLL
-							for (int te = lc; te < cnt; te += 4) {
-								int texel = (int)(s_wtc[off + te] & 0xFF);
-								wb[texel] = bilinear_infill(di, uqf, texel);
-							}
-						}
-						wsync();
-					}
-#endif
-				}
-			}
-			continue;
-		}
-#if ASTC_WARP == 1
-		const int slot = 0;
-#else
-		int slot = w.lane >> 2;
-		int lc = w.lane & 3;
-		float ew_c = lane(ew, lc);
-#endif
+		// serial form (one simulated lane / the single-lane debug build): the reference's loop as it stands
 		ASTC_NOUNROLL
 		for (int we = 0; we < weight_count; we++) {
 			uint32_t pn = s_pn[we];
@@ -1456,84 +1304,33 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 			float uqw_diff_up = uqw_up - uqw_base;
 			int off = s_wto[we];
 			int cnt = s_wto[we + 1] - off;
-			float error_base, error_down, error_up;
-#if ASTC_WARP == 1
-			{
-				// serial form: 12 ordered channel sums, then the weighted (x + z) + (y + w) fold
-				float acc[12];
-				for (int k = 0; k < 12; k++) acc[k] = 0.0f;
-				for (int te = 0; te < cnt; te++) {
-					uint32_t e = s_wtc[off + te];
-					int texel = (int)(e & 0xFF);
-					float tw_base = static_cast<float>(e >> 8) * (1.0f / 16.0f);
-					float weight_base = wb[texel];
-					float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
-					float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
-					int partition = s_pot[texel];
-					for (int c = 0; c < 4; c++) {
-						float color_offset = eo[partition * 4 + c];
-						float color = eb[partition * 4 + c] + color_offset * weight_base;
-						float orig = sptr<float>(b0.off + (uint32_t)c * cs)[texel];
-						float color_diff = color - orig;
-						float color_down_diff = color_diff + color_offset * weight_down;
-						float color_up_diff = color_diff + color_offset * weight_up;
-						acc[c] = acc[c] + color_diff * color_diff;
-						acc[4 + c] = acc[4 + c] + color_down_diff * color_down_diff;
-						acc[8 + c] = acc[8 + c] + color_up_diff * color_up_diff;
-					}
+			// 12 ordered channel sums, then the weighted (x + z) + (y + w) fold
+			float acc[12];
+			for (int k = 0; k < 12; k++) acc[k] = 0.0f;
+			for (int te = 0; te < cnt; te++) {
+				uint32_t e = s_wtc[off + te];
+				int texel = (int)(e & 0xFF);
+				float tw_base = static_cast<float>(e >> 8) * (1.0f / 16.0f);
+				float weight_base = wb[texel];
+				float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
+				float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
+				int partition = s_pot[texel];
+				for (int c = 0; c < 4; c++) {
+					float color_offset = eo[partition * 4 + c];
+					float color = eb[partition * 4 + c] + color_offset * weight_base;
+					float orig = sptr<float>(b0.off + (uint32_t)c * cs)[texel];
+					float color_diff = color - orig;
+					float color_down_diff = color_diff + color_offset * weight_down;
+					float color_up_diff = color_diff + color_offset * weight_up;
+					acc[c] = acc[c] + color_diff * color_diff;
+					acc[4 + c] = acc[4 + c] + color_down_diff * color_down_diff;
+					acc[8 + c] = acc[8 + c] + color_up_diff * color_up_diff;
 				}
-				for (int k = 0; k < 12; k++) acc[k] = acc[k] * lane(ew, k & 3);
-				error_base = (acc[0] + acc[2]) + (acc[1] + acc[3]);
-				error_down = (acc[4] + acc[6]) + (acc[5] + acc[7]);
-				error_up = (acc[8] + acc[10]) + (acc[9] + acc[11]);
 			}
-			(void)slot;
-#else
-			{
-				// lane (slot, c): channel c of the slot-th texel of the current chunk of 8; every lane then gathers the
-				// chunk's terms of ITS channel in texel order, so all lanes of a channel hold the same ordered sums
-				float sb = 0.0f, sd = 0.0f, su = 0.0f;
-				ASTC_NOUNROLL
-				for (int te0 = 0; te0 < cnt; te0 += 8) {
-					int te = te0 + slot;
-					float xb = 0.0f, xd = 0.0f, xu = 0.0f;
-					if (te < cnt) {
-						uint32_t e = s_wtc[off + te];
-						int texel = (int)(e & 0xFF);
-						float tw_base = static_cast<float>(e >> 8) * (1.0f / 16.0f);
-						float weight_base = wb[texel];
-						float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
-						float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
-						int pidx = s_pot[texel] * 4 + lc;
-						float color_offset = eo[pidx];
-						float color = eb[pidx] + color_offset * weight_base;
-						float orig = sptr<float>(b0.off + (uint32_t)lc * cs)[texel];
-						float color_diff = color - orig;
-						float color_down_diff = color_diff + color_offset * weight_down;
-						float color_up_diff = color_diff + color_offset * weight_up;
-						xb = color_diff * color_diff;
-						xd = color_down_diff * color_down_diff;
-						xu = color_up_diff * color_up_diff;
-					}
-					int m = cnt - te0 < 8 ? cnt - te0 : 8;
-					ASTC_NOUNROLL
-					for (int k = 0; k < m; k++) {
-						int src = k * 4 + lc;
-						sb = sb + __shfl_sync(0xffffffffu, xb, src);
-						sd = sd + __shfl_sync(0xffffffffu, xd, src);
-						su = su + __shfl_sync(0xffffffffu, xu, src);
-					}
-				}
-				// dot with the channel weights: (x + z) + (y + w); fp addition commutes, so every lane gets the same bits
-				float vb = sb * ew_c, vd = sd * ew_c, vu = su * ew_c;
-				vb = vb + __shfl_xor_sync(0xffffffffu, vb, 2);
-				vd = vd + __shfl_xor_sync(0xffffffffu, vd, 2);
-				vu = vu + __shfl_xor_sync(0xffffffffu, vu, 2);
-				error_base = vb + __shfl_xor_sync(0xffffffffu, vb, 1);
-				error_down = vd + __shfl_xor_sync(0xffffffffu, vd, 1);
-				error_up = vu + __shfl_xor_sync(0xffffffffu, vu, 1);
-			}
-#endif
+			for (int k = 0; k < 12; k++) acc[k] = acc[k] * lane(ew, k & 3);
+			float error_base = (acc[0] + acc[2]) + (acc[1] + acc[3]);
+			float error_down = (acc[4] + acc[6]) + (acc[5] + acc[7]);
+			float error_up = (acc[8] + acc[10]) + (acc[9] + acc[11]);
 			float new_uqw = -1.0f;
 			if ((error_up < error_base) && (error_up < error_down) && (uqw < 64)) {
 				new_uqw = uqw_up;
@@ -1541,21 +1338,151 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 				new_uqw = uqw_down;
 			}
 			if (new_uqw >= 0.0f) {
-				if (w.lane == 0) {
-					uqf[we] = new_uqw;
-					dec_weights_uquant[we] = static_cast<uint8_t>(new_uqw);
-				}
+				uqf[we] = new_uqw;
+				dec_weights_uquant[we] = static_cast<uint8_t>(new_uqw);
 				adjustments = true;
-				wsync();
-				// the infill changed for this weight's texels only
-				ASTC_NOUNROLL
-				for (int te = w.lane; te < cnt; te += ASTC_WARP) {
+				for (int te = 0; te < cnt; te++) {
 					int texel = (int)(s_wtc[off + te] & 0xFF);
 					wb[texel] = bilinear_infill(di, uqf, texel);
 				}
-				wsync();
 			}
 		}
+#else
+		// The reference visits the weights in index order and a weight that moves changes the infill its grid neighbours see,
+		// so the loop is sequential - but only ~1 weight in 7 moves (measured: 13.5 % at 6x6 -medium). So: evaluate EVERY
+		// weight against the current state at once (group of four lanes = one weight, one lane per channel, each lane walking its
+		// weight's texels in order - eight weights per pass), then replay the reference's order over the outcomes: the first
+		// weight that wants to move moves; the only outcomes this can invalidate are those of its LATER grid neighbours
+		// (x+1, y), (x-1, y+1), (x, y+1), (x+1, y+1) - weights further away share no texel with it - so exactly those are
+		// evaluated again (four groups at once) before the scan goes on. Every weight is therefore decided on the state the
+		// sequential loop would show it: same decisions, a handful of sequential steps instead of weight_count.
+		const DevDecMode* dmp = BSD.dec_modes + d;
+		const int gw = ASTC_LDG(&dmp->weight_x);
+		const int grp = w.lane >> 2;
+		const int lc = w.lane & 3;
+		const float ew_c = lane(ew, lc);
+		SPtr<uint8_t> s_new = sptr<uint8_t>(rs.tile + 128 + 136 + 144 + 1152);   // [64] the value a weight wants to move to
+		// decision of weight `we` on the current state; all 32 lanes call it (shuffles inside), act = group has a weight
+		auto evaluate = [&](int we, bool act) -> int {
+			int off = 0, cnt = 0, uqw = 0;
+			float uqw_down = 0.0f, uqw_up = 0.0f, uqw_diff_down = 0.0f, uqw_diff_up = 0.0f;
+			if (act) {
+				uint32_t pn = s_pn[we];
+				float uqw_base = uqf[we];
+				uqw = (int)uqw_base;
+				uqw_down = static_cast<float>(pn & 0xFF);
+				uqw_up = static_cast<float>((pn >> 8) & 0xFF);
+				uqw_diff_down = uqw_down - uqw_base;
+				uqw_diff_up = uqw_up - uqw_base;
+				off = s_wto[we];
+				cnt = s_wto[we + 1] - off;
+			}
+			float sb = 0.0f, sd = 0.0f, su = 0.0f;
+			ASTC_NOUNROLL
+			for (int te = 0; te < cnt; te++) {
+				uint32_t e = s_wtc[off + te];
+				int texel = (int)(e & 0xFF);
+				float tw_base = static_cast<float>(e >> 8) * (1.0f / 16.0f);
+				float weight_base = wb[texel];
+				float weight_down = weight_base + uqw_diff_down * tw_base - weight_base;
+				float weight_up = weight_base + uqw_diff_up * tw_base - weight_base;
+				int pidx = s_pot[texel] * 4 + lc;
+				float color_offset = eo[pidx];
+				float color = eb[pidx] + color_offset * weight_base;
+				float orig = sptr<float>(b0.off + (uint32_t)lc * cs)[texel];
+				float color_diff = color - orig;
+				float color_down_diff = color_diff + color_offset * weight_down;
+				float color_up_diff = color_diff + color_offset * weight_up;
+				sb = sb + color_diff * color_diff;
+				sd = sd + color_down_diff * color_down_diff;
+				su = su + color_up_diff * color_up_diff;
+			}
+			// dot with the channel weights: (x + z) + (y + w); fp addition commutes, so the four lanes get the same bits
+			float vb = sb * ew_c, vd = sd * ew_c, vu = su * ew_c;
+			vb = vb + __shfl_xor_sync(0xffffffffu, vb, 2);
+			vd = vd + __shfl_xor_sync(0xffffffffu, vd, 2);
+			vu = vu + __shfl_xor_sync(0xffffffffu, vu, 2);
+			float error_base = vb + __shfl_xor_sync(0xffffffffu, vb, 1);
+			float error_down = vd + __shfl_xor_sync(0xffffffffu, vd, 1);
+			float error_up = vu + __shfl_xor_sync(0xffffffffu, vu, 1);
+			int nv = -1;
+			if (act) {
+				if ((error_up < error_base) && (error_up < error_down) && (uqw < 64)) {
+					nv = (int)uqw_up;
+				} else if ((error_down < error_base) && (uqw > 0)) {
+					nv = (int)uqw_down;
+				}
+			}
+			return nv;
+		};
+		// pass 1: everybody against the state at entry; pending = the weights that want to move (bit we of a 64-bit set)
+		uint32_t pend_lo = 0, pend_hi = 0;
+		ASTC_NOUNROLL
+		for (int we0 = 0; we0 < weight_count; we0 += 8) {
+			int we = we0 + grp;
+			bool act = we < weight_count;
+			int nv = evaluate(we, act);
+			if (act && lc == 0 && nv >= 0) {
+				s_new[we] = (uint8_t)nv;
+			}
+			uint32_t m = __ballot_sync(0xffffffffu, act && lc == 0 && nv >= 0);
+			// lane 4 g -> bit we0 + g
+			uint32_t bits = (m & 1u) | ((m >> 3) & 2u) | ((m >> 6) & 4u) | ((m >> 9) & 8u) | ((m >> 12) & 16u) | ((m >> 15) & 32u) | ((m >> 18) & 64u) | ((m >> 21) & 128u);
+			if (we0 < 32) pend_lo |= bits << we0;
+			else pend_hi |= bits << (we0 - 32);
+		}
+		wsync();
+		// pass 2: the reference's order over the outcomes
+		ASTC_NOUNROLL
+		while ((pend_lo | pend_hi) != 0) {
+			int f = pend_lo != 0 ? __ffs((int)pend_lo) - 1 : 32 + __ffs((int)pend_hi) - 1;
+			if (f < 32) pend_lo &= ~(1u << f);
+			else pend_hi &= ~(1u << (f - 32));
+			adjustments = true;
+			int off = s_wto[f];
+			int cnt = s_wto[f + 1] - off;
+			float nvf = static_cast<float>(s_new[f]);
+			wsync();                       // (everybody has read s_new[f] / the old state before lane 0 overwrites it)
+			if (w.lane == 0) {
+				uqf[f] = nvf;
+				dec_weights_uquant[f] = (uint8_t)s_new[f];
+			}
+			wsync();
+			// the infill changed for this weight's texels only
+			ASTC_NOUNROLL
+			for (int te = w.lane; te < cnt; te += ASTC_WARP) {
+				int texel = (int)(s_wtc[off + te] & 0xFF);
+				wb[texel] = bilinear_infill(di, uqf, texel);
+			}
+			wsync();
+			// later grid neighbours of f = (fx, fy): group 0 (fx+1, fy), 1 (fx-1, fy+1), 2 (fx, fy+1), 3 (fx+1, fy+1)
+			int fy = f / gw;
+			int fx = f - fy * gw;
+			int dx = grp == 1 ? -1 : (grp == 2 ? 0 : 1);
+			int dy = grp == 0 ? 0 : 1;
+			int nx = fx + dx;
+			int j = f + dy * gw + dx;
+			bool act = grp < 4 && nx >= 0 && nx < gw && j < weight_count;
+			int nv = evaluate(j, act);
+			if (act && lc == 0 && nv >= 0) {
+				s_new[j] = (uint8_t)nv;
+			}
+			uint32_t redo = __ballot_sync(0xffffffffu, act && lc == 0);
+			uint32_t want = __ballot_sync(0xffffffffu, act && lc == 0 && nv >= 0);
+			// every lane folds the four outcomes into its copy of the pending set (lane 4 g <-> neighbour g)
+			ASTC_NOUNROLL
+			for (int g = 0; g < 4; g++) {
+				if ((redo >> (4 * g)) & 1u) {
+					int gdx = g == 1 ? -1 : (g == 2 ? 0 : 1);
+					int jj = f + (g == 0 ? 0 : gw) + gdx;
+					uint32_t on = (want >> (4 * g)) & 1u;
+					if (jj < 32) pend_lo = (pend_lo & ~(1u << jj)) | (on << jj);
+					else pend_hi = (pend_hi & ~(1u << (jj - 32))) | (on << (jj - 32));
+				}
+			}
+			wsync();
+		}
+#endif
 	}
 	return wany(adjustments);
 }

@@ -54,16 +54,6 @@ ASTC_FN uint32_t q_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v);
 ASTC_FN uint32_t q_load(const uint32_t* p) { return __ldcg(p); }
 #endif
 
-ASTC_FN uint32_t wbroadcast0(const WCtx& w, uint32_t v) {
-#if defined(ASTC_ONE_LANE)
-	(void)w;
-	return v;
-#else
-	(void)w;
-	return __shfl_sync(0xffffffffu, v, 0);
-#endif
-}
-
 ASTC_FN bool q_pop(const WCtx& w, const WaveArgs& a, int kind, int wave, unsigned int& b) {
 	uint32_t i = 0;
 	if (w.lane == 0) {
@@ -123,22 +113,13 @@ ASTC_FN BlockSearch& search_of(const WCtx& w) { return *reinterpret_cast<BlockSe
 ASTC_FN Trial& trial_of(const WCtx& w) { return *reinterpret_cast<Trial*>(astc_smem + w.base + A_TRIAL); }
 static_assert(sizeof(BlockSearch) <= 128 && sizeof(Trial) <= 64, "search state must fit its arena slots");
 
-// park the search state in the arena and write the record
-ASTC_FN void record_save(const WCtx& w, const WaveArgs& a, unsigned int b, const BlockSearch& s, const Trial& t, bool with_texels = false) {
-	// (the refine kernel keeps s and t in their arena slots already)
-	if (w.lane == 0 && &s != &search_of(w)) {
-		search_of(w) = s;
-		trial_of(w) = t;
-	}
+// the search state already lives in its arena slots: saving / restoring a record moves it with the rest of the head
+ASTC_FN void record_save(const WCtx& w, const WaveArgs& a, unsigned int b, bool with_texels = false) {
 	wsync();
 	record_copy(w, a, b, true, with_texels);
 }
-ASTC_FN void record_restore(const WCtx& w, const WaveArgs& a, unsigned int b, BlockSearch& s, Trial& t) {
+ASTC_FN void record_restore(const WCtx& w, const WaveArgs& a, unsigned int b) {
 	record_copy(w, a, b, false);
-	if (&s != &search_of(w)) {
-		s = search_of(w);
-		t = trial_of(w);
-	}
 }
 
 ASTC_FN int trial_class(const Trial& t) {
@@ -146,35 +127,16 @@ ASTC_FN int trial_class(const Trial& t) {
 	return c < 0 ? 0 : (c >= ASTC_Q_CLASSES ? ASTC_Q_CLASSES - 1 : c);
 }
 
-// where a block goes after its state machine advanced (t: the trial it will run next, if any)
-ASTC_FN void route_block(const WCtx& w, const WaveArgs& a, unsigned int b, int next, const Trial& t) {
-	if (next == NEXT_TRIAL) {
-		q_push(w, a, Q_SETUP + trial_class(t), a.wave + 1, b);
-	} else if (next == NEXT_PREPARE) {
-		q_push(w, a, Q_PREPARE, a.wave, b);
-	} else {
-		q_push(w, a, Q_EMIT, 0, b);
-	}
-}
-
 // ---------------------------------------------------------------------------------------------
 // S: trial setup. Wave 0 reads the image (load_block, constant-colour blocks are emitted on the spot).
 // ---------------------------------------------------------------------------------------------
 ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
-	// one copy of the search state per warp, in the arena slots the record keeps it in (see wave_refine); the widened
-	// copy of the trial used by the shared set-up sits in the work / mod colour slots, which only refinement uses
-#if defined(ASTC_HOSTSIM_LANES32) && !defined(ASTC_HOSTSIM_SHARED_STATE)
-	// (the thread-per-lane simulation has no lockstep execution between collectives: private copies, see wave_refine)
-	BlockSearch s_private;
-	Trial t_private, tf_private;
-	BlockSearch& s = s_private;
-	Trial& t = t_private;
-	Trial& tf = tf_private;
-#else
+	// one copy of the search state per warp, in the arena slots the record keeps it in (discipline: astc_dev_lockstep.cuh,
+	// "THE SEARCH STATE ..."); the widened copy of the trial used by the shared set-up sits in the work / mod colour slots,
+	// which only refinement uses
 	BlockSearch& s = search_of(w);
 	Trial& t = trial_of(w);
 	Trial& tf = *reinterpret_cast<Trial*>(astc_smem + w.base + A_SCB + 160);
-#endif
 	BlockFeed feed;
 	feed.ticket = a.ticket;      // wave 0 has no queue: a ticket counter hands out the band's blocks
 	feed.total = a.band_blocks;
@@ -190,6 +152,7 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 				unsigned int bx = b - by * a.blocks_x;
 				if (IMG.alpha_avg != nullptr && !block_has_alpha(w, IMG.alpha_avg, IMG.alpha_threshold, bx * BSD.dim_x, (by + IMG.block_row0) * BSD.dim_y)) {
 					// alpha-scale RDO (astcenc_entry.cpp:1021-1030): the block is treated as all-zero
+					wsync();
 					if (w.lane == 0) {
 						BlkInfo& bi = bi_of(w);
 						bi.origin_texel = bi.data_min = bi.data_mean = bi.data_max = splat4(0.0f);
@@ -203,14 +166,13 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 				if (emit_if_constant(w, b)) {
 					continue;
 				}
-				block_search_begin(w, s);
-				s.out_index = b;
+				block_search_begin(w, s, b);
 				block_search_advance(w, s, t);       // phase 0 always yields a trial
 				active = true;
 				break;
 			}
 		} else if (q_pop_classes(w, a, Q_SETUP, a.wave, cls, b)) {
-			record_restore(w, a, b, s, t);
+			record_restore(w, a, b);
 			active = true;
 		}
 		// one CTA-wide vote per round: it doubles as the barrier that keeps the warps loosely phase-aligned
@@ -224,10 +186,12 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 		// One set-up over the full range therefore serves both; the second candidate list waits in A_CAND2.
 		bool shared = active && !t.dual && t.only_always && t.partition_count == 1;
 		if (active) {
-			tf = t;
-			if (shared) {
-				tf.only_always = 0;
-			}
+			ST_WRITE_BEGIN(w)
+				tf = t;
+				if (shared) {
+					tf.only_always = 0;
+				}
+			ST_WRITE_END(w)
 		}
 		if (active) stage_ideal(w, tf);
 		if (a.sync_mask & 1) cta_sync();
@@ -241,29 +205,37 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 		if (active) quantize_and_score_modes(w, tf.start_mode, tf.end_mode, tf.dual ? 2 : 1, tf.partition_count, tf.max_weight_quant, tf.cutoff1, tf.cutoff2);
 		if (a.sync_mask & 8) cta_sync();
 		if (active) {
-			t.cutoff1 = tf.cutoff1;
-			t.cutoff2 = tf.cutoff2;
-			t.start_mode = tf.start_mode;
-			t.end_mode = tf.end_mode;
-			t.candidate_count_next = 0;
+			unsigned int count = 0, count_next = 0;
 			if (shared) {
 				PartView pi = part_view_packed(1, 0);
 				SPtr<f4> ep = ep_of(w);
-				endpoint_formats_prepare(w, pi, EP_EI1_0, EP_EI1_1, 1, 0, tf.end_mode);
-				t.end_mode = BSD.block_mode_count_1plane_always;
-				t.candidate_count = endpoint_formats_select(w, 1, 1, 0, t.end_mode, w.base + A_CAND, true);
-				t.candidate_count_next = endpoint_formats_select(w, 1, 1, 0, tf.end_mode, w.base + A_CAND2, false);
+				unsigned int end_full = tf.end_mode;
+				endpoint_formats_prepare(w, pi, EP_EI1_0, EP_EI1_1, 1, 0, end_full);
+				count = endpoint_formats_select(w, 1, 1, 0, BSD.block_mode_count_1plane_always, w.base + A_CAND, true);
+				count_next = endpoint_formats_select(w, 1, 1, 0, end_full, w.base + A_CAND2, false);
 				ASTC_NOUNROLL
 				for (int k = w.lane; k < 4; k += ASTC_WARP) {
 					ep[EP_BASE_0 + k] = ep[EP_EI1_0 + k];
 					ep[EP_BASE_1 + k] = ep[EP_EI1_1 + k];
 				}
-				wsync();
-			} else {
+			}
+			ST_WRITE_BEGIN(w)
+				t.cutoff1 = tf.cutoff1;
+				t.cutoff2 = tf.cutoff2;
+				t.start_mode = tf.start_mode;
+				t.end_mode = shared ? BSD.block_mode_count_1plane_always : tf.end_mode;
+				t.candidate_count_next = count_next;
+				if (shared) {
+					t.candidate_count = count;
+				}
+			ST_WRITE_END(w)
+			if (!shared) {
 				stage_formats(w, t);
 			}
 			// the refinement kernel has no decimated ideal weights: quantise every candidate's weights now
 			SPtr<uint32_t> ww = sptr<uint32_t>(work_weights_of(w).off);
+			int nplanes = t.dual ? 2 : 1;
+			float cutoff1 = t.cutoff1, cutoff2 = t.cutoff2;
 			ASTC_NOUNROLL
 			for (int list = 0; list < 2; list++) {
 				unsigned int n = list == 0 ? t.candidate_count : t.candidate_count_next;
@@ -273,7 +245,7 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 				for (unsigned int i = 0; i < n; i++) {
 					Candidate cd = cl[(int)i];
 					const DevBlockMode* bm = BSD.block_modes + cd.block_mode;
-					quantize_candidate_weights(w, ASTC_LDG(&bm->decimation_mode), ASTC_LDG(&bm->quant_mode), t.dual ? 2 : 1, t.cutoff1, t.cutoff2);
+					quantize_candidate_weights(w, ASTC_LDG(&bm->decimation_mode), ASTC_LDG(&bm->quant_mode), nplanes, cutoff1, cutoff2);
 					ASTC_NOUNROLL
 					for (int k = w.lane; k < 16; k += ASTC_WARP) {
 						cw[(int)i * 16 + k] = ww[k];
@@ -281,8 +253,9 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 					wsync();
 				}
 			}
-			record_save(w, a, b, s, t, a.wave == 0);
-			q_push(w, a, Q_REFINE + trial_class(t), a.wave, b);
+			int klass = trial_class(t);
+			record_save(w, a, b, a.wave == 0);
+			q_push(w, a, Q_REFINE + klass, a.wave, b);
 		}
 	}
 }
@@ -294,8 +267,15 @@ ASTC_COOP void wave_finish_trial(WCtx w, const WaveArgs& a, unsigned int b, Bloc
 	unsigned int ready = t.candidate_count_next;
 	block_search_after_trial(w, s, t, errorval);
 	int next = block_search_advance(w, s, t);
-	t.candidate_count_next = 0;
-	if (ready != 0 && next == NEXT_TRIAL && s.phase == 0) {
+	bool straight = ready != 0 && next == NEXT_TRIAL && s.phase == 0;
+	ST_WRITE_BEGIN(w)
+		t.candidate_count_next = 0;
+		if (straight) {
+			t.candidate_count = ready;
+		}
+	ST_WRITE_END(w)
+	int klass = trial_class(t);
+	if (straight) {
 		// the set-up of the trial just finished already selected this trial's candidates: go straight to refinement
 		SPtr<uint32_t> dst = sptr<uint32_t>(w.base + A_CAND);
 		SPtr<uint32_t> src = sptr<uint32_t>(w.base + A_CAND2);
@@ -303,19 +283,23 @@ ASTC_COOP void wave_finish_trial(WCtx w, const WaveArgs& a, unsigned int b, Bloc
 		for (int k = w.lane; k < (64 + 512) / 4; k += ASTC_WARP) {
 			dst[k] = src[k];
 		}
-		wsync();
-		t.candidate_count = ready;
-		record_save(w, a, b, s, t);
-		q_push(w, a, Q_REFINE + trial_class(t), a.wave + 1, b);
+		record_save(w, a, b);
+		q_push(w, a, Q_REFINE + klass, a.wave + 1, b);
 		return;
 	}
-	record_save(w, a, b, s, t);
-	route_block(w, a, b, next, t);
+	record_save(w, a, b);
+	if (next == NEXT_TRIAL) {
+		q_push(w, a, Q_SETUP + klass, a.wave + 1, b);
+	} else if (next == NEXT_PREPARE) {
+		q_push(w, a, Q_PREPARE, a.wave, b);
+	} else {
+		q_push(w, a, Q_EMIT, 0, b);
+	}
 }
 
 #if defined(ASTC_STEP_STATS)
 // dev instrumentation (make libastcenc_b200_stats.so, tools/step_stats.py): cycles per refinement-step part by kind
-// of step, [class][part]; class = realign path (0 undecimated, 1 dense wavefront, 2 per-weight) + 3 for the first step
+// of step, [class][part]; class = realign path (0 undecimated, 1 dense, 2 sparse) + 3 for the first step
 // of a candidate; parts: recompute, pack, score1, realign, score2, block change, wait at the vote, number of steps
 __device__ unsigned long long g_step_stats[6][8];
 #define STAT_T(v) long long v = clock64()
@@ -323,40 +307,21 @@ __device__ unsigned long long g_step_stats[6][8];
 #define STAT_T(v)
 #endif
 
-// The search state (BlockSearch, Trial, Refine) is identical in every lane of the warp and every step function takes it by
-// reference - as automatic variables the three structs live in local memory, 32 copies per warp (~10 KB), far more than the
-// L1 left beside the arenas holds (ncu: L1 hit rate 39 %, long-scoreboard stalls on local loads). The refine kernel therefore
-// works on ONE copy per warp in shared memory: BlockSearch and Trial in their arena slots (where the record keeps them
-// anyway), Refine in a slot behind the arenas. Every lane stores the same values at the same (converged) instruction, so
-// the concurrent stores are benign; this leans on the warp executing the scalar bookkeeping between two __syncwarp()s in
-// lockstep, which the thread-per-lane host simulation does not provide - that build keeps private copies (building it with
-// -DASTC_HOSTSIM_SHARED_STATE shows the dependence: with arbitrary lane timing a lagging lane reads the next step's flags).
-// The read-modify-write counters do not lean on it (block_search_advance); compute-sanitizer's racecheck lists the
-// remaining accesses as warnings (profiles/r01_summary.md).
+// The refine kernel works on ONE copy of the search state per warp in shared memory: BlockSearch and Trial in their arena
+// slots (where the record keeps them anyway), Refine in a slot behind the arenas (as per-lane automatic variables the three
+// structs were ~10 KB of local memory per warp: ncu showed an L1 hit rate of 39 % and long-scoreboard stalls on local loads).
+// Reads and writes follow the lane-0-publishes discipline of astc_dev_lockstep.cuh, so the result does not depend on how
+// the lanes of a warp are scheduled (the thread-per-lane host simulation runs this very code).
 #define ASTC_REFINE_STATE_BYTES 128
 static_assert(sizeof(Refine) <= ASTC_REFINE_STATE_BYTES, "Refine must fit its shared-memory slot");
 
 ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
-#if defined(ASTC_HOSTSIM_LANES32) && !defined(ASTC_HOSTSIM_SHARED_STATE)
-	BlockSearch s_private;
-	Trial t_private;
-	Refine r_private;
-	BlockSearch& s = s_private;
-	Trial& t = t_private;
-	Refine& r = r_private;
-	(void)warp_index;
-#else
 	BlockSearch& s = search_of(w);
 	Trial& t = trial_of(w);
 	Refine& r = *reinterpret_cast<Refine*>(astc_smem + a.refine_state_off + warp_index * ASTC_REFINE_STATE_BYTES);
-#endif
 	bool has_item = false;
 	bool drained = false;
 	unsigned int b = 0;
-	r.running = false;
-	t.dual = 0;
-	t.partition_count = 1;
-	t.packed = 0;
 	unsigned int round = 0;
 	int cls = 0;
 	const unsigned int vote_mask = (1u << ((a.sync_mask >> 8) & 7)) - 1u;
@@ -370,15 +335,8 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 				drained = true;
 				break;
 			}
-			record_restore(w, a, b, s, t);
-			r.i = 0;
-			r.l = 0;
-			r.running = t.candidate_count > 0;
-			r.in_step = false;
-			r.best_errorval_in_mode = ERROR_CALC_DEFAULT;
-			r.best_errorval_in_scb = s.scb.errorval;
-			r.adjustments = false;
-			r.from_candw = true;
+			record_restore(w, a, b);
+			refine_begin_trial(w, t, r, s, true);
 			if (!r.running) {
 				wave_finish_trial(w, a, b, s, t, r.best_errorval_in_mode);
 				continue;
@@ -395,16 +353,13 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 		STAT_T(t0);
 #if defined(ASTC_STEP_STATS)
 		bool st_on = has_item;
-		int st_first = r.l == 0 ? 3 : 0;
+		int st_first = has_item && r.l == 0 ? 3 : 0;
 		if (st_on && w.lane == 0 && st_prev_class >= 0) {
 			atomicAdd(&g_step_stats[st_prev_class][5], (unsigned long long)(tv - st_prev_end));
 			atomicAdd(&g_step_stats[st_prev_class][6], (unsigned long long)(t0 - tv));
 		}
 #endif
-		if (has_item) {
-			r.in_step = true;
-			refine_recompute(w, t, r);
-		}
+		if (has_item) refine_recompute(w, t, r);
 		STAT_T(t1);
 		if (a.sync_mask & 16) cta_sync();
 		if (has_item) refine_pack(w, t, r);
@@ -413,10 +368,7 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 		if (has_item && r.l == 0) refine_first_score(w, t, r, s);
 		STAT_T(t3);
 		if (a.sync_mask & 64) cta_sync();
-		if (has_item && r.running && r.in_step) {
-			PartView pi = part_view_packed(t.partition_count, t.packed);
-			r.adjustments = realign_weights(w, t.partition_count, r.formats, t.plane2_component, pi, r.qmode, t.dual != 0, (unsigned int)r.dmode);
-		}
+		if (has_item && r.running && r.in_step) refine_realign(w, t, r);
 		STAT_T(t4);
 		if (a.sync_mask & 128) cta_sync();
 		if (has_item && r.running && r.in_step) refine_second_score(w, t, r, s);
@@ -448,15 +400,8 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 // P: block statistics / partition search.
 // ---------------------------------------------------------------------------------------------
 ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
-#if defined(ASTC_HOSTSIM_LANES32) && !defined(ASTC_HOSTSIM_SHARED_STATE)
-	BlockSearch s_private;
-	Trial t_private;
-	BlockSearch& s = s_private;
-	Trial& t = t_private;
-#else
 	BlockSearch& s = search_of(w);
 	Trial& t = trial_of(w);
-#endif
 	while (true) {
 		unsigned int b = 0;
 		bool active = q_pop(w, a, Q_PREPARE, a.wave, b);
@@ -464,14 +409,19 @@ ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
 			break;
 		}
 		if (active) {
-			record_restore(w, a, b, s, t);
+			record_restore(w, a, b);
 			int next;
 			do {
 				block_search_prepare(w, s);
 				next = block_search_advance(w, s, t);
 			} while (next == NEXT_PREPARE);
-			record_save(w, a, b, s, t);
-			route_block(w, a, b, next, t);
+			int klass = trial_class(t);
+			record_save(w, a, b);
+			if (next == NEXT_TRIAL) {
+				q_push(w, a, Q_SETUP + klass, a.wave + 1, b);
+			} else {
+				q_push(w, a, Q_EMIT, 0, b);
+			}
 		}
 	}
 }

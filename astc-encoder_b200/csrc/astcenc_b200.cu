@@ -217,7 +217,8 @@ astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__
 		feed.ticket = ticket;
 		feed.total = total;
 		feed.blocks_x = blocks_x;
-		compress_blocks_lockstep(w, feed);
+		// (the Refine slots sit behind the arenas: the host sizes the window for them)
+		compress_blocks_lockstep(w, feed, ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + (uint32_t)(blockDim.x >> 5) * bsd.arena_bytes + (uint32_t)warp * ASTC_REFINE_STATE_BYTES);
 		return;
 	}
 	while (true) {
@@ -527,7 +528,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 		// The per-warp arena lives in shared memory only: one CTA per SM with as many warps as fit (at most 16).
 		size_t smem_limit = prop.sharedMemPerBlockOptin;
 		size_t arena = ctx->tables->bsd.arena_bytes;
-		int warps = (int)((smem_limit - ASTC_SMEM_HDR - ASTC_SMEM_SINCOS_BYTES) / arena);
+		int warps = (int)((smem_limit - ASTC_SMEM_HDR - ASTC_SMEM_SINCOS_BYTES) / (arena + ASTC_REFINE_STATE_BYTES));
 		if (warps > ASTC_CTA_THREADS_MAX / 32) warps = ASTC_CTA_THREADS_MAX / 32;
 		if (warps < 1) {
 			// block sizes / presets whose working set exceeds one SM's shared memory are not supported by this build
@@ -550,7 +551,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			if (!strcmp(e, "lockstep")) { ctx->driver = 1; ctx->lockstep = 1; }
 			else if (!strcmp(e, "warp")) { ctx->driver = 1; ctx->lockstep = 0; }
 		}
-		ctx->smem_bytes = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + arena * ctx->warps_per_cta;
+		ctx->smem_bytes = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + (arena + ASTC_REFINE_STATE_BYTES) * ctx->warps_per_cta;
 		CUDA_TRY(cudaFuncSetAttribute(astc_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
 		// wave pipeline: the setup kernel needs the full arena, refinement / preparation only up to the union scratch
 		{

@@ -122,7 +122,7 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 			feed.ticket = &counter;
 			feed.total = img.blocks_x * img.block_rows;
 			feed.blocks_x = img.blocks_x;
-			compress_blocks_lockstep(w, feed);
+			compress_blocks_lockstep(w, feed, ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + pk.bsd.arena_bytes + 32 * EMIT_SLICE + 16);
 		} else {
 			// the wave pipeline, driven like the CUDA host code does (one simulated warp per "kernel")
 			WaveArgs a;

@@ -112,5 +112,6 @@ template <typename T> static inline unsigned int __match_any_sync(unsigned int, 
 	return m;
 }
 static inline int __popc(unsigned int v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 // (one simulated warp: the queue counters are only ever touched by lane 0 of that warp)
 static inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
