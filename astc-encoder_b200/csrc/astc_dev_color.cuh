@@ -607,28 +607,11 @@ ASTC_NOINLINE uint8_t pack_color_endpoints(f4 color0, f4 color1, f4 rgbs_color, 
 		quantize_rgbs(rgbs_color, output, q);
 		retval = FMT_RGB_SCALE;
 		break;
-	case FMT_HDR_RGB_SCALE:
-		quantize_hdr_rgbo(rgbo_color, output, q);
-		retval = FMT_HDR_RGB_SCALE;
-		break;
-	case FMT_HDR_RGB:
-		quantize_hdr_rgb(color0, color1, output, q);
-		retval = FMT_HDR_RGB;
-		break;
 	case FMT_RGB_SCALE_ALPHA:
 		output[4] = (uint8_t)quant_color_f(q, f2i_rtn(c0l.w), c0l.w);
 		output[5] = (uint8_t)quant_color_f(q, f2i_rtn(c1l.w), c1l.w);
 		quantize_rgbs(rgbs_color, output, q);
 		retval = FMT_RGB_SCALE_ALPHA;
-		break;
-	case FMT_HDR_LUMINANCE_SMALL_RANGE:
-	case FMT_HDR_LUMINANCE_LARGE_RANGE:
-		if (try_quantize_hdr_luminance_small_range(color0, color1, output, q)) {
-			retval = FMT_HDR_LUMINANCE_SMALL_RANGE;
-			break;
-		}
-		quantize_hdr_luminance_large_range(color0, color1, output, q);
-		retval = FMT_HDR_LUMINANCE_LARGE_RANGE;
 		break;
 	case FMT_LUMINANCE:
 		quantize_luminance(c0l, c1l, output, q);
@@ -644,15 +627,43 @@ ASTC_NOINLINE uint8_t pack_color_endpoints(f4 color0, f4 color1, f4 rgbs_color, 
 		quantize_luminance_alpha(c0l, c1l, output, q);
 		retval = FMT_LUMINANCE_ALPHA;
 		break;
-	case FMT_HDR_RGB_LDR_ALPHA:
-		quantize_hdr_rgb_ldr_alpha(color0, color1, output, q);
-		retval = FMT_HDR_RGB_LDR_ALPHA;
-		break;
-	case FMT_HDR_RGBA:
-		quantize_hdr_rgb_alpha(color0, color1, output, q);
-		retval = FMT_HDR_RGBA;
-		break;
 	}
 	return retval;
 }
 
+// The HDR formats (2, 3, 7, 11, 14, 15) are packed by the whole warp: their sub-mode ladders run lane-parallel
+// (astc_dev_color_hdr_pack.cuh). Every lane passes the same arguments; `output` is shared memory (the winning lane of each
+// ladder stores the bytes, the caller synchronises); returns the format used.
+ASTC_FN bool is_hdr_format(int format) { return ((0xC88Cu >> format) & 1u) != 0; }
+
+ASTC_NOINLINE uint8_t pack_hdr_endpoints(int lane, f4 color0, f4 color1, f4 rgbo_color, int format, uint8_t* output, int quant_level) {
+	QuantCtx q;
+	q.tab = STAGED.cq_smem_off != 0 ? astc_smem + STAGED.cq_smem_off + 512 * (quant_level - QUANT_6)
+	                                : ASTC_CT->color_unquant_to_uquant[quant_level - QUANT_6];
+	q.quant_level = quant_level;
+	color0 = vclamp4(0.0f, 65535.0f, color0);
+	color1 = vclamp4(0.0f, 65535.0f, color1);
+	switch (format) {
+	case FMT_HDR_RGB_SCALE:
+		quantize_hdr_rgbo(lane, rgbo_color, output, q);
+		return FMT_HDR_RGB_SCALE;
+	case FMT_HDR_RGB:
+		quantize_hdr_rgb(lane, color0, color1, output, q);
+		return FMT_HDR_RGB;
+	case FMT_HDR_RGB_LDR_ALPHA:
+		if (lane == 0) {      // (:1791-1817: LDR alpha beside the HDR colour)
+			float a0 = clampf(color0.w * (1.0f / 257.0f), 0.0f, 255.0f);
+			float a1 = clampf(color1.w * (1.0f / 257.0f), 0.0f, 255.0f);
+			output[6] = (uint8_t)quant_color_f(q, f2i_rtn(a0), a0);
+			output[7] = (uint8_t)quant_color_f(q, f2i_rtn(a1), a1);
+		}
+		quantize_hdr_rgb(lane, color0, color1, output, q);
+		return FMT_HDR_RGB_LDR_ALPHA;
+	case FMT_HDR_RGBA:
+		quantize_hdr_rgb(lane, color0, color1, output, q);
+		quantize_hdr_alpha(lane, color0.w, color1.w, output + 6, q);
+		return FMT_HDR_RGBA;
+	default:      // FMT_HDR_LUMINANCE_SMALL_RANGE / _LARGE_RANGE: the small range form when it fits
+		return (uint8_t)quantize_hdr_luminance(lane, color0, color1, output, q);
+	}
+}

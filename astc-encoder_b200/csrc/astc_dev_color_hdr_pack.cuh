@@ -1,476 +1,414 @@
-// HDR endpoint quantisers (astcenc_color_quantize.cpp:856-1906). Included by astc_dev_color.cuh.
+// HDR endpoint quantisers, lane-parallel (what astcenc_color_quantize.cpp:856-1906 computes). Included by astc_dev_color.cuh.
+//
+// The HDR endpoint formats are "try sub-mode after sub-mode until one can represent the value" ladders: 5 sub-modes + a
+// flat fallback for RGB+offset (format 7), 8 + fallback for RGB (format 11), 3 + fallback for the alpha pair, 2 + the large
+// range form for luminance. The sub-modes are independent of each other, only their PRIORITY matters. So the warp tries
+// them all at once - attempt k on lane k, every lane running the same code on per-mode parameters it unpacks from small
+// packed tables (shift amounts, field widths, and a routing table that says which bit of which intermediate goes into
+// which spare bit of the output bytes) - and the attempt with the highest priority that succeeded
+// (__ffs(__ballot_sync(ok))) stores its bytes. Cost = one attempt instead of up to nine in a row on a single lane.
+//
+// Every attempt is the arithmetic the format defines (scale by 2^-k, round to nearest, keep the top bits through the
+// quantiser) in the order the reference evaluates it - the results are the reference's bytes; only who computes what differs.
 
-ASTC_NOINLINE uint8_t quant_retain_top_bits(QuantCtx q, uint8_t value, int topmask) {   // :856-919
-	int perform_loop;
-	uint8_t quantval;
-	do {
-		quantval = (uint8_t)quant_color(q, value);
-		perform_loop = (value & topmask) != (quantval & topmask);
-		if ((quantval & topmask) > (value & topmask)) {
-			value--;
-		} else if ((quantval & topmask) < (value & topmask)) {
-			value--;
-		}
-	} while (perform_loop);
-	return quantval;
+// result of one attempt: up to 8 output bytes (little endian in two words) and whether the sub-mode could hold the value
+struct HdrTry {
+	uint32_t lo, hi;
+	bool ok;
+};
+ASTC_FN uint32_t hdr_b4(int a, int b, int c, int d) { return (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)(d & 0xFF) << 24); }
+
+// lowest lane whose attempt succeeded (-1: none); one-lane builds pass their single attempt through
+ASTC_FN int hdr_first_ok(bool ok, int lane) {
+#if defined(ASTC_ONE_LANE)
+	return ok ? lane : -1;
+#else
+	(void)lane;
+	unsigned int m = __ballot_sync(0xffffffffu, ok);
+	return m ? __ffs((int)m) - 1 : -1;
+#endif
 }
 
-ASTC_NOINLINE void quantize_hdr_rgbo(f4 color, uint8_t output[4], QuantCtx q) {   // :925-1250
+// Run attempts 0..n-1 (priority order) over the lanes, store the bytes of the first that succeeds; the last one never fails.
+template <typename TryFn>
+ASTC_FN void hdr_try_all(int lane, int n, int nbytes, uint8_t* output, TryFn attempt) {
+	int base = 0;
+	ASTC_NOUNROLL
+	while (base < n) {
+		int k = base + lane;
+		HdrTry t;
+		t.lo = t.hi = 0;
+		t.ok = false;
+		if (k < n) {
+			t = attempt(k);
+		}
+		int win = hdr_first_ok(t.ok, lane);
+		if (win >= 0) {
+			if (lane == win) {
+				for (int i = 0; i < nbytes; i++) {
+					output[i] = (uint8_t)((i < 4 ? t.lo >> (8 * i) : t.hi >> (8 * (i - 4))) & 0xFF);
+				}
+			}
+			return;
+		}
+		base += ASTC_WARP;
+	}
+}
+
+// quantise `value` so that the bits in `topmask` survive the round trip: step the input down until they do (:856-919)
+ASTC_NOINLINE uint8_t quant_retain_top_bits(QuantCtx q, uint8_t value, int topmask) {
+	while (true) {
+		uint8_t quantval = (uint8_t)quant_color(q, value);
+		if (((value ^ quantval) & topmask) == 0) {
+			return quantval;
+		}
+		value--;
+	}
+}
+
+// one routed bit: descriptor = (source index << 4) | bit position, sources in src[]
+ASTC_FN int hdr_route(uint32_t desc, const int src[4]) {
+	return (src[(desc >> 4) & 3] >> (desc & 15)) & 1;
+}
+#define HDR_NIB(word, k) ((int)(((word) >> (4 * (k))) & 0xF))
+
+// ---- format 7: RGB + offset ("RGBO") --------------------------------------------------------------------------------
+// Sub-mode m = 0..4: the major component is kept with 9..11 bits, the two others as differences to it, the offset with
+// 5..8 bits, all scaled by 2^-sh. Per-mode parameters (nibble m of each word):
+//   sh       scale shift                     5 5 6 7 8
+//   gb_bits  width of the difference fields  5 6 5 6 7
+//   s_bits   width of the offset field       7 5 8 7 6
+//   cut0/1   value ranges: differences <= 1 << cut0, offset <= 1 << cut1
+// Routing (source 0 = major, 1 / 2 = differences, 3 = offset; entry k = spare bit k): which bit the sub-mode parks where.
+ASTC_FN HdrTry hdr_rgbo_attempt(int m, f4 color, f4 color_bak, int majcomp, QuantCtx q) {
+	HdrTry out;
+	out.lo = out.hi = 0;
+	out.ok = false;
+	if (m == 5) {
+		// flat form: 7 bits per component at 1/512 (:1221-1250)
+		float v0 = clampf(color_bak.x, 0.0f, 65020.0f), v1 = clampf(color_bak.y, 0.0f, 65020.0f), v2 = clampf(color_bak.z, 0.0f, 65020.0f);
+		int i0 = f2i_rtn(v0 * (1.0f / 512.0f)), i1 = f2i_rtn(v1 * (1.0f / 512.0f)), i2 = f2i_rtn(v2 * (1.0f / 512.0f));
+		float c0 = static_cast<float>(i0) * 512.0f, c1 = static_cast<float>(i1) * 512.0f, c2 = static_cast<float>(i2) * 512.0f;
+		float rgb_errorsum = (c0 - v0) + (c1 - v1) + (c2 - v2);
+		float v3 = color_bak.w + rgb_errorsum * (1.0f / 3.0f);
+		v3 = clampf(v3, 0.0f, 65020.0f);
+		int i3 = f2i_rtn(v3 * (1.0f / 512.0f));
+		out.lo = hdr_b4(quant_retain_top_bits(q, (uint8_t)((i0 & 0x3f) | 0xC0), 0xF0), quant_retain_top_bits(q, (uint8_t)((i1 & 0x7f) | 0x80), 0xF0),
+		                quant_retain_top_bits(q, (uint8_t)((i2 & 0x7f) | 0x80), 0xF0), quant_retain_top_bits(q, (uint8_t)((i3 & 0x7f) | ((i0 & 0x40) << 1)), 0xF0));
+		out.ok = true;
+		return out;
+	}
+	const uint32_t SH = 0x87655u, GB_BITS = 0x76565u, S_BITS = 0x67857u, CUT0 = 0xFDBBAu, CUT1 = 0xEEEACu;
+	// routing of spare bits 0..6 per sub-mode
+	const uint8_t ROUTE[5][7] = {
+		{0x09, 0x08, 0x07, 0x0A, 0x06, 0x36, 0x35},
+		{0x08, 0x15, 0x07, 0x25, 0x06, 0x0A, 0x09},
+		{0x09, 0x08, 0x07, 0x06, 0x37, 0x36, 0x35},
+		{0x08, 0x15, 0x07, 0x25, 0x06, 0x36, 0x35},
+		{0x16, 0x15, 0x26, 0x25, 0x06, 0x07, 0x35}};
+	float r_base = color.x;
+	float g_base = color.x - color.y;
+	float b_base = color.x - color.z;
+	float s_base = color.w;
+	float cut0 = static_cast<float>(1 << HDR_NIB(CUT0, m)), cut1 = static_cast<float>(1 << HDR_NIB(CUT1, m));
+	if (g_base > cut0 || b_base > cut0 || s_base > cut1) {
+		return out;
+	}
+	int sh = HDR_NIB(SH, m);
+	float mode_rscale = static_cast<float>(1 << sh);
+	float mode_scale = 1.0f / mode_rscale;
+	int mode_enc = m < 4 ? (m | (majcomp << 2)) : (majcomp | 0xC);
+	int src[4];
+	// major component: low 6 bits + two mode bits on top
+	int r_intval = f2i_rtn(r_base * mode_scale);
+	uint8_t r_quantval = quant_retain_top_bits(q, (uint8_t)((r_intval & 0x3f) | ((mode_enc & 3) << 6)), 0xC0);
+	r_intval = (r_intval & ~0x3f) | (r_quantval & 0x3f);
+	float r_fval = static_cast<float>(r_intval) * mode_rscale;
+	// the two differences against the quantised major component
+	float g_fval = clampf(r_fval - color.y, 0.0f, 65535.0f);
+	float b_fval = clampf(r_fval - color.z, 0.0f, 65535.0f);
+	int g_intval = f2i_rtn(g_fval * mode_scale);
+	int b_intval = f2i_rtn(b_fval * mode_scale);
+	int gb_limit = 1 << HDR_NIB(GB_BITS, m);
+	if (g_intval >= gb_limit || b_intval >= gb_limit) {
+		return out;
+	}
+	src[0] = r_intval; src[1] = g_intval; src[2] = b_intval; src[3] = 0;
+	int g_field = (g_intval & 0x1f) | ((mode_enc & 0x4) << 5) | (hdr_route(ROUTE[m][0], src) << 6) | (hdr_route(ROUTE[m][1], src) << 5);
+	int b_field = (b_intval & 0x1f) | ((mode_enc & 0x8) << 4) | (hdr_route(ROUTE[m][2], src) << 6) | (hdr_route(ROUTE[m][3], src) << 5);
+	uint8_t g_quantval = quant_retain_top_bits(q, (uint8_t)g_field, 0xF0);
+	uint8_t b_quantval = quant_retain_top_bits(q, (uint8_t)b_field, 0xF0);
+	g_intval = (g_intval & ~0x1f) | (g_quantval & 0x1f);
+	b_intval = (b_intval & ~0x1f) | (b_quantval & 0x1f);
+	g_fval = static_cast<float>(g_intval) * mode_rscale;
+	b_fval = static_cast<float>(b_intval) * mode_rscale;
+	// the offset absorbs the mean error made on the colour
+	float rgb_errorsum = (r_fval - color.x) + (r_fval - g_fval - color.y) + (r_fval - b_fval - color.z);
+	float s_fval = clampf(s_base + rgb_errorsum * (1.0f / 3.0f), 0.0f, 1e9f);
+	int s_intval = f2i_rtn(s_fval * mode_scale);
+	if (s_intval >= (1 << HDR_NIB(S_BITS, m))) {
+		return out;
+	}
+	src[3] = s_intval;
+	int s_field = (s_intval & 0x1f) | (hdr_route(ROUTE[m][6], src) << 5) | (hdr_route(ROUTE[m][5], src) << 6) | (hdr_route(ROUTE[m][4], src) << 7);
+	uint8_t s_quantval = quant_retain_top_bits(q, (uint8_t)s_field, 0xF0);
+	out.lo = hdr_b4(r_quantval, g_quantval, b_quantval, s_quantval);
+	out.ok = true;
+	return out;
+}
+
+ASTC_FN void quantize_hdr_rgbo(int lane, f4 color, uint8_t output[4], QuantCtx q) {   // :925-1250
 	color.x = color.x + color.w;
 	color.y = color.y + color.w;
 	color.z = color.z + color.w;
 	color = vclamp4(0.0f, 65535.0f, color);
 	f4 color_bak = color;
-	int majcomp;
-	if (color.x > color.y && color.x > color.z) {
-		majcomp = 0;
-	} else if (color.y > color.z) {
-		majcomp = 1;
-	} else {
-		majcomp = 2;
+	// the largest component leads; the others are coded against it
+	int majcomp = (color.x > color.y && color.x > color.z) ? 0 : (color.y > color.z ? 1 : 2);
+	if (majcomp == 1) {
+		color = mk4(color.y, color.x, color.z, color.w);
+	} else if (majcomp == 2) {
+		color = mk4(color.z, color.y, color.x, color.w);
 	}
-	switch (majcomp) {
-	case 1: color = mk4(color.y, color.x, color.z, color.w); break;
-	case 2: color = mk4(color.z, color.y, color.x, color.w); break;
-	default: break;
-	}
-	const int mode_bits[5][3] = {{11, 5, 7}, {11, 6, 5}, {10, 5, 8}, {9, 6, 7}, {8, 7, 6}};
-	const float mode_cutoffs[5][2] = {{1024, 4096}, {2048, 1024}, {2048, 16384}, {8192, 16384}, {32768, 16384}};
-	const float mode_rscales[5] = {32.0f, 32.0f, 64.0f, 128.0f, 256.0f};
-	const float mode_scales[5] = {1.0f / 32.0f, 1.0f / 32.0f, 1.0f / 64.0f, 1.0f / 128.0f, 1.0f / 256.0f};
-	float r_base = color.x;
-	float g_base = color.x - color.y;
-	float b_base = color.x - color.z;
-	float s_base = color.w;
-	for (int mode = 0; mode < 5; mode++) {
-		if (g_base > mode_cutoffs[mode][0] || b_base > mode_cutoffs[mode][0] || s_base > mode_cutoffs[mode][1]) {
-			continue;
-		}
-		int mode_enc = mode < 4 ? (mode | (majcomp << 2)) : (majcomp | 0xC);
-		float mode_scale = mode_scales[mode];
-		float mode_rscale = mode_rscales[mode];
-		int gb_intcutoff = 1 << mode_bits[mode][1];
-		int s_intcutoff = 1 << mode_bits[mode][2];
-		int r_intval = f2i_rtn(r_base * mode_scale);
-		int r_lowbits = r_intval & 0x3f;
-		r_lowbits |= (mode_enc & 3) << 6;
-		uint8_t r_quantval = quant_retain_top_bits(q, (uint8_t)r_lowbits, 0xC0);
-		r_intval = (r_intval & ~0x3f) | (r_quantval & 0x3f);
-		float r_fval = static_cast<float>(r_intval) * mode_rscale;
-		float g_fval = r_fval - color.y;
-		float b_fval = r_fval - color.z;
-		g_fval = clampf(g_fval, 0.0f, 65535.0f);
-		b_fval = clampf(b_fval, 0.0f, 65535.0f);
-		int g_intval = f2i_rtn(g_fval * mode_scale);
-		int b_intval = f2i_rtn(b_fval * mode_scale);
-		if (g_intval >= gb_intcutoff || b_intval >= gb_intcutoff) {
-			continue;
-		}
-		int g_lowbits = g_intval & 0x1f;
-		int b_lowbits = b_intval & 0x1f;
-		int bit0 = 0, bit1 = 0, bit2 = 0, bit3 = 0;
-		switch (mode) {
-		case 0: case 2: bit0 = (r_intval >> 9) & 1; break;
-		case 1: case 3: bit0 = (r_intval >> 8) & 1; break;
-		case 4: case 5: bit0 = (g_intval >> 6) & 1; break;
-		}
-		switch (mode) {
-		case 0: case 1: case 2: case 3: bit2 = (r_intval >> 7) & 1; break;
-		case 4: case 5: bit2 = (b_intval >> 6) & 1; break;
-		}
-		switch (mode) {
-		case 0: case 2: bit1 = (r_intval >> 8) & 1; break;
-		case 1: case 3: case 4: case 5: bit1 = (g_intval >> 5) & 1; break;
-		}
-		switch (mode) {
-		case 0: bit3 = (r_intval >> 10) & 1; break;
-		case 2: bit3 = (r_intval >> 6) & 1; break;
-		case 1: case 3: case 4: case 5: bit3 = (b_intval >> 5) & 1; break;
-		}
-		g_lowbits |= (mode_enc & 0x4) << 5;
-		b_lowbits |= (mode_enc & 0x8) << 4;
-		g_lowbits |= bit0 << 6;
-		g_lowbits |= bit1 << 5;
-		b_lowbits |= bit2 << 6;
-		b_lowbits |= bit3 << 5;
-		uint8_t g_quantval = quant_retain_top_bits(q, (uint8_t)g_lowbits, 0xF0);
-		uint8_t b_quantval = quant_retain_top_bits(q, (uint8_t)b_lowbits, 0xF0);
-		g_intval = (g_intval & ~0x1f) | (g_quantval & 0x1f);
-		b_intval = (b_intval & ~0x1f) | (b_quantval & 0x1f);
-		g_fval = static_cast<float>(g_intval) * mode_rscale;
-		b_fval = static_cast<float>(b_intval) * mode_rscale;
-		float rgb_errorsum = (r_fval - color.x) + (r_fval - g_fval - color.y) + (r_fval - b_fval - color.z);
-		float s_fval = s_base + rgb_errorsum * (1.0f / 3.0f);
-		s_fval = clampf(s_fval, 0.0f, 1e9f);
-		int s_intval = f2i_rtn(s_fval * mode_scale);
-		if (s_intval >= s_intcutoff) {
-			continue;
-		}
-		int s_lowbits = s_intval & 0x1f;
-		int bit4, bit5, bit6;
-		switch (mode) {
-		case 1: bit6 = (r_intval >> 9) & 1; break;
-		default: bit6 = (s_intval >> 5) & 1; break;
-		}
-		switch (mode) {
-		case 4: bit5 = (r_intval >> 7) & 1; break;
-		case 1: bit5 = (r_intval >> 10) & 1; break;
-		default: bit5 = (s_intval >> 6) & 1; break;
-		}
-		switch (mode) {
-		case 2: bit4 = (s_intval >> 7) & 1; break;
-		default: bit4 = (r_intval >> 6) & 1; break;
-		}
-		s_lowbits |= bit6 << 5;
-		s_lowbits |= bit5 << 6;
-		s_lowbits |= bit4 << 7;
-		uint8_t s_quantval = quant_retain_top_bits(q, (uint8_t)s_lowbits, 0xF0);
-		output[0] = r_quantval;
-		output[1] = g_quantval;
-		output[2] = b_quantval;
-		output[3] = s_quantval;
-		return;
-	}
-	// failed to encode with any of the modes above: encode as flat RGB (mode 5)
-	float vals[4] = {color_bak.x, color_bak.y, color_bak.z, color_bak.w};
-	int ivals[4];
-	float cvals[3];
-	for (int i = 0; i < 3; i++) {
-		vals[i] = clampf(vals[i], 0.0f, 65020.0f);
-		ivals[i] = f2i_rtn(vals[i] * (1.0f / 512.0f));
-		cvals[i] = static_cast<float>(ivals[i]) * 512.0f;
-	}
-	float rgb_errorsum = (cvals[0] - vals[0]) + (cvals[1] - vals[1]) + (cvals[2] - vals[2]);
-	vals[3] += rgb_errorsum * (1.0f / 3.0f);
-	vals[3] = clampf(vals[3], 0.0f, 65020.0f);
-	ivals[3] = f2i_rtn(vals[3] * (1.0f / 512.0f));
-	int encvals[4];
-	encvals[0] = (ivals[0] & 0x3f) | 0xC0;
-	encvals[1] = (ivals[1] & 0x7f) | 0x80;
-	encvals[2] = (ivals[2] & 0x7f) | 0x80;
-	encvals[3] = (ivals[3] & 0x7f) | ((ivals[0] & 0x40) << 1);
-	for (int i = 0; i < 4; i++) {
-		output[i] = quant_retain_top_bits(q, (uint8_t)encvals[i], 0xF0);
-	}
+	hdr_try_all(lane, 6, 4, output, [&](int k) { return hdr_rgbo_attempt(k, color, color_bak, majcomp, q); });
 }
 
-ASTC_NOINLINE void quantize_hdr_rgb(f4 color0, f4 color1, uint8_t output[6], QuantCtx q) {   // :1253-1788
-	color0 = vclamp4(0.0f, 65535.0f, color0);
-	color1 = vclamp4(0.0f, 65535.0f, color1);
-	f4 color0_bak = color0;
-	f4 color1_bak = color1;
-	int majcomp;
-	if (color1.x > color1.y && color1.x > color1.z) {
-		majcomp = 0;
-	} else if (color1.y > color1.z) {
-		majcomp = 1;
-	} else {
-		majcomp = 2;
+// ---- format 11: RGB, two endpoints ------------------------------------------------------------------------------------
+// Value a = the major component of endpoint 1, b0 / b1 = its distance to the two other components of endpoint 1, c = its
+// distance to the major component of endpoint 0, d0 / d1 = what is left for endpoint 0's other components (signed).
+// Sub-modes 7 (finest, smallest range) .. 0; attempt k tries sub-mode 7 - k, attempt 8 is the flat form. Per sub-mode:
+//   sh scale shift 7 7 6 6 5 5 4 4; widths of the b / c / d fields (the a field is 9..12 bits); log2 of the three value ranges.
+// Routing sources: 0 = a, 1 = b0 or b1 / d0 or d1 (by slot), 2 = c, 3 = the other of the pair - see the table.
+ASTC_FN HdrTry hdr_rgb_attempt(int k, f4 color0, f4 color1, f4 color0_bak, f4 color1_bak, int majcomp, QuantCtx q) {
+	HdrTry out;
+	out.lo = out.hi = 0;
+	out.ok = false;
+	if (k == 8) {
+		// flat form: 8 bits per component at 1/256, the last pair at 1/512 with the format's marker bit (:1777-1788)
+		float v[6] = {color0_bak.x, color1_bak.x, color0_bak.y, color1_bak.y, color0_bak.z, color1_bak.z};
+		int o[6];
+		for (int i = 0; i < 6; i++) {
+			float c = clampf(v[i], 0.0f, 65020.0f);
+			o[i] = i < 4 ? quant_color(q, f2i_rtn(c * 1.0f / 256.0f)) : quant_retain_top_bits(q, (uint8_t)(f2i_rtn(c * 1.0f / 512.0f) + 128), 0xC0);
+		}
+		out.lo = hdr_b4(o[0], o[1], o[2], o[3]);
+		out.hi = hdr_b4(o[4], o[5], 0, 0);
+		out.ok = true;
+		return out;
 	}
-	switch (majcomp) {
-	case 1:
-		color0 = mk4(color0.y, color0.x, color0.z, color0.w);
-		color1 = mk4(color1.y, color1.x, color1.z, color1.w);
-		break;
-	case 2:
-		color0 = mk4(color0.z, color0.y, color0.x, color0.w);
-		color1 = mk4(color1.z, color1.y, color1.x, color1.w);
-		break;
-	default: break;
-	}
-	float a_base = color1.x;
-	a_base = clampf(a_base, 0.0f, 65535.0f);
+	int mode = 7 - k;
+	// nibble `mode` of each word
+	const uint32_t SH = 0x44556677u, B_BITS = 0x67687687u, C_BITS = 0x77867766u, D_BITS = 0x65656767u;
+	const uint32_t CUTB = 0xABBDDCFEu, CUTC = 0xBBDBDDDDu, CUTD = 0x98A9BCCDu;
+	// spare bits 0..5: sources 0 a, 1 b0, 2 b1, 3 c, 4 d0, 5 d1 (3 bits) | position (4 bits)
+	const uint8_t ROUTE[8][6] = {
+		{0x16, 0x26, 0x46, 0x56, 0x45, 0x55},
+		{0x16, 0x26, 0x17, 0x27, 0x45, 0x55},
+		{0x09, 0x36, 0x46, 0x56, 0x45, 0x55},
+		{0x16, 0x26, 0x09, 0x36, 0x45, 0x55},
+		{0x16, 0x26, 0x17, 0x27, 0x09, 0x0A},
+		{0x09, 0x0A, 0x37, 0x36, 0x45, 0x55},
+		{0x16, 0x26, 0x0B, 0x36, 0x09, 0x0A},
+		{0x09, 0x0A, 0x0B, 0x36, 0x45, 0x55}};
+	float a_base = clampf(color1.x, 0.0f, 65535.0f);
 	float b0_base = a_base - color1.y;
 	float b1_base = a_base - color1.z;
 	float c_base = a_base - color0.x;
 	float d0_base = a_base - b0_base - c_base - color0.y;
 	float d1_base = a_base - b1_base - c_base - color0.z;
-	const int mode_bits[8][4] = {{9, 7, 6, 7}, {9, 8, 6, 6}, {10, 6, 7, 7}, {10, 7, 7, 6},
-	                                    {11, 8, 6, 5}, {11, 6, 8, 6}, {12, 7, 7, 5}, {12, 6, 7, 6}};
-	const float mode_cutoffs[8][4] = {{16384, 8192, 8192, 8}, {32768, 8192, 4096, 8}, {4096, 8192, 4096, 4}, {8192, 8192, 2048, 4},
-	                                         {8192, 2048, 512, 2}, {2048, 8192, 1024, 2}, {2048, 2048, 256, 1}, {1024, 2048, 512, 1}};
-	const float mode_scales[8] = {1.0f / 128.0f, 1.0f / 128.0f, 1.0f / 64.0f, 1.0f / 64.0f, 1.0f / 32.0f, 1.0f / 32.0f, 1.0f / 16.0f, 1.0f / 16.0f};
-	const float mode_rscales[8] = {128.0f, 128.0f, 64.0f, 64.0f, 32.0f, 32.0f, 16.0f, 16.0f};
-	for (int mode = 7; mode >= 0; mode--) {
-		float b_cutoff = mode_cutoffs[mode][0];
-		float c_cutoff = mode_cutoffs[mode][1];
-		float d_cutoff = mode_cutoffs[mode][2];
-		if (b0_base > b_cutoff || b1_base > b_cutoff || c_base > c_cutoff || fabsf(d0_base) > d_cutoff || fabsf(d1_base) > d_cutoff) {
-			continue;
-		}
-		float mode_scale = mode_scales[mode];
-		float mode_rscale = mode_rscales[mode];
-		int b_intcutoff = 1 << mode_bits[mode][1];
-		int c_intcutoff = 1 << mode_bits[mode][2];
-		int d_intcutoff = 1 << (mode_bits[mode][3] - 1);
-		int a_intval = f2i_rtn(a_base * mode_scale);
-		int a_lowbits = a_intval & 0xFF;
-		int a_quantval = quant_color(q, a_lowbits);
-		int a_uquantval = a_quantval;
-		a_intval = (a_intval & ~0xFF) | a_uquantval;
-		float a_fval = static_cast<float>(a_intval) * mode_rscale;
-		float c_fval = a_fval - color0.x;
-		c_fval = clampf(c_fval, 0.0f, 65535.0f);
-		int c_intval = f2i_rtn(c_fval * mode_scale);
-		if (c_intval >= c_intcutoff) {
-			continue;
-		}
-		int c_lowbits = c_intval & 0x3f;
-		c_lowbits |= (mode & 1) << 7;
-		c_lowbits |= (a_intval & 0x100) >> 2;
-		uint8_t c_quantval = quant_retain_top_bits(q, (uint8_t)c_lowbits, 0xC0);
-		c_intval = (c_intval & ~0x3F) | (c_quantval & 0x3F);
-		c_fval = static_cast<float>(c_intval) * mode_rscale;
-		float b0_fval = a_fval - color1.y;
-		float b1_fval = a_fval - color1.z;
-		b0_fval = clampf(b0_fval, 0.0f, 65535.0f);
-		b1_fval = clampf(b1_fval, 0.0f, 65535.0f);
-		int b0_intval = f2i_rtn(b0_fval * mode_scale);
-		int b1_intval = f2i_rtn(b1_fval * mode_scale);
-		if (b0_intval >= b_intcutoff || b1_intval >= b_intcutoff) {
-			continue;
-		}
-		int b0_lowbits = b0_intval & 0x3f;
-		int b1_lowbits = b1_intval & 0x3f;
-		int bit0 = 0, bit1 = 0;
-		switch (mode) {
-		case 0: case 1: case 3: case 4: case 6: bit0 = (b0_intval >> 6) & 1; break;
-		case 2: case 5: case 7: bit0 = (a_intval >> 9) & 1; break;
-		}
-		switch (mode) {
-		case 0: case 1: case 3: case 4: case 6: bit1 = (b1_intval >> 6) & 1; break;
-		case 2: bit1 = (c_intval >> 6) & 1; break;
-		case 5: case 7: bit1 = (a_intval >> 10) & 1; break;
-		}
-		b0_lowbits |= bit0 << 6;
-		b1_lowbits |= bit1 << 6;
-		b0_lowbits |= ((mode >> 1) & 1) << 7;
-		b1_lowbits |= ((mode >> 2) & 1) << 7;
-		uint8_t b0_quantval = quant_retain_top_bits(q, (uint8_t)b0_lowbits, 0xC0);
-		uint8_t b1_quantval = quant_retain_top_bits(q, (uint8_t)b1_lowbits, 0xC0);
-		b0_intval = (b0_intval & ~0x3f) | (b0_quantval & 0x3f);
-		b1_intval = (b1_intval & ~0x3f) | (b1_quantval & 0x3f);
-		b0_fval = static_cast<float>(b0_intval) * mode_rscale;
-		b1_fval = static_cast<float>(b1_intval) * mode_rscale;
-		float d0_fval = a_fval - b0_fval - c_fval - color0.y;
-		float d1_fval = a_fval - b1_fval - c_fval - color0.z;
-		d0_fval = clampf(d0_fval, -65535.0f, 65535.0f);
-		d1_fval = clampf(d1_fval, -65535.0f, 65535.0f);
-		int d0_intval = f2i_rtn(d0_fval * mode_scale);
-		int d1_intval = f2i_rtn(d1_fval * mode_scale);
-		if (abs(d0_intval) >= d_intcutoff || abs(d1_intval) >= d_intcutoff) {
-			continue;
-		}
-		int d0_lowbits = d0_intval & 0x1f;
-		int d1_lowbits = d1_intval & 0x1f;
-		int bit2 = 0, bit3 = 0, bit4, bit5;
-		switch (mode) {
-		case 0: case 2: bit2 = (d0_intval >> 6) & 1; break;
-		case 1: case 4: bit2 = (b0_intval >> 7) & 1; break;
-		case 3: bit2 = (a_intval >> 9) & 1; break;
-		case 5: bit2 = (c_intval >> 7) & 1; break;
-		case 6: case 7: bit2 = (a_intval >> 11) & 1; break;
-		}
-		switch (mode) {
-		case 0: case 2: bit3 = (d1_intval >> 6) & 1; break;
-		case 1: case 4: bit3 = (b1_intval >> 7) & 1; break;
-		case 3: case 5: case 6: case 7: bit3 = (c_intval >> 6) & 1; break;
-		}
-		switch (mode) {
-		case 4: case 6:
-			bit4 = (a_intval >> 9) & 1;
-			bit5 = (a_intval >> 10) & 1;
-			break;
-		default:
-			bit4 = (d0_intval >> 5) & 1;
-			bit5 = (d1_intval >> 5) & 1;
-			break;
-		}
-		d0_lowbits |= bit2 << 6;
-		d1_lowbits |= bit3 << 6;
-		d0_lowbits |= bit4 << 5;
-		d1_lowbits |= bit5 << 5;
-		d0_lowbits |= (majcomp & 1) << 7;
-		d1_lowbits |= ((majcomp >> 1) & 1) << 7;
-		uint8_t d0_quantval = quant_retain_top_bits(q, (uint8_t)d0_lowbits, 0xF0);
-		uint8_t d1_quantval = quant_retain_top_bits(q, (uint8_t)d1_lowbits, 0xF0);
-		output[0] = (uint8_t)a_quantval;
-		output[1] = c_quantval;
-		output[2] = b0_quantval;
-		output[3] = b1_quantval;
-		output[4] = d0_quantval;
-		output[5] = d1_quantval;
-		return;
+	float b_cutoff = static_cast<float>(1 << HDR_NIB(CUTB, mode));
+	float c_cutoff = static_cast<float>(1 << HDR_NIB(CUTC, mode));
+	float d_cutoff = static_cast<float>(1 << HDR_NIB(CUTD, mode));
+	if (b0_base > b_cutoff || b1_base > b_cutoff || c_base > c_cutoff || fabsf(d0_base) > d_cutoff || fabsf(d1_base) > d_cutoff) {
+		return out;
 	}
-	// flat (no-submode) fallback
-	float vals[6] = {color0_bak.x, color1_bak.x, color0_bak.y, color1_bak.y, color0_bak.z, color1_bak.z};
-	for (int i = 0; i < 6; i++) {
-		vals[i] = clampf(vals[i], 0.0f, 65020.0f);
+	int sh = HDR_NIB(SH, mode);
+	float mode_rscale = static_cast<float>(1 << sh);
+	float mode_scale = 1.0f / mode_rscale;
+	int v[6];      // a, b0, b1, c, d0, d1 as scaled integers
+	// a: its low 8 bits go through the quantiser as they are
+	int a_intval = f2i_rtn(a_base * mode_scale);
+	int a_quantval = quant_color(q, a_intval & 0xFF);
+	a_intval = (a_intval & ~0xFF) | a_quantval;
+	float a_fval = static_cast<float>(a_intval) * mode_rscale;
+	// c against the quantised a
+	float c_fval = clampf(a_fval - color0.x, 0.0f, 65535.0f);
+	int c_intval = f2i_rtn(c_fval * mode_scale);
+	if (c_intval >= (1 << HDR_NIB(C_BITS, mode))) {
+		return out;
 	}
-	for (int i = 0; i < 4; i++) {
-		int idx = f2i_rtn(vals[i] * 1.0f / 256.0f);
-		output[i] = (uint8_t)quant_color(q, idx);
+	uint8_t c_quantval = quant_retain_top_bits(q, (uint8_t)((c_intval & 0x3f) | ((mode & 1) << 7) | ((a_intval & 0x100) >> 2)), 0xC0);
+	c_intval = (c_intval & ~0x3F) | (c_quantval & 0x3F);
+	c_fval = static_cast<float>(c_intval) * mode_rscale;
+	// b0, b1 against the quantised a
+	float b0_fval = clampf(a_fval - color1.y, 0.0f, 65535.0f);
+	float b1_fval = clampf(a_fval - color1.z, 0.0f, 65535.0f);
+	int b0_intval = f2i_rtn(b0_fval * mode_scale);
+	int b1_intval = f2i_rtn(b1_fval * mode_scale);
+	int b_limit = 1 << HDR_NIB(B_BITS, mode);
+	if (b0_intval >= b_limit || b1_intval >= b_limit) {
+		return out;
 	}
-	for (int i = 4; i < 6; i++) {
-		int idx = f2i_rtn(vals[i] * 1.0f / 512.0f) + 128;
-		output[i] = quant_retain_top_bits(q, (uint8_t)idx, 0xC0);
+	v[0] = a_intval; v[1] = b0_intval; v[2] = b1_intval; v[3] = c_intval; v[4] = 0; v[5] = 0;
+	auto route = [&](int slot) { uint32_t d = ROUTE[mode][slot]; return (v[(d >> 4) & 7] >> (d & 15)) & 1; };
+	uint8_t b0_quantval = quant_retain_top_bits(q, (uint8_t)((b0_intval & 0x3f) | (route(0) << 6) | (((mode >> 1) & 1) << 7)), 0xC0);
+	uint8_t b1_quantval = quant_retain_top_bits(q, (uint8_t)((b1_intval & 0x3f) | (route(1) << 6) | (((mode >> 2) & 1) << 7)), 0xC0);
+	b0_intval = (b0_intval & ~0x3f) | (b0_quantval & 0x3f);
+	b1_intval = (b1_intval & ~0x3f) | (b1_quantval & 0x3f);
+	b0_fval = static_cast<float>(b0_intval) * mode_rscale;
+	b1_fval = static_cast<float>(b1_intval) * mode_rscale;
+	// d0, d1: what the quantised a, b, c leave over (signed)
+	float d0_fval = clampf(a_fval - b0_fval - c_fval - color0.y, -65535.0f, 65535.0f);
+	float d1_fval = clampf(a_fval - b1_fval - c_fval - color0.z, -65535.0f, 65535.0f);
+	int d0_intval = f2i_rtn(d0_fval * mode_scale);
+	int d1_intval = f2i_rtn(d1_fval * mode_scale);
+	int d_limit = 1 << (HDR_NIB(D_BITS, mode) - 1);
+	if (abs(d0_intval) >= d_limit || abs(d1_intval) >= d_limit) {
+		return out;
 	}
+	v[1] = b0_intval; v[2] = b1_intval; v[4] = d0_intval; v[5] = d1_intval;
+	int d0_field = (d0_intval & 0x1f) | (route(2) << 6) | (route(4) << 5) | ((majcomp & 1) << 7);
+	int d1_field = (d1_intval & 0x1f) | (route(3) << 6) | (route(5) << 5) | (((majcomp >> 1) & 1) << 7);
+	uint8_t d0_quantval = quant_retain_top_bits(q, (uint8_t)d0_field, 0xF0);
+	uint8_t d1_quantval = quant_retain_top_bits(q, (uint8_t)d1_field, 0xF0);
+	out.lo = hdr_b4(a_quantval, c_quantval, b0_quantval, b1_quantval);
+	out.hi = hdr_b4(d0_quantval, d1_quantval, 0, 0);
+	out.ok = true;
+	return out;
 }
 
-ASTC_FN void quantize_hdr_rgb_ldr_alpha(f4 color0, f4 color1, uint8_t output[8], QuantCtx q) {   // :1791-1817
-	float scale = 1.0f / 257.0f;
-	float a0 = clampf(color0.w * scale, 0.0f, 255.0f);
-	float a1 = clampf(color1.w * scale, 0.0f, 255.0f);
-	output[6] = (uint8_t)quant_color_f(q, f2i_rtn(a0), a0);
-	output[7] = (uint8_t)quant_color_f(q, f2i_rtn(a1), a1);
-	quantize_hdr_rgb(color0, color1, output, q);
+ASTC_FN void quantize_hdr_rgb(int lane, f4 color0, f4 color1, uint8_t output[6], QuantCtx q) {   // :1253-1788
+	color0 = vclamp4(0.0f, 65535.0f, color0);
+	color1 = vclamp4(0.0f, 65535.0f, color1);
+	f4 color0_bak = color0;
+	f4 color1_bak = color1;
+	int majcomp = (color1.x > color1.y && color1.x > color1.z) ? 0 : (color1.y > color1.z ? 1 : 2);
+	if (majcomp == 1) {
+		color0 = mk4(color0.y, color0.x, color0.z, color0.w);
+		color1 = mk4(color1.y, color1.x, color1.z, color1.w);
+	} else if (majcomp == 2) {
+		color0 = mk4(color0.z, color0.y, color0.x, color0.w);
+		color1 = mk4(color1.z, color1.y, color1.x, color1.w);
+	}
+	hdr_try_all(lane, 9, 6, output, [&](int k) { return hdr_rgb_attempt(k, color0, color1, color0_bak, color1_bak, majcomp, q); });
 }
 
-ASTC_NOINLINE void quantize_hdr_luminance_large_range(f4 color0, f4 color1, uint8_t output[2], QuantCtx q) {   // :1659-1720
-	float lum0 = hadd_rgb_s(color0) * (1.0f / 3.0f);
-	float lum1 = hadd_rgb_s(color1) * (1.0f / 3.0f);
-	if (lum1 < lum0) {
-		float avg = (lum0 + lum1) * 0.5f;
-		lum0 = avg;
-		lum1 = avg;
+// ---- HDR alpha pair (:1820-1890): precision levels 2, 1, 0 (attempts 0..2), then the flat 7-bit form ----------------------
+ASTC_FN HdrTry hdr_alpha_attempt(int k, int ialpha0, int ialpha1, QuantCtx q) {
+	HdrTry out;
+	out.lo = out.hi = 0;
+	out.ok = false;
+	if (k == 3) {
+		out.lo = hdr_b4(quant_color(q, ((ialpha0 + 256) >> 9) | 0x80), quant_color(q, ((ialpha1 + 256) >> 9) | 0x80), 0, 0);
+		out.ok = true;
+		return out;
 	}
-	int ilum1 = f2i_rtn(lum1);
-	int ilum0 = f2i_rtn(lum0);
-	int upper_v0 = (ilum0 + 128) >> 8;
-	int upper_v1 = (ilum1 + 128) >> 8;
-	upper_v0 = clampi(upper_v0, 0, 255);
-	upper_v1 = clampi(upper_v1, 0, 255);
-	int lower_v0 = (ilum1 + 256) >> 8;
-	int lower_v1 = ilum0 >> 8;
-	lower_v0 = clampi(lower_v0, 0, 255);
-	lower_v1 = clampi(lower_v1, 0, 255);
-	int upper0_dec = upper_v0 << 8;
-	int upper1_dec = upper_v1 << 8;
-	int lower0_dec = (lower_v1 << 8) + 128;
-	int lower1_dec = (lower_v0 << 8) - 128;
-	int upper0_diff = upper0_dec - ilum0;
-	int upper1_diff = upper1_dec - ilum1;
-	int lower0_diff = lower0_dec - ilum0;
-	int lower1_diff = lower1_dec - ilum1;
-	int upper_error = (upper0_diff * upper0_diff) + (upper1_diff * upper1_diff);
-	int lower_error = (lower0_diff * lower0_diff) + (lower1_diff * lower1_diff);
-	int v0, v1;
-	if (upper_error < lower_error) {
-		v0 = upper_v0;
-		v1 = upper_v1;
-	} else {
-		v0 = lower_v0;
-		v1 = lower_v1;
+	int i = 2 - k;
+	int val0 = (ialpha0 + (128 >> i)) >> (8 - i);
+	int val1 = (ialpha1 + (128 >> i)) >> (8 - i);
+	int v6 = (val0 & 0x7F) | ((i & 1) << 7);
+	int v6e = quant_color(q, v6);
+	if ((v6 ^ v6e) & 0x80) {
+		return out;
 	}
-	output[0] = (uint8_t)quant_color(q, v0);
-	output[1] = (uint8_t)quant_color(q, v1);
+	val0 = (val0 & ~0x7f) | (v6e & 0x7f);
+	int diffval = val1 - val0;
+	int cutoff = 32 >> i;
+	if (diffval < -cutoff || diffval >= cutoff) {
+		return out;
+	}
+	int v7 = ((i & 2) << 6) | ((val0 >> 7) << (6 - i)) | (diffval & (2 * cutoff - 1));
+	int v7e = quant_color(q, v7);
+	int keep = i == 0 ? 0xE0 : (i == 1 ? 0xF0 : 0xF8);      // the bits of the second byte that carry the base
+	if ((v7 ^ v7e) & keep) {
+		return out;
+	}
+	out.lo = hdr_b4(v6e, v7e, 0, 0);
+	out.ok = true;
+	return out;
 }
 
-ASTC_NOINLINE bool try_quantize_hdr_luminance_small_range(f4 color0, f4 color1, uint8_t output[2], QuantCtx q) {   // :1723-1817
-	float lum0 = hadd_rgb_s(color0) * (1.0f / 3.0f);
-	float lum1 = hadd_rgb_s(color1) * (1.0f / 3.0f);
-	if (lum1 < lum0) {
-		float avg = (lum0 + lum1) * 0.5f;
-		lum0 = avg;
-		lum1 = avg;
+ASTC_FN void quantize_hdr_alpha(int lane, float alpha0, float alpha1, uint8_t output[2], QuantCtx q) {
+	int ialpha0 = f2i_rtn(clampf(alpha0, 0.0f, 65280.0f));
+	int ialpha1 = f2i_rtn(clampf(alpha1, 0.0f, 65280.0f));
+	hdr_try_all(lane, 4, 2, output, [&](int k) { return hdr_alpha_attempt(k, ialpha0, ialpha1, q); });
+}
+
+// ---- HDR luminance (:1659-1817): small range at 1/32 (attempt 0) or 1/64 (attempt 1), else the large range form (2) -------
+ASTC_FN HdrTry hdr_luminance_attempt(int k, int ilum0, int ilum1, QuantCtx q) {
+	HdrTry out;
+	out.lo = out.hi = 0;
+	out.ok = false;
+	if (k == 2) {
+		// large range: both ends at 1/256, rounding the pair up or down together - whichever lands closer
+		int upper_v0 = clampi((ilum0 + 128) >> 8, 0, 255), upper_v1 = clampi((ilum1 + 128) >> 8, 0, 255);
+		int lower_v0 = clampi((ilum1 + 256) >> 8, 0, 255), lower_v1 = clampi(ilum0 >> 8, 0, 255);
+		int u0 = (upper_v0 << 8) - ilum0, u1 = (upper_v1 << 8) - ilum1;
+		int l0 = ((lower_v1 << 8) + 128) - ilum0, l1 = ((lower_v0 << 8) - 128) - ilum1;
+		bool upper = (u0 * u0 + u1 * u1) < (l0 * l0 + l1 * l1);
+		out.lo = hdr_b4(quant_color(q, upper ? upper_v0 : lower_v0), quant_color(q, upper ? upper_v1 : lower_v1), 0, 0);
+		out.ok = true;
+		return out;
 	}
-	int ilum1 = f2i_rtn(lum1);
-	int ilum0 = f2i_rtn(lum0);
 	if (ilum1 - ilum0 > 2048) {
-		return false;
+		return out;
 	}
-	int lowval, highval, diffval;
-	int v0, v1, v0e, v1e, v0d, v1d;
-	lowval = (ilum0 + 16) >> 5;
-	highval = (ilum1 + 16) >> 5;
-	lowval = clampi(lowval, 0, 2047);
-	highval = clampi(highval, 0, 2047);
-	v0 = lowval & 0x7F;
-	v0e = quant_color(q, v0);
-	v0d = v0e;
-	if (v0d < 0x80) {
-		lowval = (lowval & ~0x7F) | v0d;
-		diffval = highval - lowval;
-		if (diffval >= 0 && diffval <= 15) {
-			v1 = ((lowval >> 3) & 0xF0) | diffval;
-			v1e = quant_color(q, v1);
-			v1d = v1e;
-			if ((v1d & 0xF0) == (v1 & 0xF0)) {
-				output[0] = (uint8_t)v0e;
-				output[1] = (uint8_t)v1e;
-				return true;
+	// k = 0: 11-bit base, 4-bit difference; k = 1: 10-bit base, 5-bit difference, marker bit set
+	int sh = 5 + k, top = k == 0 ? 2047 : 1023, dmax = k == 0 ? 15 : 31;
+	int lowval = clampi((ilum0 + (16 << k)) >> sh, 0, top);
+	int highval = clampi((ilum1 + (16 << k)) >> sh, 0, top);
+	int v0 = (lowval & 0x7F) | (k << 7);
+	int v0e = quant_color(q, v0);
+	if ((v0e & 0x80) != (k << 7)) {
+		return out;
+	}
+	lowval = (lowval & ~0x7F) | (v0e & 0x7F);
+	int diffval = highval - lowval;
+	if (diffval < 0 || diffval > dmax) {
+		return out;
+	}
+	int keep = k == 0 ? 0xF0 : 0xE0;
+	int v1 = ((lowval >> (3 - k)) & keep) | diffval;
+	int v1e = quant_color(q, v1);
+	if ((v1e & keep) != (v1 & keep)) {
+		return out;
+	}
+	out.lo = hdr_b4(v0e, v1e, 0, 0);
+	out.ok = true;
+	return out;
+}
+
+// returns the format that was used (small range when one of its two forms fits)
+ASTC_FN int quantize_hdr_luminance(int lane, f4 color0, f4 color1, uint8_t output[2], QuantCtx q) {
+	float lum0 = hadd_rgb_s(color0) * (1.0f / 3.0f);
+	float lum1 = hadd_rgb_s(color1) * (1.0f / 3.0f);
+	if (lum1 < lum0) {
+		float avg = (lum0 + lum1) * 0.5f;
+		lum0 = avg;
+		lum1 = avg;
+	}
+	int ilum1 = f2i_rtn(lum1);
+	int ilum0 = f2i_rtn(lum0);
+	// (every lane can tell which attempt wins from the flags alone: recompute the winner index for the return value)
+	int base = 0, win = -1;
+	ASTC_NOUNROLL
+	while (win < 0) {
+		int k = base + lane;
+		HdrTry t;
+		t.lo = t.hi = 0;
+		t.ok = false;
+		if (k < 3) {
+			t = hdr_luminance_attempt(k, ilum0, ilum1, q);
+		}
+		int wl = hdr_first_ok(t.ok, lane);
+		if (wl >= 0) {
+			win = base + wl;
+			if (lane == wl) {
+				output[0] = (uint8_t)(t.lo & 0xFF);
+				output[1] = (uint8_t)((t.lo >> 8) & 0xFF);
 			}
 		}
+		base += ASTC_WARP;
 	}
-	lowval = (ilum0 + 32) >> 6;
-	highval = (ilum1 + 32) >> 6;
-	lowval = clampi(lowval, 0, 1023);
-	highval = clampi(highval, 0, 1023);
-	v0 = (lowval & 0x7F) | 0x80;
-	v0e = quant_color(q, v0);
-	v0d = v0e;
-	if ((v0d & 0x80) == 0) {
-		return false;
-	}
-	lowval = (lowval & ~0x7F) | (v0d & 0x7F);
-	diffval = highval - lowval;
-	if (diffval < 0 || diffval > 31) {
-		return false;
-	}
-	v1 = ((lowval >> 2) & 0xE0) | diffval;
-	v1e = quant_color(q, v1);
-	v1d = v1e;
-	if ((v1d & 0xE0) != (v1 & 0xE0)) {
-		return false;
-	}
-	output[0] = (uint8_t)v0e;
-	output[1] = (uint8_t)v1e;
-	return true;
-}
-
-ASTC_NOINLINE void quantize_hdr_alpha(float alpha0, float alpha1, uint8_t output[2], QuantCtx q) {   // :1820-1890
-	alpha0 = clampf(alpha0, 0.0f, 65280.0f);
-	alpha1 = clampf(alpha1, 0.0f, 65280.0f);
-	int ialpha0 = f2i_rtn(alpha0);
-	int ialpha1 = f2i_rtn(alpha1);
-	int val0, val1, diffval;
-	int v6, v7, v6e, v7e, v6d, v7d;
-	for (int i = 2; i >= 0; i--) {
-		val0 = (ialpha0 + (128 >> i)) >> (8 - i);
-		val1 = (ialpha1 + (128 >> i)) >> (8 - i);
-		v6 = (val0 & 0x7F) | ((i & 1) << 7);
-		v6e = quant_color(q, v6);
-		v6d = v6e;
-		if ((v6 ^ v6d) & 0x80) {
-			continue;
-		}
-		val0 = (val0 & ~0x7f) | (v6d & 0x7f);
-		diffval = val1 - val0;
-		int cutoff = 32 >> i;
-		int mask = 2 * cutoff - 1;
-		if (diffval < -cutoff || diffval >= cutoff) {
-			continue;
-		}
-		v7 = ((i & 2) << 6) | ((val0 >> 7) << (6 - i)) | (diffval & mask);
-		v7e = quant_color(q, v7);
-		v7d = v7e;
-		const int testbits[3] = {0xE0, 0xF0, 0xF8};
-		if ((v7 ^ v7d) & testbits[i]) {
-			continue;
-		}
-		output[0] = (uint8_t)v6e;
-		output[1] = (uint8_t)v7e;
-		return;
-	}
-	val0 = (ialpha0 + 256) >> 9;
-	val1 = (ialpha1 + 256) >> 9;
-	v6 = val0 | 0x80;
-	v7 = val1 | 0x80;
-	output[0] = (uint8_t)quant_color(q, v6);
-	output[1] = (uint8_t)quant_color(q, v7);
-}
-
-ASTC_FN void quantize_hdr_rgb_alpha(f4 color0, f4 color1, uint8_t output[8], QuantCtx q) {   // :1893-1906
-	quantize_hdr_rgb(color0, color1, output, q);
-	quantize_hdr_alpha(color0.w, color1.w, output + 6, q);
+	return win < 2 ? FMT_HDR_LUMINANCE_SMALL_RANGE : FMT_HDR_LUMINANCE_LARGE_RANGE;
 }

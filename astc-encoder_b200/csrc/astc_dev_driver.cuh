@@ -39,21 +39,35 @@ ASTC_COOP void copy_work_to_best(WCtx w) {
 }
 
 // Pack the endpoints of partitions 0..pc-1 of the work candidate at quant_level into colors (work_colors or
-// mod_colors); lanes over partitions. The resulting formats come back packed 8 bits each (exchanged via tmpf).
+// mod_colors). LDR formats: lanes over partitions; HDR formats: one partition after the other, the warp running the
+// format's sub-mode ladder lane-parallel. The resulting formats come back packed 8 bits each (exchanged via tmpf).
 ASTC_COOP uint32_t pack_work_endpoints(WCtx w, unsigned int pc, uint32_t formats_in, int quant_level, uint32_t colors_off) {
 	SPtr<f4> ep = ep_of(w);
 	SPtr<uint8_t> colors = sptr<uint8_t>(colors_off);
+	SPtr<uint32_t> colors32 = sptr<uint32_t>(colors_off);
 	SPtr<uint32_t> xch = sptr<uint32_t>(w.base + A_TMPF);
 	ASTC_NOUNROLL
+	for (int k = w.lane; k < 2 * (int)pc; k += ASTC_WARP) {
+		colors32[k] = 0;
+	}
+	wsync();
+	ASTC_NOUNROLL
 	for (unsigned int j = (unsigned int)w.lane; j < pc; j += ASTC_WARP) {
-		// (packed straight into the shared arena: a local byte array behind a pointer would live in local memory)
-		uint8_t* out = &colors[(int)j * 8];
-		for (int k = 0; k < 8; k++) {
-			out[k] = 0;
+		int fmt_in = (int)((formats_in >> (8 * j)) & 0xFF);
+		if (!is_hdr_format(fmt_in)) {
+			// (packed straight into the shared arena: a local byte array behind a pointer would live in local memory)
+			xch[(int)j] = pack_color_endpoints(ep[EP_WORK_0 + (int)j], ep[EP_WORK_1 + (int)j], ep[EP_RGBS + (int)j], ep[EP_RGBO + (int)j], fmt_in, &colors[(int)j * 8], quant_level);
 		}
-		uint8_t fmt = pack_color_endpoints(ep[EP_WORK_0 + (int)j], ep[EP_WORK_1 + (int)j], ep[EP_RGBS + (int)j], ep[EP_RGBO + (int)j],
-		                                   (int)((formats_in >> (8 * j)) & 0xFF), out, quant_level);
-		xch[(int)j] = fmt;
+	}
+	ASTC_NOUNROLL
+	for (unsigned int j = 0; j < pc; j++) {
+		int fmt_in = (int)((formats_in >> (8 * j)) & 0xFF);
+		if (is_hdr_format(fmt_in)) {
+			uint8_t fmt = pack_hdr_endpoints(w.lane, ep[EP_WORK_0 + (int)j], ep[EP_WORK_1 + (int)j], ep[EP_RGBO + (int)j], fmt_in, &colors[(int)j * 8], quant_level);
+			if (w.lane == 0) {
+				xch[(int)j] = fmt;
+			}
+		}
 	}
 	wsync();
 	uint32_t r = 0;
