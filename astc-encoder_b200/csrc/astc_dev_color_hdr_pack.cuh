@@ -157,7 +157,7 @@ ASTC_FN HdrTry hdr_rgbo_attempt(int m, f4 color, f4 color_bak, int majcomp, Quan
 	return out;
 }
 
-ASTC_FN void quantize_hdr_rgbo(int lane, f4 color, uint8_t output[4], QuantCtx q) {   // :925-1250
+ASTC_NOINLINE void quantize_hdr_rgbo(int lane, f4 color, uint8_t output[4], QuantCtx q) {   // :925-1250
 	color.x = color.x + color.w;
 	color.y = color.y + color.w;
 	color.z = color.z + color.w;
@@ -277,7 +277,7 @@ ASTC_FN HdrTry hdr_rgb_attempt(int k, f4 color0, f4 color1, f4 color0_bak, f4 co
 	return out;
 }
 
-ASTC_FN void quantize_hdr_rgb(int lane, f4 color0, f4 color1, uint8_t output[6], QuantCtx q) {   // :1253-1788
+ASTC_NOINLINE void quantize_hdr_rgb(int lane, f4 color0, f4 color1, uint8_t output[6], QuantCtx q) {   // :1253-1788
 	color0 = vclamp4(0.0f, 65535.0f, color0);
 	color1 = vclamp4(0.0f, 65535.0f, color1);
 	f4 color0_bak = color0;
@@ -328,7 +328,7 @@ ASTC_FN HdrTry hdr_alpha_attempt(int k, int ialpha0, int ialpha1, QuantCtx q) {
 	return out;
 }
 
-ASTC_FN void quantize_hdr_alpha(int lane, float alpha0, float alpha1, uint8_t output[2], QuantCtx q) {
+ASTC_NOINLINE void quantize_hdr_alpha(int lane, float alpha0, float alpha1, uint8_t output[2], QuantCtx q) {
 	int ialpha0 = f2i_rtn(clampf(alpha0, 0.0f, 65280.0f));
 	int ialpha1 = f2i_rtn(clampf(alpha1, 0.0f, 65280.0f));
 	hdr_try_all(lane, 4, 2, output, [&](int k) { return hdr_alpha_attempt(k, ialpha0, ialpha1, q); });
@@ -379,7 +379,7 @@ ASTC_FN HdrTry hdr_luminance_attempt(int k, int ilum0, int ilum1, QuantCtx q) {
 }
 
 // returns the format that was used (small range when one of its two forms fits)
-ASTC_FN int quantize_hdr_luminance(int lane, f4 color0, f4 color1, uint8_t output[2], QuantCtx q) {
+ASTC_NOINLINE int quantize_hdr_luminance(int lane, f4 color0, f4 color1, uint8_t output[2], QuantCtx q) {
 	float lum0 = hadd_rgb_s(color0) * (1.0f / 3.0f);
 	float lum1 = hadd_rgb_s(color1) * (1.0f / 3.0f);
 	if (lum1 < lum0) {

@@ -36,6 +36,8 @@
 		#define ASTC_ONE_LANE 1
 	#endif
 	#define ASTC_NOUNROLL
+	#define ASTC_UNROLL2
+	#define ASTC_UNROLL4
 	#define ASTC_RINT(a) nearbyintf(a)
 	static inline uint32_t astc_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 	static inline float astc_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
@@ -62,6 +64,17 @@
 		#define ASTC_NOUNROLL                     /* experiment: leave loop unrolling to the compiler */
 	#else
 		#define ASTC_NOUNROLL _Pragma("unroll 1")
+	#endif
+	// The warps are latency bound (one warp issues ~1 instruction in 20 cycles): the few short loops that sit on every
+	// step's critical path - an LDS feeding an ordered add, a chain of dependent table look-ups per texel - are unrolled a
+	// little so that the loads of the next trips are in flight while the current one computes. Everything else stays
+	// rolled: the kernels are instruction-cache sensitive (unrolling everything: 78 -> 90 ms).
+	#if defined(ASTC_NO_HOT_UNROLL)
+		#define ASTC_UNROLL2 _Pragma("unroll 1")
+		#define ASTC_UNROLL4 _Pragma("unroll 1")
+	#else
+		#define ASTC_UNROLL2 _Pragma("unroll 2")
+		#define ASTC_UNROLL4 _Pragma("unroll 4")
 	#endif
 	#define ASTC_RINT(a) rintf(a)
 	#define ASTC_F2U(f) __float_as_uint(f)
@@ -432,7 +445,7 @@ ASTC_FN void chain_sums(const WCtx& w, int n, uint32_t tile, SPtr<float> acc, in
 			}
 			float s = acc[id];
 			SPtr<float> row = st + (k * CHAIN_STRIDE - base);
-			ASTC_NOUNROLL
+			ASTC_UNROLL4
 			for (; p < hi; p += step) {
 				s = s + row[p];
 			}
@@ -643,7 +656,7 @@ ASTC_COOP void compute_dirs(WCtx w, const PartView& pi, uint32_t chan, int ncomp
 		const uint8_t* tix = pi.texels + pv_start(pi, (unsigned int)p);
 		int n = pv_count(pi, (unsigned int)p);
 		float s = 0.0f;
-		ASTC_NOUNROLL
+		ASTC_UNROLL4
 		for (int i = 0; i < n; i++) {
 			int t = ASTC_LDG(&tix[i]);
 			float vK = dK[t] - avgK;
@@ -1000,7 +1013,7 @@ ASTC_COOP void compute_ideal_weights_for_decimation(WCtx w, unsigned int d, int 
 		float initial_weight = 0.0f;
 		int off = ASTC_LDD(&di.wto[i]);
 		int end = ASTC_LDD(&di.wto[i + 1]);
-		ASTC_NOUNROLL
+		ASTC_UNROLL4
 		for (int j = off; j < end; j++) {
 			uint32_t e = ASTC_LDD(&di.wtc[j]);
 			int texel = (int)(e & 0xFF);
@@ -1036,7 +1049,7 @@ ASTC_COOP void compute_ideal_weights_for_decimation(WCtx w, unsigned int d, int 
 		float error_change1 = 0.0f;
 		int off = ASTC_LDD(&di.wto[i]);
 		int end = ASTC_LDD(&di.wto[i + 1]);
-		ASTC_NOUNROLL
+		ASTC_UNROLL4
 		for (int j = off; j < end; j++) {
 			uint32_t e = ASTC_LDD(&di.wtc[j]);
 			int texel = (int)(e & 0xFF);
@@ -1184,7 +1197,7 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 			float anglesum_x = 0.0f, anglesum_y = 0.0f;
 			SPtr<float> cosp = sptr<float>(ASTC_SMEM_HDR) + sp;
 			SPtr<float> sinp = cosp + 64 * ASTC_ANGULAR_STEPS;
-			ASTC_NOUNROLL
+			ASTC_UNROLL4
 			for (int j = 0; j < pW; j++) {
 				int row = is[j] * ASTC_ANGULAR_STEPS;
 				anglesum_x += cosp[row];
@@ -1198,7 +1211,7 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 			float minidx = ASTC_RINT(pmin[pr] * rcp_stepsize - offset);
 			float maxidx = ASTC_RINT(pmax[pr] * rcp_stepsize - offset);
 			float errval = 0.0f, cut_low = 0.0f, cut_high = 0.0f;
-			ASTC_NOUNROLL
+			ASTC_UNROLL4
 			for (int j = 0; j < pW; j++) {
 				float sval = v[j] * rcp_stepsize - offset;
 				float svalrte = ASTC_RINT(sval);
