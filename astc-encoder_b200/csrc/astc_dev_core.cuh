@@ -36,8 +36,13 @@
 		#define ASTC_ONE_LANE 1
 	#endif
 	#define ASTC_NOUNROLL
-	#define ASTC_UNROLL2
-	#define ASTC_UNROLL4
+	#define ASTC_UNROLL_S2
+	#define ASTC_UNROLL_S4
+	#define ASTC_UNROLL_R2
+	#define ASTC_UNROLL_R4
+	#define ASTC_UNROLL_C4
+	#define ASTC_UNROLL_X2
+	#define ASTC_UNROLL_X4
 	#define ASTC_RINT(a) nearbyintf(a)
 	static inline uint32_t astc_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 	static inline float astc_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
@@ -66,15 +71,41 @@
 		#define ASTC_NOUNROLL _Pragma("unroll 1")
 	#endif
 	// The warps are latency bound (one warp issues ~1 instruction in 20 cycles): the few short loops that sit on every
-	// step's critical path - an LDS feeding an ordered add, a chain of dependent table look-ups per texel - are unrolled a
+	// item's critical path - an LDS feeding an ordered add, a chain of dependent table look-ups per texel - are unrolled a
 	// little so that the loads of the next trips are in flight while the current one computes. Everything else stays
-	// rolled: the kernels are instruction-cache sensitive (unrolling everything: 78 -> 90 ms).
-	#if defined(ASTC_NO_HOT_UNROLL)
-		#define ASTC_UNROLL2 _Pragma("unroll 1")
-		#define ASTC_UNROLL4 _Pragma("unroll 1")
+	// rolled: the kernels are instruction-cache sensitive (unrolling everything: 78 -> 90 ms). Groups (ASTC_UNROLL_GROUPS,
+	// measured one by one): 1 set-up kernel loops, 2 refinement loops (realign / score), 4 the ordered-sum chains,
+	// 8 further set-up loops.
+	#ifndef ASTC_UNROLL_GROUPS
+		#define ASTC_UNROLL_GROUPS 1
+	#endif
+	#define ASTC_PRAGMA_(x) _Pragma(#x)
+	#define ASTC_PRAGMA(x) ASTC_PRAGMA_(x)
+	#if (ASTC_UNROLL_GROUPS & 1)
+		#define ASTC_UNROLL_S2 ASTC_PRAGMA(unroll 2)
+		#define ASTC_UNROLL_S4 ASTC_PRAGMA(unroll 4)
 	#else
-		#define ASTC_UNROLL2 _Pragma("unroll 2")
-		#define ASTC_UNROLL4 _Pragma("unroll 4")
+		#define ASTC_UNROLL_S2 ASTC_PRAGMA(unroll 1)
+		#define ASTC_UNROLL_S4 ASTC_PRAGMA(unroll 1)
+	#endif
+	#if (ASTC_UNROLL_GROUPS & 2)
+		#define ASTC_UNROLL_R2 ASTC_PRAGMA(unroll 2)
+		#define ASTC_UNROLL_R4 ASTC_PRAGMA(unroll 4)
+	#else
+		#define ASTC_UNROLL_R2 ASTC_PRAGMA(unroll 1)
+		#define ASTC_UNROLL_R4 ASTC_PRAGMA(unroll 1)
+	#endif
+	#if (ASTC_UNROLL_GROUPS & 4)
+		#define ASTC_UNROLL_C4 ASTC_PRAGMA(unroll 4)
+	#else
+		#define ASTC_UNROLL_C4 ASTC_PRAGMA(unroll 1)
+	#endif
+	#if (ASTC_UNROLL_GROUPS & 8)
+		#define ASTC_UNROLL_X2 ASTC_PRAGMA(unroll 2)
+		#define ASTC_UNROLL_X4 ASTC_PRAGMA(unroll 4)
+	#else
+		#define ASTC_UNROLL_X2 ASTC_PRAGMA(unroll 1)
+		#define ASTC_UNROLL_X4 ASTC_PRAGMA(unroll 1)
 	#endif
 	#define ASTC_RINT(a) rintf(a)
 	#define ASTC_F2U(f) __float_as_uint(f)
@@ -445,7 +476,7 @@ ASTC_FN void chain_sums(const WCtx& w, int n, uint32_t tile, SPtr<float> acc, in
 			}
 			float s = acc[id];
 			SPtr<float> row = st + (k * CHAIN_STRIDE - base);
-			ASTC_UNROLL4
+			ASTC_UNROLL_C4
 			for (; p < hi; p += step) {
 				s = s + row[p];
 			}
@@ -656,7 +687,7 @@ ASTC_COOP void compute_dirs(WCtx w, const PartView& pi, uint32_t chan, int ncomp
 		const uint8_t* tix = pi.texels + pv_start(pi, (unsigned int)p);
 		int n = pv_count(pi, (unsigned int)p);
 		float s = 0.0f;
-		ASTC_UNROLL4
+		ASTC_UNROLL_S4
 		for (int i = 0; i < n; i++) {
 			int t = ASTC_LDG(&tix[i]);
 			float vK = dK[t] - avgK;
@@ -1013,7 +1044,7 @@ ASTC_COOP void compute_ideal_weights_for_decimation(WCtx w, unsigned int d, int 
 		float initial_weight = 0.0f;
 		int off = ASTC_LDD(&di.wto[i]);
 		int end = ASTC_LDD(&di.wto[i + 1]);
-		ASTC_UNROLL4
+		ASTC_UNROLL_S4
 		for (int j = off; j < end; j++) {
 			uint32_t e = ASTC_LDD(&di.wtc[j]);
 			int texel = (int)(e & 0xFF);
@@ -1049,7 +1080,7 @@ ASTC_COOP void compute_ideal_weights_for_decimation(WCtx w, unsigned int d, int 
 		float error_change1 = 0.0f;
 		int off = ASTC_LDD(&di.wto[i]);
 		int end = ASTC_LDD(&di.wto[i + 1]);
-		ASTC_UNROLL4
+		ASTC_UNROLL_S4
 		for (int j = off; j < end; j++) {
 			uint32_t e = ASTC_LDD(&di.wtc[j]);
 			int texel = (int)(e & 0xFF);
@@ -1161,7 +1192,7 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 			float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
 			if (steps != 0) {
 				SPtr<float> v = dwi + doff;
-				ASTC_NOUNROLL
+				ASTC_UNROLL_X4
 				for (int i = 0; i < W; i++) {
 					float x = v[i];
 					mn = minf(x, mn);
@@ -1197,7 +1228,7 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 			float anglesum_x = 0.0f, anglesum_y = 0.0f;
 			SPtr<float> cosp = sptr<float>(ASTC_SMEM_HDR) + sp;
 			SPtr<float> sinp = cosp + 64 * ASTC_ANGULAR_STEPS;
-			ASTC_UNROLL4
+			ASTC_UNROLL_S4
 			for (int j = 0; j < pW; j++) {
 				int row = is[j] * ASTC_ANGULAR_STEPS;
 				anglesum_x += cosp[row];
@@ -1211,7 +1242,7 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 			float minidx = ASTC_RINT(pmin[pr] * rcp_stepsize - offset);
 			float maxidx = ASTC_RINT(pmax[pr] * rcp_stepsize - offset);
 			float errval = 0.0f, cut_low = 0.0f, cut_high = 0.0f;
-			ASTC_UNROLL4
+			ASTC_UNROLL_S4
 			for (int j = 0; j < pW; j++) {
 				float sval = v[j] * rcp_stepsize - offset;
 				float svalrte = ASTC_RINT(sval);
@@ -1272,7 +1303,7 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 					int bidx = -1;
 					float bcut = 0.0f;
 					SPtr<AngStep> rp = rec + p_first;
-					ASTC_NOUNROLL
+					ASTC_UNROLL_X2
 					for (int sp = 0; sp < p_steps; sp++) {
 						AngStep r = rp[sp];
 						int span = r.span;

@@ -49,7 +49,7 @@ ASTC_COOP void quantize_and_score_modes(WCtx w, unsigned int start_mode, unsigne
 		WeightQuantizer z1 = make_weight_quantizer(low1, high1, quant_mode);
 		float rscale2 = z1.rscale, lowb2 = z1.low_bound;
 		SPtr<float> ideal1 = dwi + di.dwi_offset;
-		ASTC_UNROLL2
+		ASTC_UNROLL_S2
 		for (int k = 0; k < W; k++) {
 			uqrow[k] = (uint8_t)quantize_weight(z1, ideal1[k]);
 		}
@@ -59,7 +59,7 @@ ASTC_COOP void quantize_and_score_modes(WCtx w, unsigned int start_mode, unsigne
 			rscale2 = z2.rscale;
 			lowb2 = z2.low_bound;
 			SPtr<float> ideal2 = ideal1 + W;
-			ASTC_NOUNROLL
+			ASTC_UNROLL_X2
 			for (int k = 0; k < W; k++) {
 				uqrow[32 + k] = (uint8_t)quantize_weight(z2, ideal2[k]);
 			}
@@ -67,7 +67,7 @@ ASTC_COOP void quantize_and_score_modes(WCtx w, unsigned int start_mode, unsigne
 		// compute_error_of_weight_set_1plane / _2planes: texel t feeds accumulator lane t & 3
 		float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
 		float rscale1 = z1.rscale, lowb1 = z1.low_bound;
-		ASTC_UNROLL2
+		ASTC_UNROLL_S2
 		for (int t = 0; t < T; t++) {
 			uint32_t ix = ASTC_LDD(&di.twi[t]);
 			f4 cf = dec_contribs(di, t);
@@ -698,7 +698,7 @@ ASTC_COOP void recompute_ideal_colors_1plane(WCtx w, const PartView& pi, unsigne
 			int n = pv_count(pi, p);
 			SPtr<float> dch = sptr<float>(b0.off + (uint32_t)c * cs);
 			float s = 0.0f;
-			ASTC_UNROLL4
+			ASTC_UNROLL_R4
 			for (int j = 0; j < n; j++) {
 				s = s + dch[ASTC_LDG(&tix[j])];
 			}
@@ -1147,7 +1147,7 @@ ASTC_COOP float compute_symbolic_block_difference(WCtx w, unsigned int pc, uint3
 		ASTC_NOUNROLL
 		for (int l = w.lane; l < 4; l += ASTC_WARP) {
 			float s = 0.0f;
-			ASTC_UNROLL4
+			ASTC_UNROLL_R4
 			for (int t = l; t < T; t += 4) {
 				s = s + texel_err[t];
 			}
@@ -1378,7 +1378,7 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 				cnt = s_wto[we + 1] - off;
 			}
 			float sb = 0.0f, sd = 0.0f, su = 0.0f;
-			ASTC_UNROLL2
+			ASTC_UNROLL_R2
 			for (int te = 0; te < cnt; te++) {
 				uint32_t e = s_wtc[off + te];
 				int texel = (int)(e & 0xFF);
