@@ -194,6 +194,23 @@ astcenc_error astcenc_b200_load_cimage(const char* filename, astcenc_b200_cimage
 	return status;
 }
 
+// bytes of the block grid a header describes (false on zero dimensions / overflow)
+static bool grid_bytes(const astcenc_b200_cimage_header& h, size_t* out) {
+	if (h.block_x == 0 || h.block_y == 0 || h.block_z == 0 || h.dim_x == 0 || h.dim_y == 0 || h.dim_z == 0) {
+		return false;
+	}
+	unsigned long long bx = ((unsigned long long)h.dim_x + h.block_x - 1) / h.block_x;
+	unsigned long long by = ((unsigned long long)h.dim_y + h.block_y - 1) / h.block_y;
+	unsigned long long bz = ((unsigned long long)h.dim_z + h.block_z - 1) / h.block_z;
+	unsigned long long n = bx * by;
+	if (by != 0 && n / by != bx) return false;
+	unsigned long long m = n * bz;
+	if (bz != 0 && m / bz != n) return false;
+	if (m > (~0ull) / 16) return false;
+	*out = (size_t)(m * 16);
+	return true;
+}
+
 astcenc_error astcenc_b200_store_ktx_cimage(const char* filename, const astcenc_b200_cimage_header* hdr, int is_srgb, const uint8_t* data, size_t data_len) {
 	if (!filename || !hdr || (!data && data_len) || data_len > 0xFFFFFFFFull || hdr->dim_x == 0 || hdr->dim_y == 0 || hdr->dim_z == 0) {
 		return ASTCENC_ERR_BAD_PARAM;
@@ -201,6 +218,11 @@ astcenc_error astcenc_b200_store_ktx_cimage(const char* filename, const astcenc_
 	uint32_t fmt = gl_format_of(hdr->block_x, hdr->block_y, hdr->block_z, is_srgb != 0);
 	if (fmt == 0) {
 		return ASTCENC_ERR_BAD_BLOCK_SIZE;
+	}
+	// the payload must be exactly the block grid of the header (as store_cimage checks); 2D footprints describe 2D images
+	size_t want = 0;
+	if (!grid_bytes(*hdr, &want) || want != data_len || (hdr->block_z == 1 && hdr->dim_z != 1)) {
+		return ASTCENC_ERR_BAD_PARAM;
 	}
 	KtxHeader k;
 	memcpy(k.magic, k_ktx_magic, 12);
@@ -275,6 +297,12 @@ astcenc_error astcenc_b200_load_ktx_cimage(const char* filename, astcenc_b200_ci
 			long end = ftell(f);
 			if (end < at || (size_t)(end - at) < (size_t)len32) {
 				status = ASTCENC_ERR_BAD_PARAM;      // truncated payload
+			}
+			// the first mip level must hold the block grid of the header (a larger value would be trailing garbage,
+			// a smaller one a short payload that only fails later in decompression)
+			size_t want = 0;
+			if (status == ASTCENC_SUCCESS && (!grid_bytes(*hdr, &want) || want != (size_t)len32)) {
+				status = ASTCENC_ERR_BAD_PARAM;
 			}
 			fseek(f, at, SEEK_SET);
 		}

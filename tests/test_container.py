@@ -136,6 +136,16 @@ def test_ktx_refusals(pkg, tmp_path):
                      ("base.ktx", dict(fields=good[:5] + [0x1907] + good[6:])), ("short.ktx", dict(payload=bytes(8)))):
         with pytest.raises(pkg.AstcencError):
             pkg.load_ktx_cimage(write(name, **kw))
+    # a level size that is not the block grid of the header: trailing garbage / a short first level
+    for name, kw in (("long.ktx", dict(payload=bytes(32), length=32)), ("dims.ktx", dict(fields=good[:6] + [13, 6] + good[8:]))):
+        with pytest.raises(pkg.AstcencError):
+            pkg.load_ktx_cimage(write(name, **kw))
     with pytest.raises(pkg.AstcencError) as e:
         pkg.store_ktx_cimage(str(tmp_path / "x.ktx"), bytes(16), 7, 7, 7, 7)      # no GL enum for a 7x7 footprint
     assert e.value.code == pkg.ERR_BAD_BLOCK_SIZE
+    # store checks the payload against the header's block grid like store_cimage does, and refuses volumes with a 2D footprint
+    with pytest.raises(pkg.AstcencError) as e:
+        pkg.store_ktx_cimage(str(tmp_path / "y.ktx"), bytes(32), 6, 6, 6, 6)
+    assert e.value.code == pkg.ERR_BAD_PARAM
+    with pytest.raises(pkg.AstcencError):
+        pkg.store_ktx_cimage(str(tmp_path / "z.ktx"), bytes(32), 6, 6, 6, 6, dim_z=2)
