@@ -1494,6 +1494,17 @@ astcenc_error astcenc_b200_stage_timing(astcenc_context* ctx, int enable, float 
 
 extern "C" {
 
+// dev aid (tools/diag_*.py): the per-block search records of the last pass, for post-mortem comparison of two passes
+__attribute__((visibility("default"))) astcenc_error astcenc_b200_debug_records(astcenc_context* ctx, void** records, size_t* record_bytes, size_t* capacity_bytes) {
+	if (!ctx || !records || !record_bytes || !capacity_bytes) {
+		return ASTCENC_ERR_BAD_PARAM;
+	}
+	*records = ctx->d_records;
+	*record_bytes = ctx->tables->bsd.record_bytes;
+	*capacity_bytes = ctx->d_records_bytes;
+	return ASTCENC_SUCCESS;
+}
+
 unsigned long long astcenc_b200_launch_count(astcenc_context* ctx) {
 	return ctx->launches;
 }

@@ -158,9 +158,10 @@ class ClockSampler:
 def make_image(c, seed):
     import astc_images
     cfg = CONFIGS[c]
+    # (C-contiguous: the device-resident path uploads the array's memory as it lies; the generators may return other strides)
     if cfg["dtype"] == "f16":
-        return astc_images.hdr_noise(cfg["dim"], cfg["dim"], seed=seed, dtype=np.float16)
-    return astc_images.photo_like(cfg["dim"], cfg["dim"], seed=seed)
+        return np.ascontiguousarray(astc_images.hdr_noise(cfg["dim"], cfg["dim"], seed=seed, dtype=np.float16))
+    return np.ascontiguousarray(astc_images.photo_like(cfg["dim"], cfg["dim"], seed=seed))
 
 
 def variant(image, k):
