@@ -286,7 +286,9 @@ struct Knobs {
 	int coherence_probe;         // ASTCENC_B200_COHERENCE_PROBE (single-kernel driver experiment)
 	int upload_bands;            // ASTCENC_B200_UPLOAD_BANDS: bands the host-pointer path cuts an image into (1 = one copy)
 	int stage_print;             // ASTCENC_B200_STAGE_PRINT
+	int pipes;                   // ASTCENC_B200_PIPES: independent sub-slab pipelines of one pass (1 = the plain wave loop)
 };
+#define ASTC_MAX_PIPES 8
 #define ASTC_MAX_BANDS 8
 #define ASTC_COUNTER_WORDS (2 * ASTC_Q_KINDS * ASTC_MAX_WAVES + ASTC_MAX_BANDS)
 
@@ -344,6 +346,10 @@ struct astcenc_context {
 	cudaStream_t copy_stream;
 	cudaEvent_t band_ready[ASTC_MAX_BANDS];
 	cudaEvent_t out_ready;
+	// sub-slab pipelines of one pass (launch_pipes): one stream each, joined to the caller's stream by events
+	cudaStream_t pipe_stream[ASTC_MAX_PIPES];
+	cudaEvent_t pipe_done[ASTC_MAX_PIPES];
+	cudaEvent_t pipe_start;
 	uint8_t* d_image2;           // second image buffer of the batch API (double-buffered uploads)
 	size_t d_image2_bytes;
 	// multi-GPU (astc_host_multi.inl): one process per GPU, NCCL for the payload gather
@@ -439,6 +445,11 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	for (int i = 0; i < ASTC_MAX_BANDS; i++) {
 		ctx->band_ready[i] = nullptr;
 	}
+	for (int i = 0; i < ASTC_MAX_PIPES; i++) {
+		ctx->pipe_stream[i] = nullptr;
+		ctx->pipe_done[i] = nullptr;
+	}
+	ctx->pipe_start = nullptr;
 	ctx->d_ticket = nullptr;
 	ctx->d_records = nullptr;
 	ctx->d_records_bytes = 0;
@@ -480,6 +491,11 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	}
 	ctx->knobs.coherence_probe = getenv("ASTCENC_B200_COHERENCE_PROBE") ? 1 : 0;
 	ctx->knobs.stage_print = getenv("ASTCENC_B200_STAGE_PRINT") ? 1 : 0;
+	ctx->knobs.pipes = 4;
+	if (const char* e = getenv("ASTCENC_B200_PIPES")) {
+		int v = atoi(e);
+		if (v >= 1 && v <= ASTC_MAX_PIPES) ctx->knobs.pipes = v;
+	}
 	ctx->knobs.upload_bands = 4;
 	if (const char* e = getenv("ASTCENC_B200_UPLOAD_BANDS")) {
 		int v = atoi(e);
@@ -609,7 +625,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			if (waves > ASTC_MAX_WAVES - 1) waves = ASTC_MAX_WAVES - 1;
 			ctx->max_waves = waves;
 			// count[kinds][waves], head[kinds][waves], then one image ticket per upload band
-			CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(uint32_t) * ASTC_COUNTER_WORDS), ALLOC_FAIL(ASTCENC_ERR_OUT_OF_MEM));
+			CUDA_TRY(cudaMalloc(&ctx->d_counters, sizeof(uint32_t) * ASTC_COUNTER_WORDS * ASTC_MAX_PIPES), ALLOC_FAIL(ASTCENC_ERR_OUT_OF_MEM));
 		}
 		CUDA_TRY(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)), ALLOC_FAIL(ASTCENC_ERR_OUT_OF_MEM));
 	}
@@ -624,6 +640,11 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	for (int i = 0; i < ASTC_MAX_BANDS; i++) {
 		CUDA_TRY(cudaEventCreateWithFlags(&ctx->band_ready[i], cudaEventDisableTiming), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
 	}
+	for (int i = 0; i < ASTC_MAX_PIPES; i++) {
+		CUDA_TRY(cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+		CUDA_TRY(cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
+	}
+	CUDA_TRY(cudaEventCreateWithFlags(&ctx->pipe_start, cudaEventDisableTiming), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
 	#undef ALLOC_FAIL
 	*context = ctx;
 	return ASTCENC_SUCCESS;
@@ -664,6 +685,14 @@ void astcenc_context_free(astcenc_context* ctx) {
 	for (int i = 0; i < ASTC_MAX_BANDS; i++) {
 		if (ctx->band_ready[i]) cudaEventDestroy(ctx->band_ready[i]);
 	}
+	for (int i = 0; i < ASTC_MAX_PIPES; i++) {
+		if (ctx->pipe_stream[i]) {
+			cudaStreamSynchronize(ctx->pipe_stream[i]);
+			cudaStreamDestroy(ctx->pipe_stream[i]);
+		}
+		if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
+	}
+	if (ctx->pipe_start) cudaEventDestroy(ctx->pipe_start);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	release_tables(ctx->tables);
@@ -734,6 +763,117 @@ static astcenc_error upload_whole(astcenc_context* ctx, const UploadPlan& up, un
 	return ASTCENC_SUCCESS;
 }
 
+// One pass as P independent sub-slab pipelines. The search is a chain of waves (set-up -> refine -> prepare, ~10 times) and
+// every kernel of the chain ends with a drain: the last blocks of a wave keep a few SMs busy while the others idle, and the
+// late waves never fill 148 SMs at all. Blocks are independent, so the slab is cut into P ranges of block rows, each with
+// its own records / queues / counters, and the P chains are enqueued breadth-first on P streams: while the kernel of one
+// chain drains, the CTAs of the next chain's kernel take over the SMs that became free (every kernel is one CTA per SM,
+// so the hardware block scheduler does the interleaving). Same kernels, same results; wave 0 of chain p waits only for the
+// upload of its own rows (the band scheme of the host-pointer path with bands = pipelines).
+static astcenc_error launch_pipes(astcenc_context* ctx, int pipes, const void* d_pixels, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
+                                  unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream, const UploadPlan* up) {
+	const DevBsd& bsd = ctx->tables->bsd;
+	unsigned int blocks_x = (dim_x + bsd.dim_x - 1) / bsd.dim_x;
+	size_t total = (size_t)blocks_x * block_rows;
+	if (total > ctx->queue_capacity) {
+		cudaFree(ctx->d_queues);
+		ctx->d_queues = nullptr;
+		ctx->queue_capacity = 0;
+		CUDA_TRY(cudaMalloc(&ctx->d_queues, sizeof(uint32_t) * ASTC_Q_KINDS * total), return ASTCENC_ERR_OUT_OF_MEM);
+		ctx->queue_capacity = total;
+	}
+	size_t rec_bytes = total * (size_t)bsd.record_bytes;
+	if (rec_bytes > ctx->d_records_bytes) {
+		cudaFree(ctx->d_records);
+		ctx->d_records = nullptr;
+		ctx->d_records_bytes = 0;
+		CUDA_TRY(cudaMalloc(&ctx->d_records, rec_bytes), return ASTCENC_ERR_OUT_OF_MEM);
+		ctx->d_records_bytes = rec_bytes;
+	}
+	DevImage img[ASTC_MAX_PIPES];
+	WaveArgs a[ASTC_MAX_PIPES];
+	if (up != nullptr && ctx->scratch_used) {
+		CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->scratch_done, 0), return ASTCENC_ERR_BAD_CONTEXT);
+	}
+	CUDA_TRY(cudaEventRecord(ctx->pipe_start, stream), return ASTCENC_ERR_BAD_CONTEXT);
+	for (int p = 0; p < pipes; p++) {
+		unsigned int r0 = (unsigned int)((size_t)block_rows * p / pipes), r1 = (unsigned int)((size_t)block_rows * (p + 1) / pipes);
+		size_t first = (size_t)r0 * blocks_x;
+		cudaStream_t ps = ctx->pipe_stream[p];
+		CUDA_TRY(cudaStreamWaitEvent(ps, ctx->pipe_start, 0), return ASTCENC_ERR_BAD_CONTEXT);
+		DevImage& im = img[p];
+		im.data = d_pixels;
+		im.data_type = data_type;
+		im.dim_x = dim_x;
+		im.dim_y = dim_y;
+		im.blocks_x = blocks_x;
+		im.block_row0 = block_row0 + r0;
+		im.block_rows = r1 - r0;
+		for (int i = 0; i < 4; i++) {
+			im.swz[i] = swz[i];
+		}
+		im.out = d_out + first * 16;
+		im.alpha_avg = ctx->config.a_scale_radius != 0 ? ctx->d_alpha : nullptr;
+		im.alpha_threshold = ctx->alpha_threshold;
+		uint32_t* counters = ctx->d_counters + (size_t)p * ASTC_COUNTER_WORDS;
+		CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * ASTC_COUNTER_WORDS, ps), return ASTCENC_ERR_BAD_CONTEXT);
+		WaveArgs& w = a[p];
+		w.records = ctx->d_records + first * (size_t)bsd.record_bytes;
+		for (int k = 0; k < ASTC_Q_KINDS; k++) {
+			w.queue[k] = ctx->d_queues + (size_t)k * ctx->queue_capacity + first;
+		}
+		w.count = counters;
+		w.head = counters + ASTC_Q_KINDS * ASTC_MAX_WAVES;
+		w.total = (r1 - r0) * blocks_x;
+		w.blocks_x = blocks_x;
+		w.ticket = counters + 2 * ASTC_Q_KINDS * ASTC_MAX_WAVES;
+		w.first_block = 0;
+		w.band_blocks = w.total;
+		w.stage_bytes = ctx->refine_stage_bytes;
+		w.refine_state_off = (uint32_t)(ASTC_SMEM_HDR + ctx->refine_stage_bytes + (size_t)bsd.arena_bytes_small * ctx->warps_small);
+		w.stage_bytes_setup = ctx->setup_stage_bytes;
+		w.sync_mask = ctx->knobs.sync_mask;
+		if (up != nullptr) {
+			// this pipeline's rows go up on the copy stream; only its wave 0 waits for them
+			size_t y0 = (size_t)(block_row0 + r0) * bsd.dim_y, y1 = (size_t)(block_row0 + r1) * bsd.dim_y;
+			if (y1 > dim_y) y1 = dim_y;
+			if (y1 > y0) {
+				CUDA_TRY(cudaMemcpyAsync(up->device + y0 * up->row_bytes, up->host + y0 * up->row_bytes, (y1 - y0) * up->row_bytes, cudaMemcpyHostToDevice, ctx->copy_stream),
+				         return ASTCENC_ERR_BAD_CONTEXT);
+			}
+			CUDA_TRY(cudaEventRecord(ctx->band_ready[p], ctx->copy_stream), return ASTCENC_ERR_BAD_CONTEXT);
+			CUDA_TRY(cudaStreamWaitEvent(ps, ctx->band_ready[p], 0), return ASTCENC_ERR_BAD_CONTEXT);
+		}
+	}
+	int grid = ctx->grid;
+	int wp = ctx->warps_small >= 2 ? ctx->warps_small / 2 : 1;
+	for (int wave = 0; wave < ctx->max_waves; wave++) {
+		for (int p = 0; p < pipes; p++) {
+			if (a[p].total == 0) {
+				continue;
+			}
+			a[p].wave = wave;
+			cudaStream_t ps = ctx->pipe_stream[p];
+			astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
+			astc_wave_refine_kernel<<<grid, ctx->warps_small * 32, ctx->smem_refine, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
+			astc_wave_prepare_kernel<<<grid * 2, wp * 32, ASTC_SMEM_HDR + (size_t)bsd.arena_bytes_small * wp, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
+			ctx->launches += 3;
+		}
+	}
+	for (int p = 0; p < pipes; p++) {
+		cudaStream_t ps = ctx->pipe_stream[p];
+		if (a[p].total != 0) {
+			a[p].wave = 0;
+			astc_wave_emit_kernel<<<grid * 4, ASTC_EMIT_THREADS, ASTC_SMEM_HDR + (ASTC_EMIT_THREADS / 32) * 32 * EMIT_SLICE, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
+			ctx->launches++;
+		}
+		CUDA_TRY(cudaEventRecord(ctx->pipe_done[p], ps), return ASTCENC_ERR_BAD_CONTEXT);
+		CUDA_TRY(cudaStreamWaitEvent(stream, ctx->pipe_done[p], 0), return ASTCENC_ERR_BAD_CONTEXT);
+	}
+	CUDA_TRY(cudaGetLastError(), return ASTCENC_ERR_BAD_CONTEXT);
+	return ASTCENC_SUCCESS;
+}
+
 static astcenc_error launch_slab_locked(astcenc_context* ctx, const void* d_pixels, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
                                         unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream, const UploadPlan* up) {
 	const DevBsd& bsd = ctx->tables->bsd;
@@ -741,8 +881,13 @@ static astcenc_error launch_slab_locked(astcenc_context* ctx, const void* d_pixe
 	size_t rows_per_batch = ctx->knobs.batch_blocks / (blocks_x ? blocks_x : 1);
 	if (rows_per_batch < 1) rows_per_batch = 1;
 	const unsigned int radius = ctx->config.a_scale_radius;
+	// big single-batch slabs run as independent sub-slab pipelines (launch_pipes); per-launch timing wants one stream
+	bool single_batch = (size_t)block_rows <= rows_per_batch;
+	int pipes = ctx->knobs.pipes;
+	bool use_pipes = pipes > 1 && ctx->driver == 0 && !ctx->stage_timing && single_batch && block_rows >= (unsigned int)pipes * 4 &&
+	                 blocks_x * block_rows >= (size_t)pipes * 8192;
 	// banded uploads need the whole slab in one batch on the wave pipeline, and no pre-pass that reads the whole image first
-	bool banded = up != nullptr && up->bands > 1 && radius == 0 && ctx->driver == 0 && (size_t)block_rows <= rows_per_batch && block_rows >= (unsigned int)up->bands * 4;
+	bool banded = up != nullptr && radius == 0 && ctx->driver == 0 && single_batch && (use_pipes || (up->bands > 1 && block_rows >= (unsigned int)up->bands * 4));
 	if (up != nullptr && !banded) {
 		// the upload streams on the copy stream; it must not overtake a pass that still reads the image buffer
 		if (ctx->scratch_used) {
@@ -791,6 +936,9 @@ static astcenc_error launch_slab_locked(astcenc_context* ctx, const void* d_pixe
 		size_t y_footprint = bsd.dim_y + 2 * ((size_t)radius - 1);
 		float footprint = static_cast<float>(x_footprint * y_footprint);
 		ctx->alpha_threshold = 0.9f / (255.0f * footprint);
+	}
+	if (use_pipes) {
+		return launch_pipes(ctx, pipes, d_pixels, data_type, dim_x, dim_y, swz, block_row0, block_rows, d_out, stream, banded ? up : nullptr);
 	}
 	unsigned int done = 0;
 	while (done < block_rows) {

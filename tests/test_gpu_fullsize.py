@@ -76,6 +76,40 @@ def test_banded_upload_equals_single_copy(gpu):
         assert all(np.array_equal(v[0], x) for x in v[1:]), k
 
 
+def test_sub_slab_pipelines_equal_the_plain_wave_loop(gpu):
+    """A pass may run as P independent sub-slab pipelines on P streams (ASTCENC_B200_PIPES, read when the context is made):
+    every P gives the bytes of the plain wave loop, host-pointer path and device-resident path alike, ragged sizes included."""
+    import torch
+    dev = torch.device("cuda", 0)
+    img = I.photo_like(1500, 1210, seed=12)
+    d_img = torch.from_numpy(img).to(dev)
+    outs = []
+    for pipes in ("1", "2", "4", "8"):
+        os.environ["ASTCENC_B200_PIPES"] = pipes
+        try:
+            ctx = gpu.Context(gpu.config_init(PRF_LDR, 5, 5, PRE_FAST, S))
+            host = ctx.compress_image(img).copy()
+            nbx, nby = ctx.blocks(1210, 1500)
+            d_out = torch.zeros(nbx * nby * 16, dtype=torch.uint8, device=dev)
+            st = torch.cuda.Stream(device=dev)
+            torch.cuda.synchronize()
+            for _ in range(2):
+                ctx.compress_device(d_img.data_ptr(), gpu.TYPE_U8, 1210, 1500, d_out.data_ptr(), stream=st.cuda_stream)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_out.cpu().numpy(), host)
+            # a slab of the image through the same machinery
+            r0, r1 = 31, 257
+            d_slab = torch.zeros((r1 - r0) * nbx * 16, dtype=torch.uint8, device=dev)
+            ctx.compress_device(d_img.data_ptr(), gpu.TYPE_U8, 1210, 1500, d_slab.data_ptr(), block_row0=r0, block_rows=r1 - r0, stream=st.cuda_stream)
+            torch.cuda.synchronize()
+            assert np.array_equal(d_slab.cpu().numpy(), host[r0 * nbx * 16:r1 * nbx * 16])
+            outs.append(host)
+            ctx.close()
+        finally:
+            del os.environ["ASTCENC_B200_PIPES"]
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])
+
+
 def test_one_context_two_streams_are_ordered(gpu):
     """Two device-resident passes of ONE context on different streams share the context's scratch: the library orders
     them (mutex + event chain), so both results are right whatever the streams do."""
