@@ -356,7 +356,7 @@ ASTC_FN DecView dec_view(unsigned int d) {
 	v.T = BSD.texel_count;
 	v.W = ASTC_LDG(&dm->weight_count);
 	v.max_twc = ASTC_LDG(&dm->max_texel_weight_count);
-	v.dwi_offset = ASTC_LDG(&dm->dwi_offset);
+	v.dwi_offset = BSD.layout_planes == 1 ? ASTC_LDG(&dm->dwi_offset_1p) : ASTC_LDG(&dm->dwi_offset);
 	v.tcf = reinterpret_cast<const float*>(blob);
 	v.twi = reinterpret_cast<const uint32_t*>(blob + 16 * v.T);
 	v.tci = reinterpret_cast<const uint32_t*>(blob + 20 * v.T);
@@ -1176,7 +1176,7 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 			steps = angular_steps_of((unsigned int)d, nplanes, mask, max_weight_quant, max_precision);
 			const DevDecMode* dm = BSD.dec_modes + d;
 			W = ASTC_LDG(&dm->weight_count);
-			doff = (int)ASTC_LDG(&dm->dwi_offset) + pl * W;
+			doff = (int)(BSD.layout_planes == 1 ? ASTC_LDG(&dm->dwi_offset_1p) : ASTC_LDG(&dm->dwi_offset)) + pl * W;
 		}
 		int incl = wscan_incl(steps, w.lane);
 		bool in_round = id < pairs && incl <= cap;
@@ -1219,7 +1219,7 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 			int ppl = pid - pd * nplanes;
 			const DevDecMode* dm = BSD.dec_modes + pd;
 			int pW = ASTC_LDG(&dm->weight_count);
-			int pdoff = (int)ASTC_LDG(&dm->dwi_offset) + ppl * pW;
+			int pdoff = (int)(BSD.layout_planes == 1 ? ASTC_LDG(&dm->dwi_offset_1p) : ASTC_LDG(&dm->dwi_offset)) + ppl * pW;
 			unsigned int mp;
 			int psteps = angular_steps_of((unsigned int)pd, nplanes, mask, max_weight_quant, mp);
 			SPtr<float> v = dwi + pdoff;
@@ -1341,7 +1341,7 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 					float lwi = r.minidx + bcut;
 					float hwi = lwi + static_cast<float>(q) - 1.0f;
 					float stepsize = 1.0f / (1.0f + static_cast<float>(bsi));
-					SPtr<float> lh = lowhigh + (p_d * 2 + p_pl) * 16;
+					SPtr<float> lh = lowhigh + (p_d * (int)BSD.layout_planes + p_pl) * 16;
 					lh[2 * qi] = (r.offset + lwi) * stepsize;
 					lh[2 * qi + 1] = (r.offset + hwi) * stepsize;
 				}
@@ -1357,7 +1357,7 @@ ASTC_COOP void compute_angular_endpoints(WCtx w, bool only_always, int nplanes, 
 // astcenc_compress_symbolic.cpp:459 / :819-827.
 ASTC_FN void mode_low_high(const WCtx& w, int decimation_mode, int quant_mode, int plane, float min_wt_cutoff, float& low, float& high) {
 	if (quant_mode <= TUNE_MAX_ANGULAR_QUANT) {
-		SPtr<float> lh = lowhigh_of(w) + ((decimation_mode * 2 + plane) * 16 + quant_mode * 2);
+		SPtr<float> lh = lowhigh_of(w) + ((decimation_mode * (int)BSD.layout_planes + plane) * 16 + quant_mode * 2);
 		low = lh[0];
 		high = lh[1];
 	} else {

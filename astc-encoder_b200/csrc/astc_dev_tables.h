@@ -72,6 +72,7 @@ struct DevDecMode {
 	uint16_t wto_offset;      // byte offset of wto inside the blob (= 24 * T)
 	uint16_t wtc_offset;      // byte offset of wtc
 	uint16_t max_weight_texels;   // longest weight -> texel list of this grid
+	uint16_t dwi_offset_1p;   // the same in the compact one-plane arena layout (DevBsd::layout_planes == 1)
 	uint32_t blob_offset;     // byte offset of the blob in dec_blob
 };
 
@@ -103,6 +104,10 @@ struct DevBsd {
 	uint32_t off_scratch, off_ei, off_dwi, off_lowhigh, off_mode_err;
 	uint32_t scratch_bytes;      // size of the union scratch at off_scratch
 	uint32_t record_bytes;       // ASTC_ARENA_PERSIST_HEAD + 16 * Tp, rounded to 16
+	// Two plans of the set-up tail exist: the general one (ideal weights, decimated weights and angular ranges for TWO weight
+	// planes) and a compact one for trials with ONE plane (wave 0 - every block's first trial - never has two): fewer bytes
+	// per block, more blocks in flight per SM. The kernel is told which plan its launch uses.
+	uint32_t layout_planes;      // 2 (general) or 1 (compact)
 };
 
 // The search configuration consumed on the device (subset of astcenc_config, astcenc.h:427-605).

@@ -14,6 +14,7 @@ namespace astc_host {
 struct PackedTables {
 	std::vector<uint8_t> blob;
 	DevBsd bsd;              // pointer fields = offsets until relocate_bsd()
+	DevBsd bsd_1p;           // the same tables with the compact one-plane arena plan (DevBsd::layout_planes == 1)
 	DevConstTables consts;
 };
 
@@ -98,7 +99,7 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 	// decimation modes + blobs
 	std::vector<DevDecMode> dms(t.decimation_mode_count_all);
 	std::vector<uint8_t> dblob;
-	uint32_t dwi_total = 0;
+	uint32_t dwi_total = 0, dwi_total_1p = 0;
 	unsigned int max_wtc = 1;
 	for (unsigned int d = 0; d < t.decimation_mode_count_all; d++) {
 		const DecimationInfo& di = t.decimation_tables[d];
@@ -158,10 +159,13 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 		dm.max_weight_texels = (uint16_t)grid_max_wtc;
 		// arena slot for the decimated ideal weights (only grids the search can reference)
 		dm.dwi_offset = (uint16_t)dwi_total;
+		dm.dwi_offset_1p = (uint16_t)dwi_total_1p;
 		if (d < t.decimation_mode_count_selected) {
 			b.dec_stage_bytes = (uint32_t)((dblob.size() + 15) / 16 * 16);
 			dwi_total += W * (dm.maxprec_2planes >= 0 ? 2u : 1u);
 			dwi_total = (dwi_total + 3u) & ~3u;
+			dwi_total_1p += W;
+			dwi_total_1p = (dwi_total_1p + 3u) & ~3u;
 		}
 	}
 	b.max_weight_texel_count = (uint8_t)max_wtc;
@@ -241,8 +245,25 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 	b.off_lowhigh = o;    o = align16(o + 128 * t.decimation_mode_count_selected);
 	b.off_mode_err = o;   o = align16(o + 4 * t.block_mode_count_1plane_2plane_selected);
 	b.arena_bytes = o;
+	b.layout_planes = 2;
+	// the compact plan for one-plane trials: same head, texels and scratch (the records and the refinement kernels never see
+	// the tail), one plane's worth of ideal weights, decimated weights and angular ranges, errors of the 1-plane modes only
+	DevBsd& c = out.bsd_1p;
+	c = b;
+	o = b.arena_bytes_small;
+	c.off_ei = o;         o = align16(o + 8 * Tp);
+	c.off_dwi = o;        o = align16(o + 4 * (dwi_total_1p ? dwi_total_1p : 4));
+	c.off_lowhigh = o;    o = align16(o + 64 * t.decimation_mode_count_selected);
+	c.off_mode_err = o;   o = align16(o + 4 * t.block_mode_count_1plane_selected);
+	c.arena_bytes = o;
+	c.layout_planes = 1;
 }
 
+static inline void relocate_bsd(DevBsd& b, const uint8_t* base);
+static inline void relocate_tables(PackedTables& pk, const uint8_t* base) {
+	relocate_bsd(pk.bsd, base);
+	relocate_bsd(pk.bsd_1p, base);
+}
 static inline void relocate_bsd(DevBsd& b, const uint8_t* base) {
 	auto rel = [&](const void* p) { return base + reinterpret_cast<uintptr_t>(p); };
 	b.block_modes = reinterpret_cast<const DevBlockMode*>(rel(b.block_modes));

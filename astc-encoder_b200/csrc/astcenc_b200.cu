@@ -107,7 +107,7 @@ static __device__ __forceinline__ bool wave_queue_empty(const WaveArgs& a, int k
 	return n == 0;
 }
 
-#define ASTC_SETUP_THREADS_MAX 512
+#define ASTC_SETUP_THREADS_MAX 640      /* 20 warps x <= 102 registers (the compact one-plane plan fits 19-20 arenas per SM at 6x6) */
 #ifndef ASTC_REFINE_THREADS_MAX
 #define ASTC_REFINE_THREADS_MAX 768      /* 24 warps x 80 registers; 26 / 28 warps x 72 registers: refine 38.1 / 36.9 vs 37.3 ms, prepare +0.1 / +0.4 ms */
 #endif
@@ -296,6 +296,7 @@ struct DeviceTables {            // shared between a parent context and its chil
 	std::atomic<int> refcount;
 	uint8_t* d_blob;
 	DevBsd bsd;                  // device pointers
+	DevBsd bsd_1p;               // the same tables, compact one-plane arena plan (wave 0 of the pipeline)
 	astc_host::BlockSizeTables* host_tables;
 };
 
@@ -314,7 +315,8 @@ struct astcenc_context {
 	int lockstep;                // single-kernel drivers: phase-aligned CTA (1) or independent warps (0)
 	int driver;                  // 0 = wave pipeline (default), 1 = single kernel
 	int warps_setup, warps_small;   // warps per CTA of the setup / refine+prepare kernels
-	size_t smem_setup, smem_small, smem_refine;
+	int warps_setup_1p;             // set-up kernel on the compact one-plane plan (0 = plan not used)
+	size_t smem_setup, smem_setup_1p, smem_small, smem_refine;
 	uint32_t setup_stage_bytes;
 	uint32_t refine_stage_bytes;   // tables staged behind the header of the refine kernel's shared window (0 = none)
 	int max_waves;
@@ -478,6 +480,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	ctx->last_kernel_ms = 0.0f;
 	ctx->last_h2d = ctx->last_d2h = 0;
 	ctx->warps_per_cta = ctx->grid = 0;
+	ctx->warps_setup_1p = 0;
 	ctx->max_waves = 0;
 	// environment knobs: read here, once
 	ctx->knobs.batch_blocks = (size_t)1 << 20;
@@ -491,7 +494,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	}
 	ctx->knobs.coherence_probe = getenv("ASTCENC_B200_COHERENCE_PROBE") ? 1 : 0;
 	ctx->knobs.stage_print = getenv("ASTCENC_B200_STAGE_PRINT") ? 1 : 0;
-	ctx->knobs.pipes = 4;
+	ctx->knobs.pipes = 1;      // measured at 4K 6x6 -medium: 1 / 2 / 4 / 8 pipelines = 76.1 / 76.7 / 78.0 / 80.1 ms (the idle warps are inside the CTAs, not between kernels)
 	if (const char* e = getenv("ASTCENC_B200_PIPES")) {
 		int v = atoi(e);
 		if (v >= 1 && v <= ASTC_MAX_PIPES) ctx->knobs.pipes = v;
@@ -534,7 +537,9 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 		CUDA_TRY(cudaMalloc(&t->d_blob, pk.blob.size()), ALLOC_FAIL(ASTCENC_ERR_OUT_OF_MEM));
 		CUDA_TRY(cudaMemcpy(t->d_blob, pk.blob.data(), pk.blob.size(), cudaMemcpyHostToDevice), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
 		t->bsd = pk.bsd;
+		t->bsd_1p = pk.bsd_1p;
 		astc_host::relocate_bsd(t->bsd, t->d_blob);
+		astc_host::relocate_bsd(t->bsd_1p, t->d_blob);
 	}
 	astc_host::make_device_config(cfg, ctx->dcfg);
 
@@ -611,6 +616,18 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 				}
 			}
 			ctx->smem_setup = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + ctx->setup_stage_bytes + arena * ws;
+			// wave 0 (every block's first trial has one weight plane) runs on the compact plan: more arenas per SM
+			{
+				size_t arena1 = ctx->tables->bsd_1p.arena_bytes;
+				int w1 = (int)((smem_limit - ASTC_SMEM_HDR - ASTC_SMEM_SINCOS_BYTES - ctx->setup_stage_bytes) / arena1);
+				if (w1 > ASTC_SETUP_THREADS_MAX / 32) w1 = ASTC_SETUP_THREADS_MAX / 32;
+				if (const char* e = getenv("ASTCENC_B200_WARPS_SETUP_1P")) {
+					int v = atoi(e);
+					if (v >= 0 && v < w1) w1 = v;
+				}
+				ctx->warps_setup_1p = w1 > ws ? w1 : 0;      // only when it buys warps
+				ctx->smem_setup_1p = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + ctx->setup_stage_bytes + arena1 * (size_t)w1;
+			}
 			ctx->smem_small = ASTC_SMEM_HDR + arena_small * wr;
 			ctx->smem_refine = ASTC_SMEM_HDR + ctx->refine_stage_bytes + arena_small * wr + (size_t)ASTC_REFINE_STATE_BYTES * wr;
 			CUDA_TRY(cudaFuncSetAttribute(astc_wave_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit), ALLOC_FAIL(ASTCENC_ERR_BAD_CONTEXT));
@@ -854,7 +871,11 @@ static astcenc_error launch_pipes(astcenc_context* ctx, int pipes, const void* d
 			}
 			a[p].wave = wave;
 			cudaStream_t ps = ctx->pipe_stream[p];
-			astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
+			if (wave == 0 && ctx->warps_setup_1p) {
+				astc_wave_setup_kernel<<<grid, ctx->warps_setup_1p * 32, ctx->smem_setup_1p, ps>>>(ctx->tables->bsd_1p, ctx->dcfg, img[p], a[p]);
+			} else {
+				astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
+			}
 			astc_wave_refine_kernel<<<grid, ctx->warps_small * 32, ctx->smem_refine, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
 			astc_wave_prepare_kernel<<<grid * 2, wp * 32, ASTC_SMEM_HDR + (size_t)bsd.arena_bytes_small * wp, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
 			ctx->launches += 3;
@@ -1057,14 +1078,22 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 					a.ticket = ctx->d_counters + 2 * ASTC_Q_KINDS * ASTC_MAX_WAVES + k;
 					a.first_block = row * img.blocks_x;
 					a.band_blocks = (row_end - row) * img.blocks_x;
-					astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
+					if (ctx->warps_setup_1p) {
+						astc_wave_setup_kernel<<<grid, ctx->warps_setup_1p * 32, ctx->smem_setup_1p, stream>>>(ctx->tables->bsd_1p, ctx->dcfg, img, a);
+					} else {
+						astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
+					}
 					ctx->launches++;
 					row = row_end;
 				}
 				mark(0);
 				ctx->launches--;      // (the loop below counts one set-up launch per wave)
 			} else {
-				astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
+				if (wave == 0 && ctx->warps_setup_1p) {
+					astc_wave_setup_kernel<<<grid, ctx->warps_setup_1p * 32, ctx->smem_setup_1p, stream>>>(ctx->tables->bsd_1p, ctx->dcfg, img, a);
+				} else {
+					astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
+				}
 				mark(0);
 			}
 			astc_wave_refine_kernel<<<grid, ctx->warps_small * 32, ctx->smem_refine, stream>>>(bsd, ctx->dcfg, img, a);

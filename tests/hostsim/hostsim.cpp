@@ -42,6 +42,8 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	unsigned int lim[3] = {cfg.tune_2partition_index_limit, cfg.tune_3partition_index_limit, cfg.tune_4partition_index_limit};
 	astc_host::pack_device_tables(*t, lim, pk);
 	astc_host::relocate_bsd(pk.bsd, pk.blob.data());
+	astc_host::relocate_bsd(pk.bsd_1p, pk.blob.data());
+	const DevBsd bsd_1p = pk.bsd_1p;
 	astc_host::fill_dev_const_tables(pk.consts);
 	g_astc_ct = &pk.consts;
 	DevConfig dcfg;
@@ -141,6 +143,12 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 			a.stage_bytes_setup = 0;
 			for (int wave = 0; wave < ASTC_MAX_WAVES - 1; wave++) {
 				a.wave = wave;
+				// (like the CUDA host code: wave 0 runs on the compact one-plane arena plan)
+				cta_sync();
+				if (lane == 0) {
+					hdr->bsd = wave == 0 && !getenv("HOSTSIM_NO_1P") ? bsd_1p : pk.bsd;
+				}
+				cta_sync();
 				wave_setup(w, a);
 				wave_refine(w, a, 0);
 				wave_prepare(w, a);
