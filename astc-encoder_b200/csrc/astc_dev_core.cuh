@@ -77,7 +77,7 @@
 	// measured one by one): 1 set-up kernel loops, 2 refinement loops (realign / score), 4 the ordered-sum chains,
 	// 8 further set-up loops.
 	#ifndef ASTC_UNROLL_GROUPS
-		#define ASTC_UNROLL_GROUPS 1
+		#define ASTC_UNROLL_GROUPS 5      /* measured at 4K 6x6 -medium: groups 1 / 1+2 / 1+4 / 1+8 / 1+4+8 = 75.8 / 76.6 / 75.5 / 76.1 / 75.6 ms */
 	#endif
 	#define ASTC_PRAGMA_(x) _Pragma(#x)
 	#define ASTC_PRAGMA(x) ASTC_PRAGMA_(x)
@@ -288,10 +288,11 @@ enum {
 	A_EP = 1680,           // f4[EP_COUNT] endpoint slots (640), the trial's base endpoints first
 	A_PERSIST = ASTC_ARENA_PERSIST_HEAD,   // = A_EP + 128
 	A_TMPF = 2320,         // float[128] chain results / partial sums
+	A_MBAR = 2832,         // the warp's mbarrier for bulk (TMA) copies of its record (8 bytes used)
 	A_BLK = ASTC_ARENA_FIXED   // float[4][Tp] block texels
 };
 static_assert(sizeof(BlkInfo) == 112, "BlkInfo layout");
-static_assert(A_TMPF + 512 == A_BLK && A_EP + 128 == A_PERSIST && A_EP + 640 == A_TMPF, "arena head layout");
+static_assert(A_TMPF + 512 == A_MBAR && A_MBAR + 16 == A_BLK && A_EP + 128 == A_PERSIST && A_EP + 640 == A_TMPF, "arena head layout");
 
 // endpoint slots (f4 units)
 enum { EP_BASE_0 = 0, EP_BASE_1 = 4, EP_EI1_0 = 8, EP_EI1_1 = 12, EP_EI2_0 = 16, EP_EI2_1 = 20, EP_WORK_0 = 24, EP_WORK_1 = 28, EP_RGBS = 32, EP_RGBO = 36, EP_COUNT = 40 };
@@ -386,6 +387,10 @@ struct PartView {
 };
 ASTC_FN int pv_count(const PartView& v, unsigned int p) { return (int)((v.counts >> (8 * p)) & 0xFF); }
 ASTC_FN int pv_start(const PartView& v, unsigned int p) { return (int)((v.starts >> (8 * p)) & 0xFF); }
+// texel at position pos of the concatenated texels_of_partition lists. With one partition the list is the identity
+// (partition_tables.cpp: texels_of_partition[0][i] = i), so the look-up - a dependent load in front of every per-texel
+// computation of the latency-bound loops - is skipped.
+ASTC_FN int pv_texel(const PartView& v, int pos) { return v.partition_count > 1 ? (int)ASTC_LDG(&v.texels[pos]) : pos; }
 
 ASTC_FN PartView part_view_packed(unsigned int pc, unsigned int packed) {
 	PartView v;
@@ -689,7 +694,7 @@ ASTC_COOP void compute_dirs(WCtx w, const PartView& pi, uint32_t chan, int ncomp
 		float s = 0.0f;
 		ASTC_UNROLL_S4
 		for (int i = 0; i < n; i++) {
-			int t = ASTC_LDG(&tix[i]);
+			int t = pc > 1 ? (int)ASTC_LDG(&tix[i]) : i;
 			float vK = dK[t] - avgK;
 			float vc = dc[t] - avgc;
 			s = s + (vK > 0.0f ? vc : 0.0f);
@@ -791,7 +796,7 @@ ASTC_COOP void compute_ideal_colors_and_weights_1_comp(WCtx w, const PartView& p
 		float lowvalue = 1e10f, highvalue = -1e10f;
 		ASTC_NOUNROLL
 		for (int j = w.lane; j < n; j += ASTC_WARP) {
-			float value = data_vr[ASTC_LDG(&tix[j])];
+			float value = data_vr[pc > 1 ? (int)ASTC_LDG(&tix[j]) : j];
 			lowvalue = minf(value, lowvalue);
 			highvalue = maxf(value, highvalue);
 		}
@@ -811,7 +816,7 @@ ASTC_COOP void compute_ideal_colors_and_weights_1_comp(WCtx w, const PartView& p
 		}
 		ASTC_NOUNROLL
 		for (int j = w.lane; j < n; j += ASTC_WARP) {
-			int t = ASTC_LDG(&tix[j]);
+			int t = pc > 1 ? (int)ASTC_LDG(&tix[j]) : j;
 			float value = (data_vr[t] - lowvalue) * scale;
 			value = clamp1f(value);
 			weights[t] = value;
@@ -855,7 +860,7 @@ ASTC_COOP void ideal_project(WCtx w, const PartView& pi, int which, const Partit
 		float lowparam = 1e10f, highparam = -1e10f;
 		ASTC_NOUNROLL
 		for (int j = w.lane; j < n; j += ASTC_WARP) {
-			int t = ASTC_LDG(&tix[j]);
+			int t = pc > 1 ? (int)ASTC_LDG(&tix[j]) : j;
 			f4 point = mk4(c0[t], c1[t], ncomp > 2 ? c2[t] : 0.0f, ncomp > 3 ? c3[t] : 0.0f);
 			float param = ncomp == 3 ? dot3_s(point - la, lb) : dot_s(point - la, lb);
 			weights[t] = param;
@@ -880,7 +885,7 @@ ASTC_COOP void ideal_project(WCtx w, const PartView& pi, int which, const Partit
 		wsync();
 		ASTC_NOUNROLL
 		for (int j = w.lane; j < n; j += ASTC_WARP) {
-			int t = ASTC_LDG(&tix[j]);
+			int t = pc > 1 ? (int)ASTC_LDG(&tix[j]) : j;
 			float idx = (weights[t] - lowparam) * scale;
 			idx = clamp1f(idx);
 			weights[t] = idx;

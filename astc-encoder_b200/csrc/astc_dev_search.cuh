@@ -156,7 +156,7 @@ ASTC_COOP void compute_encoding_choice_errors(WCtx w, const PartView& pi, int ep
 	const float u3 = 0.577350258827209473f;
 	chain_sums<5>(w, w.T, su_of(w), tmpf, nchains,
 		[&](int pos, float* term) {
-			int t = ASTC_LDG(&pi.texels[pos]);
+			int t = pv_texel(pi, pos);
 			int p = pc > 1 ? (int)ASTC_LDG(&pi.partition_of_texel[t]) : 0;
 			SPtr<float> l = lines + p * 12;
 			float dr = br[t], dg = bg[t], db = bb[t];
@@ -731,7 +731,7 @@ ASTC_COOP void recompute_ideal_colors_1plane(WCtx w, const PartView& pi, unsigne
 	// phase B: the weighted sums
 	chain_sums<14>(w, w.T, rs.tile, tmpf, nchains,
 		[&](int pos, float* term) {
-			int t = ASTC_LDG(&pi.texels[pos]);
+			int t = pv_texel(pi, pos);
 			int p = pc > 1 ? (int)ASTC_LDG(&pi.partition_of_texel[t]) : 0;
 			float idx0 = undec[t];
 			float om_idx0 = 1.0f - idx0;
@@ -772,7 +772,7 @@ ASTC_COOP void recompute_ideal_colors_1plane(WCtx w, const PartView& pi, unsigne
 		float a = 1.0f, b = 0.0f, c = 1e10f, dd = 0.0f;
 		ASTC_NOUNROLL
 		for (int j = w.lane; j < n; j += ASTC_WARP) {
-			int t = ASTC_LDG(&tix[j]);
+			int t = pc > 1 ? (int)ASTC_LDG(&tix[j]) : j;
 			float idx0 = undec[t];
 			a = minf(idx0, a);
 			b = maxf(idx0, b);

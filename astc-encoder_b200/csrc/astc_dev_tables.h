@@ -17,7 +17,7 @@
 #define ASTC_MAX_KMEANS_TEXELS 64
 /* Per-warp arena head (astc_dev_core.cuh A_*): bytes before the block texels, and the part of it that, together with the
    block texels, forms a block's persistent record between stage kernels */
-#define ASTC_ARENA_FIXED 2832
+#define ASTC_ARENA_FIXED 2848      /* head 2320 + chain results 512 + 16 for the warp's bulk-copy mbarrier */
 #define ASTC_ARENA_PERSIST_HEAD 1808
 #define ASTC_ANGULAR_STEPS 12     /* TUNE_MAX_ANGULAR_QUANT = 7 -> at most 12 steps are ever evaluated */
 

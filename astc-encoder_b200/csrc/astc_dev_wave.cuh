@@ -39,6 +39,9 @@ struct WaveArgs {
 	// a wave-0 launch takes blocks [first_block, first_block + band_blocks) from its own ticket counter
 	uint32_t* ticket;
 	unsigned int first_block, band_blocks;
+	// set-up launches of waves >= 1 may be split by class of trial: [cls_lo, cls_hi) of the ASTC_Q_CLASSES queues (the one-plane
+	// classes run on the compact arena plan)
+	int cls_lo, cls_hi;
 	int wave;
 	unsigned int sync_mask;      // tuning: which stage barriers are active (bit i = i-th barrier of the kernel loop)
 	uint32_t stage_bytes_setup;  // set-up kernel: the same (decimation tables only)
@@ -68,8 +71,8 @@ ASTC_FN bool q_pop(const WCtx& w, const WaveArgs& a, int kind, int wave, unsigne
 }
 
 // pop from the classes of a kind in order; cls is the warp's cursor
-ASTC_FN bool q_pop_classes(const WCtx& w, const WaveArgs& a, int kind, int wave, int& cls, unsigned int& b) {
-	while (cls < ASTC_Q_CLASSES) {
+ASTC_FN bool q_pop_classes(const WCtx& w, const WaveArgs& a, int kind, int wave, int& cls, unsigned int& b, int cls_end = ASTC_Q_CLASSES) {
+	while (cls < cls_end) {
 		if (q_pop(w, a, kind + cls, wave, b)) {
 			return true;
 		}
@@ -85,12 +88,19 @@ ASTC_FN void q_push(const WCtx& w, const WaveArgs& a, int kind, int wave, unsign
 	}
 }
 
-// record <-> arena: [0, A_PERSIST) and the block texels, 16 bytes per lane and trip
+// record <-> arena: the persistent head [0, A_PERSIST) and the block texels.
+// On the device both directions are BULK ASYNCHRONOUS COPIES (the 1-D form of TMA, cp.async.bulk): one lane hands the two
+// ranges to the copy engine of the SM - global -> shared completes on the warp's mbarrier (A_MBAR), shared -> global as a
+// bulk group - instead of 32 lanes moving 16 bytes per trip through registers. Addresses and sizes are multiples of 16
+// bytes by construction (arena bases, A_BLK, record_bytes). The host simulation copies word by word.
+// (the texels never change after the first save: later saves write the head only)
 struct alignas(16) U128 {
 	uint32_t x, y, z, w;
 };
-// (the texels never change after the first save: later saves write the head only)
-ASTC_FN void record_copy(const WCtx& w, const WaveArgs& a, unsigned int b, bool save, bool with_texels = true) {
+#if defined(ASTC_HOSTSIM)
+ASTC_FN void record_mbar_init(const WCtx& w) { (void)w; }
+ASTC_FN void record_copy(const WCtx& w, const WaveArgs& a, unsigned int b, bool save, bool with_texels, uint32_t& phase) {
+	(void)phase;
 	U128* g = reinterpret_cast<U128*>(a.records + (size_t)b * BSD.record_bytes);
 	const int n1 = A_PERSIST / 16;
 	int n2 = with_texels ? ((w.T + 3) & ~3) : 0;      // 4 channels x Tp floats = Tp x 16 bytes
@@ -108,6 +118,59 @@ ASTC_FN void record_copy(const WCtx& w, const WaveArgs& a, unsigned int b, bool 
 	}
 	wsync();
 }
+#else
+ASTC_FN uint32_t smem_addr(uint32_t off) { return (uint32_t)__cvta_generic_to_shared(astc_smem + off); }
+// once per warp, before its first restore: one pending arrival per phase (the lane that issues the copies)
+ASTC_FN void record_mbar_init(const WCtx& w) {
+	if (w.lane == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(w.base + A_MBAR)));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+}
+ASTC_FN void record_copy(const WCtx& w, const WaveArgs& a, unsigned int b, bool save, bool with_texels, uint32_t& phase) {
+	const uint8_t* g = a.records + (size_t)b * BSD.record_bytes;
+	const uint32_t n1 = A_PERSIST;
+	const uint32_t n2 = with_texels ? (uint32_t)((w.T + 3) & ~3) * 16u : 0u;
+	const uint32_t s_head = smem_addr(w.base), s_tex = smem_addr(w.base + A_BLK), bar = smem_addr(w.base + A_MBAR);
+	__syncwarp();      // every lane is done with the arena contents that are about to be replaced / has written what is saved
+	if (save) {
+		if (w.lane == 0) {
+			// the lanes' (generic proxy) stores to shared memory must be visible to the copy engine (async proxy)
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(s_head), "r"(n1) : "memory");
+			if (n2) {
+				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g + n1), "r"(s_tex), "r"(n2) : "memory");
+			}
+			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			// the arena may be overwritten as soon as the engine has READ it (the stores to HBM complete behind our back;
+			// the consumer is a later kernel launch)
+			asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+		}
+		__syncwarp();
+		return;
+	}
+	if (w.lane == 0) {
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n1 + n2) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_head), "l"(g), "r"(n1), "r"(bar) : "memory");
+		if (n2) {
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_tex), "l"(g + n1), "r"(n2), "r"(bar) : "memory");
+		}
+	}
+	// every lane waits for the phase to complete: the bytes are then visible to it
+	uint32_t done = 0;
+	unsigned int spins = 0;
+	while (!done) {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+		if (!done && ++spins > (1u << 26)) {
+			__trap();      // (a copy that never completes would otherwise hang the GPU: fail loudly instead)
+		}
+	}
+	phase ^= 1u;
+	__syncwarp();
+}
+#endif
 
 ASTC_FN BlockSearch& search_of(const WCtx& w) { return *reinterpret_cast<BlockSearch*>(astc_smem + w.base + A_SEARCH); }
 ASTC_FN Trial& trial_of(const WCtx& w) { return *reinterpret_cast<Trial*>(astc_smem + w.base + A_TRIAL); }
@@ -115,11 +178,13 @@ static_assert(sizeof(BlockSearch) <= 128 && sizeof(Trial) <= 64, "search state m
 
 // the search state already lives in its arena slots: saving / restoring a record moves it with the rest of the head
 ASTC_FN void record_save(const WCtx& w, const WaveArgs& a, unsigned int b, bool with_texels = false) {
+	uint32_t unused = 0;
 	wsync();
-	record_copy(w, a, b, true, with_texels);
+	record_copy(w, a, b, true, with_texels, unused);
 }
-ASTC_FN void record_restore(const WCtx& w, const WaveArgs& a, unsigned int b) {
-	record_copy(w, a, b, false);
+// phase: the parity of the warp's mbarrier, kept by the caller's item loop (flips with every restore)
+ASTC_FN void record_restore(const WCtx& w, const WaveArgs& a, unsigned int b, uint32_t& phase) {
+	record_copy(w, a, b, false, true, phase);
 }
 
 ASTC_FN int trial_class(const Trial& t) {
@@ -141,7 +206,9 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 	feed.ticket = a.ticket;      // wave 0 has no queue: a ticket counter hands out the band's blocks
 	feed.total = a.band_blocks;
 	feed.blocks_x = a.blocks_x;
-	int cls = 0;
+	int cls = a.cls_lo;
+	uint32_t rec_phase = 0;
+	record_mbar_init(w);
 	while (true) {
 		bool active = false;
 		unsigned int b = 0;
@@ -171,8 +238,8 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 				active = true;
 				break;
 			}
-		} else if (q_pop_classes(w, a, Q_SETUP, a.wave, cls, b)) {
-			record_restore(w, a, b);
+		} else if (q_pop_classes(w, a, Q_SETUP, a.wave, cls, b, a.cls_hi)) {
+			record_restore(w, a, b, rec_phase);
 			active = true;
 		}
 		// one CTA-wide vote per round: it doubles as the barrier that keeps the warps loosely phase-aligned
@@ -324,6 +391,8 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 	unsigned int b = 0;
 	unsigned int round = 0;
 	int cls = 0;
+	uint32_t rec_phase = 0;
+	record_mbar_init(w);
 	const unsigned int vote_mask = (1u << ((a.sync_mask >> 8) & 7)) - 1u;
 #if defined(ASTC_STEP_STATS)
 	int st_prev_class = -1;
@@ -335,7 +404,7 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 				drained = true;
 				break;
 			}
-			record_restore(w, a, b);
+			record_restore(w, a, b, rec_phase);
 			refine_begin_trial(w, t, r, s, true);
 			if (!r.running) {
 				wave_finish_trial(w, a, b, s, t, r.best_errorval_in_mode);
@@ -402,6 +471,8 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
 	BlockSearch& s = search_of(w);
 	Trial& t = trial_of(w);
+	uint32_t rec_phase = 0;
+	record_mbar_init(w);
 	while (true) {
 		unsigned int b = 0;
 		bool active = q_pop(w, a, Q_PREPARE, a.wave, b);
@@ -409,7 +480,7 @@ ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
 			break;
 		}
 		if (active) {
-			record_restore(w, a, b);
+			record_restore(w, a, b, rec_phase);
 			int next;
 			do {
 				block_search_prepare(w, s);

@@ -99,15 +99,15 @@ static __device__ __forceinline__ void stage_sincos_tables() {
 
 // ---- the stage kernels of the wave pipeline (astc_dev_wave.cuh) ----
 // nothing queued in any class of this kind for the launch's wave?
-static __device__ __forceinline__ bool wave_queue_empty(const WaveArgs& a, int kind) {
+static __device__ __forceinline__ bool wave_queue_empty(const WaveArgs& a, int kind, int c0 = 0, int c1 = ASTC_Q_CLASSES) {
 	uint32_t n = 0;
-	for (int c = 0; c < ASTC_Q_CLASSES; c++) {
+	for (int c = c0; c < c1; c++) {
 		n += __ldcg(a.count + (kind + c) * ASTC_MAX_WAVES + a.wave);
 	}
 	return n == 0;
 }
 
-#define ASTC_SETUP_THREADS_MAX 640      /* 20 warps x <= 102 registers (the compact one-plane plan fits 19-20 arenas per SM at 6x6) */
+#define ASTC_SETUP_THREADS_MAX 640      /* 20 warps x <= 102 registers (registers are granted per 4 warps: 21 warps would be charged as 24 and cap the kernel at 80) */
 #ifndef ASTC_REFINE_THREADS_MAX
 #define ASTC_REFINE_THREADS_MAX 768      /* 24 warps x 80 registers; 26 / 28 warps x 72 registers: refine 38.1 / 36.9 vs 37.3 ms, prepare +0.1 / +0.4 ms */
 #endif
@@ -115,7 +115,7 @@ static __device__ __forceinline__ bool wave_queue_empty(const WaveArgs& a, int k
 
 __global__ void __launch_bounds__(ASTC_SETUP_THREADS_MAX, 1)
 astc_wave_setup_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img, const __grid_constant__ WaveArgs a) {
-	if (a.wave != 0 && wave_queue_empty(a, Q_SETUP)) {
+	if (a.wave != 0 && wave_queue_empty(a, Q_SETUP, a.cls_lo, a.cls_hi)) {
 		return;
 	}
 	stage_launch_constants(bsd, cfg, img);
@@ -846,6 +846,8 @@ static astcenc_error launch_pipes(astcenc_context* ctx, int pipes, const void* d
 		w.ticket = counters + 2 * ASTC_Q_KINDS * ASTC_MAX_WAVES;
 		w.first_block = 0;
 		w.band_blocks = w.total;
+		w.cls_lo = 0;
+		w.cls_hi = ASTC_Q_CLASSES;
 		w.stage_bytes = ctx->refine_stage_bytes;
 		w.refine_state_off = (uint32_t)(ASTC_SMEM_HDR + ctx->refine_stage_bytes + (size_t)bsd.arena_bytes_small * ctx->warps_small);
 		w.stage_bytes_setup = ctx->setup_stage_bytes;
@@ -871,8 +873,18 @@ static astcenc_error launch_pipes(astcenc_context* ctx, int pipes, const void* d
 			}
 			a[p].wave = wave;
 			cudaStream_t ps = ctx->pipe_stream[p];
-			if (wave == 0 && ctx->warps_setup_1p) {
+			if (ctx->warps_setup_1p) {
+				if (wave != 0) {
+					a[p].cls_lo = 0;
+					a[p].cls_hi = 1;
+					astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
+					ctx->launches++;
+					a[p].cls_lo = 1;
+					a[p].cls_hi = ASTC_Q_CLASSES;
+				}
 				astc_wave_setup_kernel<<<grid, ctx->warps_setup_1p * 32, ctx->smem_setup_1p, ps>>>(ctx->tables->bsd_1p, ctx->dcfg, img[p], a[p]);
+				a[p].cls_lo = 0;
+				a[p].cls_hi = ASTC_Q_CLASSES;
 			} else {
 				astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
 			}
@@ -1022,6 +1034,8 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 		a.ticket = ctx->d_counters + 2 * ASTC_Q_KINDS * ASTC_MAX_WAVES;
 		a.first_block = 0;
 		a.band_blocks = (unsigned int)total;
+		a.cls_lo = 0;
+		a.cls_hi = ASTC_Q_CLASSES;
 		a.stage_bytes = ctx->refine_stage_bytes;
 		a.refine_state_off = (uint32_t)(ASTC_SMEM_HDR + ctx->refine_stage_bytes + (size_t)bsd.arena_bytes_small * ctx->warps_small);
 		a.stage_bytes_setup = ctx->setup_stage_bytes;
@@ -1088,12 +1102,23 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 				}
 				mark(0);
 				ctx->launches--;      // (the loop below counts one set-up launch per wave)
-			} else {
-				if (wave == 0 && ctx->warps_setup_1p) {
-					astc_wave_setup_kernel<<<grid, ctx->warps_setup_1p * 32, ctx->smem_setup_1p, stream>>>(ctx->tables->bsd_1p, ctx->dcfg, img, a);
-				} else {
+			} else if (ctx->warps_setup_1p) {
+				// class 0 of the later waves holds the two-plane trials (general plan); wave 0 and the n-partition classes have
+				// one weight plane and run on the compact plan with more warps per SM
+				if (wave != 0) {
+					a.cls_lo = 0;
+					a.cls_hi = 1;
 					astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
+					ctx->launches++;
+					a.cls_lo = 1;
+					a.cls_hi = ASTC_Q_CLASSES;
 				}
+				astc_wave_setup_kernel<<<grid, ctx->warps_setup_1p * 32, ctx->smem_setup_1p, stream>>>(ctx->tables->bsd_1p, ctx->dcfg, img, a);
+				a.cls_lo = 0;
+				a.cls_hi = ASTC_Q_CLASSES;
+				mark(0);
+			} else {
+				astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
 				mark(0);
 			}
 			astc_wave_refine_kernel<<<grid, ctx->warps_small * 32, ctx->smem_refine, stream>>>(bsd, ctx->dcfg, img, a);

@@ -137,19 +137,41 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 			a.ticket = &counter;
 			a.first_block = 0;
 			a.band_blocks = total;
+			a.cls_lo = 0;
+			a.cls_hi = ASTC_Q_CLASSES;
 			a.sync_mask = 0xFF;
 			a.stage_bytes = 0;
 			a.refine_state_off = ASTC_SMEM_HDR + ASTC_SMEM_SINCOS_BYTES + pk.bsd.arena_bytes + 32 * EMIT_SLICE + 16;
 			a.stage_bytes_setup = 0;
 			for (int wave = 0; wave < ASTC_MAX_WAVES - 1; wave++) {
 				a.wave = wave;
-				// (like the CUDA host code: wave 0 runs on the compact one-plane arena plan)
+				// (like the CUDA host code: trials with one weight plane - wave 0, the n-partition classes - run on the compact plan)
+				const bool compact = !getenv("HOSTSIM_NO_1P");
+				if (wave != 0 && compact) {
+					cta_sync();
+					if (lane == 0) {
+						hdr->bsd = pk.bsd;
+					}
+					cta_sync();
+					a.cls_lo = 0;
+					a.cls_hi = 1;
+					wave_setup(w, a);
+					a.cls_lo = 1;
+					a.cls_hi = ASTC_Q_CLASSES;
+				}
 				cta_sync();
 				if (lane == 0) {
-					hdr->bsd = wave == 0 && !getenv("HOSTSIM_NO_1P") ? bsd_1p : pk.bsd;
+					hdr->bsd = compact ? bsd_1p : pk.bsd;
 				}
 				cta_sync();
 				wave_setup(w, a);
+				a.cls_lo = 0;
+				a.cls_hi = ASTC_Q_CLASSES;
+				cta_sync();
+				if (lane == 0) {
+					hdr->bsd = pk.bsd;
+				}
+				cta_sync();
 				wave_refine(w, a, 0);
 				wave_prepare(w, a);
 			}
