@@ -192,6 +192,19 @@ ASTC_FN int trial_class(const Trial& t) {
 	return c < 0 ? 0 : (c >= ASTC_Q_CLASSES ? ASTC_Q_CLASSES - 1 : c);
 }
 
+#if defined(ASTC_STEP_STATS)
+// dev instrumentation (make -C astc-encoder_b200 variant NAME=stats DEFS=-DASTC_STEP_STATS=1): cycles per part, printed by the emit kernel.
+// refinement: [class][part]; class = realign path (0 undecimated, 1 dense, 2 sparse) + 3 for the first step of a candidate;
+//             parts: recompute, pack, score1, realign, score2, block change, wait at the vote, number of steps
+// set-up:     [kind][part]; kind 0 shared 1-plane set-up (wave 0), 1 two planes, 2 n partitions;
+//             parts: ideal, decimate, angular, quantise+score, formats + candidate weights, record save, wait, items
+__device__ unsigned long long g_step_stats[6][8];
+__device__ unsigned long long g_setup_stats[3][8];
+#define STAT_T(v) long long v = clock64()
+#else
+#define STAT_T(v)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // S: trial setup. Wave 0 reads the image (load_block, constant-colour blocks are emitted on the spot).
 // ---------------------------------------------------------------------------------------------
@@ -244,9 +257,11 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 		}
 		// one CTA-wide vote per round: it doubles as the barrier that keeps the warps loosely phase-aligned
 		// (without it: 95.6 -> 126 ms at 4K 6x6 medium)
+		STAT_T(sv);
 		if (!cta_any(active)) {
 			break;
 		}
+		STAT_T(s0);
 		// The mode-0 trial (only the "always" modes) and the full 1-plane trial that follows it differ in nothing but
 		// the range of grids / block modes they look at: ideal weights, decimated weights, angular ranges and per-mode
 		// errors of the shared modes are identical (compress_symbolic.cpp:1243-1270 runs the same code twice).
@@ -261,15 +276,19 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 			ST_WRITE_END(w)
 		}
 		if (active) stage_ideal(w, tf);
+		STAT_T(s1);
 		if (a.sync_mask & 1) cta_sync();
 		if (active) stage_decimate(w, tf);
+		STAT_T(s2);
 		if (a.sync_mask & 2) cta_sync();
 		if (active) {
 			trial_cutoffs(w, tf);
 			compute_angular_endpoints(w, tf.only_always != 0, tf.dual ? 2 : 1, (unsigned int)tf.max_weight_quant);
 		}
+		STAT_T(s3);
 		if (a.sync_mask & 4) cta_sync();
 		if (active) quantize_and_score_modes(w, tf.start_mode, tf.end_mode, tf.dual ? 2 : 1, tf.partition_count, tf.max_weight_quant, tf.cutoff1, tf.cutoff2);
+		STAT_T(s4);
 		if (a.sync_mask & 8) cta_sync();
 		if (active) {
 			unsigned int count = 0, count_next = 0;
@@ -321,8 +340,23 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 				}
 			}
 			int klass = trial_class(t);
+			STAT_T(s5);
 			record_save(w, a, b, a.wave == 0);
 			q_push(w, a, Q_REFINE + klass, a.wave, b);
+#if defined(ASTC_STEP_STATS)
+			if (w.lane == 0) {
+				long long s6 = clock64();
+				int kind = t.dual ? 1 : (t.partition_count > 1 ? 2 : 0);
+				atomicAdd(&g_setup_stats[kind][0], (unsigned long long)(s1 - s0));
+				atomicAdd(&g_setup_stats[kind][1], (unsigned long long)(s2 - s1));
+				atomicAdd(&g_setup_stats[kind][2], (unsigned long long)(s3 - s2));
+				atomicAdd(&g_setup_stats[kind][3], (unsigned long long)(s4 - s3));
+				atomicAdd(&g_setup_stats[kind][4], (unsigned long long)(s5 - s4));
+				atomicAdd(&g_setup_stats[kind][5], (unsigned long long)(s6 - s5));
+				atomicAdd(&g_setup_stats[kind][6], (unsigned long long)(s0 - sv));
+				atomicAdd(&g_setup_stats[kind][7], 1ull);
+			}
+#endif
 		}
 	}
 }
@@ -363,16 +397,6 @@ ASTC_COOP void wave_finish_trial(WCtx w, const WaveArgs& a, unsigned int b, Bloc
 		q_push(w, a, Q_EMIT, 0, b);
 	}
 }
-
-#if defined(ASTC_STEP_STATS)
-// dev instrumentation (make libastcenc_b200_stats.so, tools/step_stats.py): cycles per refinement-step part by kind
-// of step, [class][part]; class = realign path (0 undecimated, 1 dense, 2 sparse) + 3 for the first step
-// of a candidate; parts: recompute, pack, score1, realign, score2, block change, wait at the vote, number of steps
-__device__ unsigned long long g_step_stats[6][8];
-#define STAT_T(v) long long v = clock64()
-#else
-#define STAT_T(v)
-#endif
 
 // The refine kernel works on ONE copy of the search state per warp in shared memory: BlockSearch and Trial in their arena
 // slots (where the record keeps them anyway), Refine in a slot behind the arenas (as per-lane automatic variables the three
@@ -505,6 +529,13 @@ ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
 ASTC_COOP void wave_emit(int lane, uint32_t slices_base, WaveArgs a) {
 #if defined(ASTC_STEP_STATS)
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		for (int c = 0; c < 3; c++) {
+			unsigned long long n = g_setup_stats[c][7];
+			printf("setup kind %d n %llu: ideal %llu decimate %llu angular %llu quantscore %llu formats %llu save %llu wait %llu (cycles per item)\n", c, n,
+			       g_setup_stats[c][0] / (n ? n : 1), g_setup_stats[c][1] / (n ? n : 1), g_setup_stats[c][2] / (n ? n : 1), g_setup_stats[c][3] / (n ? n : 1),
+			       g_setup_stats[c][4] / (n ? n : 1), g_setup_stats[c][5] / (n ? n : 1), g_setup_stats[c][6] / (n ? n : 1));
+			for (int k = 0; k < 8; k++) g_setup_stats[c][k] = 0;
+		}
 		for (int c = 0; c < 6; c++) {
 			unsigned long long n = g_step_stats[c][7];
 			printf("steps class %d n %llu: recompute %llu pack %llu score1 %llu realign %llu score2 %llu change %llu wait %llu (cycles per step)\n", c, n,
