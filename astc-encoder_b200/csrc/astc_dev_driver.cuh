@@ -10,10 +10,10 @@ ASTC_FN float min_ep_cutoff(float e0, float e1, float cur) {
 
 // Quantise the decimated ideal weights of one winning block mode straight into the work candidate
 // (the reference keeps every mode's quantised set in dec_weights_uquant; we recompute the winners).
-ASTC_COOP void quantize_candidate_weights(WCtx w, int decimation_mode, int quant_mode, int nplanes, float cutoff1, float cutoff2) {
+// (dst: 64 bytes, plane 2 at +32; no barrier inside - the caller synchronises once after its last call)
+ASTC_FN void quantize_candidate_weights_to(const WCtx& w, SPtr<uint8_t> dst, int decimation_mode, int quant_mode, int nplanes, float cutoff1, float cutoff2) {
 	DecView di = dec_view((unsigned int)decimation_mode);
 	int W = di.W;
-	SPtr<uint8_t> ww = work_weights_of(w);
 	SPtr<float> dwi = dwi_of(w) + di.dwi_offset;
 	ASTC_NOUNROLL
 	for (int id = w.lane; id < W * nplanes; id += ASTC_WARP) {
@@ -22,8 +22,11 @@ ASTC_COOP void quantize_candidate_weights(WCtx w, int decimation_mode, int quant
 		float low, high;
 		mode_low_high(w, decimation_mode, quant_mode, pl, pl ? cutoff2 : cutoff1, low, high);
 		WeightQuantizer z = make_weight_quantizer(low, high, quant_mode);
-		ww[pl * 32 + k] = (uint8_t)quantize_weight(z, dwi[id]);
+		dst[pl * 32 + k] = (uint8_t)quantize_weight(z, dwi[id]);
 	}
+}
+ASTC_COOP void quantize_candidate_weights(WCtx w, int decimation_mode, int quant_mode, int nplanes, float cutoff1, float cutoff2) {
+	quantize_candidate_weights_to(w, work_weights_of(w), decimation_mode, quant_mode, nplanes, cutoff1, cutoff2);
 	wsync();
 }
 

@@ -64,11 +64,11 @@ ASTC_COOP void quantize_and_score_modes(WCtx w, unsigned int start_mode, unsigne
 				uqrow[32 + k] = (uint8_t)quantize_weight(z2, ideal2[k]);
 			}
 		}
-		// compute_error_of_weight_set_1plane / _2planes: texel t feeds accumulator lane t & 3
+		// compute_error_of_weight_set_1plane / _2planes: texel t feeds accumulator lane t & 3 - four texels per trip, one per
+		// accumulator (no selection chain), the odd texels of footprints that are not a multiple of four afterwards
 		float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
 		float rscale1 = z1.rscale, lowb1 = z1.low_bound;
-		ASTC_UNROLL_S2
-		for (int t = 0; t < T; t++) {
+		auto texel_error = [&](int t) -> float {
 			uint32_t ix = ASTC_LDD(&di.twi[t]);
 			f4 cf = dec_contribs(di, t);
 			int i0 = (int)(ix & 0xFF), i1 = (int)((ix >> 8) & 0xFF), i2 = (int)((ix >> 16) & 0xFF), i3 = (int)(ix >> 24);
@@ -84,11 +84,23 @@ ASTC_COOP void quantize_and_score_modes(WCtx w, unsigned int start_mode, unsigne
 				float error2 = diff2 * diff2 * eis2[t];
 				error = error + error2;
 			}
+			return error;
+		};
+		int t = 0;
+		ASTC_NOUNROLL
+		for (; t + 4 <= T; t += 4) {
+			acc0 = acc0 + texel_error(t);
+			acc1 = acc1 + texel_error(t + 1);
+			acc2 = acc2 + texel_error(t + 2);
+			acc3 = acc3 + texel_error(t + 3);
+		}
+		ASTC_NOUNROLL
+		for (; t < T; t++) {
+			float error = texel_error(t);
 			int a = t & 3;
 			if (a == 0) acc0 = acc0 + error;
 			else if (a == 1) acc1 = acc1 + error;
-			else if (a == 2) acc2 = acc2 + error;
-			else acc3 = acc3 + error;
+			else acc2 = acc2 + error;
 		}
 		mode_err[(int)i] = (acc0 + acc2) + (acc1 + acc3);
 	}
@@ -563,15 +575,21 @@ ASTC_COOP unsigned int endpoint_formats_select(WCtx w, int pc, int nplanes, unsi
 			taken[2 * (int)k] = ASTC_U2F((uint32_t)best_idx);
 			taken[2 * (int)k + 1] = best;
 			mode_err[best_idx] = ERROR_CALC_DEFAULT;
-			Candidate c;
-			c.block_mode = (uint16_t)best_idx;
-			c.formats[0] = c.formats[1] = c.formats[2] = c.formats[3] = 0;
-			find_best_combination_for_bitcount(pc, ef_off, mode_bitcount(ASTC_LDG(&BSD.block_modes[best_idx].weight_bits), nplanes, pc), c.quant_level, c.quant_level_mod, c.formats);
-			cands[(int)k] = c;
 		}
 		count++;
 		wsync();
 	}
+	// the winners' quant levels and formats: one lane per candidate (the look-up chain is long and serial)
+	ASTC_NOUNROLL
+	for (unsigned int k = (unsigned int)w.lane; k < count; k += ASTC_WARP) {
+		int best_idx = (int)ASTC_F2U(taken[2 * (int)k]);
+		Candidate c;
+		c.block_mode = (uint16_t)best_idx;
+		c.formats[0] = c.formats[1] = c.formats[2] = c.formats[3] = 0;
+		find_best_combination_for_bitcount(pc, ef_off, mode_bitcount(ASTC_LDG(&BSD.block_modes[best_idx].weight_bits), nplanes, pc), c.quant_level, c.quant_level_mod, c.formats);
+		cands[(int)k] = c;
+	}
+	wsync();
 	if (keep_errors && w.lane == 0) {
 		for (unsigned int k = 0; k < count; k++) {
 			mode_err[(int)ASTC_F2U(taken[2 * (int)k])] = taken[2 * (int)k + 1];

@@ -318,27 +318,23 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 			if (!shared) {
 				stage_formats(w, t);
 			}
-			// the refinement kernel has no decimated ideal weights: quantise every candidate's weights now
-			SPtr<uint32_t> ww = sptr<uint32_t>(work_weights_of(w).off);
+			// the refinement kernel has no decimated ideal weights: quantise every candidate's weights now, straight into the
+			// candidates' slots (unused bytes of a slot are never read), one barrier at the end
 			int nplanes = t.dual ? 2 : 1;
 			float cutoff1 = t.cutoff1, cutoff2 = t.cutoff2;
 			ASTC_NOUNROLL
 			for (int list = 0; list < 2; list++) {
 				unsigned int n = list == 0 ? t.candidate_count : t.candidate_count_next;
 				SPtr<Candidate> cl = sptr<Candidate>(w.base + (list == 0 ? A_CAND : A_CAND2));
-				SPtr<uint32_t> cw = sptr<uint32_t>(w.base + (list == 0 ? A_CANDW : A_CANDW2));
+				SPtr<uint8_t> cw = sptr<uint8_t>(w.base + (list == 0 ? A_CANDW : A_CANDW2));
 				ASTC_NOUNROLL
 				for (unsigned int i = 0; i < n; i++) {
 					Candidate cd = cl[(int)i];
 					const DevBlockMode* bm = BSD.block_modes + cd.block_mode;
-					quantize_candidate_weights(w, ASTC_LDG(&bm->decimation_mode), ASTC_LDG(&bm->quant_mode), nplanes, cutoff1, cutoff2);
-					ASTC_NOUNROLL
-					for (int k = w.lane; k < 16; k += ASTC_WARP) {
-						cw[(int)i * 16 + k] = ww[k];
-					}
-					wsync();
+					quantize_candidate_weights_to(w, cw + (int)i * 64, ASTC_LDG(&bm->decimation_mode), ASTC_LDG(&bm->quant_mode), nplanes, cutoff1, cutoff2);
 				}
 			}
+			wsync();
 			int klass = trial_class(t);
 			STAT_T(s5);
 			record_save(w, a, b, a.wave == 0);

@@ -488,7 +488,10 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 		long v = atol(e);
 		if (v > 0) ctx->knobs.batch_blocks = (size_t)v;
 	}
-	ctx->knobs.sync_mask = 0;      // measured: once every kernel runs one kind of work, the stage barriers no longer pay (110.7 -> 106.5 ms)
+	// stage barriers of the wave kernels (bit i = i-th barrier of the kernel loop). Measured at 4K 6x6 -medium (70.0 ms without): only
+	// the one in front of the endpoint-format stage of the set-up kernel pays (bit 3: 68.5 ms; bits 0-2: 70.1 / 68.9 / 68.6; the four
+	// refinement barriers 16 / 32 / 64 / 128: 69.9 / 70.0 / 70.7 / 71.0)
+	ctx->knobs.sync_mask = 8;
 	if (const char* e = getenv("ASTCENC_B200_SYNC_MASK")) {
 		ctx->knobs.sync_mask = (unsigned int)strtoul(e, nullptr, 0);
 	}
