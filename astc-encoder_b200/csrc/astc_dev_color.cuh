@@ -667,3 +667,120 @@ ASTC_NOINLINE uint8_t pack_hdr_endpoints(int lane, f4 color0, f4 color1, f4 rgbo
 		return (uint8_t)quantize_hdr_luminance(lane, color0, color1, output, q);
 	}
 }
+
+// FMT_RGB / FMT_RGBA, the formats of nearly every candidate of an LDR image, are a contest of four encodings of the same
+// endpoint pair (:1953-2050): base + offset with blue contraction, base + offset, blue contraction, plain - the one with the
+// smallest round-trip error wins, the earlier one on a tie. For a single-partition candidate the four run on four lanes
+// (the two offset forms share their instruction stream, as do the four round-trip error evaluations); the winner stores
+// the bytes. `output` is shared memory, every lane passes the same arguments, the caller synchronises.
+ASTC_NOINLINE uint8_t pack_rgb_endpoints_coop(int lane, f4 color0, f4 color1, int format, uint8_t* output, int quant_level) {
+	QuantCtx q;
+	q.tab = STAGED.cq_smem_off != 0 ? astc_smem + STAGED.cq_smem_off + 512 * (quant_level - QUANT_6)
+	                                : ASTC_CT->color_unquant_to_uquant[quant_level - QUANT_6];
+	q.quant_level = quant_level;
+	color0 = vclamp4(0.0f, 65535.0f, color0);
+	color1 = vclamp4(0.0f, 65535.0f, color1);
+	const f4 c0l = color0 * (1.0f / 257.0f);
+	const f4 c1l = color1 * (1.0f / 257.0f);
+	const bool has_a = format == FMT_RGBA;
+	float best = 3.0e38f;
+	int best_k = 0x7FFFFFFF;
+	i4 b0 = mki4(0, 0, 0, 0), b1 = b0;
+	ASTC_NOUNROLL
+	for (int k = lane; k < 4; k += ASTC_WARP) {
+		// which encodings the quant level admits (:1957, :1999)
+		if ((k < 2 && quant_level > QUANT_160) || (k == 2 && quant_level >= QUANT_256)) {
+			continue;
+		}
+		i4 o0 = mki4(0, 0, 0, 0), o1 = o0;
+		bool ok;
+		if (k < 2) {
+			// base + offset; the blue-contracted form starts from the swapped, contracted pair and wants a negative offset sum
+			const bool bc = k == 0;
+			f4 a = bc ? c1l : c0l, b = bc ? c0l : c1l;
+			ok = true;
+			if (bc) {
+				a = blue_contract_fwd(a);
+				b = blue_contract_fwd(b);
+				ok = in_0_255(a) && in_0_255(b);
+			}
+			if (ok) {
+				QEnds r = rgb_delta_core_v(a, b, q, bc);
+				ok = r.ok;
+				o0 = r.a;
+				o1 = r.b;
+			}
+			if (ok && has_a) {
+				QAlpha ra = try_quantize_alpha_delta_v(bc ? c1l : c0l, bc ? c0l : c1l, q);
+				ok = ra.ok;
+				o0.w = ra.a0;
+				o1.w = ra.a1;
+			}
+		} else if (k == 2) {
+			QEnds r = try_quantize_rgb_blue_contract_v(c0l, c1l, q);
+			ok = r.ok;
+			o0 = r.a;
+			o1 = r.b;
+			if (ok && has_a) {
+				o0.w = quant_color_f(q, f2i_rtn(c1l.w), c1l.w);
+				o1.w = quant_color_f(q, f2i_rtn(c0l.w), c0l.w);
+			}
+		} else {
+			QEnds r = quantize_rgb_v(c0l, c1l, q);
+			ok = true;
+			o0 = r.a;
+			o1 = r.b;
+			if (has_a) {
+				o0.w = quant_color_f(q, f2i_rtn(c0l.w), c0l.w);
+				o1.w = quant_color_f(q, f2i_rtn(c1l.w), c1l.w);
+			}
+		}
+		if (ok) {
+			i4 u0, u1;
+			if (k < 2) {
+				rgba_delta_unpack(o0, o1, u0, u1);
+			} else {
+				rgba_unpack(o0, o1, u0, u1);
+			}
+			float error = get_rgba_encoding_error(c0l, c1l, u0, u1);
+			if (error < best) {
+				best = error;
+				best_k = k;
+				b0 = o0;
+				b1 = o1;
+			}
+		}
+	}
+#if !defined(ASTC_ONE_LANE)
+	// smallest error, the earlier encoding on a tie; every lane learns the winner
+	{
+		float e = best;
+		int ik = best_k;
+		ASTC_NOUNROLL
+		for (int o = 16; o > 0; o >>= 1) {
+			float e2 = __shfl_xor_sync(0xffffffffu, e, o);
+			int i2 = __shfl_xor_sync(0xffffffffu, ik, o);
+			bool take = (e2 < e) || (e2 == e && i2 < ik);
+			e = take ? e2 : e;
+			ik = take ? i2 : ik;
+		}
+		if (ik != best_k) {
+			best_k = ik;
+			best = -1.0f;      // not this lane's
+		}
+	}
+#endif
+	if (best >= 0.0f) {
+		output[0] = (uint8_t)b0.x;
+		output[1] = (uint8_t)b1.x;
+		output[2] = (uint8_t)b0.y;
+		output[3] = (uint8_t)b1.y;
+		output[4] = (uint8_t)b0.z;
+		output[5] = (uint8_t)b1.z;
+		if (has_a) {
+			output[6] = (uint8_t)b0.w;
+			output[7] = (uint8_t)b1.w;
+		}
+	}
+	return (uint8_t)(best_k < 2 ? (has_a ? FMT_RGBA_DELTA : FMT_RGB_DELTA) : (has_a ? FMT_RGBA : FMT_RGB));
+}

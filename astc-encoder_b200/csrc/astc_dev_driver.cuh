@@ -54,8 +54,17 @@ ASTC_COOP uint32_t pack_work_endpoints(WCtx w, unsigned int pc, uint32_t formats
 		colors32[k] = 0;
 	}
 	wsync();
+	// one partition, RGB / RGBA (nearly every LDR candidate): the four encodings of the pair run on four lanes
+	const int fmt0 = (int)(formats_in & 0xFF);
+	const bool rgb_coop = pc == 1 && (fmt0 == FMT_RGB || fmt0 == FMT_RGBA);
+	if (rgb_coop) {
+		uint8_t fmt = pack_rgb_endpoints_coop(w.lane, ep[EP_WORK_0], ep[EP_WORK_1], fmt0, &colors[0], quant_level);
+		if (w.lane == 0) {
+			xch[0] = fmt;
+		}
+	}
 	ASTC_NOUNROLL
-	for (unsigned int j = (unsigned int)w.lane; j < pc; j += ASTC_WARP) {
+	for (unsigned int j = (unsigned int)w.lane; j < pc && !rgb_coop; j += ASTC_WARP) {
 		int fmt_in = (int)((formats_in >> (8 * j)) & 0xFF);
 		if (!is_hdr_format(fmt_in)) {
 			// (packed straight into the shared arena: a local byte array behind a pointer would live in local memory)
