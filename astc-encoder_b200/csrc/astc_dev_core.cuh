@@ -1104,139 +1104,6 @@ ASTC_COOP void compute_ideal_weights_for_decimation(WCtx w, unsigned int d, int 
 	wsync();
 }
 
-// compute_ideal_weights_for_decimation for EVERY grid a trial looks at, in three passes over all of them instead of three
-// passes per grid: lanes over the (grid, plane, weight) slots of the decimated-weight area (DevBsd::dwi_map), over the
-// (grid, plane, texel) infill values, and over the slots again - full warps and 3 barriers per chunk of grids instead of
-// ragged ones and 3 per grid. The chunk is what the infill scratch holds. Each slot's sums run over its weight's texel list in
-// list order, exactly as in the per-grid form above (which the single-kernel drivers and the tests still use).
-ASTC_COOP void compute_ideal_weights_all(WCtx w, unsigned int ndm, int nplanes, uint16_t refmask, bool dual) {
-	const int T = w.T;
-	SPtr<float> dwi = dwi_of(w);
-	SPtr<float> eiw0 = eiw_of(w, 0);
-	const uint32_t plane_stride = 2 * tp4(w);        // eiw[1] - eiw[0] == eis[1] - eis[0] in bytes
-	const uint32_t wes_off = tp4(w);                 // eis[pl] - eiw[pl]
-	SPtr<float> infilled = sptr<float>(su_of(w));    // [grid of the chunk][plane][T]
-	const uint16_t* map = BSD.dwi_map;
-	const BlkInfo& bi = bi_of(w);
-	const int per_grid = T * nplanes;
-	int cap = (int)(BSD.scratch_bytes / (uint32_t)(per_grid * 4));
-	if (cap < 1) cap = 1;
-	const float inv_per_grid = 1.0f / static_cast<float>(per_grid), inv_T = 1.0f / static_cast<float>(T);
-	const float stepsize = 0.25f;
-	const float chd_scale = -16.0f;
-	ASTC_NOUNROLL
-	for (int m0 = 0; m0 < (int)ndm; m0 += cap) {
-		int m1 = m0 + cap < (int)ndm ? m0 + cap : (int)ndm;
-		int lo = ASTC_LDG(&BSD.dec_modes[m0].dwi_offset);
-		if (BSD.layout_planes == 1) lo = ASTC_LDG(&BSD.dec_modes[m0].dwi_offset_1p);
-		int hi = (int)BSD.dwi_slots;
-		if (m1 < (int)BSD.decimation_mode_count_selected) {
-			hi = BSD.layout_planes == 1 ? ASTC_LDG(&BSD.dec_modes[m1].dwi_offset_1p) : ASTC_LDG(&BSD.dec_modes[m1].dwi_offset);
-		}
-		// pass 1: the weighted mean of the texels' ideal weights under every grid weight
-		ASTC_NOUNROLL
-		for (int idx = lo + w.lane; idx < hi; idx += ASTC_WARP) {
-			uint32_t m = ASTC_LDG(&map[idx]);
-			if (m == 0xFFFFu) continue;
-			unsigned int d = m >> 8;
-			const DevDecMode* dm = BSD.dec_modes + d;
-			uint16_t ref = dual ? ASTC_LDG(&dm->refprec_2planes) : ASTC_LDG(&dm->refprec_1plane);
-			if ((ref & refmask) == 0) continue;
-			DecView di = dec_view(d);
-			int W = di.W;
-			int j = (int)(m & 0xFF);
-			int pl = j >= W ? 1 : 0;
-			if (pl >= nplanes) continue;
-			int i = j - pl * W;
-			SPtr<float> eiw = sptr<float>(eiw0.off + (uint32_t)pl * plane_stride);
-			if (T == W) {
-				dwi[idx] = eiw[i];
-				continue;
-			}
-			SPtr<float> eis = sptr<float>(eiw.off + wes_off);
-			bool constant_wes = bi.ei_const_wes[pl] != 0;
-			float wes0 = eis[0];
-			float weight_weight = 1e-10f;
-			float initial_weight = 0.0f;
-			int off = ASTC_LDD(&di.wto[i]);
-			int end = ASTC_LDD(&di.wto[i + 1]);
-			ASTC_UNROLL_S4
-			for (int e = off; e < end; e++) {
-				uint32_t en = ASTC_LDD(&di.wtc[e]);
-				int texel = (int)(en & 0xFF);
-				float weight = static_cast<float>(en >> 8);
-				float wes = constant_wes ? wes0 : eis[texel];
-				float contrib_weight = weight * wes;
-				weight_weight += contrib_weight;
-				initial_weight += eiw[texel] * contrib_weight;
-			}
-			dwi[idx] = initial_weight / weight_weight;
-		}
-		wsync();
-		// pass 2: what every texel sees of those weights
-		int n2 = (m1 - m0) * per_grid;
-		ASTC_NOUNROLL
-		for (int it = w.lane; it < n2; it += ASTC_WARP) {
-			// (it + 0.5) / n is never within rounding distance of an integer: the truncated quotient is exact
-			int c = (int)((static_cast<float>(it) + 0.5f) * inv_per_grid);
-			int r = it - c * per_grid;
-			int pl = (int)((static_cast<float>(r) + 0.5f) * inv_T);
-			int t = r - pl * T;
-			unsigned int d = (unsigned int)(m0 + c);
-			const DevDecMode* dm = BSD.dec_modes + d;
-			uint16_t ref = dual ? ASTC_LDG(&dm->refprec_2planes) : ASTC_LDG(&dm->refprec_1plane);
-			if ((ref & refmask) == 0) continue;
-			DecView di = dec_view(d);
-			if (di.W == T) continue;
-			infilled[it] = bilinear_infill(di, dwi + (di.dwi_offset + pl * di.W), t);
-		}
-		wsync();
-		// pass 3: one step towards the least-squares weights
-		ASTC_NOUNROLL
-		for (int idx = lo + w.lane; idx < hi; idx += ASTC_WARP) {
-			uint32_t m = ASTC_LDG(&map[idx]);
-			if (m == 0xFFFFu) continue;
-			unsigned int d = m >> 8;
-			const DevDecMode* dm = BSD.dec_modes + d;
-			uint16_t ref = dual ? ASTC_LDG(&dm->refprec_2planes) : ASTC_LDG(&dm->refprec_1plane);
-			if ((ref & refmask) == 0) continue;
-			DecView di = dec_view(d);
-			int W = di.W;
-			if (T == W) continue;
-			int j = (int)(m & 0xFF);
-			int pl = j >= W ? 1 : 0;
-			if (pl >= nplanes) continue;
-			int i = j - pl * W;
-			SPtr<float> eiw = sptr<float>(eiw0.off + (uint32_t)pl * plane_stride);
-			SPtr<float> eis = sptr<float>(eiw.off + wes_off);
-			SPtr<float> inf = infilled + (((int)d - m0) * per_grid + pl * T);
-			bool constant_wes = bi.ei_const_wes[pl] != 0;
-			float wes0 = eis[0];
-			float weight_val = dwi[idx];
-			float error_change0 = 1e-10f;
-			float error_change1 = 0.0f;
-			int off = ASTC_LDD(&di.wto[i]);
-			int end = ASTC_LDD(&di.wto[i + 1]);
-			ASTC_UNROLL_S4
-			for (int e = off; e < end; e++) {
-				uint32_t en = ASTC_LDD(&di.wtc[e]);
-				int texel = (int)(en & 0xFF);
-				float contrib_weight = static_cast<float>(en >> 8);
-				float wes = constant_wes ? wes0 : eis[texel];
-				float scale = wes * contrib_weight;
-				float old_weight = inf[texel];
-				float ideal_weight = eiw[texel];
-				error_change0 += contrib_weight * scale;
-				error_change1 += (old_weight - ideal_weight) * scale;
-			}
-			float step = (error_change1 * chd_scale) / error_change0;
-			step = vclampf(-stepsize, stepsize, step);
-			dwi[idx] = weight_val + step;
-		}
-		wsync();
-	}
-}
-
 // =============================================================================================
 // Angular weight-range search (astcenc_weight_align.cpp:94-355).
 // Work items are (grid, plane, angular step) triples, compacted so that every lane has one:

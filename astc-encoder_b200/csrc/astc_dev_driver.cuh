@@ -56,7 +56,11 @@ ASTC_COOP uint32_t pack_work_endpoints(WCtx w, unsigned int pc, uint32_t formats
 	wsync();
 	// one partition, RGB / RGBA (nearly every LDR candidate): the four encodings of the pair run on four lanes
 	const int fmt0 = (int)(formats_in & 0xFF);
+#if defined(ASTC_PACK_ONE_LANE)
+	const bool rgb_coop = false;
+#else
 	const bool rgb_coop = pc == 1 && (fmt0 == FMT_RGB || fmt0 == FMT_RGBA);
+#endif
 	if (rgb_coop) {
 		uint8_t fmt = pack_rgb_endpoints_coop(w.lane, ep[EP_WORK_0], ep[EP_WORK_1], fmt0, &colors[0], quant_level);
 		if (w.lane == 0) {

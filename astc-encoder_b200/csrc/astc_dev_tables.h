@@ -108,10 +108,6 @@ struct DevBsd {
 	// planes) and a compact one for trials with ONE plane (wave 0 - every block's first trial - never has two): fewer bytes
 	// per block, more blocks in flight per SM. The kernel is told which plan its launch uses.
 	uint32_t layout_planes;      // 2 (general) or 1 (compact)
-	// every float slot of the decimated-ideal-weight area of this plan -> (grid << 8) | (plane * weight_count + weight),
-	// 0xFFFF for padding: lets one pass run over the weights of ALL grids at once (compute_ideal_weights_all)
-	const uint16_t* dwi_map;
-	uint32_t dwi_slots;          // used length of that area in floats
 };
 
 // The search configuration consumed on the device (subset of astcenc_config, astcenc.h:427-605).

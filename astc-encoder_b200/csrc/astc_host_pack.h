@@ -100,7 +100,6 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 	std::vector<DevDecMode> dms(t.decimation_mode_count_all);
 	std::vector<uint8_t> dblob;
 	uint32_t dwi_total = 0, dwi_total_1p = 0;
-	std::vector<uint16_t> map2p, map1p;
 	unsigned int max_wtc = 1;
 	for (unsigned int d = 0; d < t.decimation_mode_count_all; d++) {
 		const DecimationInfo& di = t.decimation_tables[d];
@@ -163,22 +162,13 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 		dm.dwi_offset_1p = (uint16_t)dwi_total_1p;
 		if (d < t.decimation_mode_count_selected) {
 			b.dec_stage_bytes = (uint32_t)((dblob.size() + 15) / 16 * 16);
-			unsigned int n2 = W * (dm.maxprec_2planes >= 0 ? 2u : 1u);
-			for (unsigned int j = 0; j < n2; j++) map2p.push_back((uint16_t)((d << 8) | j));
-			dwi_total += n2;
+			dwi_total += W * (dm.maxprec_2planes >= 0 ? 2u : 1u);
 			dwi_total = (dwi_total + 3u) & ~3u;
-			map2p.resize(dwi_total, 0xFFFF);
-			for (unsigned int j = 0; j < W; j++) map1p.push_back((uint16_t)((d << 8) | j));
 			dwi_total_1p += W;
 			dwi_total_1p = (dwi_total_1p + 3u) & ~3u;
-			map1p.resize(dwi_total_1p, 0xFFFF);
 		}
 	}
 	b.max_weight_texel_count = (uint8_t)max_wtc;
-	map2p.resize(map2p.size() + 4, 0xFFFF);
-	map1p.resize(map1p.size() + 4, 0xFFFF);
-	size_t off_map2p = blob_append(blob, map2p.data(), map2p.size() * sizeof(uint16_t));
-	size_t off_map1p = blob_append(blob, map1p.data(), map1p.size() * sizeof(uint16_t));
 	size_t off_dm = blob_append(blob, dms.data(), dms.size() * sizeof(DevDecMode));
 	size_t off_dblob = blob_append(blob, dblob.data(), dblob.size());
 
@@ -217,8 +207,6 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 	b.block_mode_packed_index = reinterpret_cast<const uint16_t*>(off_bmpi);
 	b.dec_modes = reinterpret_cast<const DevDecMode*>(off_dm);
 	b.dec_blob = reinterpret_cast<const uint8_t*>(off_dblob);
-	b.dwi_map = reinterpret_cast<const uint16_t*>(off_map2p);
-	b.dwi_slots = dwi_total;
 	for (unsigned int pc = 1; pc <= 4; pc++) {
 		b.partitions[pc] = reinterpret_cast<const uint8_t*>(off_part[pc]);
 		if (pc >= 2) {
@@ -269,8 +257,7 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 	c.off_mode_err = o;   o = align16(o + 4 * t.block_mode_count_1plane_selected);
 	c.arena_bytes = o;
 	c.layout_planes = 1;
-	c.dwi_map = reinterpret_cast<const uint16_t*>(off_map1p);
-	c.dwi_slots = dwi_total_1p;
+
 }
 
 static inline void relocate_bsd(DevBsd& b, const uint8_t* base);
@@ -284,7 +271,6 @@ static inline void relocate_bsd(DevBsd& b, const uint8_t* base) {
 	b.block_mode_packed_index = reinterpret_cast<const uint16_t*>(rel(b.block_mode_packed_index));
 	b.dec_modes = reinterpret_cast<const DevDecMode*>(rel(b.dec_modes));
 	b.dec_blob = rel(b.dec_blob);
-	b.dwi_map = reinterpret_cast<const uint16_t*>(rel(b.dwi_map));
 	for (unsigned int pc = 1; pc <= 4; pc++) {
 		b.partitions[pc] = rel(b.partitions[pc]);
 		if (pc >= 2) {
