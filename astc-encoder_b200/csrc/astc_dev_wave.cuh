@@ -70,27 +70,6 @@ ASTC_FN bool q_pop(const WCtx& w, const WaveArgs& a, int kind, int wave, unsigne
 	return true;
 }
 
-// The two halves of a pop, for callers that can take the ticket early: lane 0's atomic is issued, its result is not
-// consumed before q_pop_finish - the round trip to L2 runs under whatever the warp does in between.
-ASTC_FN uint32_t q_pop_ticket(const WCtx& w, const WaveArgs& a, int kind, int wave) {
-	uint32_t i = 0;
-	if (w.lane == 0) {
-		i = q_atomic_add(a.head + kind * ASTC_MAX_WAVES + wave, 1u);
-	}
-	return i;
-}
-ASTC_FN bool q_pop_finish(const WCtx& w, const WaveArgs& a, int kind, int wave, uint32_t ticket_lane0, unsigned int& b) {
-	uint32_t i = wbroadcast0(w, ticket_lane0);
-	// both loads in flight together (the entry is only meaningful below the count; tickets beyond the capacity read nothing)
-	uint32_t n = q_load(a.count + kind * ASTC_MAX_WAVES + wave);
-	uint32_t e = i < a.total ? q_load(a.queue[kind] + i) : 0u;
-	if (i >= n) {
-		return false;
-	}
-	b = e;
-	return true;
-}
-
 // pop from the classes of a kind in order; cls is the warp's cursor
 ASTC_FN bool q_pop_classes(const WCtx& w, const WaveArgs& a, int kind, int wave, int& cls, unsigned int& b, int cls_end = ASTC_Q_CLASSES) {
 	while (cls < cls_end) {
@@ -120,10 +99,8 @@ struct alignas(16) U128 {
 };
 #if defined(ASTC_HOSTSIM)
 ASTC_FN void record_mbar_init(const WCtx& w) { (void)w; }
-ASTC_FN void record_drain(const WCtx& w) { (void)w; }
-ASTC_FN void record_copy(const WCtx& w, const WaveArgs& a, unsigned int b, bool save, bool with_texels, uint32_t& phase, bool defer_wait = false) {
+ASTC_FN void record_copy(const WCtx& w, const WaveArgs& a, unsigned int b, bool save, bool with_texels, uint32_t& phase) {
 	(void)phase;
-	(void)defer_wait;
 	U128* g = reinterpret_cast<U128*>(a.records + (size_t)b * BSD.record_bytes);
 	const int n1 = A_PERSIST / 16;
 	int n2 = with_texels ? ((w.T + 3) & ~3) : 0;      // 4 channels x Tp floats = Tp x 16 bytes
@@ -151,15 +128,7 @@ ASTC_FN void record_mbar_init(const WCtx& w) {
 	}
 	__syncwarp();
 }
-// defer_wait (saves only): return without waiting for the engine to have read the arena - the caller promises not to write
-// the arena before its next record_copy (which waits first) or record_drain()
-ASTC_FN void record_drain(const WCtx& w) {
-	if (w.lane == 0) {
-		asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-	}
-	__syncwarp();
-}
-ASTC_FN void record_copy(const WCtx& w, const WaveArgs& a, unsigned int b, bool save, bool with_texels, uint32_t& phase, bool defer_wait = false) {
+ASTC_FN void record_copy(const WCtx& w, const WaveArgs& a, unsigned int b, bool save, bool with_texels, uint32_t& phase) {
 	const uint8_t* g = a.records + (size_t)b * BSD.record_bytes;
 	const uint32_t n1 = A_PERSIST;
 	const uint32_t n2 = with_texels ? (uint32_t)((w.T + 3) & ~3) * 16u : 0u;
@@ -176,15 +145,12 @@ ASTC_FN void record_copy(const WCtx& w, const WaveArgs& a, unsigned int b, bool 
 			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 			// the arena may be overwritten as soon as the engine has READ it (the stores to HBM complete behind our back;
 			// the consumer is a later kernel launch)
-			if (!defer_wait) {
-				asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-			}
+			asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 		}
 		__syncwarp();
 		return;
 	}
 	if (w.lane == 0) {
-		asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // (a deferred save of this warp: its source is this arena)
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n1 + n2) : "memory");
 		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_head), "l"(g), "r"(n1), "r"(bar) : "memory");
@@ -211,10 +177,10 @@ ASTC_FN Trial& trial_of(const WCtx& w) { return *reinterpret_cast<Trial*>(astc_s
 static_assert(sizeof(BlockSearch) <= 128 && sizeof(Trial) <= 64, "search state must fit its arena slots");
 
 // the search state already lives in its arena slots: saving / restoring a record moves it with the rest of the head
-ASTC_FN void record_save(const WCtx& w, const WaveArgs& a, unsigned int b, bool with_texels = false, bool defer_wait = false) {
+ASTC_FN void record_save(const WCtx& w, const WaveArgs& a, unsigned int b, bool with_texels = false) {
 	uint32_t unused = 0;
 	wsync();
-	record_copy(w, a, b, true, with_texels, unused, defer_wait);
+	record_copy(w, a, b, true, with_texels, unused);
 }
 // phase: the parity of the warp's mbarrier, kept by the caller's item loop (flips with every restore)
 ASTC_FN void record_restore(const WCtx& w, const WaveArgs& a, unsigned int b, uint32_t& phase) {
@@ -414,11 +380,11 @@ ASTC_COOP void wave_finish_trial(WCtx w, const WaveArgs& a, unsigned int b, Bloc
 		for (int k = w.lane; k < (64 + 512) / 4; k += ASTC_WARP) {
 			dst[k] = src[k];
 		}
-		record_save(w, a, b, false, true);
+		record_save(w, a, b);
 		q_push(w, a, Q_REFINE + klass, a.wave + 1, b);
 		return;
 	}
-	record_save(w, a, b, false, true);      // (the refine loop's next arena write is a record_restore, which waits; see record_drain at its end)
+	record_save(w, a, b);
 	if (next == NEXT_TRIAL) {
 		q_push(w, a, Q_SETUP + klass, a.wave + 1, b);
 	} else if (next == NEXT_PREPARE) {
@@ -452,35 +418,15 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 	int st_prev_class = -1;
 	long long st_prev_end = 0;
 #endif
-	// a warp whose trial ends takes the ticket for its next item BEFORE it files the finished block (the atomic's round trip
-	// runs under that work); ticket_valid says a ticket of class `cls` is in flight
-	uint32_t ticket = 0;
-	bool ticket_valid = false;
 	while (true) {
 		while (!has_item && !drained) {
-			bool got = false;
-			while (cls < ASTC_Q_CLASSES) {
-				if (!ticket_valid) {
-					ticket = q_pop_ticket(w, a, Q_REFINE + cls, a.wave);
-				}
-				ticket_valid = false;
-				if (q_pop_finish(w, a, Q_REFINE + cls, a.wave, ticket, b)) {
-					got = true;
-					break;
-				}
-				cls++;
-			}
-			if (!got) {
+			if (!q_pop_classes(w, a, Q_REFINE, a.wave, cls, b)) {
 				drained = true;
 				break;
 			}
 			record_restore(w, a, b, rec_phase);
 			refine_begin_trial(w, t, r, s, true);
 			if (!r.running) {
-				if (cls < ASTC_Q_CLASSES) {
-					ticket = q_pop_ticket(w, a, Q_REFINE + cls, a.wave);
-					ticket_valid = true;
-				}
 				wave_finish_trial(w, a, b, s, t, r.best_errorval_in_mode);
 				continue;
 			}
@@ -533,15 +479,10 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 		}
 #endif
 		if (has_item && !r.running) {
-			if (!drained && cls < ASTC_Q_CLASSES) {
-				ticket = q_pop_ticket(w, a, Q_REFINE + cls, a.wave);
-				ticket_valid = true;
-			}
 			wave_finish_trial(w, a, b, s, t, r.best_errorval_in_mode);
 			has_item = false;
 		}
 	}
-	record_drain(w);
 }
 
 // ---------------------------------------------------------------------------------------------
