@@ -128,7 +128,10 @@ astc_wave_setup_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant
 	wave_setup(w, a);
 }
 
-__global__ void __launch_bounds__(ASTC_REFINE_THREADS_MAX, 1)
+#ifndef ASTC_REFINE_MIN_CTAS
+#define ASTC_REFINE_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(ASTC_REFINE_THREADS_MAX, ASTC_REFINE_MIN_CTAS)
 astc_wave_refine_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img, const __grid_constant__ WaveArgs a) {
 	if (wave_queue_empty(a, Q_REFINE)) {
 		return;
@@ -283,6 +286,7 @@ struct DeviceGuard {
 struct Knobs {
 	size_t batch_blocks;         // ASTCENC_B200_BATCH_BLOCKS: blocks per batch of a slab (records are reused batch after batch)
 	unsigned int sync_mask;      // ASTCENC_B200_SYNC_MASK: stage barriers of the wave kernels
+	unsigned int sync_mask_tail; // ASTCENC_B200_SYNC_MASK_TAIL: the same for the waves after the first (default: the same mask)
 	int coherence_probe;         // ASTCENC_B200_COHERENCE_PROBE (single-kernel driver experiment)
 	int upload_bands;            // ASTCENC_B200_UPLOAD_BANDS: bands the host-pointer path cuts an image into (1 = one copy)
 	int stage_print;             // ASTCENC_B200_STAGE_PRINT
@@ -315,6 +319,7 @@ struct astcenc_context {
 	int lockstep;                // single-kernel drivers: phase-aligned CTA (1) or independent warps (0)
 	int driver;                  // 0 = wave pipeline (default), 1 = single kernel
 	int warps_setup, warps_small;   // warps per CTA of the setup / refine+prepare kernels
+	int refine_ctas;                // CTAs per SM of the refine kernel (experiment: ASTCENC_B200_REFINE_CTAS)
 	int warps_setup_1p;             // set-up kernel on the compact one-plane plan (0 = plan not used)
 	size_t smem_setup, smem_setup_1p, smem_small, smem_refine;
 	uint32_t setup_stage_bytes;
@@ -495,6 +500,10 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	if (const char* e = getenv("ASTCENC_B200_SYNC_MASK")) {
 		ctx->knobs.sync_mask = (unsigned int)strtoul(e, nullptr, 0);
 	}
+	ctx->knobs.sync_mask_tail = ctx->knobs.sync_mask;
+	if (const char* e = getenv("ASTCENC_B200_SYNC_MASK_TAIL")) {
+		ctx->knobs.sync_mask_tail = (unsigned int)strtoul(e, nullptr, 0);
+	}
 	ctx->knobs.coherence_probe = getenv("ASTCENC_B200_COHERENCE_PROBE") ? 1 : 0;
 	ctx->knobs.stage_print = getenv("ASTCENC_B200_STAGE_PRINT") ? 1 : 0;
 	ctx->knobs.pipes = 1;      // measured at 4K 6x6 -medium: 1 / 2 / 4 / 8 pipelines = 76.1 / 76.7 / 78.0 / 80.1 ms (the idle warps are inside the CTAs, not between kernels)
@@ -582,7 +591,13 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 			size_t arena_small = ctx->tables->bsd.arena_bytes_small;
 			int ws = (int)((smem_limit - ASTC_SMEM_HDR - ASTC_SMEM_SINCOS_BYTES) / arena);
 			if (ws > ASTC_SETUP_THREADS_MAX / 32) ws = ASTC_SETUP_THREADS_MAX / 32;
-			int wr = (int)((smem_limit - ASTC_SMEM_HDR) / (arena_small + ASTC_REFINE_STATE_BYTES));
+			ctx->refine_ctas = 1;
+			if (const char* e = getenv("ASTCENC_B200_REFINE_CTAS")) {
+				int v = atoi(e);
+				if (v >= 1 && v <= 4) ctx->refine_ctas = v;
+			}
+			// (per CTA: 1 KB of shared memory is reserved by the system)
+			int wr = (int)((smem_limit / ctx->refine_ctas - (ctx->refine_ctas > 1 ? 1024 : 0) - ASTC_SMEM_HDR) / (arena_small + ASTC_REFINE_STATE_BYTES));
 			if (wr > ASTC_REFINE_THREADS_MAX / 32) wr = ASTC_REFINE_THREADS_MAX / 32;
 			// Staging the decimation (+ colour quantisation) tables in the refine kernel's spare shared memory is possible
 			// without losing a warp at 6x6, but measured no gain (refine 42.4 vs 41.8 ms: L1 already serves these loads): opt-in.
@@ -875,6 +890,7 @@ static astcenc_error launch_pipes(astcenc_context* ctx, int pipes, const void* d
 				continue;
 			}
 			a[p].wave = wave;
+			a[p].sync_mask = wave == 0 ? ctx->knobs.sync_mask : ctx->knobs.sync_mask_tail;
 			cudaStream_t ps = ctx->pipe_stream[p];
 			if (ctx->warps_setup_1p) {
 				if (wave != 0) {
@@ -891,7 +907,7 @@ static astcenc_error launch_pipes(astcenc_context* ctx, int pipes, const void* d
 			} else {
 				astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
 			}
-			astc_wave_refine_kernel<<<grid, ctx->warps_small * 32, ctx->smem_refine, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
+			astc_wave_refine_kernel<<<grid * ctx->refine_ctas, ctx->warps_small * 32, ctx->smem_refine, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
 			astc_wave_prepare_kernel<<<grid * 2, wp * 32, ASTC_SMEM_HDR + (size_t)bsd.arena_bytes_small * wp, ps>>>(bsd, ctx->dcfg, img[p], a[p]);
 			ctx->launches += 3;
 		}
@@ -1067,6 +1083,7 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 		mark(-1);
 		for (int wave = 0; wave < ctx->max_waves; wave++) {
 			a.wave = wave;
+			a.sync_mask = wave == 0 ? ctx->knobs.sync_mask : ctx->knobs.sync_mask_tail;
 			if (wave == 0 && up != nullptr) {
 				// bands of block rows, growing (1 : 3 : 4 : 8 ...) so that the first copy - the only one nothing hides - is short
 				static const unsigned int shares[ASTC_MAX_BANDS] = {1, 3, 4, 8, 8, 8, 8, 8};
@@ -1124,7 +1141,7 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 				astc_wave_setup_kernel<<<grid, ctx->warps_setup * 32, ctx->smem_setup, stream>>>(bsd, ctx->dcfg, img, a);
 				mark(0);
 			}
-			astc_wave_refine_kernel<<<grid, ctx->warps_small * 32, ctx->smem_refine, stream>>>(bsd, ctx->dcfg, img, a);
+			astc_wave_refine_kernel<<<grid * ctx->refine_ctas, ctx->warps_small * 32, ctx->smem_refine, stream>>>(bsd, ctx->dcfg, img, a);
 			mark(1);
 			// (statistics / partition search gain nothing from phase alignment: two half-size CTAs per SM wait less; measured 5.1 -> 4.4 ms)
 			int wp = ctx->warps_small >= 2 ? ctx->warps_small / 2 : 1;
