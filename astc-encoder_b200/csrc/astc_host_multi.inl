@@ -377,10 +377,7 @@ astcenc_error astcenc_b200_compress_batch(astcenc_context* ctx, astcenc_image* c
 			CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->scratch_done, 0), return ASTCENC_ERR_BAD_CONTEXT);
 		}
 	}
-	st = upload(0);
-	if (st != ASTCENC_SUCCESS) {
-		return st;
-	}
+	// (round 0 has nothing to hide its upload behind: it goes up in bands under its own first wave, as in astcenc_compress_image)
 	for (unsigned int round = 0; round < rounds; round++) {
 		unsigned int i = round * (unsigned int)ctx->world + (unsigned int)ctx->rank;
 		int b = (int)(round & 1);
@@ -391,8 +388,17 @@ astcenc_error astcenc_b200_compress_batch(astcenc_context* ctx, astcenc_image* c
 			CUDA_TRY(cudaStreamWaitEvent(ctx->stream, slots_free[b], 0), return ASTCENC_ERR_BAD_CONTEXT);
 		}
 		if (i < image_count) {
-			CUDA_TRY(cudaStreamWaitEvent(ctx->stream, up_done[b], 0), return ASTCENC_ERR_BAD_CONTEXT);
-			st = launch_slab(ctx, bufs[b], (int)ref->data_type, ref->dim_x, ref->dim_y, swz, 0, (unsigned int)blocks_y, mine, ctx->stream);
+			UploadPlan first;
+			first.host = static_cast<const uint8_t*>(images[i]->data[0]);
+			first.device = bufs[b];
+			first.row_bytes = (size_t)ref->dim_x * bpt;
+			first.bands = ctx->knobs.upload_bands;
+			if (round != 0) {
+				CUDA_TRY(cudaStreamWaitEvent(ctx->stream, up_done[b], 0), return ASTCENC_ERR_BAD_CONTEXT);
+			} else {
+				ctx->last_h2d += slice_bytes;
+			}
+			st = launch_slab(ctx, bufs[b], (int)ref->data_type, ref->dim_x, ref->dim_y, swz, 0, (unsigned int)blocks_y, mine, ctx->stream, round == 0 ? &first : nullptr);
 			if (st != ASTCENC_SUCCESS) {
 				return st;
 			}
