@@ -1,12 +1,19 @@
 #!/bin/bash
-# Dev tool, run on the GPU box: tools/profile_round.sh <tag>
-# 1. bench line (own arm, with the CPU baseline) -> gpurun_out/bench_<tag>.json
-# 2. reference arm                                -> gpurun_out/bench_ref_<tag>.json
-# 3. ncu launch list of the same bench command (durations + DRAM bytes per launch) -> gpurun_out/launches_<tag>.csv
-tag=$1
-cd /root/repo
-python bench.py --steps 5 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_$tag.json
-python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > gpurun_out/bench_ref_$tag.json
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio \
-    --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench_$tag.log 2>&1
-head -c 600 gpurun_out/bench_$tag.json; echo; head -c 400 gpurun_out/bench_ref_$tag.json; echo
+# dev tool (GPU box): bench lines of every config (both arms for the headline) -> gpurun_out/
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+T=${1:-r02}
+for c in 1 0 2 3; do
+  timeout 900 python bench.py --config $c --steps 10 --warmup 3 > gpurun_out/bench_${T}_c$c.json 2> gpurun_out/bench_${T}_c$c.err
+done
+timeout 900 python bench.py --impl reference --config 1 --steps 5 --warmup 1 > gpurun_out/bench_${T}_reference_c1.json 2>> gpurun_out/bench_${T}_c1.err
+timeout 600 python bench.py --config 4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${T}_c4.json 2> gpurun_out/bench_${T}_c4.err
+python - <<PY
+import json,glob
+for f in sorted(glob.glob('gpurun_out/bench_${T}_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, 'ms', round(d['ms_per_step'],2), 'val', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'cpu', d.get('cpu_baseline',{}).get('value'), d.get('cpu_baseline',{}).get('cores'))
+    except Exception as e:
+        print(f, 'ERR', e)
+PY
