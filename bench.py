@@ -469,7 +469,7 @@ def main():
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_from_profile() if c in (1, 4) else None,
                              "peak_source": peak_kind + " copy bandwidth (MEASURED_PEAKS.json)",
-                             "kernel": "wave pipeline = astc_wave_{setup,refine,prepare,emit}_kernel, one pass over the image (%d launches)" % sum(stage_launches.values()),
+                             "kernel": "wave pipeline = astc_wave_{setup,refine,prepare,emit}_kernel, one pass over the image (%d launches)" % (launches // max(1, K)),
                              "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
                              "stage_ms": stage_ms, "stage_launches": stage_launches,
                              "dominant_kernel": "astc_wave_%s_kernel" % max(stage_ms, key=stage_ms.get),
