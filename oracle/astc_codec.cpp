@@ -83,19 +83,22 @@ static float approx_pow(float x, float y) {
 	return approx_exp2(approx_log2(x) * y);
 }
 
-int config_init(int profile, unsigned int block_x, unsigned int block_y, float quality, unsigned int flags, Config& cfg) {
+int config_init(int profile, unsigned int block_x, unsigned int block_y, float quality, unsigned int flags, Config& cfg, unsigned int block_z) {
 	memset(&cfg, 0, sizeof(cfg));
-	if (!is_legal_2d_block_size(block_x, block_y)) {
+	block_z = block_z < 1 ? 1 : block_z;      // (Z == 0 is accepted for 2D sizes, :527)
+	bool legal = block_z <= 1 ? is_legal_2d_block_size(block_x, block_y) : is_legal_3d_block_size(block_x, block_y, block_z);
+	if (!legal) {
 		return 4;   // ASTCENC_ERR_BAD_BLOCK_SIZE
 	}
 	cfg.block_x = block_x;
 	cfg.block_y = block_y;
-	float texels = static_cast<float>(block_x * block_y);
+	cfg.block_z = block_z;
+	float texels = static_cast<float>(block_x * block_y * block_z);
 	float ltexels = logf(texels) / logf(10.0f);
 	if (quality < 0.0f || quality > 100.0f) {
 		return 6;   // ASTCENC_ERR_BAD_QUALITY
 	}
-	unsigned int texels_int = block_x * block_y;
+	unsigned int texels_int = block_x * block_y * block_z;
 	const Preset* presets = texels_int < 25 ? PRESETS_HIGH : texels_int < 64 ? PRESETS_MID : PRESETS_LOW;
 	size_t end;
 	for (end = 0; end < 6; end++) {
@@ -281,7 +284,7 @@ Context* context_create(const Config& cfg) {
 	Context* ctx = new Context;
 	ctx->config = cfg;
 	bool can_omit = (cfg.flags & FLG_SELF_DECOMPRESS_ONLY) != 0;
-	ctx->bsd = build_block_size_tables(cfg.block_x, cfg.block_y, can_omit, cfg.tune_partition_count_limit,
+	ctx->bsd = build_block_size_tables(cfg.block_x, cfg.block_y, cfg.block_z < 1 ? 1 : cfg.block_z, can_omit, cfg.tune_partition_count_limit,
 	                                   static_cast<float>(cfg.tune_block_mode_limit) / 100.0f);
 	ctx->work = new WorkBuf;
 	return ctx;
@@ -315,12 +318,12 @@ static inline bool is_luminancealpha(const ImageBlock& b) {
 // Block load (astcenc_image.cpp:162-342)
 // =============================================================================================
 void load_block(const Context& ctx, const void* data, int data_type, unsigned int dim_x, unsigned int dim_y,
-                unsigned int pos_x, unsigned int pos_y, const int swz[4], ImageBlock& blk) {
+                unsigned int pos_x, unsigned int pos_y, const int swz[4], ImageBlock& blk, unsigned int dim_z, unsigned int pos_z) {
 	const BlockSizeTables& bsd = *ctx.bsd;
 	int profile = ctx.config.profile;
 	bool needs_swz = swz[0] != 0 || swz[1] != 1 || swz[2] != 2 || swz[3] != 3;
 	bool needs_hdr = profile == PRF_HDR || profile == PRF_HDR_RGB_LDR_A;
-	bool fast = !needs_swz && !needs_hdr && data_type == 0;
+	bool fast = !needs_swz && !needs_hdr && data_type == 0 && bsd.dim_z == 1;      // (astcenc_entry.cpp:946-947)
 
 	blk.texel_count = bsd.texel_count;
 	blk.decode_unorm8 = (ctx.config.flags & FLG_USE_DECODE_UNORM8) != 0;
@@ -363,11 +366,13 @@ void load_block(const Context& ctx, const void* data, int data_type, unsigned in
 	float mean_scale = 1.0f / static_cast<float>(bsd.texel_count);
 	uint8_t rgb_lns = needs_hdr ? 1 : 0;
 	uint8_t a_lns = profile == PRF_HDR ? 1 : 0;
+	for (unsigned int z = 0; z < bsd.dim_z; z++) {
+	unsigned int zi = pos_z + z < dim_z - 1 ? pos_z + z : dim_z - 1;
 	for (unsigned int y = 0; y < bsd.dim_y; y++) {
 		unsigned int yi = pos_y + y < dim_y - 1 ? pos_y + y : dim_y - 1;
 		for (unsigned int x = 0; x < bsd.dim_x; x++) {
 			unsigned int xi = pos_x + x < dim_x - 1 ? pos_x + x : dim_x - 1;
-			size_t off = (4 * (size_t)dim_x * yi) + (4 * xi);
+			size_t off = (4 * (size_t)dim_x * dim_y * zi) + (4 * (size_t)dim_x * yi) + (4 * xi);
 			f4 v;
 			if (data_type == 0) {
 				const uint8_t* p = static_cast<const uint8_t*>(data) + off;
@@ -400,6 +405,7 @@ void load_block(const Context& ctx, const void* data, int data_type, unsigned in
 			blk.data_a[idx] = v.w;
 			idx++;
 		}
+	}
 	}
 	blk.rgb_lns0 = rgb_lns;
 	blk.alpha_lns0 = a_lns;

@@ -22,7 +22,7 @@ static const unsigned int FLG_MAP_RGBM = 1 << 6;
 struct Config {
 	int profile;
 	unsigned int flags;
-	unsigned int block_x, block_y;
+	unsigned int block_x, block_y, block_z;
 	float cw_r_weight, cw_g_weight, cw_b_weight, cw_a_weight;
 	unsigned int a_scale_radius;
 	float rgbm_m_scale;
@@ -40,7 +40,7 @@ struct Config {
 };
 
 // astcenc_config_init (astcenc_entry.cpp:504-723). Returns 0 on success, else the astcenc_error value.
-int config_init(int profile, unsigned int block_x, unsigned int block_y, float quality, unsigned int flags, Config& cfg);
+int config_init(int profile, unsigned int block_x, unsigned int block_y, float quality, unsigned int flags, Config& cfg, unsigned int block_z = 1);
 // validate_config clamps + dB->error conversion done by astcenc_context_alloc (astcenc_entry.cpp:434-501, 814-821)
 int config_finalize(Config& cfg);
 
@@ -82,16 +82,17 @@ void context_destroy(Context* ctx);
 // data_type: 0 = U8, 1 = F16, 2 = F32 (astcenc_type). swz: 4 entries of astcenc_swz.
 // load_image_block / load_image_block_fast_ldr (astcenc_image.cpp:162, :278)
 void load_block(const Context& ctx, const void* data, int data_type, unsigned int dim_x, unsigned int dim_y,
-                unsigned int pos_x, unsigned int pos_y, const int swz[4], ImageBlock& blk);
+                unsigned int pos_x, unsigned int pos_y, const int swz[4], ImageBlock& blk, unsigned int dim_z = 1, unsigned int pos_z = 0);
 
 // compress_block (astcenc_compress_symbolic.cpp:1162)
 void compress_block(const Context& ctx, const ImageBlock& blk, uint8_t pcb[16]);
 
-// whole-image loop of compress_image (astcenc_entry.cpp:891-1043), single slice
-// astcenc_decompress_image (astcenc_entry.cpp:1274-1385), single slice; swz uses astcenc_swz numbering (6 = Z)
-void decompress_image(const Context& ctx, const uint8_t* data, void* out, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4]);
+// whole-image loop of compress_image (astcenc_entry.cpp:891-1043); a volume is dim_z slices of dim_x * dim_y texels, contiguous
+// astcenc_decompress_image (astcenc_entry.cpp:1274-1385); swz uses astcenc_swz numbering (6 = Z)
+void decompress_image(const Context& ctx, const uint8_t* data, void* out, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
+                      unsigned int dim_z = 1);
 void compress_image(const Context& ctx, const void* data, int data_type, unsigned int dim_x, unsigned int dim_y,
-                    const int swz[4], uint8_t* out);
+                    const int swz[4], uint8_t* out, unsigned int dim_z = 1);
 
 void symbolic_to_physical(const BlockSizeTables& bsd, const SymbolicBlock& scb, uint8_t pcb[16]);
 

@@ -1892,7 +1892,7 @@ void compress_block(const Context& ctx, const ImageBlock& blk, uint8_t pcb[16]) 
 	float errorval_mult[2] = {1.0f / config.tune_mse_overshoot, 1.0f};
 	const float errorval_overshoot = 1.0f / config.tune_mse_overshoot;
 	int start_trial = 1;
-	if (config.tune_search_mode0_enable >= 0.85f) {
+	if (config.tune_search_mode0_enable >= 0.85f && bsd.dim_z == 1) {      // (:1287: no mode-0 trial for 3D block sizes)
 		start_trial = 0;
 	}
 	int quant_limit = QUANT_32;
@@ -2072,17 +2072,20 @@ static void compute_alpha_averages(const void* data, int data_type, unsigned int
 	}
 }
 
-void compress_image(const Context& ctx, const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4], uint8_t* out) {
-	unsigned int bx = ctx.bsd->dim_x, by = ctx.bsd->dim_y;
+void compress_image(const Context& ctx, const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4], uint8_t* out, unsigned int dim_z) {
+	unsigned int bx = ctx.bsd->dim_x, by = ctx.bsd->dim_y, bz = ctx.bsd->dim_z;
 	unsigned int blocks_x = (dim_x + bx - 1) / bx;
 	unsigned int blocks_y = (dim_y + by - 1) / by;
+	unsigned int blocks_z = (dim_z + bz - 1) / bz;
 	ImageBlock blk;
 	std::vector<float> alpha_averages;
-	unsigned int radius = ctx.config.a_scale_radius;
+	// (the alpha averages only steer 2D block sizes, astcenc_entry.cpp:975; volumes with a radius are not restated)
+	unsigned int radius = bz == 1 && dim_z == 1 ? ctx.config.a_scale_radius : 0;
 	if (radius != 0) {
 		alpha_averages.resize((size_t)dim_x * dim_y);
 		compute_alpha_averages(data, data_type, dim_x, dim_y, swz, radius, alpha_averages.data());
 	}
+	for (unsigned int z = 0; z < blocks_z; z++) {
 	for (unsigned int y = 0; y < blocks_y; y++) {
 		for (unsigned int x = 0; x < blocks_x; x++) {
 			// alpha-scale RDO (astcenc_entry.cpp:973-1003): blocks whose footprint has (almost) no alpha become constant zero
@@ -2105,7 +2108,7 @@ void compress_image(const Context& ctx, const void* data, int data_type, unsigne
 				}
 			}
 			if (use_full_block) {
-				load_block(ctx, data, data_type, dim_x, dim_y, x * bx, y * by, swz, blk);
+				load_block(ctx, data, data_type, dim_x, dim_y, x * bx, y * by, swz, blk, dim_z, z * bz);
 				if (ctx.config.flags & FLG_USE_ALPHA_WEIGHT) {
 					float alpha_scale = blk.data_max.w * (1.0f / 65535.0f);
 					blk.channel_weight = mk4(ctx.config.cw_r_weight * alpha_scale, ctx.config.cw_g_weight * alpha_scale,
@@ -2118,7 +2121,8 @@ void compress_image(const Context& ctx, const void* data, int data_type, unsigne
 				blk.data_max = splat4(0.0f);
 				blk.grayscale = true;
 			}
-			compress_block(ctx, blk, out + ((size_t)y * blocks_x + x) * 16);
+			compress_block(ctx, blk, out + (((size_t)z * blocks_y + y) * blocks_x + x) * 16);
 		}
+	}
 	}
 }

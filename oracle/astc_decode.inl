@@ -303,15 +303,16 @@ static void decompress_symbolic_block(int decode_mode, const BlockSizeTables& bs
 
 // store_image_block: swz entries use astcenc_swz numbering (0..3 = r,g,b,a, 4 = 0, 5 = 1, 6 = Z)
 static void store_image_block(void* out, int data_type, unsigned int dim_x, unsigned int dim_y, const DecodedBlock& blk, const BlockSizeTables& bsd,
-                              unsigned int pos_x, unsigned int pos_y, const int swz[4]) {
-	unsigned int bx = bsd.dim_x, by = bsd.dim_y;
+                              unsigned int pos_x, unsigned int pos_y, const int swz[4], unsigned int dim_z = 1, unsigned int pos_z = 0) {
+	unsigned int bx = bsd.dim_x, by = bsd.dim_y, bz = bsd.dim_z;
 	bool needs_swz = swz[0] != 0 || swz[1] != 1 || swz[2] != 2 || swz[3] != 3;
 	bool needs_z = swz[0] == 6 || swz[1] == 6 || swz[2] == 6 || swz[3] == 6;
+	for (unsigned int z = pos_z; z < pos_z + bz && z < dim_z; z++) {
 	for (unsigned int y = pos_y; y < pos_y + by && y < dim_y; y++) {
 		for (unsigned int x = pos_x; x < pos_x + bx && x < dim_x; x++) {
-			unsigned int idx = (y - pos_y) * bx + (x - pos_x);
+			unsigned int idx = ((z - pos_z) * by + (y - pos_y)) * bx + (x - pos_x);
 			float d[4] = {blk.r[idx], blk.g[idx], blk.b[idx], blk.a[idx]};
-			size_t o = (4 * (size_t)dim_x * y) + 4 * (size_t)x;
+			size_t o = (4 * (size_t)dim_x * dim_y * z) + (4 * (size_t)dim_x * y) + 4 * (size_t)x;
 			if (data_type == 0) {
 				int v[7];
 				v[4] = 0;
@@ -378,20 +379,23 @@ static void store_image_block(void* out, int data_type, unsigned int dim_x, unsi
 			}
 		}
 	}
+	}
 }
 
-void decompress_image(const Context& ctx, const uint8_t* data, void* out, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4]) {
+void decompress_image(const Context& ctx, const uint8_t* data, void* out, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4], unsigned int dim_z) {
 	const BlockSizeTables& bsd = *ctx.bsd;
-	unsigned int bx = bsd.dim_x, by = bsd.dim_y;
-	unsigned int blocks_x = (dim_x + bx - 1) / bx, blocks_y = (dim_y + by - 1) / by;
-	for (unsigned int y = 0; y < blocks_y; y++) {
-		for (unsigned int x = 0; x < blocks_x; x++) {
-			SymbolicBlock scb;
-			memset(&scb, 0, sizeof(scb));
-			physical_to_symbolic(bsd, data + ((size_t)y * blocks_x + x) * 16, scb);
-			DecodedBlock blk;
-			decompress_symbolic_block(ctx.config.profile, bsd, scb, data_type == 0, blk);
-			store_image_block(out, data_type, dim_x, dim_y, blk, bsd, x * bx, y * by, swz);
+	unsigned int bx = bsd.dim_x, by = bsd.dim_y, bz = bsd.dim_z;
+	unsigned int blocks_x = (dim_x + bx - 1) / bx, blocks_y = (dim_y + by - 1) / by, blocks_z = (dim_z + bz - 1) / bz;
+	for (unsigned int z = 0; z < blocks_z; z++) {
+		for (unsigned int y = 0; y < blocks_y; y++) {
+			for (unsigned int x = 0; x < blocks_x; x++) {
+				SymbolicBlock scb;
+				memset(&scb, 0, sizeof(scb));
+				physical_to_symbolic(bsd, data + (((size_t)z * blocks_y + y) * blocks_x + x) * 16, scb);
+				DecodedBlock blk;
+				decompress_symbolic_block(ctx.config.profile, bsd, scb, data_type == 0, blk);
+				store_image_block(out, data_type, dim_x, dim_y, blk, bsd, x * bx, y * by, swz, dim_z, z * bz);
+			}
 		}
 	}
 }

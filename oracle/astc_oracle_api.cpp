@@ -24,6 +24,18 @@ void* oracle_context_create(int profile, unsigned int block_x, unsigned int bloc
 	return context_create(cfg);
 }
 
+// The same for any block size: block_z > 1 selects one of the ten 3D footprints.
+void* oracle_context_create_3d(int profile, unsigned int block_x, unsigned int block_y, unsigned int block_z, float quality, unsigned int flags) {
+	Config cfg;
+	if (config_init(profile, block_x, block_y, quality, flags, cfg, block_z) != 0) {
+		return nullptr;
+	}
+	if (config_finalize(cfg) != 0) {
+		return nullptr;
+	}
+	return context_create(cfg);
+}
+
 void oracle_context_destroy(void* ctx) {
 	context_destroy(static_cast<Context*>(ctx));
 }
@@ -39,6 +51,19 @@ int oracle_compress_image(void* ctx, const void* data, int data_type, unsigned i
 int oracle_decompress_image(void* ctx, const uint8_t* data, void* out, int data_type, unsigned int dim_x, unsigned int dim_y, const int* swz) {
 	static const int ident[4] = {0, 1, 2, 3};
 	decompress_image(*static_cast<Context*>(ctx), data, out, data_type, dim_x, dim_y, swz ? swz : ident);
+	return 0;
+}
+
+// Volumes: data / out hold dim_z slices of dim_x * dim_y texels, contiguous; blocks come out in (z, y, x) order.
+int oracle_compress_volume(void* ctx, const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, unsigned int dim_z, const int* swz, uint8_t* out) {
+	static const int ident[4] = {0, 1, 2, 3};
+	compress_image(*static_cast<Context*>(ctx), data, data_type, dim_x, dim_y, swz ? swz : ident, out, dim_z);
+	return 0;
+}
+
+int oracle_decompress_volume(void* ctx, const uint8_t* data, void* out, int data_type, unsigned int dim_x, unsigned int dim_y, unsigned int dim_z, const int* swz) {
+	static const int ident[4] = {0, 1, 2, 3};
+	decompress_image(*static_cast<Context*>(ctx), data, out, data_type, dim_x, dim_y, swz ? swz : ident, dim_z);
 	return 0;
 }
 

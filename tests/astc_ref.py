@@ -132,6 +132,69 @@ class AstcencLib:
 
     NP_TYPES = {TYPE_U8: np.uint8, TYPE_F16: np.float16, TYPE_F32: np.float32}
 
+    # ---- volumes: vol is numpy (D, H, W, 4); any block size, block_z > 1 = the 3D footprints ----
+    def config3(self, profile, bx, by, bz, quality, flags=0, **overrides):
+        cfg = Config()
+        err = self.lib.astcenc_config_init(profile, bx, by, bz, quality, flags, C.byref(cfg))
+        if err:
+            raise RuntimeError("config_init failed: %d" % err)
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        return cfg
+
+    def compress_volume(self, vol, profile, bx, by, bz, quality, flags=0, swz=(0, 1, 2, 3), threads=1, **overrides):
+        vol = np.ascontiguousarray(vol)
+        d, h, w = vol.shape[:3]
+        cfg = self.config3(profile, bx, by, bz, quality, flags, **overrides)
+        ctx = C.c_void_p()
+        err = self.lib.astcenc_context_alloc(C.byref(cfg), threads, C.byref(ctx), None)
+        if err:
+            raise RuntimeError("context_alloc failed: %d" % err)
+        try:
+            dt = _NP2TYPE[vol.dtype]
+            slices = (C.c_void_p * d)(*[vol[z].ctypes.data for z in range(d)])
+            image = Image(w, h, d, dt, slices)
+            sw = Swizzle(*swz)
+            nblocks = ((w + bx - 1) // bx) * ((h + by - 1) // by) * ((d + bz - 1) // bz)
+            out = np.zeros(nblocks * 16, dtype=np.uint8)
+            if threads == 1:
+                err = self.lib.astcenc_compress_image(ctx, C.byref(image), C.byref(sw), out.ctypes.data, out.nbytes, 0)
+                if err:
+                    raise RuntimeError("compress_image failed: %d" % err)
+            else:
+                import threading
+                errs = [0] * threads
+
+                def run(i):
+                    errs[i] = self.lib.astcenc_compress_image(ctx, C.byref(image), C.byref(sw), out.ctypes.data, out.nbytes, i)
+                ts = [threading.Thread(target=run, args=(i,)) for i in range(threads)]
+                [t.start() for t in ts]
+                [t.join() for t in ts]
+                if any(errs):
+                    raise RuntimeError("compress_image failed: %s" % errs)
+            return out
+        finally:
+            self.lib.astcenc_context_free(ctx)
+
+    def decompress_volume(self, blocks, w, h, d, profile, bx, by, bz, out_type=TYPE_U8, flags=0, swz=(0, 1, 2, 3), quality=PRE_MEDIUM):
+        cfg = self.config3(profile, bx, by, bz, quality, flags)
+        ctx = C.c_void_p()
+        err = self.lib.astcenc_context_alloc(C.byref(cfg), 1, C.byref(ctx), None)
+        if err:
+            raise RuntimeError("context_alloc failed: %d" % err)
+        try:
+            blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+            out = np.zeros((d, h, w, 4), dtype=self.NP_TYPES[out_type])
+            slices = (C.c_void_p * d)(*[out[z].ctypes.data for z in range(d)])
+            image = Image(w, h, d, out_type, slices)
+            sw = Swizzle(*swz)
+            err = self.lib.astcenc_decompress_image(ctx, blocks.ctypes.data, blocks.nbytes, C.byref(image), C.byref(sw), 0)
+            if err:
+                raise RuntimeError("decompress_image failed: %d" % err)
+            return out
+        finally:
+            self.lib.astcenc_context_free(ctx)
+
     def error_metrics(self, img1, img2, hdr=False, normal=False, components=4, fstop_lo=-10, fstop_hi=10):
         """astcenc_b200_compute_error_metrics (product library only)."""
         fn = self.lib.astcenc_b200_compute_error_metrics
@@ -265,7 +328,7 @@ def ref_lib():
 
 class OracleConfig(C.Structure):
     _fields_ = [
-        ("profile", C.c_int), ("flags", C.c_uint), ("block_x", C.c_uint), ("block_y", C.c_uint),
+        ("profile", C.c_int), ("flags", C.c_uint), ("block_x", C.c_uint), ("block_y", C.c_uint), ("block_z", C.c_uint),
         ("cw_r_weight", C.c_float), ("cw_g_weight", C.c_float), ("cw_b_weight", C.c_float), ("cw_a_weight", C.c_float),
         ("a_scale_radius", C.c_uint), ("rgbm_m_scale", C.c_float),
         ("tune_partition_count_limit", C.c_uint), ("tune_2partition_index_limit", C.c_uint),
@@ -331,6 +394,40 @@ class Oracle:
             out = np.zeros(nblocks * 16, dtype=np.uint8)
             sw = (C.c_int * 4)(*swz) if swz is not None else None
             self.lib.oracle_compress_image(ctx, img.ctypes.data, dt, w, h, sw, out.ctypes.data)
+            return out
+        finally:
+            self.lib.oracle_context_destroy(ctx)
+
+    def compress_volume(self, vol, profile, bx, by, bz, quality, flags=0, swz=None):
+        vol = np.ascontiguousarray(vol)
+        d, h, w = vol.shape[:3]
+        self.lib.oracle_context_create_3d.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_float, C.c_uint]
+        self.lib.oracle_context_create_3d.restype = C.c_void_p
+        self.lib.oracle_compress_volume.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_int), C.c_void_p]
+        ctx = self.lib.oracle_context_create_3d(profile, bx, by, bz, quality, flags)
+        if not ctx:
+            raise RuntimeError("oracle context failed")
+        try:
+            nblocks = ((w + bx - 1) // bx) * ((h + by - 1) // by) * ((d + bz - 1) // bz)
+            out = np.zeros(nblocks * 16, dtype=np.uint8)
+            sw = (C.c_int * 4)(*swz) if swz is not None else None
+            self.lib.oracle_compress_volume(ctx, vol.ctypes.data, _NP2TYPE[vol.dtype], w, h, d, sw, out.ctypes.data)
+            return out
+        finally:
+            self.lib.oracle_context_destroy(ctx)
+
+    def decompress_volume(self, blocks, w, h, d, profile, bx, by, bz, out_type=TYPE_U8, flags=0, swz=None, quality=PRE_MEDIUM):
+        self.lib.oracle_context_create_3d.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_float, C.c_uint]
+        self.lib.oracle_context_create_3d.restype = C.c_void_p
+        self.lib.oracle_decompress_volume.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_int)]
+        ctx = self.lib.oracle_context_create_3d(profile, bx, by, bz, quality, flags)
+        if not ctx:
+            raise RuntimeError("oracle context failed")
+        try:
+            blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+            out = np.zeros((d, h, w, 4), dtype=AstcencLib.NP_TYPES[out_type])
+            sw = (C.c_int * 4)(*swz) if swz is not None else None
+            self.lib.oracle_decompress_volume(ctx, blocks.ctypes.data, out.ctypes.data, out_type, w, h, d, sw)
             return out
         finally:
             self.lib.oracle_context_destroy(ctx)

@@ -11,7 +11,7 @@ static int fails = 0;
 static void check_bsd(unsigned bx, unsigned by, bool can_omit, unsigned pcut, float mcut) {
 	block_size_descriptor* bsd = aligned_malloc<block_size_descriptor>(sizeof(block_size_descriptor), 64);
 	init_block_size_descriptor(bx, by, 1, can_omit, pcut, mcut, *bsd);
-	ao::BlockSizeTables* t = ao::build_block_size_tables(bx, by, can_omit, pcut, mcut);
+	ao::BlockSizeTables* t = ao::build_block_size_tables(bx, by, 1, can_omit, pcut, mcut);
 	CHECK(bsd->texel_count == t->texel_count, "texel_count");
 	CHECK(bsd->decimation_mode_count_always == t->decimation_mode_count_always, "dm always %u %u", bsd->decimation_mode_count_always, t->decimation_mode_count_always);
 	CHECK(bsd->decimation_mode_count_selected == t->decimation_mode_count_selected, "dm sel");
