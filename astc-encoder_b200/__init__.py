@@ -205,8 +205,9 @@ class Context:
         image = Image(w, h, d, _DTYPES[img.dtype], slices)
         sw = Swizzle(*swizzle)
         nbx, nby = self.blocks(w, h)
+        bz = max(1, self.config.block_z)      # 3D block sizes: blocks come out in (z, y, x) order
         if out is None:
-            out = np.empty(nbx * nby * d * 16, dtype=np.uint8)
+            out = np.empty(nbx * nby * ((d + bz - 1) // bz) * 16, dtype=np.uint8)
         err = lib().astcenc_compress_image(self.handle, C.byref(image), C.byref(sw), out.ctypes.data, out.nbytes, thread_index)
         if err:
             raise AstcencError(err, "astcenc_compress_image")

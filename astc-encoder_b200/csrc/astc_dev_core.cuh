@@ -494,12 +494,21 @@ ASTC_FN void chain_sums(const WCtx& w, int n, uint32_t tile, SPtr<float> acc, in
 // =============================================================================================
 // Block load (astcenc_image.cpp:162-342). Lanes over texels; the per-channel mean is a chain.
 // =============================================================================================
-ASTC_COOP void load_block(WCtx w, unsigned int pos_x, unsigned int pos_y) {
+// (block_x, block_row): block coordinates; for 3D block sizes block_row counts layer * IMG.blocks_y + row and the texels of a
+// block run x fastest, then y, then z (:221-270)
+ASTC_COOP void load_block(WCtx w, unsigned int block_x, unsigned int block_row) {
 	const DevImage& img = IMG;
 	int profile = CFG.profile;
 	bool needs_swz = img.swz[0] != 0 || img.swz[1] != 1 || img.swz[2] != 2 || img.swz[3] != 3;
 	bool needs_hdr = profile == PRF_HDR || profile == PRF_HDR_RGB_LDR_A;
-	bool fast = !needs_swz && !needs_hdr && img.data_type == 0;
+	const bool volume = BSD.dim_z > 1;
+	bool fast = !needs_swz && !needs_hdr && img.data_type == 0 && !volume;      // (astcenc_entry.cpp:946-947)
+	unsigned int pos_x = block_x * BSD.dim_x, pos_y = block_row * BSD.dim_y, pos_z = 0;
+	if (volume) {
+		unsigned int layer = block_row / img.blocks_y;
+		pos_y = (block_row - layer * img.blocks_y) * BSD.dim_y;
+		pos_z = layer * BSD.dim_z;
+	}
 	uint8_t rgb_lns = needs_hdr ? 1 : 0;
 	uint8_t a_lns = profile == PRF_HDR ? 1 : 0;
 	int T = w.T;
@@ -513,10 +522,19 @@ ASTC_COOP void load_block(WCtx w, unsigned int pos_x, unsigned int pos_y) {
 	ASTC_NOUNROLL
 	for (int t = w.lane; t < T; t += ASTC_WARP) {
 		unsigned int x = pos_x + (unsigned int)t % bx;
-		unsigned int y = pos_y + (unsigned int)t / bx;
+		unsigned int ty = (unsigned int)t / bx;
+		size_t off = 0;
+		if (volume) {
+			unsigned int tz = ty / BSD.dim_y;
+			ty -= tz * BSD.dim_y;
+			unsigned int z = pos_z + tz;
+			unsigned int zi = z < img.dim_z - 1 ? z : img.dim_z - 1;
+			off = 4 * (size_t)img.dim_x * img.dim_y * zi;
+		}
+		unsigned int y = pos_y + ty;
 		unsigned int xi = x < img.dim_x - 1 ? x : img.dim_x - 1;
 		unsigned int yi = y < img.dim_y - 1 ? y : img.dim_y - 1;
-		size_t off = (4 * (size_t)img.dim_x * yi) + (4 * xi);
+		off += (4 * (size_t)img.dim_x * yi) + (4 * xi);
 		f4 v;
 		if (fast) {
 			uint32_t px = ASTC_LDG(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(img.data) + off));

@@ -95,6 +95,19 @@ ASTC_NOINLINE void physical_to_symbolic(uint32_t slice, uint64_t lo, uint64_t hi
 		for (int i = 0; i < 4; i++) {
 			h.constant_color[i] = (int)rd_bits(hi, 0, 16, 16 * (unsigned int)i);
 		}
+		if (BSD.dim_z > 1) {
+			// 3D void extent (astcenc_symbolic_physical.cpp:348-366): six 9-bit coordinates, no reserved bits
+			int v[6];
+			bool ones = true;
+			for (int k = 0; k < 6; k++) {
+				v[k] = (int)rd_bits(lo, hi, 9, 10 + 9 * (unsigned int)k);
+				ones = ones && v[k] == 0x1FF;
+			}
+			if ((v[0] >= v[1] || v[2] >= v[3] || v[4] >= v[5]) && !ones) {
+				h.block_type = SYM_BTYPE_ERROR;
+			}
+			return;
+		}
 		int rsvbits = (int)rd_bits(lo, hi, 2, 10);
 		if (rsvbits != 3) {
 			h.block_type = SYM_BTYPE_ERROR;
@@ -223,10 +236,10 @@ ASTC_FN float decode_component(int v, bool lns) {   // decode_texel :66-87
 }
 
 // store one texel (store_image_block); swz uses astcenc_swz numbering (4 = 0, 5 = 1, 6 = Z)
-ASTC_FN void store_texel(const DevImage& img, unsigned int x, unsigned int y, f4 d) {
+ASTC_FN void store_texel(const DevImage& img, unsigned int x, unsigned int y, unsigned int z, f4 d) {
 	bool needs_swz = img.swz[0] != 0 || img.swz[1] != 1 || img.swz[2] != 2 || img.swz[3] != 3;
 	bool needs_z = img.swz[0] == 6 || img.swz[1] == 6 || img.swz[2] == 6 || img.swz[3] == 6;
-	size_t o = (4 * (size_t)img.dim_x * y) + 4 * (size_t)x;
+	size_t o = (4 * (size_t)img.dim_x * img.dim_y * z) + (4 * (size_t)img.dim_x * y) + 4 * (size_t)x;
 	void* base = const_cast<void*>(img.data);
 	if (img.data_type == 0) {
 		int vr = f2i_rtn(clampzo(d.x) * 255.0f), vg = f2i_rtn(clampzo(d.y) * 255.0f), vb = f2i_rtn(clampzo(d.z) * 255.0f), va = f2i_rtn(clampzo(d.w) * 255.0f);
@@ -305,7 +318,16 @@ ASTC_COOP void decompress_block(int lane, uint32_t slice, const uint8_t* pcb, un
 	int decode_mode = CFG.profile;
 	int block_type = h.block_type;
 	bool u8 = img.data_type == 0 || decode_mode == PRF_LDR_SRGB;
-	unsigned int pos_x = bx_i * bdx, pos_y = by_i * BSD.dim_y;
+	// 3D block sizes: by_i counts layer * IMG.blocks_y + row; texels run x fastest, then y, then z (store_image_block, astcenc_image.cpp:366-420)
+	const bool volume = BSD.dim_z > 1;
+	unsigned int pos_x = bx_i * bdx, pos_y = by_i * BSD.dim_y, pos_z = 0;
+	unsigned int lim_z = 1;
+	if (volume) {
+		unsigned int layer = by_i / img.blocks_y;
+		pos_y = (by_i - layer * img.blocks_y) * BSD.dim_y;
+		pos_z = layer * BSD.dim_z;
+		lim_z = img.dim_z;
+	}
 	if (block_type != SYM_BTYPE_NONCONST) {
 		f4 c = splat4(error_color_nan());
 		if (block_type == SYM_BTYPE_CONST_U16) {
@@ -328,9 +350,10 @@ ASTC_COOP void decompress_block(int lane, uint32_t slice, const uint8_t* pcb, un
 		}
 		ASTC_NOUNROLL
 		for (int t = lane; t < T; t += ASTC_WARP) {
-			unsigned int x = pos_x + (unsigned int)t % bdx, y = pos_y + (unsigned int)t / bdx;
-			if (x < img.dim_x && y < img.dim_y) {
-				store_texel(img, x, y, c);
+			unsigned int tyz = (unsigned int)t / bdx, tz = volume ? tyz / BSD.dim_y : 0u;
+			unsigned int x = pos_x + (unsigned int)t % bdx, y = pos_y + tyz - tz * BSD.dim_y, z = pos_z + tz;
+			if (x < img.dim_x && y < img.dim_y && z < lim_z) {
+				store_texel(img, x, y, z, c);
 			}
 		}
 		wsync();
@@ -382,9 +405,10 @@ ASTC_COOP void decompress_block(int lane, uint32_t slice, const uint8_t* pcb, un
 		           decode_component(lerp1(u8, e[1], e[5], plane2_component == 1 ? w2 : w1), rgb_lns),
 		           decode_component(lerp1(u8, e[2], e[6], plane2_component == 2 ? w2 : w1), rgb_lns),
 		           decode_component(lerp1(u8, e[3], e[7], plane2_component == 3 ? w2 : w1), a_lns));
-		unsigned int x = pos_x + (unsigned int)t % bdx, y = pos_y + (unsigned int)t / bdx;
-		if (x < img.dim_x && y < img.dim_y) {
-			store_texel(img, x, y, d);
+		unsigned int tyz = (unsigned int)t / bdx, tz = volume ? tyz / BSD.dim_y : 0u;
+		unsigned int x = pos_x + (unsigned int)t % bdx, y = pos_y + tyz - tz * BSD.dim_y, z = pos_z + tz;
+		if (x < img.dim_x && y < img.dim_y && z < lim_z) {
+			store_texel(img, x, y, z, d);
 		}
 	}
 	wsync();
@@ -397,7 +421,7 @@ struct DevBlockInfo {
 	int is_error_block, is_constant_block, is_hdr_block, is_dual_plane_block;
 	unsigned int partition_count, partition_index, dual_plane_component;
 	unsigned int color_endpoint_modes[4];
-	unsigned int color_level_count, weight_level_count, weight_x, weight_y;
+	unsigned int color_level_count, weight_level_count, weight_x, weight_y, weight_z;
 	float color_endpoints[4][2][4];
 	float weight_values_plane1[ASTC_MAX_TEXELS];
 	float weight_values_plane2[ASTC_MAX_TEXELS];
@@ -428,6 +452,7 @@ ASTC_COOP void block_info(int lane, uint32_t slice, uint64_t lo, uint64_t hi, De
 	if (lane == 0) {
 		out->weight_x = ASTC_LDG(&BSD.dec_modes[d].weight_x);
 		out->weight_y = ASTC_LDG(&BSD.dec_modes[d].weight_y);
+		out->weight_z = ASTC_LDG(&BSD.dec_modes[d].weight_z);
 		out->is_dual_plane_block = dual ? 1 : 0;
 		out->partition_count = (unsigned int)pc;
 		out->partition_index = (unsigned int)h.partition_index;

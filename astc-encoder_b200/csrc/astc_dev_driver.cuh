@@ -503,7 +503,7 @@ ASTC_COOP void compress_block(WCtx w, uint8_t* out) {
 	float best_pc1 = ERROR_CALC_DEFAULT;     // best_errorvals_for_pcount[0]
 	const float errorval_overshoot = 1.0f / CFG.tune_mse_overshoot;
 	int start_trial = 1;
-	if (CFG.tune_search_mode0_enable >= 0.85f) {
+	if (CFG.tune_search_mode0_enable >= 0.85f && BSD.dim_z == 1) {
 		start_trial = 0;
 	}
 	int quant_limit = QUANT_32;

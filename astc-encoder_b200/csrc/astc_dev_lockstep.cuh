@@ -113,7 +113,7 @@ ASTC_FN void block_search_begin(const WCtx& w, BlockSearch& s, unsigned int out_
 		s.best_error_cur = ERROR_CALC_DEFAULT;
 		s.quant_limit = QUANT_32;
 		s.phase = 0;
-		s.idx = CFG.tune_search_mode0_enable >= 0.85f ? 0 : 1;
+		s.idx = (CFG.tune_search_mode0_enable >= 0.85f && BSD.dim_z == 1) ? 0 : 1;      // (compress_symbolic.cpp:1287: no mode-0 trial for 3D block sizes)
 		s.pc = 2;
 		s.actual_trials = 0;
 		s.phase_entered = false;
@@ -768,7 +768,7 @@ ASTC_COOP void compress_blocks_lockstep(WCtx w, BlockFeed feed, uint32_t refine_
 					emit_if_constant(w, b);
 					continue;
 				}
-				load_block(w, bx * BSD.dim_x, (by + IMG.block_row0) * BSD.dim_y);
+				load_block(w, bx, by + IMG.block_row0);
 				if (emit_if_constant(w, b)) {
 					continue;
 				}

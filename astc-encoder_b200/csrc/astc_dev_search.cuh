@@ -1283,8 +1283,9 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 		// the list entries, the partition of every texel.
 		SPtr<uint16_t> s_pn = sptr<uint16_t>(rs.tile);                       // [64]
 		SPtr<uint16_t> s_wto = sptr<uint16_t>(rs.tile + 128);                // [65]
-		SPtr<uint8_t> s_pot = sptr<uint8_t>(rs.tile + 128 + 136);           // [T] (<= 144)
-		SPtr<uint16_t> s_wtc = sptr<uint16_t>(rs.tile + 128 + 136 + 144);    // [E] (<= 4 T)
+		const uint32_t tp = (uint32_t)((T + 3) & ~3);                        // (T <= 216: 264 + 216 + 1728 + 64 <= REFINE_TILE_BYTES)
+		SPtr<uint8_t> s_pot = sptr<uint8_t>(rs.tile + 128 + 136);           // [T]
+		SPtr<uint16_t> s_wtc = sptr<uint16_t>(rs.tile + 128 + 136 + tp);     // [E] (<= 4 T)
 		ASTC_NOUNROLL
 		for (int we = w.lane; we <= weight_count; we += ASTC_WARP) {
 			s_wto[we] = ASTC_LDD(&di.wto[we]);
@@ -1374,12 +1375,14 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 		// (x+1, y), (x-1, y+1), (x, y+1), (x+1, y+1) - weights further away share no texel with it - so exactly those are
 		// evaluated again (four groups at once) before the scan goes on. Every weight is therefore decided on the state the
 		// sequential loop would show it: same decisions, a handful of sequential steps instead of weight_count.
+		// (3D block sizes: seven later neighbours, see below.)
 		const DevDecMode* dmp = BSD.dec_modes + d;
 		const int gw = ASTC_LDG(&dmp->weight_x);
+		const bool volume = BSD.dim_z > 1;
 		const int grp = w.lane >> 2;
 		const int lc = w.lane & 3;
 		const float ew_c = lane(ew, lc);
-		SPtr<uint8_t> s_new = sptr<uint8_t>(rs.tile + 128 + 136 + 144 + 1152);   // [64] the value a weight wants to move to
+		SPtr<uint8_t> s_new = sptr<uint8_t>(rs.tile + 128 + 136 + tp + 8 * tp);   // [64] the value a weight wants to move to
 		// decision of weight `we` on the current state; all 32 lanes call it (shuffles inside), act = group has a weight
 		auto evaluate = [&](int we, bool act) -> int {
 			int off = 0, cnt = 0, uqw = 0;
@@ -1473,29 +1476,62 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 				wb[texel] = bilinear_infill(di, uqf, texel);
 			}
 			wsync();
-			// later grid neighbours of f = (fx, fy): group 0 (fx+1, fy), 1 (fx-1, fy+1), 2 (fx, fy+1), 3 (fx+1, fy+1)
-			int fy = f / gw;
-			int fx = f - fy * gw;
-			int dx = grp == 1 ? -1 : (grp == 2 ? 0 : 1);
-			int dy = grp == 0 ? 0 : 1;
-			int nx = fx + dx;
-			int j = f + dy * gw + dx;
-			bool act = grp < 4 && nx >= 0 && nx < gw && j < weight_count;
-			int nv = evaluate(j, act);
-			if (act && lc == 0 && nv >= 0) {
-				s_new[j] = (uint8_t)nv;
-			}
-			uint32_t redo = __ballot_sync(0xffffffffu, act && lc == 0);
-			uint32_t want = __ballot_sync(0xffffffffu, act && lc == 0 && nv >= 0);
-			// every lane folds the four outcomes into its copy of the pending set (lane 4 g <-> neighbour g)
-			ASTC_NOUNROLL
-			for (int g = 0; g < 4; g++) {
-				if ((redo >> (4 * g)) & 1u) {
-					int gdx = g == 1 ? -1 : (g == 2 ? 0 : 1);
-					int jj = f + (g == 0 ? 0 : gw) + gdx;
-					uint32_t on = (want >> (4 * g)) & 1u;
-					if (jj < 32) pend_lo = (pend_lo & ~(1u << jj)) | (on << jj);
-					else pend_hi = (pend_hi & ~(1u << (jj - 32))) | (on << (jj - 32));
+			// later grid neighbours of f: the weights of higher index that share a texel with it, one per group of four lanes.
+			// 2D (bilinear cells): (fx+1, fy), (fx-1, fy+1), (fx, fy+1), (fx+1, fy+1). 3D (simplex cells: the corners of a texel's
+			// simplex differ by vectors of {0,1}^3): the seven (fx+a, fy+b, fz+c), (a, b, c) != 0 - groups 0..6.
+			// (two copies of the step: the 2D one is the hot path of every refinement step and stays as lean as it was)
+			if (!volume) {
+				int fy = f / gw;
+				int fx = f - fy * gw;
+				int dx = grp == 1 ? -1 : (grp == 2 ? 0 : 1);
+				int dy = grp == 0 ? 0 : 1;
+				int nx = fx + dx;
+				int j = f + dy * gw + dx;
+				bool act = grp < 4 && nx >= 0 && nx < gw && j < weight_count;
+				int nv = evaluate(j, act);
+				if (act && lc == 0 && nv >= 0) {
+					s_new[j] = (uint8_t)nv;
+				}
+				uint32_t redo = __ballot_sync(0xffffffffu, act && lc == 0);
+				uint32_t want = __ballot_sync(0xffffffffu, act && lc == 0 && nv >= 0);
+				// every lane folds the four outcomes into its copy of the pending set (lane 4 g <-> neighbour g)
+				ASTC_NOUNROLL
+				for (int g = 0; g < 4; g++) {
+					if ((redo >> (4 * g)) & 1u) {
+						int gdx = g == 1 ? -1 : (g == 2 ? 0 : 1);
+						int jj = f + (g == 0 ? 0 : gw) + gdx;
+						uint32_t on = (want >> (4 * g)) & 1u;
+						if (jj < 32) pend_lo = (pend_lo & ~(1u << jj)) | (on << jj);
+						else pend_hi = (pend_hi & ~(1u << (jj - 32))) | (on << (jj - 32));
+					}
+				}
+			} else {
+				const int gh = ASTC_LDG(&dmp->weight_y);
+				const int gd = ASTC_LDG(&dmp->weight_z);
+				const int gwh = gw * gh;
+				int fz = f / gwh;
+				int fr = f - fz * gwh;
+				int fy = fr / gw;
+				int fx = fr - fy * gw;
+				int v = grp + 1;      // 1..7: bits = (dx, dy, dz)
+				int dx = v & 1, dy = (v >> 1) & 1, dz = (v >> 2) & 1;
+				int j = f + dz * gwh + dy * gw + dx;
+				bool act = grp < 7 && fx + dx < gw && fy + dy < gh && fz + dz < gd;
+				int nv = evaluate(j, act);
+				if (act && lc == 0 && nv >= 0) {
+					s_new[j] = (uint8_t)nv;
+				}
+				uint32_t redo = __ballot_sync(0xffffffffu, act && lc == 0);
+				uint32_t want = __ballot_sync(0xffffffffu, act && lc == 0 && nv >= 0);
+				ASTC_NOUNROLL
+				for (int g = 0; g < 7; g++) {
+					if ((redo >> (4 * g)) & 1u) {
+						int gv = g + 1;
+						int jj = f + ((gv >> 2) & 1) * gwh + ((gv >> 1) & 1) * gw + (gv & 1);
+						uint32_t on = (want >> (4 * g)) & 1u;
+						if (jj < 32) pend_lo = (pend_lo & ~(1u << jj)) | (on << jj);
+						else pend_hi = (pend_hi & ~(1u << (jj - 32))) | (on << (jj - 32));
+					}
 				}
 			}
 			wsync();

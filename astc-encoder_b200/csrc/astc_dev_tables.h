@@ -9,7 +9,7 @@
 #pragma once
 #include <stdint.h>
 
-#define ASTC_MAX_TEXELS 144
+#define ASTC_MAX_TEXELS 216     /* 6x6x6; the largest 2D block (12x12) has 144 */
 #define ASTC_MAX_WEIGHTS 64
 #define ASTC_MAX_PARTITIONINGS 1024
 #define ASTC_MAX_BLOCK_MODES 2048
@@ -73,6 +73,8 @@ struct DevDecMode {
 	uint16_t wtc_offset;      // byte offset of wtc
 	uint16_t max_weight_texels;   // longest weight -> texel list of this grid
 	uint16_t dwi_offset_1p;   // the same in the compact one-plane arena layout (DevBsd::layout_planes == 1)
+	uint8_t weight_z;         // 1 for the grids of 2D block sizes
+	uint8_t pad_[1];
 	uint32_t blob_offset;     // byte offset of the blob in dec_blob
 };
 
@@ -83,6 +85,7 @@ struct DevDecMode {
 
 struct DevBsd {
 	uint8_t dim_x, dim_y, texel_count, max_weight_texel_count;
+	uint8_t dim_z, pad_[3];      // dim_z > 1: one of the ten 3D footprints (astcenc_block_sizes.cpp:1025)
 	uint32_t decimation_mode_count_always, decimation_mode_count_selected, decimation_mode_count_all;
 	uint32_t block_mode_count_1plane_always, block_mode_count_1plane_selected, block_mode_count_1plane_2plane_selected, block_mode_count_all;
 	uint32_t partitioning_count_selected[4];
@@ -134,7 +137,9 @@ struct DevImage {
 	const void* data;          // RGBA texels, row-major, tightly packed
 	int data_type;             // 0 = U8, 1 = F16, 2 = F32
 	unsigned int dim_x, dim_y; // full image size (for clamp-to-edge)
+	unsigned int dim_z;        // slices of a volume (3D block sizes only; 2D block sizes see one slice per pass), contiguous in data
 	unsigned int blocks_x;
+	unsigned int blocks_y;     // 3D block sizes: block rows per layer of blocks; a "block row" index then counts layer * blocks_y + row
 	unsigned int block_row0;   // first block row of this launch (slab sharding)
 	unsigned int block_rows;   // number of block rows in this launch
 	int swz[4];

@@ -242,7 +242,7 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 					emit_if_constant(w, b);
 					continue;
 				}
-				load_block(w, bx * BSD.dim_x, (by + IMG.block_row0) * BSD.dim_y);
+				load_block(w, bx, by + IMG.block_row0);
 				if (emit_if_constant(w, b)) {
 					continue;
 				}

@@ -102,25 +102,10 @@ static astcenc_error validate_profile(astcenc_profile profile) {
 	}
 }
 
-static bool is_legal_3d_block_size(unsigned int x, unsigned int y, unsigned int z) {
-	static const uint8_t legal[10][3] = {{3, 3, 3}, {4, 3, 3}, {4, 4, 3}, {4, 4, 4}, {5, 4, 4}, {5, 5, 4}, {5, 5, 5}, {6, 5, 5}, {6, 6, 5}, {6, 6, 6}};
-	for (int i = 0; i < 10; i++) {
-		if (legal[i][0] == x && legal[i][1] == y && legal[i][2] == z) {
-			return true;
-		}
-	}
-	return false;
-}
-
 static astcenc_error validate_block_size(unsigned int block_x, unsigned int block_y, unsigned int block_z) {
 	bool is_legal = ((block_z <= 1) && is_legal_2d_block_size(block_x, block_y)) || ((block_z >= 2) && is_legal_3d_block_size(block_x, block_y, block_z));
 	if (!is_legal) {
 		return ASTCENC_ERR_BAD_BLOCK_SIZE;
-	}
-	// 3D blocks are legal ASTC but outside this library's scope (the hot path here is the 2D compressor);
-	// the reference reports capacity limits with the same code (astcenc_entry.cpp:281-285).
-	if (block_z >= 2) {
-		return ASTCENC_ERR_NOT_IMPLEMENTED;
 	}
 	return ASTCENC_SUCCESS;
 }

@@ -70,6 +70,7 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 	memset(&b, 0, sizeof(b));
 	b.dim_x = t.dim_x;
 	b.dim_y = t.dim_y;
+	b.dim_z = t.dim_z;
 	b.texel_count = t.texel_count;
 	b.decimation_mode_count_always = t.decimation_mode_count_always;
 	b.decimation_mode_count_selected = t.decimation_mode_count_selected;
@@ -111,6 +112,7 @@ static inline void pack_device_tables(const BlockSizeTables& t, const unsigned i
 		dm.weight_count = di.weight_count;
 		dm.weight_x = di.weight_x;
 		dm.weight_y = di.weight_y;
+		dm.weight_z = di.weight_z;
 		dm.max_texel_weight_count = di.max_texel_weight_count;
 		const unsigned int W = di.weight_count;
 		const unsigned int E = di.weight_texel_offset[W];

@@ -516,6 +516,163 @@ static void init_decimation_info_2d(unsigned int tx, unsigned int ty, unsigned i
 	di.weight_count = (uint8_t)weights;
 	di.weight_x = (uint8_t)wx;
 	di.weight_y = (uint8_t)wy;
+	di.weight_z = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3D block modes and decimation tables (astcenc_block_sizes.cpp:152-250, :450-700)
+// ---------------------------------------------------------------------------------------------
+static bool decode_block_mode_3d(unsigned int mode, unsigned int& wx, unsigned int& wy, unsigned int& wz, bool& dual,
+                                 unsigned int& quant_mode, unsigned int& weight_bits) {
+	unsigned int base_quant = (mode >> 4) & 1;
+	unsigned int H = (mode >> 9) & 1;
+	unsigned int D = (mode >> 10) & 1;
+	unsigned int A = (mode >> 5) & 3;
+	wx = wy = wz = 0;
+	if ((mode & 3) != 0) {
+		base_quant |= (mode & 3) << 1;
+		wx = A + 2;
+		wy = ((mode >> 7) & 3) + 2;
+		wz = ((mode >> 2) & 3) + 2;
+	} else {
+		unsigned int sel = (mode >> 2) & 3;
+		base_quant |= sel << 1;
+		if (sel == 0) {
+			return false;
+		}
+		unsigned int B = (mode >> 9) & 3;
+		unsigned int layout = (mode >> 7) & 3;
+		if (layout != 3) {
+			D = 0;
+			H = 0;
+		}
+		if (layout == 0) {
+			wx = 6; wy = B + 2; wz = A + 2;
+		} else if (layout == 1) {
+			wx = A + 2; wy = 6; wz = B + 2;
+		} else if (layout == 2) {
+			wx = A + 2; wy = B + 2; wz = 6;
+		} else {
+			wx = wy = wz = 2;
+			if (A == 0) wx = 6;
+			else if (A == 1) wy = 6;
+			else if (A == 2) wz = 6;
+			else return false;
+		}
+	}
+	unsigned int weight_count = wx * wy * wz * (D + 1);
+	quant_mode = (base_quant - 2) + 6 * H;
+	dual = D != 0;
+	weight_bits = ise_sequence_bitcount(weight_count, (int)quant_mode);
+	return weight_count <= 64 && weight_bits >= 24 && weight_bits <= 96;
+}
+
+// Fills the two directions of a DecimationInfo from per-texel tap lists (shared tail of the 2D and 3D builders).
+struct TapLists {
+	uint8_t weight_count_of_texel[MAX_TEXELS];
+	uint8_t grid_weights_of_texel[MAX_TEXELS][4];
+	uint8_t weights_of_texel[MAX_TEXELS][4];
+	uint8_t texel_count_of_weight[MAX_WEIGHTS];
+	uint8_t texels_of_weight[MAX_WEIGHTS][MAX_TEXELS];
+	uint8_t texel_weights_of_weight[MAX_WEIGHTS][MAX_TEXELS];
+};
+
+static void add_tap(TapLists& tl, unsigned int texel, unsigned int grid_weight, unsigned int contribution) {
+	if (contribution == 0) {
+		return;
+	}
+	unsigned int c = tl.weight_count_of_texel[texel]++;
+	tl.grid_weights_of_texel[texel][c] = (uint8_t)grid_weight;
+	tl.weights_of_texel[texel][c] = (uint8_t)contribution;
+	unsigned int tc = tl.texel_count_of_weight[grid_weight]++;
+	tl.texels_of_weight[grid_weight][tc] = (uint8_t)texel;
+	tl.texel_weights_of_weight[grid_weight][tc] = (uint8_t)contribution;
+}
+
+static void finish_decimation_info(const TapLists& tl, unsigned int texels, unsigned int weights, DecimationInfo& di) {
+	uint8_t max_texel_weight_count = 0;
+	for (unsigned int i = 0; i < texels; i++) {
+		di.texel_weight_count[i] = tl.weight_count_of_texel[i];
+		if (di.texel_weight_count[i] > max_texel_weight_count) {
+			max_texel_weight_count = di.texel_weight_count[i];
+		}
+		for (unsigned int j = 0; j < tl.weight_count_of_texel[i]; j++) {
+			di.texel_weight_contribs_int[j][i] = tl.weights_of_texel[i][j];
+			di.texel_weight_contribs_float[j][i] = static_cast<float>(tl.weights_of_texel[i][j]) * (1.0f / 16.0f);
+			di.texel_weights[j][i] = tl.grid_weights_of_texel[i][j];
+		}
+	}
+	di.max_texel_weight_count = max_texel_weight_count;
+	unsigned int off = 0;
+	for (unsigned int i = 0; i < weights; i++) {
+		unsigned int cnt = tl.texel_count_of_weight[i];
+		di.weight_texel_count[i] = (uint8_t)cnt;
+		di.weight_texel_offset[i] = (uint16_t)off;
+		for (unsigned int j = 0; j < cnt; j++) {
+			uint8_t texel = tl.texels_of_weight[i][j];
+			di.weight_texels[off + j] = texel;
+			di.weight_texel_contribs[off + j] = static_cast<float>(tl.texel_weights_of_weight[i][j]);
+			di.texel_contrib_for_weight[off + j] = 0.0f;
+			for (unsigned int k = 0; k < 4; k++) {
+				uint8_t dttw = di.texel_weights[k][texel];
+				float dttwf = di.texel_weight_contribs_float[k][texel];
+				if (dttw == i && dttwf != 0.0f) {
+					di.texel_contrib_for_weight[off + j] = dttwf;
+					break;
+				}
+			}
+		}
+		off += cnt;
+	}
+	di.weight_texel_offset[weights] = (uint16_t)off;
+	di.texel_count = (uint8_t)texels;
+	di.weight_count = (uint8_t)weights;
+}
+
+// Simplex interpolation over a 3D weight grid: every texel takes the corner of its cell, the opposite corner and the two
+// corners on the path between them that follows the fractions in descending order (:497-583).
+static void init_decimation_info_3d(unsigned int tx, unsigned int ty, unsigned int tz, unsigned int wx, unsigned int wy, unsigned int wz,
+                                    DecimationInfo& di) {
+	memset(&di, 0, sizeof(di));
+	static TapLists tl;
+	memset(tl.weight_count_of_texel, 0, sizeof(tl.weight_count_of_texel));
+	memset(tl.texel_count_of_weight, 0, sizeof(tl.texel_count_of_weight));
+	const int stride[3] = {1, (int)wx, (int)(wx * wy)};
+	for (unsigned int z = 0; z < tz; z++) {
+		for (unsigned int y = 0; y < ty; y++) {
+			for (unsigned int x = 0; x < tx; x++) {
+				unsigned int texel = (z * ty + y) * tx + x;
+				int g[3];
+				g[0] = (int)((((1024 + tx / 2) / (tx - 1)) * x * (wx - 1) + 32) >> 6);
+				g[1] = (int)((((1024 + ty / 2) / (ty - 1)) * y * (wy - 1) + 32) >> 6);
+				g[2] = (int)((((1024 + tz / 2) / (tz - 1)) * z * (wz - 1) + 32) >> 6);
+				int f[3] = {g[0] & 0xF, g[1] & 0xF, g[2] & 0xF};
+				int base = ((g[2] >> 4) * (int)wy + (g[1] >> 4)) * (int)wx + (g[0] >> 4);
+				// order the axes by descending fraction; ties resolve as the reference's comparison triple does
+				// (fs > ft, ft > fp, fs > fp): cases 7 3 5 4 2 0, the impossible 1 and 6 fall to case 0
+				bool s_gt_t = f[0] > f[1], t_gt_p = f[1] > f[2], s_gt_p = f[0] > f[2];
+				int first, second, third;
+				if (s_gt_t && t_gt_p && s_gt_p) { first = 0; second = 1; third = 2; }
+				else if (!s_gt_t && t_gt_p && s_gt_p) { first = 1; second = 0; third = 2; }
+				else if (s_gt_t && !t_gt_p && s_gt_p) { first = 0; second = 2; third = 1; }
+				else if (s_gt_t && !t_gt_p && !s_gt_p) { first = 2; second = 0; third = 1; }
+				else if (!s_gt_t && t_gt_p && !s_gt_p) { first = 1; second = 2; third = 0; }
+				else { first = 2; second = 1; third = 0; }
+				int q0 = base;
+				int q1 = q0 + stride[first];
+				int q2 = q1 + stride[second];
+				int q3 = base + stride[0] + stride[1] + stride[2];
+				add_tap(tl, texel, (unsigned int)q0, (unsigned int)(16 - f[first]));
+				add_tap(tl, texel, (unsigned int)q1, (unsigned int)(f[first] - f[second]));
+				add_tap(tl, texel, (unsigned int)q2, (unsigned int)(f[second] - f[third]));
+				add_tap(tl, texel, (unsigned int)q3, (unsigned int)f[third]);
+			}
+		}
+	}
+	finish_decimation_info(tl, tx * ty * tz, wx * wy * wz, di);
+	di.weight_x = (uint8_t)wx;
+	di.weight_y = (uint8_t)wy;
+	di.weight_z = (uint8_t)wz;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -625,12 +782,14 @@ static bool generate_one_partition_info_entry(BlockSizeTables& bsd, unsigned int
 	int counts[4] = {0, 0, 0, 0};
 	int texel_idx = 0;
 	memset(&pi, 0, sizeof(pi));
-	for (unsigned int y = 0; y < bsd.dim_y; y++) {
-		for (unsigned int x = 0; x < bsd.dim_x; x++) {
-			uint8_t part = select_partition((int)partition_index, (int)x, (int)y, 0, (int)partition_count, small_block);
-			pi.texels_of_partition[part][counts[part]++] = (uint8_t)texel_idx;
-			pi.partition_of_texel[texel_idx] = part;
-			texel_idx++;
+	for (unsigned int z = 0; z < bsd.dim_z; z++) {
+		for (unsigned int y = 0; y < bsd.dim_y; y++) {
+			for (unsigned int x = 0; x < bsd.dim_x; x++) {
+				uint8_t part = select_partition((int)partition_index, (int)x, (int)y, (int)z, (int)partition_count, small_block);
+				pi.texels_of_partition[part][counts[part]++] = (uint8_t)texel_idx;
+				pi.partition_of_texel[texel_idx] = part;
+				texel_idx++;
+			}
 		}
 	}
 	if (counts[0] == 0) pi.partition_count = 0;
@@ -724,6 +883,17 @@ static void build_partition_table(BlockSizeTables& bsd, bool can_omit, unsigned 
 	}
 }
 
+bool is_legal_3d_block_size(unsigned int x, unsigned int y, unsigned int z) {
+	// the ten footprints of the format: each axis 3..6, sizes descending by at most one step from x to z
+	static const uint8_t legal[10][3] = {{3, 3, 3}, {4, 3, 3}, {4, 4, 3}, {4, 4, 4}, {5, 4, 4}, {5, 5, 4}, {5, 5, 5}, {6, 5, 5}, {6, 6, 5}, {6, 6, 6}};
+	for (int i = 0; i < 10; i++) {
+		if (legal[i][0] == x && legal[i][1] == y && legal[i][2] == z) {
+			return true;
+		}
+	}
+	return false;
+}
+
 bool is_legal_2d_block_size(unsigned int x, unsigned int y) {
 	static const uint8_t legal[14][2] = {{4, 4}, {5, 4}, {5, 5}, {6, 5}, {6, 6}, {8, 5}, {8, 6}, {8, 8},
 	                                     {10, 5}, {10, 6}, {10, 8}, {10, 10}, {12, 10}, {12, 12}};
@@ -752,15 +922,121 @@ static void unpack_percentiles(unsigned int x, unsigned int y, float* table) {
 }
 
 // astcenc_block_sizes.cpp:822-1002 (four passes define the packed block-mode / decimation order)
-BlockSizeTables* build_block_size_tables(unsigned int tx, unsigned int ty, bool can_omit_modes,
+// construct_block_size_descriptor_3d (astcenc_block_sizes.cpp:1025-1190): every grid that fits and every legal block mode is
+// kept (no percentile selection for 3D); one-plane modes first, then two-plane modes.
+static void build_modes_3d(BlockSizeTables& bsd, unsigned int tx, unsigned int ty, unsigned int tz) {
+	int decimation_mode_index[7 * 64];
+	for (auto& v : decimation_mode_index) {
+		v = -1;
+	}
+	unsigned int dm_count = 0;
+	for (unsigned int wx = 2; wx <= tx; wx++) {
+		for (unsigned int wy = 2; wy <= ty; wy++) {
+			for (unsigned int wz = 2; wz <= tz; wz++) {
+				unsigned int weight_count = wx * wy * wz;
+				if (weight_count > (unsigned int)MAX_WEIGHTS) {
+					continue;
+				}
+				decimation_mode_index[wz * 64 + wy * 8 + wx] = (int)dm_count;
+				init_decimation_info_3d(tx, ty, tz, wx, wy, wz, bsd.decimation_tables[dm_count]);
+				int maxprec_1 = -1, maxprec_2 = -1;
+				for (int q = 0; q < 12; q++) {
+					unsigned int b1 = ise_sequence_bitcount(weight_count, q);
+					if (b1 >= 24 && b1 <= 96) maxprec_1 = q;
+					unsigned int b2 = ise_sequence_bitcount(2 * weight_count, q);
+					if (b2 >= 24 && b2 <= 96) maxprec_2 = q;
+				}
+				if (2 * weight_count > (unsigned int)MAX_WEIGHTS) {
+					maxprec_2 = -1;
+				}
+				DecimationMode& dm = bsd.decimation_modes[dm_count];
+				dm.maxprec_1plane = (int8_t)maxprec_1;
+				dm.maxprec_2planes = (int8_t)maxprec_2;
+				dm.refprec_1plane = maxprec_1 == -1 ? 0 : 0xFFFF;
+				dm.refprec_2planes = maxprec_2 == -1 ? 0 : 0xFFFF;
+				dm_count++;
+			}
+		}
+	}
+	for (unsigned int i = dm_count; i < (unsigned int)MAX_DECIMATION_MODES; i++) {
+		bsd.decimation_modes[i].maxprec_1plane = -1;
+		bsd.decimation_modes[i].maxprec_2planes = -1;
+		bsd.decimation_modes[i].refprec_1plane = 0;
+		bsd.decimation_modes[i].refprec_2planes = 0;
+	}
+	bsd.decimation_mode_count_always = 0;
+	bsd.decimation_mode_count_selected = dm_count;
+	bsd.decimation_mode_count_all = dm_count;
+
+	for (int i = 0; i < MAX_BLOCK_MODES; i++) {
+		bsd.block_mode_packed_index[i] = 0xFFFF;
+	}
+	unsigned int packed = 0, counts[2] = {0, 0};
+	for (unsigned int pass = 0; pass < 2; pass++) {
+		for (unsigned int i = 0; i < (unsigned int)MAX_BLOCK_MODES; i++) {
+			if (bsd.block_mode_packed_index[i] != 0xFFFF) {
+				continue;
+			}
+			unsigned int wx, wy, wz, quant_mode, weight_bits;
+			bool dual;
+			if (!decode_block_mode_3d(i, wx, wy, wz, dual, quant_mode, weight_bits) || wx > tx || wy > ty || wz > tz) {
+				continue;
+			}
+			if ((pass == 0) == dual) {
+				continue;
+			}
+			if ((dual ? 109 : 111) - (int)weight_bits <= 0) {
+				continue;
+			}
+			BlockMode& bm = bsd.block_modes[packed];
+			bm.decimation_mode = (uint8_t)decimation_mode_index[wz * 64 + wy * 8 + wx];
+			bm.quant_mode = (uint8_t)quant_mode;
+			bm.weight_bits = (uint8_t)weight_bits;
+			bm.is_dual_plane = dual ? 1 : 0;
+			bm.mode_index = (uint16_t)i;
+			bsd.block_mode_packed_index[i] = (uint16_t)packed;
+			counts[pass]++;
+			packed++;
+		}
+	}
+	bsd.block_mode_count_1plane_always = 0;
+	bsd.block_mode_count_1plane_selected = counts[0];
+	bsd.block_mode_count_1plane_2plane_selected = counts[0] + counts[1];
+	bsd.block_mode_count_all = counts[0] + counts[1];
+}
+
+static void build_partitions(BlockSizeTables& bsd, bool can_omit_modes, unsigned int partition_count_cutoff) {
+	bsd.partitionings[1] = new PartitionInfo[1];
+	for (int pc = 2; pc <= 4; pc++) {
+		bsd.partitionings[pc] = new PartitionInfo[MAX_PARTITIONINGS];
+		bsd.coverage_bitmaps[pc] = new uint64_t[(size_t)MAX_PARTITIONINGS * pc];
+	}
+	generate_one_partition_info_entry(bsd, 1, 0, 0, bsd.partitionings[1][0]);
+	bsd.partitioning_count_selected[0] = 1;
+	bsd.partitioning_count_all[0] = 1;
+	uint64_t* patterns = new uint64_t[(size_t)MAX_PARTITIONINGS * BIT_PATTERN_WORDS];
+	for (unsigned int pc = 2; pc <= 4; pc++) {
+		build_partition_table(bsd, can_omit_modes, partition_count_cutoff, pc, patterns);
+	}
+	delete[] patterns;
+}
+
+BlockSizeTables* build_block_size_tables(unsigned int tx, unsigned int ty, unsigned int tz, bool can_omit_modes,
                                          unsigned int partition_count_cutoff, float mode_cutoff) {
 	BlockSizeTables* bp = new BlockSizeTables;
 	BlockSizeTables& bsd = *bp;
 	memset(bp, 0, sizeof(*bp));
 	bsd.dim_x = (uint8_t)tx;
 	bsd.dim_y = (uint8_t)ty;
-	bsd.texel_count = (uint8_t)(tx * ty);
+	bsd.dim_z = (uint8_t)tz;
+	bsd.texel_count = (uint8_t)(tx * ty * tz);
 	bsd.decimation_tables = new DecimationInfo[MAX_DECIMATION_MODES];
+	if (tz > 1) {
+		build_modes_3d(bsd, tx, ty, tz);
+		assign_kmeans_texels(bsd);
+		build_partitions(bsd, can_omit_modes, partition_count_cutoff);
+		return bp;
+	}
 
 	int decimation_mode_index[12 * 16 + 12 + 16];
 	for (auto& v : decimation_mode_index) {
@@ -853,21 +1129,7 @@ BlockSizeTables* build_block_size_tables(unsigned int tx, unsigned int ty, bool 
 		bsd.decimation_modes[i].maxprec_2planes = -1;
 	}
 	assign_kmeans_texels(bsd);
-
-	// partitions
-	bsd.partitionings[1] = new PartitionInfo[1];
-	for (int pc = 2; pc <= 4; pc++) {
-		bsd.partitionings[pc] = new PartitionInfo[MAX_PARTITIONINGS];
-		bsd.coverage_bitmaps[pc] = new uint64_t[(size_t)MAX_PARTITIONINGS * pc];
-	}
-	generate_one_partition_info_entry(bsd, 1, 0, 0, bsd.partitionings[1][0]);
-	bsd.partitioning_count_selected[0] = 1;
-	bsd.partitioning_count_all[0] = 1;
-	uint64_t* patterns = new uint64_t[(size_t)MAX_PARTITIONINGS * BIT_PATTERN_WORDS];
-	for (unsigned int pc = 2; pc <= 4; pc++) {
-		build_partition_table(bsd, can_omit_modes, partition_count_cutoff, pc, patterns);
-	}
-	delete[] patterns;
+	build_partitions(bsd, can_omit_modes, partition_count_cutoff);
 	return bp;
 }
 

@@ -16,7 +16,7 @@
 
 namespace astc_host {
 
-static const int MAX_TEXELS = 144;        // largest 2D block (12x12); 3D blocks are out of scope
+static const int MAX_TEXELS = 216;        // largest block (6x6x6)
 static const int MAX_WEIGHTS = 64;
 static const int PLANE2_OFFSET = 32;
 static const int MAX_PARTITIONINGS = 1024;
@@ -50,6 +50,7 @@ struct DecimationInfo {
 	uint8_t weight_count;
 	uint8_t weight_x;
 	uint8_t weight_y;
+	uint8_t weight_z;
 	uint8_t texel_weight_count[MAX_TEXELS];
 	uint8_t texel_weights[4][MAX_TEXELS];
 	uint8_t texel_weight_contribs_int[4][MAX_TEXELS];
@@ -99,7 +100,7 @@ void ise_btq(int quant_level, unsigned int& bits, unsigned int& trits, unsigned 
 
 // Everything derived from (block size, mode cutoff, partition cutoff).
 struct BlockSizeTables {
-	uint8_t dim_x, dim_y, texel_count;
+	uint8_t dim_x, dim_y, dim_z, texel_count;
 	unsigned int decimation_mode_count_always, decimation_mode_count_selected, decimation_mode_count_all;
 	unsigned int block_mode_count_1plane_always, block_mode_count_1plane_selected,
 	             block_mode_count_1plane_2plane_selected, block_mode_count_all;
@@ -115,8 +116,10 @@ struct BlockSizeTables {
 };
 
 bool is_legal_2d_block_size(unsigned int x, unsigned int y);
+bool is_legal_3d_block_size(unsigned int x, unsigned int y, unsigned int z);
 
-BlockSizeTables* build_block_size_tables(unsigned int x, unsigned int y, bool can_omit_modes,
+// z == 1: a 2D block size (percentile-selected modes); z > 1: a 3D block size (every legal mode, astcenc_block_sizes.cpp:1025-1190)
+BlockSizeTables* build_block_size_tables(unsigned int x, unsigned int y, unsigned int z, bool can_omit_modes,
                                          unsigned int partition_count_cutoff, float mode_cutoff);
 void free_block_size_tables(BlockSizeTables* t);
 

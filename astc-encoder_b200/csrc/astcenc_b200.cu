@@ -252,7 +252,7 @@ astc_compress_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__
 		}
 		unsigned int by = b / blocks_x;
 		unsigned int bx = b - by * blocks_x;
-		load_block(w, bx * BSD.dim_x, (by + IMG.block_row0) * BSD.dim_y);
+		load_block(w, bx, by + IMG.block_row0);
 		compress_block(w, IMG.out + (size_t)b * 16);
 	}
 }
@@ -325,6 +325,7 @@ struct astcenc_context {
 	uint32_t setup_stage_bytes;
 	uint32_t refine_stage_bytes;   // tables staged behind the header of the refine kernel's shared window (0 = none)
 	int max_waves;
+	unsigned int volume_dim_z;      // slices of the volume the current pass reads (3D block sizes; 1 otherwise), set under launch_mtx
 	// wave pipeline buffers, grown on demand
 	uint8_t* d_records;
 	size_t d_records_bytes;
@@ -487,6 +488,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 	ctx->warps_per_cta = ctx->grid = 0;
 	ctx->warps_setup_1p = 0;
 	ctx->max_waves = 0;
+	ctx->volume_dim_z = 1;
 	// environment knobs: read here, once
 	ctx->knobs.batch_blocks = (size_t)1 << 20;
 	if (const char* e = getenv("ASTCENC_B200_BATCH_BLOCKS")) {
@@ -541,7 +543,7 @@ astcenc_error astcenc_context_alloc(const astcenc_config* configp, unsigned int 
 		t->host_tables = nullptr;
 		ctx->tables = t;
 		bool can_omit = (cfg.flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0;
-		t->host_tables = astc_host::build_block_size_tables(cfg.block_x, cfg.block_y, can_omit, cfg.tune_partition_count_limit,
+		t->host_tables = astc_host::build_block_size_tables(cfg.block_x, cfg.block_y, cfg.block_z > 1 ? cfg.block_z : 1, can_omit, cfg.tune_partition_count_limit,
 		                                                    static_cast<float>(cfg.tune_block_mode_limit) / 100.0f);
 		astc_host::PackedTables pk;
 		unsigned int lim[3] = {cfg.tune_2partition_index_limit, cfg.tune_3partition_index_limit, cfg.tune_4partition_index_limit};
@@ -780,8 +782,10 @@ static astcenc_error launch_slab_locked(astcenc_context* ctx, const void* d_pixe
                                         unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream, const UploadPlan* up);
 
 static astcenc_error launch_slab(astcenc_context* ctx, const void* d_pixels, int data_type, unsigned int dim_x, unsigned int dim_y, const int swz[4],
-                                 unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream, const UploadPlan* up = nullptr) {
+                                 unsigned int block_row0, unsigned int block_rows, uint8_t* d_out, cudaStream_t stream, const UploadPlan* up = nullptr,
+                                 unsigned int volume_dim_z = 1) {
 	std::lock_guard<std::mutex> lk(ctx->launch_mtx);
+	ctx->volume_dim_z = volume_dim_z;
 	if (ctx->scratch_used) {
 		CUDA_TRY(cudaStreamWaitEvent(stream, ctx->scratch_done, 0), return ASTCENC_ERR_BAD_CONTEXT);
 	}
@@ -841,14 +845,16 @@ static astcenc_error launch_pipes(astcenc_context* ctx, int pipes, const void* d
 		im.data_type = data_type;
 		im.dim_x = dim_x;
 		im.dim_y = dim_y;
+		im.dim_z = ctx->volume_dim_z;
 		im.blocks_x = blocks_x;
+		im.blocks_y = (dim_y + bsd.dim_y - 1) / bsd.dim_y;
 		im.block_row0 = block_row0 + r0;
 		im.block_rows = r1 - r0;
 		for (int i = 0; i < 4; i++) {
 			im.swz[i] = swz[i];
 		}
 		im.out = d_out + first * 16;
-		im.alpha_avg = ctx->config.a_scale_radius != 0 ? ctx->d_alpha : nullptr;
+		im.alpha_avg = ctx->config.a_scale_radius != 0 && bsd.dim_z == 1 ? ctx->d_alpha : nullptr;
 		im.alpha_threshold = ctx->alpha_threshold;
 		uint32_t* counters = ctx->d_counters + (size_t)p * ASTC_COUNTER_WORDS;
 		CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * ASTC_COUNTER_WORDS, ps), return ASTCENC_ERR_BAD_CONTEXT);
@@ -932,7 +938,7 @@ static astcenc_error launch_slab_locked(astcenc_context* ctx, const void* d_pixe
 	size_t blocks_x = (dim_x + bsd.dim_x - 1) / bsd.dim_x;
 	size_t rows_per_batch = ctx->knobs.batch_blocks / (blocks_x ? blocks_x : 1);
 	if (rows_per_batch < 1) rows_per_batch = 1;
-	const unsigned int radius = ctx->config.a_scale_radius;
+	const unsigned int radius = bsd.dim_z > 1 ? 0 : ctx->config.a_scale_radius;      // (the averages only steer 2D block sizes, astcenc_entry.cpp:975)
 	// big single-batch slabs run as independent sub-slab pipelines (launch_pipes); per-launch timing wants one stream
 	bool single_batch = (size_t)block_rows <= rows_per_batch;
 	int pipes = ctx->knobs.pipes;
@@ -1013,14 +1019,16 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 	img.data_type = data_type;
 	img.dim_x = dim_x;
 	img.dim_y = dim_y;
+	img.dim_z = ctx->volume_dim_z;
 	img.blocks_x = (dim_x + bsd.dim_x - 1) / bsd.dim_x;
+	img.blocks_y = (dim_y + bsd.dim_y - 1) / bsd.dim_y;
 	img.block_row0 = block_row0;
 	img.block_rows = block_rows;
 	for (int i = 0; i < 4; i++) {
 		img.swz[i] = swz[i];
 	}
 	img.out = d_out;
-	img.alpha_avg = ctx->config.a_scale_radius != 0 ? ctx->d_alpha : nullptr;
+	img.alpha_avg = ctx->config.a_scale_radius != 0 && bsd.dim_z == 1 ? ctx->d_alpha : nullptr;
 	img.alpha_threshold = ctx->alpha_threshold;
 	size_t total = (size_t)img.blocks_x * block_rows;
 	if (ctx->driver == 0) {
@@ -1209,6 +1217,38 @@ static astcenc_error compress_image_gpu(astcenc_context* ctx, const astcenc_imag
 	ctx->last_h2d = ctx->last_d2h = 0;
 	ctx->last_kernel_ms = 0.0f;
 	float total_ms = 0.0f;
+	if (bsd.dim_z > 1) {
+		// 3D block sizes (astcenc_entry.cpp:906-1043): the slices go up into one contiguous volume, the blocks come out in (z, y, x)
+		// order; "block rows" of the pass count layer * blocks_y + row
+		size_t blocks_z = block_count_axis(image.dim_z, bsd.dim_z);
+		size_t vol_out = out_bytes * blocks_z;
+		st = ensure_buffer(ctx->d_image, ctx->d_image_bytes, slice_bytes * image.dim_z);
+		if (st == ASTCENC_SUCCESS) {
+			st = ensure_buffer(ctx->d_out, ctx->d_out_bytes, vol_out);
+		}
+		if (st != ASTCENC_SUCCESS) {
+			return st;
+		}
+		for (unsigned int z = 0; z < image.dim_z; z++) {
+			CUDA_TRY(cudaMemcpyAsync(ctx->d_image + (size_t)z * slice_bytes, image.data[z], slice_bytes, cudaMemcpyHostToDevice, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		}
+		CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		st = launch_slab(ctx, ctx->d_image, (int)image.data_type, image.dim_x, image.dim_y, swz, 0, (unsigned int)(blocks_y * blocks_z), ctx->d_out, ctx->stream, nullptr, image.dim_z);
+		if (st != ASTCENC_SUCCESS) {
+			return st;
+		}
+		CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		CUDA_TRY(cudaMemcpyAsync(data_out, ctx->d_out, vol_out, cudaMemcpyDeviceToHost, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		CUDA_TRY(cudaStreamSynchronize(ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		cudaEventElapsedTime(&total_ms, ctx->ev0, ctx->ev1);
+		ctx->last_kernel_ms = total_ms;
+		ctx->last_h2d = slice_bytes * image.dim_z;
+		ctx->last_d2h = vol_out;
+		if (ctx->config.progress_callback) {
+			ctx->config.progress_callback(100.0f);
+		}
+		return ASTCENC_SUCCESS;
+	}
 	// 3D images with 2D blocks are an array of independent 2D slices (astcenc.h:94-100)
 	for (unsigned int z = 0; z < image.dim_z; z++) {
 		if (ctx->cancel.load()) {
@@ -1272,7 +1312,7 @@ astcenc_error astcenc_compress_image(astcenc_context* ctx, astcenc_image* imagep
 	if (data_len < block_count * 16) {
 		return ASTCENC_ERR_OUT_OF_MEM;
 	}
-	if (ctx->config.a_scale_radius != 0 && image.dim_z != 1) {
+	if (ctx->config.a_scale_radius != 0 && image.dim_z != 1 && ctx->config.block_z <= 1) {
 		// the alpha-scale pre-pass is built for 2D images; volumes would average across slices (compute_variance.cpp have_z)
 		return ASTCENC_ERR_NOT_IMPLEMENTED;
 	}
@@ -1338,13 +1378,17 @@ static astcenc_error decompress_image_gpu(astcenc_context* ctx, const uint8_t* d
 	size_t slice_bytes = (size_t)image.dim_x * image.dim_y * bpt;
 	size_t blocks_x = block_count_axis(image.dim_x, bsd.dim_x);
 	size_t blocks_y = block_count_axis(image.dim_y, bsd.dim_y);
-	size_t in_bytes = blocks_x * blocks_y * 16;
-	if (ctx->d_image_bytes < slice_bytes) {
+	// 3D block sizes decode the volume in one pass (blocks in z, y, x order); 2D block sizes take it slice by slice
+	const bool volume = bsd.dim_z > 1;
+	size_t blocks_z = volume ? block_count_axis(image.dim_z, bsd.dim_z) : 1;
+	size_t in_bytes = blocks_x * blocks_y * blocks_z * 16;
+	size_t image_bytes = volume ? slice_bytes * image.dim_z : slice_bytes;
+	if (ctx->d_image_bytes < image_bytes) {
 		cudaFree(ctx->d_image);
 		ctx->d_image = nullptr;
 		ctx->d_image_bytes = 0;
-		CUDA_TRY(cudaMalloc(&ctx->d_image, slice_bytes), return ASTCENC_ERR_OUT_OF_MEM);
-		ctx->d_image_bytes = slice_bytes;
+		CUDA_TRY(cudaMalloc(&ctx->d_image, image_bytes), return ASTCENC_ERR_OUT_OF_MEM);
+		ctx->d_image_bytes = image_bytes;
 	}
 	if (ctx->d_out_bytes < in_bytes) {
 		cudaFree(ctx->d_out);
@@ -1358,9 +1402,11 @@ static astcenc_error decompress_image_gpu(astcenc_context* ctx, const uint8_t* d
 	img.data_type = (int)image.data_type;
 	img.dim_x = image.dim_x;
 	img.dim_y = image.dim_y;
+	img.dim_z = volume ? image.dim_z : 1;
 	img.blocks_x = (unsigned int)blocks_x;
+	img.blocks_y = (unsigned int)blocks_y;
 	img.block_row0 = 0;
-	img.block_rows = (unsigned int)blocks_y;
+	img.block_rows = (unsigned int)(blocks_y * blocks_z);
 	img.swz[0] = (int)swizzle.r;
 	img.swz[1] = (int)swizzle.g;
 	img.swz[2] = (int)swizzle.b;
@@ -1370,11 +1416,22 @@ static astcenc_error decompress_image_gpu(astcenc_context* ctx, const uint8_t* d
 	img.alpha_threshold = 0.0f;
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device), return ASTCENC_ERR_BAD_CONTEXT);
-	unsigned int nblocks = (unsigned int)(blocks_x * blocks_y);
+	unsigned int nblocks = (unsigned int)(blocks_x * blocks_y * blocks_z);
 	int warps = ASTC_DECODE_THREADS / 32;
 	int grid = (int)((nblocks + warps - 1) / warps);
 	if (grid > prop.multiProcessorCount * 8) {
 		grid = prop.multiProcessorCount * 8;
+	}
+	if (volume) {
+		CUDA_TRY(cudaMemcpyAsync(ctx->d_out, data, in_bytes, cudaMemcpyHostToDevice, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		astc_decompress_kernel<<<grid, ASTC_DECODE_THREADS, ASTC_SMEM_HDR + warps * D_SLICE, ctx->stream>>>(bsd, ctx->dcfg, img, ctx->d_out, nblocks);
+		CUDA_TRY(cudaGetLastError(), return ASTCENC_ERR_BAD_CONTEXT);
+		ctx->launches++;
+		for (unsigned int z = 0; z < image.dim_z; z++) {
+			CUDA_TRY(cudaMemcpyAsync(image.data[z], ctx->d_image + (size_t)z * slice_bytes, slice_bytes, cudaMemcpyDeviceToHost, ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		}
+		CUDA_TRY(cudaStreamSynchronize(ctx->stream), return ASTCENC_ERR_BAD_CONTEXT);
+		return ASTCENC_SUCCESS;
 	}
 	// 3D images with 2D blocks are an array of independent 2D slices; blocks of slice z follow those of slice z - 1
 	for (unsigned int z = 0; z < image.dim_z; z++) {
@@ -1491,7 +1548,7 @@ astcenc_error astcenc_get_block_info(astcenc_context* ctx, const uint8_t data[16
 	info->weight_level_count = h.weight_level_count;
 	info->weight_x = h.weight_x;
 	info->weight_y = h.weight_y;
-	info->weight_z = 1;
+	info->weight_z = h.weight_z;
 	for (unsigned int p = 0; p < h.partition_count && p < 4; p++) {
 		info->color_endpoint_modes[p] = h.color_endpoint_modes[p];
 		memcpy(info->color_endpoints[p], h.color_endpoints[p], sizeof(h.color_endpoints[p]));
@@ -1663,6 +1720,9 @@ astcenc_error astcenc_b200_compress_device(astcenc_context* ctx, const void* d_p
 	}
 	if (dim_x == 0 || dim_y == 0 || !d_pixels || !d_out) {
 		return ASTCENC_ERR_BAD_PARAM;
+	}
+	if (ctx->config.block_z > 1) {
+		return ASTCENC_ERR_NOT_IMPLEMENTED;      // the device-resident entry takes one 2D image; volumes go through astcenc_compress_image
 	}
 	size_t blocks_y = block_count_axis(dim_y, ctx->config.block_y);
 	if ((size_t)block_row0 + block_rows > blocks_y) {

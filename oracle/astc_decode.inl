@@ -95,6 +95,19 @@ static void physical_to_symbolic(const BlockSizeTables& bsd, const uint8_t pcb_i
 		for (int i = 0; i < 4; i++) {
 			scb.constant_color[i] = pcb[2 * i + 8] | (pcb[2 * i + 9] << 8);
 		}
+		if (bsd.dim_z > 1) {
+			// 3D void extent (astcenc_symbolic_physical.cpp:348-366): six 9-bit coordinates, no reserved bits
+			int v[6];
+			bool ones = true;
+			for (int k = 0; k < 6; k++) {
+				v[k] = dec_read_bits(9, 10 + 9 * k, pcb);
+				ones = ones && v[k] == 0x1FF;
+			}
+			if ((v[0] >= v[1] || v[2] >= v[3] || v[4] >= v[5]) && !ones) {
+				scb.block_type = SYM_BTYPE_ERROR;
+			}
+			return;
+		}
 		// 2D void-extent checks
 		int rsvbits = dec_read_bits(2, 10, pcb);
 		if (rsvbits != 3) {

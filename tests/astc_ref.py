@@ -216,9 +216,9 @@ class AstcencLib:
         finally:
             self.lib.astcenc_context_free(ctx)
 
-    def block_infos(self, blocks, profile, bx, by, flags=0, quality=PRE_MEDIUM):
+    def block_infos(self, blocks, profile, bx, by, flags=0, quality=PRE_MEDIUM, bz=1):
         """astcenc_get_block_info of every 16-byte block; returns a list of raw struct bytes (for exact comparison)."""
-        cfg = self.config(profile, bx, by, quality, flags)
+        cfg = self.config(profile, bx, by, quality, flags) if bz <= 1 else self.config3(profile, bx, by, bz, quality, flags)
         ctx = C.c_void_p()
         err = self.lib.astcenc_context_alloc(C.byref(cfg), 1, C.byref(ctx), None)
         if err:

@@ -30,13 +30,16 @@ extern "C" int hostsim_lanes() { return ASTC_WARP; }
 static unsigned int g_hostsim_a_scale_radius = 0;
 extern "C" void hostsim_set_a_scale_radius(unsigned int r) { g_hostsim_a_scale_radius = r; }
 
-extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int by, float quality, unsigned int flags,
-                                      const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, const int* swz, uint8_t* out) {
+// Volumes / 3D block sizes: data holds dim_z slices of dim_x * dim_y texels, contiguous; bz > 1 selects a 3D footprint and the
+// blocks come out in (z, y, x) order. (2D block sizes: dim_z must be 1 here.)
+extern "C" int hostsim_compress_volume(int profile, unsigned int bx, unsigned int by, unsigned int bz, float quality, unsigned int flags,
+                                       const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, unsigned int dim_z, const int* swz, uint8_t* out) {
 	astcenc_config cfg;
-	if (astc_host::config_init((astcenc_profile)profile, bx, by, 1, quality, flags, &cfg) != ASTCENC_SUCCESS) return 1;
-	cfg.a_scale_radius = g_hostsim_a_scale_radius;
+	if (astc_host::config_init((astcenc_profile)profile, bx, by, bz, quality, flags, &cfg) != ASTCENC_SUCCESS) return 1;
+	cfg.a_scale_radius = bz > 1 ? 0 : g_hostsim_a_scale_radius;
 	if (astc_host::validate_config(cfg) != ASTCENC_SUCCESS) return 2;
-	astc_host::BlockSizeTables* t = astc_host::build_block_size_tables(bx, by, (flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0, cfg.tune_partition_count_limit,
+	if (bz <= 1 && dim_z != 1) return 3;
+	astc_host::BlockSizeTables* t = astc_host::build_block_size_tables(bx, by, bz > 1 ? bz : 1, (flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0, cfg.tune_partition_count_limit,
 	                                                                   static_cast<float>(cfg.tune_block_mode_limit) / 100.0f);
 	astc_host::PackedTables pk;
 	unsigned int lim[3] = {cfg.tune_2partition_index_limit, cfg.tune_3partition_index_limit, cfg.tune_4partition_index_limit};
@@ -56,9 +59,11 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	img.data_type = data_type;
 	img.dim_x = dim_x;
 	img.dim_y = dim_y;
+	img.dim_z = dim_z;
 	img.blocks_x = (dim_x + bx - 1) / bx;
+	img.blocks_y = (dim_y + by - 1) / by;
 	img.block_row0 = 0;
-	img.block_rows = (dim_y + by - 1) / by;
+	img.block_rows = img.blocks_y * (bz > 1 ? (dim_z + bz - 1) / bz : 1);
 	for (int i = 0; i < 4; i++) img.swz[i] = swz ? swz[i] : i;
 	img.out = out;
 	img.alpha_avg = nullptr;
@@ -115,7 +120,7 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 		if (driver && !strcmp(driver, "warp")) {
 			for (unsigned int y = 0; y < img.block_rows; y++) {
 				for (unsigned int x = 0; x < img.blocks_x; x++) {
-					load_block(w, x * bx, y * by);
+					load_block(w, x, y);
 					compress_block(w, out + ((size_t)y * img.blocks_x + x) * 16);
 				}
 			}
@@ -183,13 +188,19 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 	return 0;
 }
 
+extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int by, float quality, unsigned int flags,
+                                      const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, const int* swz, uint8_t* out) {
+	return hostsim_compress_volume(profile, bx, by, 1, quality, flags, data, data_type, dim_x, dim_y, 1, swz, out);
+}
+
 // decompression through the device source (one simulated lane). swz uses astcenc_swz numbering.
-extern "C" int hostsim_decompress_image(int profile, unsigned int bx, unsigned int by, unsigned int flags, const uint8_t* blocks, void* out, int data_type,
-                                        unsigned int dim_x, unsigned int dim_y, const int* swz) {
+extern "C" int hostsim_decompress_volume(int profile, unsigned int bx, unsigned int by, unsigned int bz, unsigned int flags, const uint8_t* blocks, void* out, int data_type,
+                                         unsigned int dim_x, unsigned int dim_y, unsigned int dim_z, const int* swz) {
 	astcenc_config cfg;
-	if (astc_host::config_init((astcenc_profile)profile, bx, by, 1, 60.0f, flags, &cfg) != ASTCENC_SUCCESS) return 1;
+	if (astc_host::config_init((astcenc_profile)profile, bx, by, bz, 60.0f, flags, &cfg) != ASTCENC_SUCCESS) return 1;
 	if (astc_host::validate_config(cfg) != ASTCENC_SUCCESS) return 2;
-	astc_host::BlockSizeTables* t = astc_host::build_block_size_tables(bx, by, (flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0, cfg.tune_partition_count_limit,
+	if (bz <= 1 && dim_z != 1) return 3;
+	astc_host::BlockSizeTables* t = astc_host::build_block_size_tables(bx, by, bz > 1 ? bz : 1, (flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0, cfg.tune_partition_count_limit,
 	                                                                   static_cast<float>(cfg.tune_block_mode_limit) / 100.0f);
 	astc_host::PackedTables pk;
 	unsigned int lim[3] = {cfg.tune_2partition_index_limit, cfg.tune_3partition_index_limit, cfg.tune_4partition_index_limit};
@@ -206,9 +217,11 @@ extern "C" int hostsim_decompress_image(int profile, unsigned int bx, unsigned i
 	img.data_type = data_type;
 	img.dim_x = dim_x;
 	img.dim_y = dim_y;
+	img.dim_z = dim_z;
 	img.blocks_x = (dim_x + bx - 1) / bx;
+	img.blocks_y = (dim_y + by - 1) / by;
 	img.block_row0 = 0;
-	img.block_rows = (dim_y + by - 1) / by;
+	img.block_rows = img.blocks_y * (bz > 1 ? (dim_z + bz - 1) / bz : 1);
 	for (int i = 0; i < 4; i++) img.swz[i] = swz ? swz[i] : i;
 	img.out = nullptr;
 	img.alpha_avg = nullptr;
@@ -230,11 +243,32 @@ extern "C" int hostsim_decompress_image(int profile, unsigned int bx, unsigned i
 	return 0;
 }
 
+extern "C" int hostsim_decompress_image(int profile, unsigned int bx, unsigned int by, unsigned int flags, const uint8_t* blocks, void* out, int data_type,
+                                        unsigned int dim_x, unsigned int dim_y, const int* swz) {
+	return hostsim_decompress_volume(profile, bx, by, 1, flags, blocks, out, data_type, dim_x, dim_y, 1, swz);
+}
+
+extern "C" unsigned int hostsim_arena_bytes_3d(int profile, unsigned int bx, unsigned int by, unsigned int bz, float quality, unsigned int flags) {
+	astcenc_config cfg;
+	if (astc_host::config_init((astcenc_profile)profile, bx, by, bz, quality, flags, &cfg) != ASTCENC_SUCCESS) return 0;
+	astc_host::validate_config(cfg);
+	astc_host::BlockSizeTables* t = astc_host::build_block_size_tables(bx, by, bz > 1 ? bz : 1, (flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0, cfg.tune_partition_count_limit,
+	                                                                   static_cast<float>(cfg.tune_block_mode_limit) / 100.0f);
+	astc_host::PackedTables pk;
+	unsigned int lim[3] = {cfg.tune_2partition_index_limit, cfg.tune_3partition_index_limit, cfg.tune_4partition_index_limit};
+	astc_host::pack_device_tables(*t, lim, pk);
+	astc_host::free_block_size_tables(t);
+	fprintf(stderr, "%ux%ux%u arena %u (1-plane plan %u) small %u | scratch@%u (%u B) ei@%u dwi@%u lowhigh@%u mode_err@%u record %u | dec modes %u block modes %u | dec tables %u B\n",
+	        bx, by, bz, pk.bsd.arena_bytes, pk.bsd_1p.arena_bytes, pk.bsd.arena_bytes_small, pk.bsd.off_scratch, pk.bsd.scratch_bytes, pk.bsd.off_ei, pk.bsd.off_dwi,
+	        pk.bsd.off_lowhigh, pk.bsd.off_mode_err, pk.bsd.record_bytes, pk.bsd.decimation_mode_count_selected, pk.bsd.block_mode_count_1plane_2plane_selected, pk.bsd.dec_stage_bytes);
+	return pk.bsd.arena_bytes;
+}
+
 extern "C" unsigned int hostsim_arena_bytes(int profile, unsigned int bx, unsigned int by, float quality, unsigned int flags) {
 	astcenc_config cfg;
 	if (astc_host::config_init((astcenc_profile)profile, bx, by, 1, quality, flags, &cfg) != ASTCENC_SUCCESS) return 0;
 	astc_host::validate_config(cfg);
-	astc_host::BlockSizeTables* t = astc_host::build_block_size_tables(bx, by, (flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0, cfg.tune_partition_count_limit,
+	astc_host::BlockSizeTables* t = astc_host::build_block_size_tables(bx, by, 1, (flags & ASTCENC_FLG_SELF_DECOMPRESS_ONLY) != 0, cfg.tune_partition_count_limit,
 	                                                                   static_cast<float>(cfg.tune_block_mode_limit) / 100.0f);
 	astc_host::PackedTables pk;
 	unsigned int lim[3] = {cfg.tune_2partition_index_limit, cfg.tune_3partition_index_limit, cfg.tune_4partition_index_limit};

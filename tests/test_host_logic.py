@@ -40,7 +40,8 @@ def test_config_init_errors(pkg):
     assert lib.astcenc_config_init(PRF_LDR, 6, 6, 1, 60.0, 1 << 9, C.byref(cfg)) == 8  # BAD_FLAGS
     assert lib.astcenc_config_init(PRF_LDR, 6, 6, 1, 60.0, FLG_MAP_NORMAL | FLG_MAP_RGBM, C.byref(cfg)) == 8
     assert lib.astcenc_config_init(PRF_HDR, 6, 6, 1, 60.0, FLG_USE_DECODE_UNORM8, C.byref(cfg)) == 11  # BAD_DECODE_MODE
-    assert lib.astcenc_config_init(PRF_LDR, 4, 4, 4, 60.0, 0, C.byref(cfg)) == 10     # 3D blocks: NOT_IMPLEMENTED (out of scope)
+    assert lib.astcenc_config_init(PRF_LDR, 4, 4, 4, 60.0, 0, C.byref(cfg)) == 0      # 3D block sizes: the ten footprints
+    assert lib.astcenc_config_init(PRF_LDR, 4, 4, 5, 60.0, 0, C.byref(cfg)) == 4      # ... and nothing else (BAD_BLOCK_SIZE)
     assert lib.astcenc_get_error_string(3) == b"ASTCENC_ERR_BAD_PARAM"
     assert lib.astcenc_get_error_string(99) is None
 
