@@ -200,6 +200,13 @@ ASTC_FN int trial_class(const Trial& t) {
 //             parts: ideal, decimate, angular, quantise+score, formats + candidate weights, record save, wait, items
 __device__ unsigned long long g_step_stats[6][8];
 __device__ unsigned long long g_setup_stats[3][8];
+// tails: histograms (4096-cycle buckets) of a step's parts over all kinds of step: 0 recompute, 1 pack, 2 score1, 3 realign, 4 score2,
+// 5 the whole step's work, 6 block change (only the warps that changed block), 7 wait at the vote
+__device__ unsigned int g_step_hist[8][32];
+__device__ __forceinline__ void stat_hist(int part, long long cycles) {
+	int b = (int)(cycles >> 12);
+	atomicAdd(&g_step_hist[part][b < 0 ? 0 : (b > 31 ? 31 : b)], 1u);
+}
 #define STAT_T(v) long long v = clock64()
 #else
 #define STAT_T(v)
@@ -446,6 +453,8 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 		if (st_on && w.lane == 0 && st_prev_class >= 0) {
 			atomicAdd(&g_step_stats[st_prev_class][5], (unsigned long long)(tv - st_prev_end));
 			atomicAdd(&g_step_stats[st_prev_class][6], (unsigned long long)(t0 - tv));
+			if (tv - st_prev_end > 512) stat_hist(6, tv - st_prev_end);
+			stat_hist(7, t0 - tv);
 		}
 #endif
 		if (has_item) refine_recompute(w, t, r);
@@ -473,6 +482,12 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 				atomicAdd(&g_step_stats[cls][3], (unsigned long long)(t4 - t3));
 				atomicAdd(&g_step_stats[cls][4], (unsigned long long)(t5 - t4));
 				atomicAdd(&g_step_stats[cls][7], 1ull);
+				stat_hist(0, t1 - t0);
+				stat_hist(1, t2 - t1);
+				stat_hist(2, t3 - t2);
+				stat_hist(3, t4 - t3);
+				stat_hist(4, t5 - t4);
+				stat_hist(5, t5 - t0);
 			}
 			st_prev_class = cls;
 			st_prev_end = t5;
@@ -538,6 +553,15 @@ ASTC_COOP void wave_emit(int lane, uint32_t slices_base, WaveArgs a) {
 			       g_step_stats[c][0] / (n ? n : 1), g_step_stats[c][1] / (n ? n : 1), g_step_stats[c][2] / (n ? n : 1), g_step_stats[c][3] / (n ? n : 1),
 			       g_step_stats[c][4] / (n ? n : 1), g_step_stats[c][5] / (n ? n : 1), g_step_stats[c][6] / (n ? n : 1));
 			for (int k = 0; k < 8; k++) g_step_stats[c][k] = 0;
+		}
+		const char* names[8] = {"recompute", "pack", "score1", "realign", "score2", "step work", "block change", "wait"};
+		for (int p = 0; p < 8; p++) {
+			printf("hist %-12s (4096-cycle buckets):", names[p]);
+			for (int b = 0; b < 32; b++) {
+				printf(" %u", g_step_hist[p][b]);
+				g_step_hist[p][b] = 0;
+			}
+			printf("\n");
 		}
 	}
 #endif
