@@ -651,6 +651,11 @@ struct RefineScratch {
 	uint32_t tile;        // chain staging tile: 20 x CHAIN_STRIDE floats
 };
 #define REFINE_TILE_BYTES (20 * CHAIN_STRIDE * 4)
+// realign_weights: the wavefront replay is taken when pending weights * DEN > fronts * NUM (see there)
+#ifndef ASTC_REALIGN_WAVE_NUM
+	#define ASTC_REALIGN_WAVE_NUM 1
+	#define ASTC_REALIGN_WAVE_DEN 2
+#endif
 
 ASTC_FN RefineScratch make_refine_scratch(const WCtx& w) {
 	RefineScratch r;
@@ -1453,7 +1458,59 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 			else pend_hi |= bits << (we0 - 32);
 		}
 		wsync();
-		// pass 2: the reference's order over the outcomes
+		// pass 2: the reference's order over the outcomes.
+		// Two ways to replay it. (a) Speculative: take the pending weights in index order; a move invalidates the outcomes of the
+		// weight's later grid neighbours only, which are evaluated again. One sequential step per MOVE: cheap for the typical step
+		// (~1 weight in 7 moves) but the tail is long - a noisy block moves most of its weights, and with one CTA-wide vote per
+		// refinement round the slowest warp of 24 sets the pace (measured: mean 15 k cycles, 1 step in 10 over 32 k, rounds of 72 k).
+		// (b) Wavefront: in a bilinear grid the earlier neighbours of (x, y) are (x-1, y), (x+1, y-1), (x, y-1), (x-1, y-1); with
+		// k = x + 2 y they sit on fronts k-1, k-1, k-2, k-3, so the weights of one front are independent and all their earlier
+		// neighbours are final: gw + 2 (gh - 1) sequential steps whatever the content (16 for a 6x6 grid), up to ceil(gw / 2) <= 8
+		// weights per step, one group of four lanes each. Used when the pending set of pass 1 says (a) would take longer
+		// (pending > fronts / 2; measured at 4K 6x6 -medium, ms per pass: never 67.8, > fronts 65.9, > 3/4 66.0, > 1/2 65.7, > 1/4 66.0,
+		// always 66.9; computing the twelve squared differences of a front's (weight, texel) pairs by one lane per pair into a tile
+		// and letting four lanes per weight add the columns in order - less latency per front on paper - measured 68.4: more
+		// instructions, more barriers; removed).
+		const int npend = __popc(pend_lo) + __popc(pend_hi);
+		const int gh = ASTC_LDG(&dmp->weight_y);
+		const int nfronts = gw + 2 * (gh - 1);
+		if (!volume && npend * ASTC_REALIGN_WAVE_DEN > nfronts * ASTC_REALIGN_WAVE_NUM) {
+			ASTC_NOUNROLL
+			for (int k = 0; k < nfronts; k++) {
+				int ylo = k - (gw - 1);
+				ylo = ylo > 0 ? (ylo + 1) >> 1 : 0;
+				int yhi = k >> 1;
+				yhi = yhi < gh - 1 ? yhi : gh - 1;
+				int y = ylo + grp;
+				bool act = y <= yhi;
+				int j = act ? y * gw + (k - 2 * y) : 0;
+				int nv = evaluate(j, act);
+				bool mv = act && nv >= 0;
+				if (!wany(mv)) {
+					continue;
+				}
+				adjustments = true;
+				wsync();                   // (every group has read the state it decides on)
+				int off = 0, cnt = 0;
+				if (mv) {
+					off = s_wto[j];
+					cnt = s_wto[j + 1] - off;
+					if (lc == 0) {
+						uqf[j] = static_cast<float>(nv);
+						dec_weights_uquant[j] = (uint8_t)nv;
+					}
+				}
+				wsync();
+				// the infill changes for the texels of the moved weights only (weights of one front share no texel)
+				ASTC_NOUNROLL
+				for (int te = lc; te < cnt; te += 4) {
+					int texel = (int)(s_wtc[off + te] & 0xFF);
+					wb[texel] = bilinear_infill(di, uqf, texel);
+				}
+				wsync();
+			}
+			continue;
+		}
 		ASTC_NOUNROLL
 		while ((pend_lo | pend_hi) != 0) {
 			int f = pend_lo != 0 ? __ffs((int)pend_lo) - 1 : 32 + __ffs((int)pend_hi) - 1;
@@ -1479,22 +1536,36 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 			// later grid neighbours of f: the weights of higher index that share a texel with it, one per group of four lanes.
 			// 2D (bilinear cells): (fx+1, fy), (fx-1, fy+1), (fx, fy+1), (fx+1, fy+1). 3D (simplex cells: the corners of a texel's
 			// simplex differ by vectors of {0,1}^3): the seven (fx+a, fy+b, fz+c), (a, b, c) != 0 - groups 0..6.
-			// (two copies of the step: the 2D one is the hot path of every refinement step and stays as lean as it was)
+			int j;
+			bool act;
 			if (!volume) {
 				int fy = f / gw;
 				int fx = f - fy * gw;
 				int dx = grp == 1 ? -1 : (grp == 2 ? 0 : 1);
 				int dy = grp == 0 ? 0 : 1;
 				int nx = fx + dx;
-				int j = f + dy * gw + dx;
-				bool act = grp < 4 && nx >= 0 && nx < gw && j < weight_count;
-				int nv = evaluate(j, act);
-				if (act && lc == 0 && nv >= 0) {
-					s_new[j] = (uint8_t)nv;
-				}
-				uint32_t redo = __ballot_sync(0xffffffffu, act && lc == 0);
-				uint32_t want = __ballot_sync(0xffffffffu, act && lc == 0 && nv >= 0);
-				// every lane folds the four outcomes into its copy of the pending set (lane 4 g <-> neighbour g)
+				j = f + dy * gw + dx;
+				act = grp < 4 && nx >= 0 && nx < gw && j < weight_count;
+			} else {
+				const int gd = ASTC_LDG(&dmp->weight_z);
+				const int gwh = gw * gh;
+				int fz = f / gwh;
+				int fr = f - fz * gwh;
+				int fy = fr / gw;
+				int fx = fr - fy * gw;
+				int v = grp + 1;      // 1..7: bits = (dx, dy, dz)
+				int dx = v & 1, dy = (v >> 1) & 1, dz = (v >> 2) & 1;
+				j = f + dz * gwh + dy * gw + dx;
+				act = grp < 7 && fx + dx < gw && fy + dy < gh && fz + dz < gd;
+			}
+			int nv = evaluate(j, act);
+			if (act && lc == 0 && nv >= 0) {
+				s_new[j] = (uint8_t)nv;
+			}
+			uint32_t redo = __ballot_sync(0xffffffffu, act && lc == 0);
+			uint32_t want = __ballot_sync(0xffffffffu, act && lc == 0 && nv >= 0);
+			// every lane folds the outcomes into its copy of the pending set (lane 4 g <-> neighbour g)
+			if (!volume) {
 				ASTC_NOUNROLL
 				for (int g = 0; g < 4; g++) {
 					if ((redo >> (4 * g)) & 1u) {
@@ -1506,32 +1577,14 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 					}
 				}
 			} else {
-				const int gh = ASTC_LDG(&dmp->weight_y);
-				const int gd = ASTC_LDG(&dmp->weight_z);
-				const int gwh = gw * gh;
-				int fz = f / gwh;
-				int fr = f - fz * gwh;
-				int fy = fr / gw;
-				int fx = fr - fy * gw;
-				int v = grp + 1;      // 1..7: bits = (dx, dy, dz)
-				int dx = v & 1, dy = (v >> 1) & 1, dz = (v >> 2) & 1;
-				int j = f + dz * gwh + dy * gw + dx;
-				bool act = grp < 7 && fx + dx < gw && fy + dy < gh && fz + dz < gd;
-				int nv = evaluate(j, act);
-				if (act && lc == 0 && nv >= 0) {
-					s_new[j] = (uint8_t)nv;
-				}
-				uint32_t redo = __ballot_sync(0xffffffffu, act && lc == 0);
-				uint32_t want = __ballot_sync(0xffffffffu, act && lc == 0 && nv >= 0);
 				ASTC_NOUNROLL
-				for (int g = 0; g < 7; g++) {
-					if ((redo >> (4 * g)) & 1u) {
-						int gv = g + 1;
-						int jj = f + ((gv >> 2) & 1) * gwh + ((gv >> 1) & 1) * gw + (gv & 1);
-						uint32_t on = (want >> (4 * g)) & 1u;
-						if (jj < 32) pend_lo = (pend_lo & ~(1u << jj)) | (on << jj);
-						else pend_hi = (pend_hi & ~(1u << (jj - 32))) | (on << (jj - 32));
-					}
+				while (redo != 0) {
+					int l0 = __ffs((int)redo) - 1;
+					redo &= redo - 1;
+					int jj = __shfl_sync(0xffffffffu, j, l0);
+					uint32_t on = (want >> l0) & 1u;
+					if (jj < 32) pend_lo = (pend_lo & ~(1u << jj)) | (on << jj);
+					else pend_hi = (pend_hi & ~(1u << (jj - 32))) | (on << (jj - 32));
 				}
 			}
 			wsync();
