@@ -654,7 +654,7 @@ struct RefineScratch {
 // realign_weights: the wavefront replay is taken when pending weights * DEN > fronts * NUM (see there)
 #ifndef ASTC_REALIGN_WAVE_NUM
 	#define ASTC_REALIGN_WAVE_NUM 1
-	#define ASTC_REALIGN_WAVE_DEN 2
+	#define ASTC_REALIGN_WAVE_DEN 1
 #endif
 
 ASTC_FN RefineScratch make_refine_scratch(const WCtx& w) {
@@ -1466,11 +1466,11 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 		// (b) Wavefront: in a bilinear grid the earlier neighbours of (x, y) are (x-1, y), (x+1, y-1), (x, y-1), (x-1, y-1); with
 		// k = x + 2 y they sit on fronts k-1, k-1, k-2, k-3, so the weights of one front are independent and all their earlier
 		// neighbours are final: gw + 2 (gh - 1) sequential steps whatever the content (16 for a 6x6 grid), up to ceil(gw / 2) <= 8
-		// weights per step, one group of four lanes each. Used when the pending set of pass 1 says (a) would take longer
-		// (pending > fronts / 2; measured at 4K 6x6 -medium, ms per pass: never 67.8, > fronts 65.9, > 3/4 66.0, > 1/2 65.7, > 1/4 66.0,
-		// always 66.9; computing the twelve squared differences of a front's (weight, texel) pairs by one lane per pair into a tile
+		// weights per step, one group of four lanes each. Used when the pending set of pass 1 says (a) would take longer:
+		// pending > fronts. Measured, ms per pass - 4K 6x6 -medium: never 67.8, > fronts 65.9, > 3/4 66.0, > 1/2 65.7, > 1/4 66.0,
+		// always 66.9; 4K 8x8 -thorough: never 313.7, > fronts 311.4, > 1/2 315.3; 2K HDR 6x6: 51.3 / 50.9 / 51.2. (Computing the twelve squared differences of a front's (weight, texel) pairs by one lane per pair into a tile
 		// and letting four lanes per weight add the columns in order - less latency per front on paper - measured 68.4: more
-		// instructions, more barriers; removed).
+		// instructions, more barriers; removed.)
 		const int npend = __popc(pend_lo) + __popc(pend_hi);
 		const int gh = ASTC_LDG(&dmp->weight_y);
 		const int nfronts = gw + 2 * (gh - 1);
