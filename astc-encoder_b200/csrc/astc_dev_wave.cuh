@@ -26,11 +26,22 @@
 // length, and warps of a CTA wait for each other every round. Each warp drains class 0, then 1, ... so that the warps
 // voting together are (almost always) doing the same kind of step.
 #define ASTC_Q_CLASSES 4
-enum { Q_SETUP = 0, Q_REFINE = ASTC_Q_CLASSES, Q_PREPARE = 2 * ASTC_Q_CLASSES, Q_EMIT = 2 * ASTC_Q_CLASSES + 1, ASTC_Q_KINDS = 2 * ASTC_Q_CLASSES + 2 };
+// Set-up items are queued by the trial's weight quantisation limit as well (Trial::max_weight_quant, 12 values): a later trial of
+// a block searches only the modes up to the limit its best result so far allows, and the cost of a set-up follows it - measured
+// for two-plane set-ups: 33 k cycles (QUANT_2) ... 174 k (QUANT_32) up to the stage barrier. Mixed in one queue, every round of a
+// CTA lasted as long as its most expensive item (mean 101 k, rounds of 160 k: 59 k of every two-plane set-up spent waiting).
+// A class is drained from the expensive end, so the warps that vote together hold items of the same cost and the cheap ones fill
+// the tail of the launch.
+#define ASTC_Q_SUB 12
+// Preparation items by what they prepare: 0 block statistics (two-plane phase), 1..3 the partition search for 2..4 partitions
+// (the search costs several times the statistics; the kernel votes once per item).
+#define ASTC_Q_PREP 4
+enum { Q_SETUP = 0, Q_REFINE = ASTC_Q_CLASSES * ASTC_Q_SUB, Q_PREPARE = Q_REFINE + ASTC_Q_CLASSES, Q_EMIT = Q_PREPARE + ASTC_Q_PREP, ASTC_Q_KINDS = Q_EMIT + 1 };
 
 struct WaveArgs {
 	uint8_t* records;            // [blocks] x record_bytes
-	uint32_t* queue[ASTC_Q_KINDS];   // item lists (block indices), capacity = blocks each
+	uint32_t* queues;            // item lists (block indices): list k at queues + k * queue_stride, capacity = blocks each
+	size_t queue_stride;
 	uint32_t* count;             // [ASTC_Q_KINDS][ASTC_MAX_WAVES] items pushed (Q_EMIT uses wave slot 0)
 	uint32_t* head;              // [ASTC_Q_KINDS][ASTC_MAX_WAVES] items popped
 	unsigned int total;          // blocks of the slab (capacity of every queue)
@@ -66,7 +77,7 @@ ASTC_FN bool q_pop(const WCtx& w, const WaveArgs& a, int kind, int wave, unsigne
 	if (i >= q_load(a.count + kind * ASTC_MAX_WAVES + wave)) {
 		return false;
 	}
-	b = q_load(a.queue[kind] + i);
+	b = q_load(a.queues + (size_t)kind * a.queue_stride + i);
 	return true;
 }
 
@@ -81,10 +92,55 @@ ASTC_FN bool q_pop_classes(const WCtx& w, const WaveArgs& a, int kind, int wave,
 	return false;
 }
 
+// set-up items: the classes' sub-queues in order, each class from the expensive end; cls is the warp's cursor over
+// [cls_lo * ASTC_Q_SUB, cls_end * ASTC_Q_SUB). Empty sub-queues are skipped 32 at a time with plain loads (a look that can be
+// stale only in the harmless direction: the atomic pop decides), so a drained launch costs a warp one round trip, not one per queue.
+ASTC_FN int sorted_kind_of_cursor(int base_kind, int nsub, int cls) {
+	int klass = cls / nsub;
+	return base_kind + klass * nsub + (nsub - 1 - (cls - klass * nsub));
+}
+// queues base_kind + klass * nsub + sub; cls = cursor over [.., cls_end * nsub)
+ASTC_FN bool q_pop_sorted(const WCtx& w, const WaveArgs& a, int base_kind, int nsub, int wave, int& cls, unsigned int& b, int cls_end) {
+	const int end = cls_end * nsub;
+	bool look = (cls % nsub) == 0;      // entering a class: find its first queue with items; otherwise pop where the last item came from
+	while (cls < end) {
+#if !defined(ASTC_ONE_LANE)
+		if (look) {
+			int k = cls + w.lane;
+			bool has = false;
+			if (k < end) {
+				int kind = sorted_kind_of_cursor(base_kind, nsub, k);
+				has = q_load(a.count + kind * ASTC_MAX_WAVES + wave) > q_load(a.head + kind * ASTC_MAX_WAVES + wave);
+			}
+			uint32_t m = __ballot_sync(0xffffffffu, has);
+			if (m == 0) {
+				cls += ASTC_WARP;
+				continue;
+			}
+			cls += __ffs((int)m) - 1;
+		}
+#endif
+		if (q_pop(w, a, sorted_kind_of_cursor(base_kind, nsub, cls), wave, b)) {
+			return true;
+		}
+		cls++;
+		look = true;
+	}
+	return false;
+}
+ASTC_FN bool q_pop_setup(const WCtx& w, const WaveArgs& a, int wave, int& cls, unsigned int& b, int cls_end) {
+	return q_pop_sorted(w, a, Q_SETUP, ASTC_Q_SUB, wave, cls, b, cls_end);
+}
+ASTC_FN int setup_queue_of(const Trial& t, int klass) {
+	int q = t.max_weight_quant;
+	q = q < 0 ? 0 : (q >= ASTC_Q_SUB ? ASTC_Q_SUB - 1 : q);
+	return Q_SETUP + klass * ASTC_Q_SUB + q;
+}
+
 ASTC_FN void q_push(const WCtx& w, const WaveArgs& a, int kind, int wave, unsigned int b) {
 	if (w.lane == 0) {
 		uint32_t i = q_atomic_add(a.count + kind * ASTC_MAX_WAVES + wave, 1u);
-		a.queue[kind][i] = b;
+		a.queues[(size_t)kind * a.queue_stride + i] = b;
 	}
 }
 
@@ -200,6 +256,9 @@ ASTC_FN int trial_class(const Trial& t) {
 //             parts: ideal, decimate, angular, quantise+score, formats + candidate weights, record save, wait, items
 __device__ unsigned long long g_step_stats[6][8];
 __device__ unsigned long long g_setup_stats[3][8];
+__device__ unsigned long long g_setup_bar[3];
+__device__ unsigned long long g_setup_q[3][12][3];      // by max_weight_quant: items, cycles before / after the stage barrier
+__device__ unsigned int g_setup_hist[3][2][32];
 // tails: histograms (4096-cycle buckets) of a step's parts over all kinds of step: 0 recompute, 1 pack, 2 score1, 3 realign, 4 score2,
 // 5 the whole step's work, 6 block change (only the warps that changed block), 7 wait at the vote
 __device__ unsigned int g_step_hist[8][32];
@@ -226,7 +285,7 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 	feed.ticket = a.ticket;      // wave 0 has no queue: a ticket counter hands out the band's blocks
 	feed.total = a.band_blocks;
 	feed.blocks_x = a.blocks_x;
-	int cls = a.cls_lo;
+	int cls = a.cls_lo * ASTC_Q_SUB;
 	uint32_t rec_phase = 0;
 	record_mbar_init(w);
 	while (true) {
@@ -258,7 +317,7 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 				active = true;
 				break;
 			}
-		} else if (q_pop_classes(w, a, Q_SETUP, a.wave, cls, b, a.cls_hi)) {
+		} else if (q_pop_setup(w, a, a.wave, cls, b, a.cls_hi)) {
 			record_restore(w, a, b, rec_phase);
 			active = true;
 		}
@@ -297,6 +356,7 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 		if (active) quantize_and_score_modes(w, tf.start_mode, tf.end_mode, tf.dual ? 2 : 1, tf.partition_count, tf.max_weight_quant, tf.cutoff1, tf.cutoff2);
 		STAT_T(s4);
 		if (a.sync_mask & 8) cta_sync();
+		STAT_T(s4b);
 		if (active) {
 			unsigned int count = 0, count_next = 0;
 			if (shared) {
@@ -354,7 +414,20 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 				atomicAdd(&g_setup_stats[kind][1], (unsigned long long)(s2 - s1));
 				atomicAdd(&g_setup_stats[kind][2], (unsigned long long)(s3 - s2));
 				atomicAdd(&g_setup_stats[kind][3], (unsigned long long)(s4 - s3));
-				atomicAdd(&g_setup_stats[kind][4], (unsigned long long)(s5 - s4));
+				atomicAdd(&g_setup_stats[kind][4], (unsigned long long)(s5 - s4b));
+				atomicAdd(&g_setup_bar[kind], (unsigned long long)(s4b - s4));
+				{
+					int q = t.max_weight_quant < 0 ? 0 : (t.max_weight_quant > 11 ? 11 : t.max_weight_quant);
+					atomicAdd(&g_setup_q[kind][q][0], 1ull);
+					atomicAdd(&g_setup_q[kind][q][1], (unsigned long long)(s4 - s0));
+					atomicAdd(&g_setup_q[kind][q][2], (unsigned long long)(s5 - s4b));
+				}
+				{
+					// tails: item work up to the stage barrier / after it, 8192-cycle buckets
+					int b1 = (int)((s4 - s0) >> 13), b2 = (int)((s5 - s4b) >> 13);
+					atomicAdd(&g_setup_hist[kind][0][b1 > 31 ? 31 : b1], 1u);
+					atomicAdd(&g_setup_hist[kind][1][b2 > 31 ? 31 : b2], 1u);
+				}
 				atomicAdd(&g_setup_stats[kind][5], (unsigned long long)(s6 - s5));
 				atomicAdd(&g_setup_stats[kind][6], (unsigned long long)(s0 - sv));
 				atomicAdd(&g_setup_stats[kind][7], 1ull);
@@ -393,9 +466,10 @@ ASTC_COOP void wave_finish_trial(WCtx w, const WaveArgs& a, unsigned int b, Bloc
 	}
 	record_save(w, a, b);
 	if (next == NEXT_TRIAL) {
-		q_push(w, a, Q_SETUP + klass, a.wave + 1, b);
+		q_push(w, a, setup_queue_of(t, klass), a.wave + 1, b);
 	} else if (next == NEXT_PREPARE) {
-		q_push(w, a, Q_PREPARE, a.wave, b);
+		int pk = s.phase == 1 ? 0 : (s.pc < 2 ? 1 : (s.pc > ASTC_Q_PREP ? ASTC_Q_PREP - 1 : s.pc - 1));
+		q_push(w, a, Q_PREPARE + pk, a.wave, b);
 	} else {
 		q_push(w, a, Q_EMIT, 0, b);
 	}
@@ -507,10 +581,12 @@ ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
 	BlockSearch& s = search_of(w);
 	Trial& t = trial_of(w);
 	uint32_t rec_phase = 0;
+	int pcls = 0;
 	record_mbar_init(w);
 	while (true) {
 		unsigned int b = 0;
-		bool active = q_pop(w, a, Q_PREPARE, a.wave, b);
+		// (the expensive kinds first)
+		bool active = q_pop_sorted(w, a, Q_PREPARE, ASTC_Q_PREP, a.wave, pcls, b, 1);
 		if (!cta_any(active)) {
 			break;
 		}
@@ -524,7 +600,7 @@ ASTC_COOP void wave_prepare(WCtx w, WaveArgs a) {
 			int klass = trial_class(t);
 			record_save(w, a, b);
 			if (next == NEXT_TRIAL) {
-				q_push(w, a, Q_SETUP + klass, a.wave + 1, b);
+				q_push(w, a, setup_queue_of(t, klass), a.wave + 1, b);
 			} else {
 				q_push(w, a, Q_EMIT, 0, b);
 			}
@@ -545,6 +621,23 @@ ASTC_COOP void wave_emit(int lane, uint32_t slices_base, WaveArgs a) {
 			printf("setup kind %d n %llu: ideal %llu decimate %llu angular %llu quantscore %llu formats %llu save %llu wait %llu (cycles per item)\n", c, n,
 			       g_setup_stats[c][0] / (n ? n : 1), g_setup_stats[c][1] / (n ? n : 1), g_setup_stats[c][2] / (n ? n : 1), g_setup_stats[c][3] / (n ? n : 1),
 			       g_setup_stats[c][4] / (n ? n : 1), g_setup_stats[c][5] / (n ? n : 1), g_setup_stats[c][6] / (n ? n : 1));
+			printf("setup kind %d: wait at the stage barrier %llu\n", c, g_setup_bar[c] / (n ? n : 1));
+			g_setup_bar[c] = 0;
+			printf("setup kind %d by max_weight_quant (items : cycles before / after the barrier):", c);
+			for (int q = 0; q < 12; q++) {
+				unsigned long long m = g_setup_q[c][q][0];
+				printf(" q%d %llu : %llu / %llu,", q, m, g_setup_q[c][q][1] / (m ? m : 1), g_setup_q[c][q][2] / (m ? m : 1));
+				g_setup_q[c][q][0] = g_setup_q[c][q][1] = g_setup_q[c][q][2] = 0;
+			}
+			printf("\n");
+			for (int h = 0; h < 2; h++) {
+				printf("hist setup kind %d %s (8192-cycle buckets):", c, h == 0 ? "before the barrier" : "after the barrier ");
+				for (int b = 0; b < 32; b++) {
+					printf(" %u", g_setup_hist[c][h][b]);
+					g_setup_hist[c][h][b] = 0;
+				}
+				printf("\n");
+			}
 			for (int k = 0; k < 8; k++) g_setup_stats[c][k] = 0;
 		}
 		for (int c = 0; c < 6; c++) {
@@ -580,7 +673,7 @@ ASTC_COOP void wave_emit(int lane, uint32_t slices_base, WaveArgs a) {
 		}
 		uint32_t i = i0 + (uint32_t)lane;
 		if (i < n) {
-			unsigned int b = q_load(a.queue[Q_EMIT] + i);
+			unsigned int b = q_load(a.queues + (size_t)Q_EMIT * a.queue_stride + i);
 			const uint8_t* rec = a.records + (size_t)b * BSD.record_bytes;
 			uint32_t slice = slices_base + (uint32_t)lane * EMIT_SLICE;
 			const uint32_t* src = reinterpret_cast<const uint32_t*>(rec + A_SCB);

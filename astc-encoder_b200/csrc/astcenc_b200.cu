@@ -106,6 +106,14 @@ static __device__ __forceinline__ bool wave_queue_empty(const WaveArgs& a, int k
 	}
 	return n == 0;
 }
+// (the set-up classes have ASTC_Q_SUB sub-queues each; a thread per sub-queue looks, the CTA votes)
+static __device__ __forceinline__ bool wave_setup_queues_empty(const WaveArgs& a) {
+	bool any = false;
+	for (int k = a.cls_lo * ASTC_Q_SUB + (int)threadIdx.x; k < a.cls_hi * ASTC_Q_SUB; k += (int)blockDim.x) {
+		any = any || __ldcg(a.count + (Q_SETUP + k) * ASTC_MAX_WAVES + a.wave) != 0;
+	}
+	return __syncthreads_or(any ? 1 : 0) == 0;
+}
 
 #define ASTC_SETUP_THREADS_MAX 640      /* 20 warps x <= 102 registers (registers are granted per 4 warps: 21 warps would be charged as 24 and cap the kernel at 80) */
 #ifndef ASTC_REFINE_THREADS_MAX
@@ -115,7 +123,7 @@ static __device__ __forceinline__ bool wave_queue_empty(const WaveArgs& a, int k
 
 __global__ void __launch_bounds__(ASTC_SETUP_THREADS_MAX, 1)
 astc_wave_setup_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img, const __grid_constant__ WaveArgs a) {
-	if (a.wave != 0 && wave_queue_empty(a, Q_SETUP, a.cls_lo, a.cls_hi)) {
+	if (a.wave != 0 && wave_setup_queues_empty(a)) {
 		return;
 	}
 	stage_launch_constants(bsd, cfg, img);
@@ -147,7 +155,7 @@ astc_wave_refine_kernel(const __grid_constant__ DevBsd bsd, const __grid_constan
 
 __global__ void __launch_bounds__(ASTC_REFINE_THREADS_MAX, 1)
 astc_wave_prepare_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img, const __grid_constant__ WaveArgs a) {
-	if (__ldcg(a.count + Q_PREPARE * ASTC_MAX_WAVES + a.wave) == 0) {
+	if (wave_queue_empty(a, Q_PREPARE, 0, ASTC_Q_PREP)) {
 		return;
 	}
 	stage_launch_constants(bsd, cfg, img);
@@ -860,9 +868,8 @@ static astcenc_error launch_pipes(astcenc_context* ctx, int pipes, const void* d
 		CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * ASTC_COUNTER_WORDS, ps), return ASTCENC_ERR_BAD_CONTEXT);
 		WaveArgs& w = a[p];
 		w.records = ctx->d_records + first * (size_t)bsd.record_bytes;
-		for (int k = 0; k < ASTC_Q_KINDS; k++) {
-			w.queue[k] = ctx->d_queues + (size_t)k * ctx->queue_capacity + first;
-		}
+		w.queues = ctx->d_queues + first;
+		w.queue_stride = ctx->queue_capacity;
 		w.count = counters;
 		w.head = counters + ASTC_Q_KINDS * ASTC_MAX_WAVES;
 		w.total = (r1 - r0) * blocks_x;
@@ -1051,9 +1058,8 @@ static astcenc_error launch_batch(astcenc_context* ctx, const void* d_pixels, in
 		CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, sizeof(uint32_t) * ASTC_COUNTER_WORDS, stream), return ASTCENC_ERR_BAD_CONTEXT);
 		WaveArgs a;
 		a.records = ctx->d_records;
-		for (int k = 0; k < ASTC_Q_KINDS; k++) {
-			a.queue[k] = ctx->d_queues + (size_t)k * ctx->queue_capacity;
-		}
+		a.queues = ctx->d_queues;
+		a.queue_stride = ctx->queue_capacity;
 		a.count = ctx->d_counters;
 		a.head = ctx->d_counters + ASTC_Q_KINDS * ASTC_MAX_WAVES;
 		a.total = (unsigned int)total;

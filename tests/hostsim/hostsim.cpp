@@ -134,7 +134,8 @@ extern "C" int hostsim_compress_volume(int profile, unsigned int bx, unsigned in
 			// the wave pipeline, driven like the CUDA host code does (one simulated warp per "kernel")
 			WaveArgs a;
 			a.records = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(records.data()) + 15) & ~(uintptr_t)15);
-			for (int k = 0; k < ASTC_Q_KINDS; k++) a.queue[k] = queues.data() + (size_t)k * total;
+			a.queues = queues.data();
+			a.queue_stride = total;
 			a.count = counters.data();
 			a.head = counters.data() + ASTC_Q_KINDS * ASTC_MAX_WAVES;
 			a.total = total;
