@@ -188,6 +188,11 @@ ASTCENC_PUBLIC const char* astcenc_get_error_string(enum astcenc_error status);
  *    enqueued runs to its end (the reference stops handing out tickets, astcenc_internal_entry.h:219).
  *  - Every entry point runs on the CUDA device that was current in astcenc_context_alloc() and restores the caller's
  *    current device before it returns.
+ *  - Block sizes: the fourteen 2D and the ten 3D footprints (block_z > 1: 3x3x3 .. 6x6x6, astcenc_block_sizes.cpp:1025). With a
+ *    3D block size the slices of astcenc_image::data are uploaded into one volume and compressed in one pass, blocks in
+ *    (z, y, x) order like the reference's (astcenc_entry.cpp:1036); a_scale_radius is ignored like the reference does
+ *    (astcenc_entry.cpp:975). The astcenc_b200_* device-resident and multi-GPU entry points take 2D block sizes only
+ *    (ASTCENC_ERR_NOT_IMPLEMENTED otherwise).
  *  - A context owns ONE set of search scratch buffers: passes of the same context are serialised - on the host by a mutex,
  *    on the device by an event chain - whatever streams they are enqueued on. Use one context per concurrent stream.
  */
