@@ -193,6 +193,9 @@ static astcenc_error check_image_args(astcenc_context* ctx, const astcenc_image*
 	if (image->dim_x == 0 || image->dim_y == 0 || image->dim_z != 1) {
 		return image->dim_z > 1 ? ASTCENC_ERR_NOT_IMPLEMENTED : ASTCENC_ERR_BAD_PARAM;
 	}
+	if (ctx->config.block_z > 1) {
+		return ASTCENC_ERR_NOT_IMPLEMENTED;      // 3D block sizes: volumes go through astcenc_compress_image (include/astcenc.h)
+	}
 	if ((int)image->data_type < 0 || (int)image->data_type > 2) {
 		return ASTCENC_ERR_BAD_PARAM;
 	}
