@@ -652,6 +652,9 @@ struct RefineScratch {
 };
 #define REFINE_TILE_BYTES (20 * CHAIN_STRIDE * 4)
 // realign_weights: the wavefront replay is taken when pending weights * DEN > fronts * NUM (see there)
+#if defined(ASTC_HOSTSIM)
+static unsigned int g_hostsim_wavefront_replays;
+#endif
 #ifndef ASTC_REALIGN_WAVE_NUM
 	#define ASTC_REALIGN_WAVE_NUM 1
 	#define ASTC_REALIGN_WAVE_DEN 1
@@ -1475,6 +1478,11 @@ ASTC_COOP bool realign_weights(WCtx w, unsigned int pc, uint32_t formats, int pl
 		const int gh = ASTC_LDG(&dmp->weight_y);
 		const int nfronts = gw + 2 * (gh - 1);
 		if (!volume && npend * ASTC_REALIGN_WAVE_DEN > nfronts * ASTC_REALIGN_WAVE_NUM) {
+#if defined(ASTC_HOSTSIM)
+			if (w.lane == 0) {
+				g_hostsim_wavefront_replays++;      // (tests assert that their inputs reach this branch)
+			}
+#endif
 			ASTC_NOUNROLL
 			for (int k = 0; k < nfronts; k++) {
 				int ylo = k - (gw - 1);

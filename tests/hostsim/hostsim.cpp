@@ -26,6 +26,8 @@ template <typename F> static void run_lanes(F fn) {
 #endif
 }
 extern "C" int hostsim_lanes() { return ASTC_WARP; }
+// realign_weights calls that took the wavefront replay since the last call (32-lane build; the one-lane build runs the serial form)
+extern "C" unsigned int hostsim_wavefront_replays() { unsigned int n = g_hostsim_wavefront_replays; g_hostsim_wavefront_replays = 0; return n; }
 
 static unsigned int g_hostsim_a_scale_radius = 0;
 extern "C" void hostsim_set_a_scale_radius(unsigned int r) { g_hostsim_a_scale_radius = r; }

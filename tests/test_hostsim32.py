@@ -44,6 +44,18 @@ def test_wave_pipeline_on_32_lanes_matches_oracle(hostsim32, name, gen, prof, bx
     assert np.array_equal(sim_compress(hostsim32, img, prof, bx, by, q, fl), want)
 
 
+@pytest.mark.parametrize("bx,by,q", [(6, 6, PRE_MEDIUM), (8, 8, PRE_MEDIUM), (10, 5, PRE_MEDIUM), (12, 10, PRE_MEDIUM)], ids=["6x6", "8x8", "10x5", "12x10"])
+def test_wavefront_replay_of_realign_weights(hostsim32, bx, by, q):
+    """Noisy blocks move most of their weights: realign_weights must take its wavefront replay (fronts k = x + 2y) - asserted through
+    the simulation's counter - and still decide every weight on the state the reference's index-order loop shows it."""
+    img = I.uniform_noise(2 * by, 3 * bx, seed=21 + bx)
+    hostsim32.hostsim_wavefront_replays.restype = C.c_uint
+    hostsim32.hostsim_wavefront_replays()
+    got = sim_compress(hostsim32, img, PRF_LDR, bx, by, q)
+    assert hostsim32.hostsim_wavefront_replays() > 0
+    assert np.array_equal(got, Oracle().compress(img, PRF_LDR, bx, by, q, S))
+
+
 @pytest.mark.parametrize("driver", ["lockstep", "warp"])
 def test_single_kernel_drivers_on_32_lanes(hostsim32, monkeypatch, driver):
     monkeypatch.setenv("HOSTSIM_DRIVER", driver)
