@@ -36,7 +36,17 @@
 // Preparation items by what they prepare: 0 block statistics (two-plane phase), 1..3 the partition search for 2..4 partitions
 // (the search costs several times the statistics; the kernel votes once per item).
 #define ASTC_Q_PREP 4
-enum { Q_SETUP = 0, Q_REFINE = ASTC_Q_CLASSES * ASTC_Q_SUB, Q_PREPARE = Q_REFINE + ASTC_Q_CLASSES, Q_EMIT = Q_PREPARE + ASTC_Q_PREP, ASTC_Q_KINDS = Q_EMIT + 1 };
+// Refinement items may be sub-queued too (experiment builds, ASTC_RSORT: 1 by the number of candidates, 2 by the kind of weight grid
+// of the first candidate, 3 by the trial's weight quantisation limit); the shipped build has one queue per class (ASTC_Q_RSUB 1).
+#ifndef ASTC_RSORT
+	#define ASTC_RSORT 0
+#endif
+#if ASTC_RSORT == 0
+	#define ASTC_Q_RSUB 1
+#else
+	#define ASTC_Q_RSUB 4
+#endif
+enum { Q_SETUP = 0, Q_REFINE = ASTC_Q_CLASSES * ASTC_Q_SUB, Q_PREPARE = Q_REFINE + ASTC_Q_CLASSES * ASTC_Q_RSUB, Q_EMIT = Q_PREPARE + ASTC_Q_PREP, ASTC_Q_KINDS = Q_EMIT + 1 };
 
 struct WaveArgs {
 	uint8_t* records;            // [blocks] x record_bytes
@@ -135,6 +145,25 @@ ASTC_FN int setup_queue_of(const Trial& t, int klass) {
 	int q = t.max_weight_quant;
 	q = q < 0 ? 0 : (q >= ASTC_Q_SUB ? ASTC_Q_SUB - 1 : q);
 	return Q_SETUP + klass * ASTC_Q_SUB + q;
+}
+
+ASTC_FN int refine_queue_of(const WCtx& w, const Trial& t, int klass) {
+#if ASTC_RSORT == 1
+	int k = (int)t.candidate_count - 1;
+#elif ASTC_RSORT == 2
+	// 0: the first candidate's grid is the full grid (no realignment replay to speak of), 1: up to 16 weights, 2: up to 32, 3: more
+	Candidate c0 = sptr<Candidate>(w.base + A_CAND)[0];
+	const DevDecMode* dm = BSD.dec_modes + ASTC_LDG(&BSD.block_modes[c0.block_mode].decimation_mode);
+	int W = ASTC_LDG(&dm->weight_count);
+	int k = W == w.T ? 0 : (W <= 16 ? 1 : (W <= 32 ? 2 : 3));
+#elif ASTC_RSORT == 3
+	int k = t.max_weight_quant / 3;
+#else
+	int k = 0;
+	(void)w; (void)t;
+#endif
+	k = k < 0 ? 0 : (k >= ASTC_Q_RSUB ? ASTC_Q_RSUB - 1 : k);
+	return Q_REFINE + klass * ASTC_Q_RSUB + k;
 }
 
 ASTC_FN void q_push(const WCtx& w, const WaveArgs& a, int kind, int wave, unsigned int b) {
@@ -405,7 +434,7 @@ ASTC_COOP void wave_setup(WCtx w, WaveArgs a) {
 			int klass = trial_class(t);
 			STAT_T(s5);
 			record_save(w, a, b, a.wave == 0);
-			q_push(w, a, Q_REFINE + klass, a.wave, b);
+			q_push(w, a, refine_queue_of(w, t, klass), a.wave, b);
 #if defined(ASTC_STEP_STATS)
 			if (w.lane == 0) {
 				long long s6 = clock64();
@@ -461,7 +490,7 @@ ASTC_COOP void wave_finish_trial(WCtx w, const WaveArgs& a, unsigned int b, Bloc
 			dst[k] = src[k];
 		}
 		record_save(w, a, b);
-		q_push(w, a, Q_REFINE + klass, a.wave + 1, b);
+		q_push(w, a, refine_queue_of(w, t, klass), a.wave + 1, b);
 		return;
 	}
 	record_save(w, a, b);
@@ -501,7 +530,11 @@ ASTC_COOP void wave_refine(WCtx w, WaveArgs a, uint32_t warp_index) {
 #endif
 	while (true) {
 		while (!has_item && !drained) {
+#if ASTC_Q_RSUB == 1
 			if (!q_pop_classes(w, a, Q_REFINE, a.wave, cls, b)) {
+#else
+			if (!q_pop_sorted(w, a, Q_REFINE, ASTC_Q_RSUB, a.wave, cls, b, ASTC_Q_CLASSES)) {
+#endif
 				drained = true;
 				break;
 			}

@@ -141,7 +141,7 @@ astc_wave_setup_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant
 #endif
 __global__ void __launch_bounds__(ASTC_REFINE_THREADS_MAX, ASTC_REFINE_MIN_CTAS)
 astc_wave_refine_kernel(const __grid_constant__ DevBsd bsd, const __grid_constant__ DevConfig cfg, const __grid_constant__ DevImage img, const __grid_constant__ WaveArgs a) {
-	if (wave_queue_empty(a, Q_REFINE)) {
+	if (wave_queue_empty(a, Q_REFINE, 0, ASTC_Q_CLASSES * ASTC_Q_RSUB)) {
 		return;
 	}
 	stage_launch_constants(bsd, cfg, img);
