@@ -1,17 +1,26 @@
 // Dev-time probe (needs /root/reference; never runs on the GPU box): compares the oracle's generated
-// tables with the reference's own tables, entry by entry.
+// tables with the reference's own tables, entry by entry - 2D and 3D block sizes.
+//   g++ -std=c++14 -O1 -I/root/reference/Source -DASTCENC_SSE=0 -DASTCENC_AVX=0 -DASTCENC_NEON=0 -DASTCENC_POPCNT=0 -DASTCENC_F16C=0 \
+//       tests/probe/probe_tables.cpp oracle/astc_tables.cpp /root/reference/Source/astcenc_{block_sizes,partition_tables,percentile_tables,quantization,weight_quant_xfer_tables,mathlib,mathlib_softfloat}.cpp -o /tmp/probe && /tmp/probe
 #include "astcenc_integer_sequence.cpp"   // for the static BISE tables
+// -DPROBE_PRODUCT: probe the PRODUCT's host-side table construction (astc-encoder_b200/csrc/astc_host_tables.cpp, link that file
+// instead of oracle/astc_tables.cpp) - the tables the GPU kernels read are then compared with the reference's directly.
+#if defined(PROBE_PRODUCT)
+#include "../../astc-encoder_b200/csrc/astc_host_tables.h"
+namespace ao = astc_host;
+#else
 #include "../../oracle/astc_tables.h"
+#endif
 #include <cstdio>
 #include <cstring>
 
 static int fails = 0;
 #define CHECK(cond, ...) do { if (!(cond)) { if (fails < 40) { printf("FAIL: " __VA_ARGS__); printf("\n"); } fails++; } } while (0)
 
-static void check_bsd(unsigned bx, unsigned by, bool can_omit, unsigned pcut, float mcut) {
+static void check_bsd(unsigned bx, unsigned by, bool can_omit, unsigned pcut, float mcut, unsigned bz = 1) {
 	block_size_descriptor* bsd = aligned_malloc<block_size_descriptor>(sizeof(block_size_descriptor), 64);
-	init_block_size_descriptor(bx, by, 1, can_omit, pcut, mcut, *bsd);
-	ao::BlockSizeTables* t = ao::build_block_size_tables(bx, by, 1, can_omit, pcut, mcut);
+	init_block_size_descriptor(bx, by, bz, can_omit, pcut, mcut, *bsd);
+	ao::BlockSizeTables* t = ao::build_block_size_tables(bx, by, bz, can_omit, pcut, mcut);
 	CHECK(bsd->texel_count == t->texel_count, "texel_count");
 	CHECK(bsd->decimation_mode_count_always == t->decimation_mode_count_always, "dm always %u %u", bsd->decimation_mode_count_always, t->decimation_mode_count_always);
 	CHECK(bsd->decimation_mode_count_selected == t->decimation_mode_count_selected, "dm sel");
@@ -35,7 +44,7 @@ static void check_bsd(unsigned bx, unsigned by, bool can_omit, unsigned pcut, fl
 		const decimation_info& da = bsd->decimation_tables[i];
 		const ao::DecimationInfo& db = t->decimation_tables[i];
 		CHECK(da.texel_count == db.texel_count && da.weight_count == db.weight_count && da.weight_x == db.weight_x &&
-		      da.weight_y == db.weight_y && da.max_texel_weight_count == db.max_texel_weight_count, "di hdr %u", i);
+		      da.weight_y == db.weight_y && da.weight_z == db.weight_z && da.max_texel_weight_count == db.max_texel_weight_count, "di hdr %u", i);
 		for (unsigned tix = 0; tix < da.texel_count; tix++) {
 			CHECK(da.texel_weight_count[tix] == db.texel_weight_count[tix], "di twc");
 			for (int k = 0; k < 4; k++) {
@@ -74,7 +83,7 @@ static void check_bsd(unsigned bx, unsigned by, bool can_omit, unsigned pcut, fl
 			}
 		}
 	}
-	printf("bsd %ux%u omit=%d pcut=%u mcut=%.2f: modes %u/%u/%u/%u dec %u/%u/%u parts %u/%u/%u  fails so far %d\n", bx, by, can_omit, pcut, mcut,
+	printf("bsd %ux%ux%u omit=%d pcut=%u mcut=%.2f: modes %u/%u/%u/%u dec %u/%u/%u parts %u/%u/%u  fails so far %d\n", bx, by, bz, can_omit, pcut, mcut,
 	       t->block_mode_count_1plane_always, t->block_mode_count_1plane_selected, t->block_mode_count_1plane_2plane_selected, t->block_mode_count_all,
 	       t->decimation_mode_count_always, t->decimation_mode_count_selected, t->decimation_mode_count_all,
 	       t->partitioning_count_selected[1], t->partitioning_count_selected[2], t->partitioning_count_selected[3], fails);
@@ -127,6 +136,11 @@ int main() {
 	check_bsd(10, 8, true, 4, 1.0f);
 	check_bsd(12, 12, true, 4, 0.98f);
 	check_bsd(12, 10, false, 2, 0.40f);
+	// the ten 3D footprints (no percentile selection: every grid that fits, every legal mode)
+	static const unsigned fp3[10][3] = {{3, 3, 3}, {4, 3, 3}, {4, 4, 3}, {4, 4, 4}, {5, 4, 4}, {5, 5, 4}, {5, 5, 5}, {6, 5, 5}, {6, 6, 5}, {6, 6, 6}};
+	for (int i = 0; i < 10; i++) {
+		check_bsd(fp3[i][0], fp3[i][1], (i & 1) != 0, 2 + (unsigned)(i % 3), 0.77f, fp3[i][2]);
+	}
 	printf("TOTAL FAILS %d\n", fails);
 	return fails != 0;
 }

@@ -50,3 +50,28 @@ def test_constant_block_golden_vector(oracle):
     assert bytes(out[:8]) == bytes([0xFC, 0xFD, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF])
     vals = out[8:16].view(np.uint16)
     assert list(vals) == [65535, 128 * 257, 0, 65535]
+
+
+@pytest.mark.parametrize("which", ["oracle", "product"])
+def test_tables_equal_reference_tables_entry_by_entry(tmp_path, which):
+    """tests/probe/probe_tables.cpp links the oracle's table construction with the reference's own (block modes, decimation tables
+    incl. the 3D simplex ones, partitionings, coverage bitmaps, k-means texels, BISE / quantisation tables) and compares every entry:
+    8 two-dimensional configurations and the ten 3D footprints. "product": the same probe over the host-side table construction of the
+    CUDA library (what the kernels read), so that it is pinned to the reference directly and not through the oracle. Needs the reference
+    sources: runs in the dev container only."""
+    import subprocess
+    src = "/root/reference/Source"
+    if not os.path.isdir(src):
+        pytest.skip("reference sources not here")
+    exe = str(tmp_path / "probe")
+    units = ["block_sizes", "partition_tables", "percentile_tables", "quantization", "weight_quant_xfer_tables", "mathlib", "mathlib_softfloat"]
+    cmd = ["g++", "-std=c++14", "-O1", "-I" + src, "-DASTCENC_SSE=0", "-DASTCENC_AVX=0", "-DASTCENC_NEON=0", "-DASTCENC_POPCNT=0", "-DASTCENC_F16C=0",
+           os.path.join(ROOT, "tests", "probe", "probe_tables.cpp")] + \
+          ([os.path.join(ROOT, "oracle", "astc_tables.cpp")] if which == "oracle" else
+           ["-DPROBE_PRODUCT=1", os.path.join(ROOT, "astc-encoder_b200", "csrc", "astc_host_tables.cpp")]) + \
+          [os.path.join(src, "astcenc_%s.cpp" % u) for u in units] + ["-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "TOTAL FAILS 0" in r.stdout, r.stdout[-2000:]
+    assert r.stdout.count("bsd ") == 18
