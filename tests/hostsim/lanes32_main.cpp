@@ -5,6 +5,7 @@
 //       astc-encoder_b200/csrc/astc_host_config.cpp -o /tmp/lanes32_tsan
 //   /tmp/lanes32_tsan <profile 0-3> <block_x> <block_y> <quality> <width> <height> <seed> [kind: 0 noise, 1 two-colour stripes, 2 hdr,
 //                     3 = stripes + decode of the result, 4 = alpha-scale pre-pass (radius 2) on stripes with transparent rows]
+//                    [block_z depth: a 3D block size on a volume of <height> x <depth> rows of noise / stripes, compressed and decoded]
 // ThreadSanitizer sees every shared-memory access of every lane; the warp collectives are its only synchronisation, so a
 // report is a missing __syncwarp() between a producer lane and a consumer lane. Prints an FNV hash of the output blocks.
 #include <cstdint>
@@ -18,6 +19,10 @@ extern "C" int hostsim_compress_image(int profile, unsigned int bx, unsigned int
 extern "C" int hostsim_decompress_image(int profile, unsigned int bx, unsigned int by, unsigned int flags, const uint8_t* blocks, void* out, int data_type,
                                         unsigned int dim_x, unsigned int dim_y, const int* swz);
 extern "C" void hostsim_set_a_scale_radius(unsigned int r);
+extern "C" int hostsim_compress_volume(int profile, unsigned int bx, unsigned int by, unsigned int bz, float quality, unsigned int flags,
+                                       const void* data, int data_type, unsigned int dim_x, unsigned int dim_y, unsigned int dim_z, const int* swz, uint8_t* out);
+extern "C" int hostsim_decompress_volume(int profile, unsigned int bx, unsigned int by, unsigned int bz, unsigned int flags, const uint8_t* blocks, void* out, int data_type,
+                                         unsigned int dim_x, unsigned int dim_y, unsigned int dim_z, const int* swz);
 
 int main(int argc, char** argv) {
 	if (argc < 8) {
@@ -59,6 +64,23 @@ int main(int argc, char** argv) {
 	}
 	if (kind == 3) {
 		flags = 0;                // full tables: the result is decoded below
+	}
+	if (argc > 10) {
+		// 3D block size: the image rows are cut into `depth` slices of h / depth rows
+		unsigned int bz = (unsigned int)atoi(argv[9]), depth = (unsigned int)atoi(argv[10]);
+		unsigned int hs = h / depth;
+		unsigned int nb3 = ((w + bx - 1) / bx) * ((hs + by - 1) / by) * ((depth + bz - 1) / bz);
+		std::vector<uint8_t> out3((size_t)nb3 * 16);
+		int rc3 = hostsim_compress_volume(profile, bx, by, bz, quality, 0, img8.data(), 0, w, hs, depth, nullptr, out3.data());
+		uint64_t hash3 = 1469598103934665603ull;
+		for (uint8_t b : out3) { hash3 = (hash3 ^ b) * 1099511628211ull; }
+		if (rc3 == 0) {
+			std::vector<uint8_t> dec((size_t)w * hs * depth * 4);
+			rc3 = hostsim_decompress_volume(profile, bx, by, bz, 0, out3.data(), dec.data(), 0, w, hs, depth, nullptr);
+			for (uint8_t b : dec) { hash3 = (hash3 ^ b) * 1099511628211ull; }
+		}
+		printf("rc %d blocks %u hash %016llx\n", rc3, nb3, (unsigned long long)hash3);
+		return rc3;
 	}
 	unsigned int nb = ((w + bx - 1) / bx) * ((h + by - 1) / by);
 	std::vector<uint8_t> out((size_t)nb * 16);

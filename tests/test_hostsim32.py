@@ -88,7 +88,8 @@ def test_decode_on_32_lanes(hostsim32):
 
 
 @pytest.mark.parametrize("args", ["1 6 6 60 18 12 1 0", "1 6 6 60 24 18 2 1", "3 6 6 60 12 12 3 2", "1 4 4 98 12 12 4 1", "1 8 8 60 16 16 5 1",
-                                  "1 6 6 10 18 18 6 3", "1 6 6 60 18 18 7 4"])      # last two: + decode of the result, alpha-scale pre-pass
+                                  "1 6 6 10 18 18 6 3", "1 6 6 60 18 18 7 4",      # these two: + decode of the result, alpha-scale pre-pass
+                                  "1 4 4 60 8 32 8 0 4 4", "1 5 5 60 10 30 9 1 4 6"])      # 3D block sizes 4x4x4 / 5x5x4 on 8x8x4 / 10x5x6 volumes, + decode
 def test_no_data_race_between_lanes(lanes32_tsan, args):
     """ThreadSanitizer over the whole wave pipeline: any report is a missing __syncwarp() between lanes (removing one is
     detected at once - tried by hand on pack_work_endpoints)."""
